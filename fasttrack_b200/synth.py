@@ -1,0 +1,181 @@
+"""Deterministic synthetic inputs for the tracking front-end.
+
+All generators are seeded numpy; no files, no network. Shapes follow the reference's
+dataset configs: EuRoC pinhole 752x480 (Examples/Stereo/EuRoC.yaml:23-26,43-44) and
+TUM-VI KannalaBrandt8 512x512 (Examples/Stereo-Inertial/TUM-VI.yaml:11-49).
+"""
+import numpy as np
+
+EUROC = dict(width=752, height=480, fx=458.654, fy=457.296, cx=367.215, cy=248.375, baseline=0.110074,
+             nfeatures=1200, nlevels=8, scale=1.2, ini_th=20, min_th=7)
+
+# Examples/Stereo-Inertial/TUM-VI.yaml (camera 1 / camera 2 intrinsics, T_c1_c2, overlap)
+TUMVI = dict(
+    width=512, height=512,
+    cam1=[190.978477, 190.973307, 254.931706, 256.897442, 0.0034823894022493434, 0.0007150348452162257,
+          -0.0020532361418706202, 0.00020293673591811182],
+    cam2=[190.442369, 190.434438, 252.597254, 254.917234, 0.0034003170790442797, 0.001766278153469831,
+          -0.00266312569781606, 0.0003299517423931039],
+    T_c1_c2=[[0.9999994317, 0.0008361597, 0.0006758557, -0.1010596120],
+             [-0.0008042732, 0.9989843, -0.0450513, -0.0019463],
+             [-0.0007128, 0.0450507, 0.9989844, -0.0015185]],
+    lap=(0, 511), nfeatures=1000, nlevels=8, scale=1.2, ini_th=20, min_th=7, bf=19.3079)
+
+
+def _orthonormalize(R):
+    u, _, vt = np.linalg.svd(np.asarray(R, np.float64))
+    return u @ vt
+
+
+def tumvi_extrinsics():
+    """returns Rlr(3x3), tlr(3), Rrl, trl as float32 (Tlr = T_c1_c2, a proper SE3)"""
+    T = np.asarray(TUMVI["T_c1_c2"], np.float64)
+    R = _orthonormalize(T[:, :3]); t = T[:, 3]
+    Rrl = R.T; trl = -Rrl @ t
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    return f(R), f(t), f(Rrl), f(trl)
+
+
+def texture(h, w, seed, n_rect=6000, n_disc=3000, noise=3):
+    """Config-1 texture: random rectangles + discs (painter's order), 3x3 box blur, uniform noise."""
+    rng = np.random.default_rng(seed)
+    area = (w * h) / (752.0 * 480.0)
+    n_rect = max(8, int(n_rect * area)); n_disc = max(4, int(n_disc * area))
+    img = np.full((h, w), 128, np.float32)
+    n = n_rect + n_disc
+    kind = np.zeros(n, np.int32); kind[n_rect:] = 1
+    rng.shuffle(kind)
+    cx = rng.integers(0, w, n); cy = rng.integers(0, h, n)
+    sx = rng.integers(3, 41, n); sy = rng.integers(3, 41, n)
+    gray = rng.integers(0, 256, n)
+    for i in range(n):
+        if kind[i] == 0:
+            x0, x1 = max(cx[i] - sx[i] // 2, 0), min(cx[i] + sx[i] // 2 + 1, w)
+            y0, y1 = max(cy[i] - sy[i] // 2, 0), min(cy[i] + sy[i] // 2 + 1, h)
+            img[y0:y1, x0:x1] = gray[i]
+        else:
+            r = sx[i] // 2 + 1
+            x0, x1 = max(cx[i] - r, 0), min(cx[i] + r + 1, w)
+            y0, y1 = max(cy[i] - r, 0), min(cy[i] + r + 1, h)
+            if x1 <= x0 or y1 <= y0:
+                continue
+            yy, xx = np.mgrid[y0:y1, x0:x1]
+            m = (xx - cx[i]) ** 2 + (yy - cy[i]) ** 2 <= r * r
+            img[y0:y1, x0:x1][m] = gray[i]
+    p = np.pad(img, 1, mode="edge")
+    img = sum(p[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)) / 9.0
+    img = img + rng.integers(-noise, noise + 1, (h, w))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def _shift_left(a, d):
+    """resample a[y, x + d] with bilinear interpolation along x (fractional d >= 0), edge-clamped"""
+    h, w = a.shape
+    x = np.arange(w, dtype=np.float64) + d
+    x0 = np.floor(x).astype(np.int64); f = (x - x0).astype(np.float32)
+    x0c = np.clip(x0, 0, w - 1); x1c = np.clip(x0 + 1, 0, w - 1)
+    return a[:, x0c] * (1 - f) + a[:, x1c] * f
+
+
+class StereoScene:
+    """Config-2/5 scene: 12 fronto-parallel textured layers with log-spaced disparities."""
+
+    def __init__(self, seed=2, width=752, height=480, n_layers=12, dmin=1.5, dmax=64.0, margin_x=128, margin_y=16):
+        self.w, self.h = width, height
+        self.mx, self.my = margin_x, margin_y
+        cw, ch = width + 2 * margin_x, height + 2 * margin_y
+        rng = np.random.default_rng(seed)
+        self.disp = np.exp(np.linspace(np.log(dmin), np.log(dmax), n_layers))
+        left = np.zeros((ch, cw), np.float32); right = np.zeros((ch, cw), np.float32)
+        for k in range(n_layers):
+            tex = texture(ch, cw, seed * 1000 + k).astype(np.float32)
+            if k == 0:
+                mask = np.ones((ch, cw), np.float32)
+            else:
+                mask = np.zeros((ch, cw), np.float32)
+                target = cw * ch / n_layers
+                while mask.sum() < target:
+                    bw, bh = rng.integers(40, 200), rng.integers(40, 160)
+                    x0, y0 = rng.integers(0, cw - 20), rng.integers(0, ch - 20)
+                    mask[y0:y0 + bh, x0:x0 + bw] = 1
+            left = np.where(mask > 0, tex, left)
+            ts, ms = _shift_left(tex, self.disp[k]), _shift_left(mask, self.disp[k])
+            right = right * (1 - ms) + ts * ms
+        self.left, self.right = left, right
+
+    def pair(self, pan=(0, 0), noise_seed=None, noise=2):
+        px = int(np.clip(round(pan[0]), -self.mx + 64, self.mx - 64)) + self.mx
+        py = int(np.clip(round(pan[1]), -self.my, self.my)) + self.my
+        L = self.left[py:py + self.h, px:px + self.w]
+        R = self.right[py:py + self.h, px:px + self.w]
+        if noise_seed is not None:
+            rng = np.random.default_rng(noise_seed)
+            L = L + rng.integers(-noise, noise + 1, L.shape)
+            R = R + rng.integers(-noise, noise + 1, R.shape)
+        f = lambda a: np.ascontiguousarray(np.clip(np.rint(a), 0, 255).astype(np.uint8))
+        return f(L), f(R)
+
+    def sequence_pan(self, t):
+        return (40.0 * np.sin(2 * np.pi * t / 200.0), 12.0 * np.sin(2 * np.pi * t / 130.0))
+
+
+def fisheye_pair(seed=3, size=512):
+    sc = StereoScene(seed=seed, width=size, height=size, dmin=1.0, dmax=40.0)
+    return sc.pair()
+
+
+def mappoints(keys, desc, scale_factors, M, seed=4, width=752, height=480, fx=458.654, fy=457.296, cx=367.215,
+              cy=248.375, frac_inside=0.7, claimed_frac=0.25):
+    """Config-4 local map: M MapPoints against a frame at identity pose.
+
+    returns dict(pos[M,3], normal[M,3], minmax[M,2], desc[M,32], flags[M], holder[N], holder_obs[N])
+    flags: bit0 = skip (bad / already matched), bit1 = Observations() > 0.
+    """
+    rng = np.random.default_rng(seed)
+    N = len(keys)
+    nl = len(scale_factors)
+    pos = np.zeros((M, 3), np.float32); normal = np.zeros((M, 3), np.float32)
+    minmax = np.zeros((M, 2), np.float32); d = np.zeros((M, 32), np.uint8)
+    inside = rng.random(M) < frac_inside
+    anchored = rng.random(M) < 0.5
+    for i in range(M):
+        z = rng.uniform(0.4, 25.0)
+        lvl = int(rng.integers(0, nl))
+        if inside[i] and anchored[i] and N > 0:
+            k = int(rng.integers(0, N))
+            lvl = int(keys[k, 5])
+            jit = 1.5 * scale_factors[lvl]
+            u = keys[k, 0] + rng.uniform(-jit, jit); v = keys[k, 1] + rng.uniform(-jit, jit)
+            bits = np.unpackbits(desc[k])
+            nflip = int(rng.integers(0, 49))
+            flip = rng.choice(256, nflip, replace=False)
+            bits[flip] ^= 1
+            d[i] = np.packbits(bits)
+        else:
+            u = rng.uniform(0, width); v = rng.uniform(0, height)
+            d[i] = rng.integers(0, 256, 32, dtype=np.uint8)
+        P = np.array([(u - cx) * z / fx, (v - cy) * z / fy, z])
+        dist = np.linalg.norm(P)
+        n = P / dist + 0.26 * rng.standard_normal(3)
+        n /= np.linalg.norm(n)
+        maxd = dist * scale_factors[lvl] * 0.95
+        mind = maxd / scale_factors[nl - 1]
+        if not inside[i]:
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                P[2] = -P[2]
+            elif mode == 1:
+                P[0] += (2.0 * width / fx) * z * (1 if rng.random() < 0.5 else -1)
+            elif mode == 2:
+                maxd = dist * 0.3; mind = maxd / scale_factors[nl - 1]
+            else:
+                n = -n
+        pos[i] = P; normal[i] = n; minmax[i] = (mind, maxd)
+    flags = np.full(M, 2, np.int32)
+    flags[rng.random(M) < 0.03] = 0          # Observations() == 0
+    flags[rng.random(M) < 0.02] |= 1         # skipped (bad / matched already)
+    holder = np.full(N, -1, np.int32); holder_obs = np.zeros(N, np.uint8)
+    cl = rng.random(N) < claimed_frac
+    holder[cl] = -2
+    holder_obs[cl] = (rng.random(int(cl.sum())) < 0.9).astype(np.uint8)
+    return dict(pos=pos, normal=normal, minmax=minmax, desc=d, flags=flags, holder=holder, holder_obs=holder_obs)

@@ -1,0 +1,318 @@
+"""ctypes bindings over the CPU ORACLE (oracle/ft_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs. The product package (fasttrack_b200) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libft_oracle.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("ft_oracle.cpp", "ft_oracle_capi.cpp", "ft_oracle.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "ft_orb_pattern.inc"))
+    if not force and os.path.exists(_SO) and all(
+        (not os.path.exists(s)) or os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs
+    ):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [
+        ("Nleft", C.c_int), ("Nright", C.c_int), ("N", C.c_int),
+        ("keys6", C.c_void_p), ("desc", C.c_void_p), ("uRight", C.c_void_p),
+        ("l2r", C.c_void_p), ("r2l", C.c_void_p),
+        ("minX", C.c_float), ("maxX", C.c_float), ("minY", C.c_float), ("maxY", C.c_float),
+        ("nlevels", C.c_int), ("scale", C.c_void_p), ("logScale", C.c_float),
+        ("camType", C.c_int), ("cam1", C.c_float * 8), ("cam2", C.c_float * 8),
+        ("mbf", C.c_float),
+        ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Rwc", C.c_float * 9), ("Ow", C.c_float * 3),
+        ("Rrl", C.c_float * 9), ("trl", C.c_float * 3), ("tlr", C.c_float * 3),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_SO)
+    L.fto_extractor_create.restype = C.c_void_p
+    L.fto_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.fto_extractor_destroy.argtypes = [C.c_void_p]
+    L.fto_extractor_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+    L.fto_extract.restype = C.c_int
+    L.fto_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, u8p,
+                              C.POINTER(C.c_int)]
+    L.fto_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fto_level_image.restype = C.c_int
+    L.fto_level_image.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p]
+    L.fto_level_candidates.restype = C.c_int
+    L.fto_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
+    L.fto_level_keys.restype = C.c_int
+    L.fto_level_keys.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, u8p]
+    L.fto_desc_borderline.restype = C.c_long
+    L.fto_desc_borderline.argtypes = [C.c_void_p]
+    L.fto_resize.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.fto_blur.argtypes = [u8p, C.c_int, C.c_int, u8p]
+    L.fto_fast.restype = C.c_int
+    L.fto_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+    L.fto_fast_atan2.restype = C.c_float
+    L.fto_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.fto_cv_round.restype = C.c_int
+    L.fto_cv_round.argtypes = [C.c_float]
+    L.fto_knn2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p]
+    L.fto_descriptor_distance.restype = C.c_int
+    L.fto_descriptor_distance.argtypes = [u8p, u8p]
+    L.fto_octree.restype = C.c_int
+    L.fto_octree.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+    L.fto_stereo.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, u8p, f32p, C.c_int, u8p, C.c_float, C.c_float,
+                             f32p, f32p, i32p, i32p]
+    L.fto_fisheye.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int, f32p, C.c_int, u8p, C.c_int, f32p, C.c_int, u8p,
+                              C.c_int, i32p, i32p, f32p, f32p, i32p]
+    L.fto_cam_project.argtypes = [C.c_int, f32p, f32p, f32p]
+    L.fto_kb8_unproject.argtypes = [f32p, C.c_float, C.c_float, f32p]
+    L.fto_frame_create.restype = C.c_void_p
+    L.fto_frame_create.argtypes = [C.POINTER(FrameDesc)]
+    L.fto_frame_destroy.argtypes = [C.c_void_p]
+    L.fto_frame_grid.restype = C.c_int
+    L.fto_frame_grid.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+    L.fto_frustum.argtypes = [C.c_void_p, C.c_int, f32p, f32p, f32p, u8p, i32p, C.c_float, i32p, f32p]
+    L.fto_search_local_points.restype = C.c_int
+    L.fto_search_local_points.argtypes = [C.c_void_p, C.c_int, f32p, f32p, f32p, u8p, i32p, C.c_float, C.c_int,
+                                          C.c_float, C.c_float, i32p, u8p, C.c_void_p, C.c_void_p]
+    L.fto_time_stereo_frame.restype = C.c_double
+    L.fto_time_stereo_frame.argtypes = [C.c_void_p, C.c_void_p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+class Extractor:
+    """Oracle mirror of ORB_SLAM3::ORBextractor (CPU branch)."""
+
+    def __init__(self, nfeatures=1200, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.h = C.c_void_p(self.L.fto_extractor_create(nfeatures, scale, nlevels, ini_th, min_th))
+        self.scale = np.zeros(nlevels, np.float32)
+        self.inv_scale = np.zeros(nlevels, np.float32)
+        self.sigma2 = np.zeros(nlevels, np.float32)
+        self.inv_sigma2 = np.zeros(nlevels, np.float32)
+        self.features_per_level = np.zeros(nlevels, np.int32)
+        self.umax = np.zeros(16, np.int32)
+        self.L.fto_extractor_tables(self.h, self.scale, self.inv_scale, self.sigma2, self.inv_sigma2,
+                                    self.features_per_level, self.umax)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fto_extractor_destroy(self.h)
+            self.h = None
+
+    def extract(self, img, lap=(0, 0)):
+        """returns (monoIndex, kps[n,6] float32, desc[n,32] uint8)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        hgt, wid = img.shape
+        cap = self.nfeatures + 64
+        kps = np.zeros((cap, 6), np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        mono = self.L.fto_extract(self.h, img.ctypes.data, wid, hgt, img.strides[0], lap[0], lap[1], cap, kps, desc,
+                                  C.byref(n))
+        assert n.value <= cap
+        return mono, kps[: n.value].copy(), desc[: n.value].copy()
+
+    def level_dims(self, level):
+        w, h = C.c_int(), C.c_int()
+        self.L.fto_level_dims(self.h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_image(self, level, blurred=False):
+        w, h = self.level_dims(level)
+        out = np.zeros((h, w), np.uint8)
+        ok = self.L.fto_level_image(self.h, level, int(blurred), out)
+        return out if ok else None
+
+    def level_candidates(self, level):
+        n = self.L.fto_level_candidates(self.h, level, 0, np.zeros((1, 3), np.float32))
+        out = np.zeros((max(n, 1), 3), np.float32)
+        self.L.fto_level_candidates(self.h, level, n, out)
+        return out[:n]
+
+    def level_keys(self, level):
+        cap = self.nfeatures + 64
+        kps = np.zeros((cap, 6), np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.fto_level_keys(self.h, level, cap, kps, desc)
+        return kps[:n].copy(), desc[:n].copy()
+
+    def desc_borderline(self):
+        return int(self.L.fto_desc_borderline(self.h))
+
+    def octree(self, xyr, min_x, max_x, min_y, max_y, n_target):
+        xyr = np.ascontiguousarray(xyr, np.float32)
+        out = np.zeros((max(len(xyr), 1), 3), np.float32)
+        n = self.L.fto_octree(self.h, xyr, len(xyr), min_x, max_x, min_y, max_y, n_target, out)
+        return out[:n].copy()
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().fto_resize(src, src.shape[1], src.shape[0], dst, dw, dh)
+    return dst
+
+
+def blur(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().fto_blur(src, src.shape[1], src.shape[0], dst)
+    return dst
+
+
+def fast(img, th):
+    """cv::FAST(img, th, nonmax=True) on a (possibly strided) 2-D uint8 view; returns [n,3] x,y,response"""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = max(1, (w * h) // 4 + 16)
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().fto_fast(img.ctypes.data, img.strides[0], w, h, th, cap, out)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return float(lib().fto_fast_atan2(float(y), float(x)))
+
+
+def cv_round(v):
+    return int(lib().fto_cv_round(float(v)))
+
+
+def knn2(q, t):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    idx = np.zeros((len(q), 2), np.int32)
+    dist = np.zeros((len(q), 2), np.int32)
+    lib().fto_knn2(q, len(q), t, len(t), idx, dist)
+    return idx, dist
+
+
+def stereo(exL, exR, kL, dL, kR, dR, mbf, mb):
+    kL = np.ascontiguousarray(kL, np.float32); kR = np.ascontiguousarray(kR, np.float32)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    n = len(kL)
+    u = np.zeros(n, np.float32); d = np.zeros(n, np.float32)
+    b = np.zeros(n, np.int32); s = np.zeros(n, np.int32)
+    lib().fto_stereo(exL.h, exR.h, kL, n, dL, kR, len(kR), dR, mbf, mb, u, d, b, s)
+    return dict(uRight=u, depth=d, bestIdxR=b, sad=s)
+
+
+def fisheye(cam1, cam2, Rlr, tlr, sigma2, kL, dL, mono_left, kR, dR, mono_right):
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    kL, kR = f(kL), f(kR)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    nL, nR = len(kL), len(kR)
+    l2r = np.zeros(max(nL, 1), np.int32); r2l = np.zeros(max(nR, 1), np.int32)
+    depth = np.zeros(max(nL, 1), np.float32); p3d = np.zeros((max(nL, 1), 3), np.float32)
+    code = np.zeros(max(nL, 1), np.int32)
+    lib().fto_fisheye(f(cam1), f(cam2), f(Rlr).reshape(-1), f(tlr), f(sigma2), len(sigma2), kL, nL, dL, mono_left, kR,
+                      nR, dR, mono_right, l2r, r2l, depth, p3d, code)
+    return dict(l2r=l2r[:nL], r2l=r2l[:nR], depth=depth[:nL], p3d=p3d[:nL], code=code[:nL])
+
+
+class Frame:
+    """Oracle mirror of the parts of ORB_SLAM3::Frame that the projection search reads."""
+
+    def __init__(self, keys, desc, scale, width, height, cam_type=0, cam1=None, cam2=None, mbf=0.0, u_right=None,
+                 n_left=-1, n_right=-1, l2r=None, r2l=None, Rcw=None, tcw=None, Rrl=None, trl=None, tlr=None):
+        self.L = lib()
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        self._keep = dict(keys=f(keys), desc=np.ascontiguousarray(desc, np.uint8), scale=f(scale))
+        d = FrameDesc()
+        d.Nleft, d.Nright, d.N = n_left, n_right, len(keys)
+        d.keys6 = self._keep["keys"].ctypes.data
+        d.desc = self._keep["desc"].ctypes.data
+        if u_right is not None:
+            self._keep["ur"] = f(u_right); d.uRight = self._keep["ur"].ctypes.data
+        if l2r is not None:
+            self._keep["l2r"] = np.ascontiguousarray(l2r, np.int32); d.l2r = self._keep["l2r"].ctypes.data
+        if r2l is not None:
+            self._keep["r2l"] = np.ascontiguousarray(r2l, np.int32); d.r2l = self._keep["r2l"].ctypes.data
+        d.minX, d.maxX, d.minY, d.maxY = 0.0, float(width), 0.0, float(height)
+        d.nlevels = len(scale)
+        d.scale = self._keep["scale"].ctypes.data
+        d.logScale = float(np.log(np.float32(scale[1]))) if len(scale) > 1 else 1.0
+        d.logScale = float(np.float32(np.log(np.float32(scale[1])))) if len(scale) > 1 else 1.0
+        d.camType = cam_type
+        cam1 = f(cam1 if cam1 is not None else np.zeros(8)); cam2 = f(cam2 if cam2 is not None else cam1)
+        for i in range(8):
+            d.cam1[i] = cam1[i]; d.cam2[i] = cam2[i]
+        d.mbf = mbf
+        Rcw = f(np.eye(3) if Rcw is None else Rcw).reshape(3, 3); tcw = f(np.zeros(3) if tcw is None else tcw)
+        Rwc = np.ascontiguousarray(Rcw.T); Ow = (-(Rwc @ tcw)).astype(np.float32)
+        Rrl = f(np.eye(3) if Rrl is None else Rrl).reshape(3, 3)
+        trl = f(np.zeros(3) if trl is None else trl); tlr = f(np.zeros(3) if tlr is None else tlr)
+        for i in range(9):
+            d.Rcw[i] = Rcw.reshape(-1)[i]; d.Rwc[i] = Rwc.reshape(-1)[i]; d.Rrl[i] = Rrl.reshape(-1)[i]
+        for i in range(3):
+            d.tcw[i] = tcw[i]; d.Ow[i] = Ow[i]; d.trl[i] = trl[i]; d.tlr[i] = tlr[i]
+        self.Rwc, self.Ow = Rwc, Ow
+        self.N = len(keys)
+        self.h = C.c_void_p(self.L.fto_frame_create(C.byref(d)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fto_frame_destroy(self.h)
+            self.h = None
+
+    def grid(self, right=False):
+        counts = np.zeros(64 * 48, np.int32)
+        idx = np.zeros(max(self.N, 1), np.int32)
+        n = self.L.fto_frame_grid(self.h, int(right), counts, idx)
+        return counts, idx[:n].copy()
+
+    @staticmethod
+    def _mp(pos, normal, minmax, desc, flags):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        return f(pos), f(normal), f(minmax), np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(flags, np.int32)
+
+    def frustum(self, pos, normal, minmax, desc, flags, view_cos_limit=0.5):
+        pos, normal, minmax, desc, flags = self._mp(pos, normal, minmax, desc, flags)
+        M = len(pos)
+        ti = np.zeros((M, 5), np.int32); tf = np.zeros((M, 9), np.float32)
+        self.L.fto_frustum(self.h, M, pos, normal, minmax, desc, flags, view_cos_limit, ti, tf)
+        return ti, tf
+
+    def search_local_points(self, pos, normal, minmax, desc, flags, th, holder, holder_obs, b_far=False, th_far=50.0,
+                            nnratio=0.8):
+        pos, normal, minmax, desc, flags = self._mp(pos, normal, minmax, desc, flags)
+        M = len(pos)
+        holder = np.ascontiguousarray(holder, np.int32).copy()
+        holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        ti = np.zeros((M, 5), np.int32); tf = np.zeros((M, 9), np.float32)
+        n = self.L.fto_search_local_points(self.h, M, pos, normal, minmax, desc, flags, th, int(b_far), th_far, nnratio,
+                                           holder, holder_obs, ti.ctypes.data, tf.ctypes.data)
+        return n, holder, holder_obs, ti, tf
+
+
+def time_stereo_frame(exL, exR, imgL, imgR, mbf, mb, two_threads=True):
+    imgL = np.ascontiguousarray(imgL, np.uint8); imgR = np.ascontiguousarray(imgR, np.uint8)
+    h, w = imgL.shape
+    nl, nr, ns = C.c_int(), C.c_int(), C.c_int()
+    ms = lib().fto_time_stereo_frame(exL.h, exR.h, imgL, imgR, w, h, w, mbf, mb, int(two_threads), C.byref(nl),
+                                     C.byref(nr), C.byref(ns))
+    return ms, nl.value, nr.value, ns.value

@@ -1,0 +1,149 @@
+// ft_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).
+//
+// Plain C++17 restatement of the reference's CPU tracking front-end
+// (sfu-rsl/FastTrack, the code executed when KernelController::*RunStatus == 0).
+// It exists to CHECK the CUDA path. Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it. The product
+// (fasttrack_b200/) never links, imports or calls anything in oracle/.
+//
+// Parity pin: the reference ships no tests or golden vectors for this path
+// (SURVEY.md section 4), and it cannot be compiled here (needs OpenCV C++, Eigen,
+// Sophus, Pangolin). The OpenCV primitives it calls are therefore pinned
+// bit-exactly against the in-container cv2 4.13.0 (tests/test_oracle_cv2.py and
+// the fixtures under tests/golden/ made by tools/make_cv2_golden.py); the
+// operator-level logic is a line-by-line restatement cited per function.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace fto {
+
+struct KeyPoint {
+  float x, y, size, angle, response;
+  int octave;
+};
+
+struct Img {
+  int w = 0, h = 0;
+  std::vector<uint8_t> d;  // tight, stride == w
+  const uint8_t* row(int y) const { return d.data() + (size_t)y * w; }
+  uint8_t* row(int y) { return d.data() + (size_t)y * w; }
+};
+
+struct Candidate {  // pre-octree FAST keypoint, coordinates relative to (minBorderX, minBorderY)
+  float x, y, response;
+};
+
+// ---- primitives (pinned against cv2) ----
+int cv_round(float v);
+void resize_linear_u8(const Img& src, Img& dst, int dw, int dh);    // cv::resize INTER_LINEAR 8UC1
+void gaussian_blur_7x7_s2(const Img& src, Img& dst);                // cv::GaussianBlur 7x7 sigma 2 REFLECT_101
+int fast_score_9_16(const uint8_t* p, int stride);                  // cv::FAST cornerScore<16> with threshold folded out
+void fast_detect(const uint8_t* roi, int stride, int w, int h, int th, std::vector<Candidate>& out);  // cv::FAST(..., nonmax=true)
+float fast_atan2(float y, float x);                                 // cv::fastAtan2
+void knn2_hamming(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx2, int* dist2);  // BFMatcher knnMatch k=2
+int descriptor_distance(const uint8_t* a, const uint8_t* b);        // ORBmatcher.cc:2256-2273
+
+// ---- ORBextractor (ORBextractor.cc CPU branches) ----
+class Extractor {
+ public:
+  Extractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+  // operator() -- returns monoIndex, -1 on empty image (ORBextractor.cc:1356-1493)
+  int extract(const uint8_t* img, int w, int h, int step, int lap0, int lap1,
+              std::vector<KeyPoint>& kps, std::vector<uint8_t>& desc);
+
+  int nfeatures, nlevels, iniTh, minTh;
+  double scaleFactor;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> featuresPerLevel;
+  std::vector<int> umax;
+  // state after extract()
+  std::vector<Img> pyramid;                          // mvImagePyramid (inner ROI)
+  std::vector<Img> blurred;                          // per-level GaussianBlur (only levels with keypoints)
+  std::vector<std::vector<Candidate>> candidates;    // vToDistributeKeys per level
+  std::vector<std::vector<KeyPoint>> levelKeys;      // after octree + orientation, level coordinates
+  std::vector<std::vector<uint8_t>> levelDesc;
+  long descBorderline = 0;                           // samples within 1e-4 of a .5 rounding boundary
+
+  void computePyramid(const uint8_t* img, int w, int h, int step);
+  void computeKeyPointsOctTree();
+  std::vector<Candidate> distributeOctTree(const std::vector<Candidate>& in, int minX, int maxX,
+                                           int minY, int maxY, int N) const;
+};
+
+// ---- pinhole stereo (Frame.cc:835-1005) ----
+struct StereoResult {
+  std::vector<float> uRight, depth;
+  std::vector<int> bestIdxR;   // coarse match index (-1 none) -- diagnostic
+  std::vector<int> sad;        // best SAD per accepted match (-1 none)
+};
+void compute_stereo_matches(const Extractor& exL, const Extractor& exR,
+                            const std::vector<KeyPoint>& kL, const std::vector<uint8_t>& dL,
+                            const std::vector<KeyPoint>& kR, const std::vector<uint8_t>& dR,
+                            float mbf, float mb, StereoResult& out);
+
+// ---- camera models ----
+struct Camera {
+  int type;        // 0 pinhole, 1 KannalaBrandt8
+  float p[8];      // fx fy cx cy k1..k4
+};
+void cam_project(const Camera& c, const float P[3], float uv[2]);          // Pinhole.cpp:43-49 / KannalaBrandt8.cpp:67-84
+void kb8_unproject(const Camera& c, float u, float v, float ray[3]);       // KannalaBrandt8.cpp:116-143
+
+// ---- fisheye stereo (Frame.cc:1231-1271 + KannalaBrandt8::TriangulateMatches) ----
+struct FisheyeResult {
+  std::vector<int> l2r, r2l;
+  std::vector<float> depth;
+  std::vector<float> p3d;       // Nleft x 3
+  std::vector<int> code;        // per left kp: 0 no ratio match, 1 accepted, <0 TriangulateMatches reject code
+  std::vector<int> knnIdx;      // per left-subset query: best train idx (diagnostic)
+};
+void compute_stereo_fisheye(const Camera& c1, const Camera& c2, const float Rlr[9], const float tlr[3],
+                            const std::vector<float>& sigma2,
+                            const std::vector<KeyPoint>& kL, const std::vector<uint8_t>& dL, int monoLeft,
+                            const std::vector<KeyPoint>& kR, const std::vector<uint8_t>& dR, int monoRight,
+                            FisheyeResult& out);
+
+// ---- frame grid + frustum + SearchByProjection ----
+struct FrameModel {
+  int Nleft = -1, Nright = -1;   // -1: pinhole/rectified (ORB-SLAM3 convention)
+  int N = 0;
+  std::vector<KeyPoint> keys;        // N (left then right for fisheye)
+  std::vector<uint8_t> desc;         // N x 32
+  std::vector<float> uRight;         // N (pinhole) / Nleft
+  std::vector<int> l2r, r2l;         // fisheye tables
+  float minX, maxX, minY, maxY, gridWInv, gridHInv;
+  std::vector<float> scale;
+  float logScale; int nlevels;
+  Camera cam1, cam2;
+  float mbf;
+  float Rcw[9], tcw[3], Ow[3], Rwc[9];
+  float Rrl[9], trl[3], tlr[3];      // fisheye extrinsics
+  std::vector<int> grid[64][48], gridR[64][48];
+  void assignFeaturesToGrid();                                      // Frame.cc:409-440,749-759
+  void featuresInArea(float x, float y, float r, int minLevel, int maxLevel, bool right,
+                      std::vector<int>& out) const;                  // Frame.cc:681-747
+};
+
+struct MapPointIn {
+  float pos[3], normal[3];
+  float minDist, maxDist;      // raw mfMinDistance / mfMaxDistance
+  uint8_t desc[32];
+  int flags;                   // bit0 skip (bad / already matched in this frame), bit1 Observations()>0
+};
+struct MapPointTrack {         // the mTrack* scratch of MapPoint.h:170-181
+  int inView = 0, inViewR = 0;
+  float projX = -1, projY = -1, projXR = 0, depth = 0, viewCos = 0;
+  float projXR_r = 0, projYR_r = 0, depthR = 0, viewCosR = 0;
+  int level = -1, levelR = -1;
+  int borderline = 0;          // PredictScale or a frustum compare within 1e-5 of its decision boundary
+};
+void is_in_frustum(const FrameModel& F, const MapPointIn& mp, float viewCosLimit, MapPointTrack& t);  // Frame.cc:536-598,1308-1382
+// SearchByProjection #1 (ORBmatcher.cc:49-225). frameMP: per keypoint -1 none, else 2*id+obs>0 encoding is NOT used:
+// holder[i] = map point index (>=0) or -1, and holderObs[i] = 1 when holder has Observations()>0.
+// Pre-existing holders are passed with index -2 (foreign map point) and their obs flag.
+int search_by_projection(FrameModel& F, const std::vector<MapPointIn>& mps, const std::vector<MapPointTrack>& tr,
+                         float th, bool bFar, float thFar, float nnratio,
+                         std::vector<int>& holder, std::vector<uint8_t>& holderObs);
+
+}  // namespace fto
