@@ -1,0 +1,280 @@
+"""fasttrack_b200 -- B200-native stereo tracking front-end (ORB extract -> stereo match -> SearchByProjection).
+
+The product is the C-ABI shared library built from fasttrack_b200/csrc (see include/fasttrack_b200.h);
+this module is a thin ctypes binding used by the tests and bench.py. There is no CPU fallback: creating a
+Context without the CUDA library or without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+__all__ = ["Config", "Context", "FtError", "load_library", "library_path", "KEYPOINT_DTYPE"]
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4")])
+
+EXPORTS = [
+    "ft_last_error", "ft_version", "ft_context_create", "ft_context_destroy", "ft_get_scale_tables",
+    "ft_extract_stereo", "ft_extract_stereo_device", "ft_stereo_match", "ft_stereo_match_fisheye", "ft_frame_counts",
+    "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
+    "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
+    "ft_context_stream", "ft_set_use_graph", "ft_launch_counts",
+]
+
+
+class FtError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("fasttrack_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device_id", C.c_int), ("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int), ("nlevels", C.c_int),
+        ("scale_factor", C.c_float), ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("camera_type", C.c_int),
+        ("cam1", C.c_float * 8), ("cam2", C.c_float * 8), ("lap_left", C.c_int * 2), ("lap_right", C.c_int * 2),
+        ("bf", C.c_float), ("Tlr", C.c_float * 12), ("max_map_points", C.c_int),
+    ]
+
+
+def library_path():
+    return _build.SO
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.SO):
+        raise FtError(-1, "CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                      % _build.SO)
+    L = C.CDLL(_build.SO)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.ft_last_error.restype = C.c_char_p
+    L.ft_version.restype = C.c_char_p
+    L.ft_context_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.ft_context_destroy.argtypes = [vp]
+    L.ft_get_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ft_extract_stereo.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.ft_extract_stereo_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.ft_stereo_match.argtypes = [vp]
+    L.ft_stereo_match_fisheye.argtypes = [vp]
+    L.ft_frame_counts.argtypes = [vp, ip, ip, ip, ip]
+    L.ft_frame_download.argtypes = [vp, C.c_int, C.c_int, vp, vp, ip, ip, vp, vp, vp, vp, vp]
+    L.ft_set_pose.argtypes = [vp, vp, vp, vp, vp]
+    L.ft_search_local_points.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float,
+                                         vp, vp, vp, ip]
+    L.ft_synchronize.argtypes = [vp]
+    L.ft_debug_level_dims.argtypes = [vp, C.c_int, ip, ip]
+    L.ft_debug_level_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.ft_debug_level_candidates.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip]
+    L.ft_debug_track.argtypes = [vp, C.c_int, vp, vp]
+    L.ft_debug_grid.argtypes = [vp, C.c_int, vp, vp, ip]
+    L.ft_debug_stats.argtypes = [vp, vp, C.c_int]
+    L.ft_context_stream.restype = vp
+    L.ft_context_stream.argtypes = [vp]
+    L.ft_set_use_graph.argtypes = [vp, C.c_int]
+    L.ft_launch_counts.argtypes = [vp, ip, ip, ip]
+    for name in EXPORTS:
+        if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One (GPU, rig, sequence) front-end context; mirrors the C ABI one to one."""
+
+    def __init__(self, width, height, nfeatures=1200, nlevels=8, scale_factor=1.2, ini_th=20, min_th=7,
+                 camera_type=0, cam1=None, cam2=None, lap_left=(0, 0), lap_right=(0, 0), bf=0.0, Tlr=None,
+                 max_map_points=25000, device_id=0):
+        self.L = load_library()
+        cfg = Config()
+        cfg.device_id = device_id
+        cfg.width, cfg.height, cfg.nfeatures, cfg.nlevels = width, height, nfeatures, nlevels
+        cfg.scale_factor, cfg.ini_th_fast, cfg.min_th_fast, cfg.camera_type = scale_factor, ini_th, min_th, camera_type
+        cam1 = np.zeros(8, np.float32) if cam1 is None else np.asarray(cam1, np.float32)
+        cam2 = cam1 if cam2 is None else np.asarray(cam2, np.float32)
+        for i in range(8):
+            cfg.cam1[i] = float(cam1[i]) if i < len(cam1) else 0.0
+            cfg.cam2[i] = float(cam2[i]) if i < len(cam2) else 0.0
+        cfg.lap_left[0], cfg.lap_left[1] = lap_left
+        cfg.lap_right[0], cfg.lap_right[1] = lap_right
+        cfg.bf = bf
+        T = np.hstack([np.eye(3), np.zeros((3, 1))]) if Tlr is None else np.asarray(Tlr, np.float64).reshape(3, 4)
+        for i in range(12):
+            cfg.Tlr[i] = float(T.reshape(-1)[i])
+        cfg.max_map_points = max_map_points
+        self.cfg = cfg
+        self.width, self.height, self.nlevels, self.nfeatures = width, height, nlevels, nfeatures
+        self.fisheye = camera_type == 1
+        h = C.c_void_p()
+        self._ck(self.L.ft_context_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.cap = nfeatures + 64 * nlevels
+
+    def _ck(self, st):
+        if st != 0:
+            raise FtError(st, self.L.ft_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ft_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables ----
+    def scale_tables(self):
+        n = self.nlevels
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        q = np.zeros(n, np.int32)
+        self._ck(self.L.ft_get_scale_tables(self.h, *[_ptr(x) for x in a], _ptr(q)))
+        return dict(scale=a[0], inv_scale=a[1], sigma2=a[2], inv_sigma2=a[3], features_per_level=q)
+
+    # ---- per-frame operators ----
+    def extract_stereo(self, imgL, imgR):
+        assert imgL.dtype == np.uint8 and imgR.dtype == np.uint8 and imgL.strides[1] == 1 and imgR.strides[1] == 1
+        assert imgL.shape == (self.height, self.width) and imgR.shape == (self.height, self.width)
+        self._ck(self.L.ft_extract_stereo(self.h, imgL.ctypes.data, imgL.strides[0], imgR.ctypes.data, imgR.strides[0]))
+
+    def extract_stereo_ptr(self, ptrL, stepL, ptrR, stepR, device=False):
+        f = self.L.ft_extract_stereo_device if device else self.L.ft_extract_stereo
+        self._ck(f(self.h, ptrL, stepL, ptrR, stepR))
+
+    def stereo_match(self):
+        self._ck(self.L.ft_stereo_match_fisheye(self.h) if self.fisheye else self.L.ft_stereo_match(self.h))
+
+    def counts(self):
+        v = [C.c_int() for _ in range(4)]
+        self._ck(self.L.ft_frame_counts(self.h, *[C.byref(x) for x in v]))
+        return dict(n_left=v[0].value, n_right=v[1].value, mono_left=v[2].value, mono_right=v[3].value)
+
+    def download(self, eye, stereo=False):
+        """returns dict(kps structured array, desc[n,32], mono_index, and stereo outputs when requested)"""
+        kps = np.zeros(self.cap, KEYPOINT_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n, mono = C.c_int(), C.c_int()
+        out = {}
+        ur = dp = l2r = r2l = p3d = None
+        if stereo:
+            ur = np.zeros(self.cap, np.float32); dp = np.zeros(self.cap, np.float32)
+            if self.fisheye:
+                l2r = np.zeros(self.cap, np.int32); r2l = np.zeros(self.cap, np.int32)
+                p3d = np.zeros((self.cap, 3), np.float32)
+        self._ck(self.L.ft_frame_download(self.h, eye, self.cap, _ptr(kps), _ptr(desc), C.byref(n), C.byref(mono),
+                                          _ptr(ur), _ptr(dp), _ptr(l2r), _ptr(r2l), _ptr(p3d)))
+        n = n.value
+        out.update(kps=kps[:n].copy(), desc=desc[:n].copy(), n=n, mono_index=mono.value)
+        if stereo:
+            c = self.counts()
+            nl, nr = c["n_left"], c["n_right"]
+            out.update(u_right=ur[:nl].copy(), depth=dp[:nl].copy())
+            if self.fisheye:
+                out.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
+        return out
+
+    def set_pose(self, Rcw, tcw, Rwc=None, Ow=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1)
+        Rcw, tcw, Rwc, Ow = f(Rcw), f(tcw), f(Rwc), f(Ow)
+        self._keep_pose = (Rcw, tcw, Rwc, Ow)
+        self._ck(self.L.ft_set_pose(self.h, _ptr(Rcw), _ptr(tcw), _ptr(Rwc), _ptr(Ow)))
+
+    def search_local_points(self, pos, normal, minmax, desc, flags, th, holder, holder_obs, b_far=False, th_far=50.0,
+                            nnratio=0.8):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        pos, normal, minmax = f(pos), f(normal), f(minmax)
+        desc = np.ascontiguousarray(desc, np.uint8); flags = np.ascontiguousarray(flags, np.int32)
+        holder = np.ascontiguousarray(holder, np.int32).copy()
+        holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        M = len(pos)
+        best = np.full((max(M, 1), 2), -1, np.int32)
+        nm = C.c_int()
+        self._ck(self.L.ft_search_local_points(self.h, M, _ptr(pos), _ptr(normal), _ptr(minmax), _ptr(desc), _ptr(flags),
+                                               th, int(b_far), th_far, nnratio, _ptr(holder), _ptr(holder_obs),
+                                               _ptr(best), C.byref(nm)))
+        return nm.value, holder, holder_obs, best[:M]
+
+    def search_local_points_raw(self, M, pos, normal, minmax, desc, flags, th, holder, holder_obs, best, b_far=False,
+                                th_far=50.0, nnratio=0.8):
+        """pointer-level call for bench.py (no numpy copies); arguments are integer addresses"""
+        nm = C.c_int()
+        self._ck(self.L.ft_search_local_points(self.h, M, pos, normal, minmax, desc, flags, th, int(b_far), th_far,
+                                               nnratio, holder, holder_obs, best, C.byref(nm)))
+        return nm.value
+
+    def synchronize(self):
+        self._ck(self.L.ft_synchronize(self.h))
+
+    def stream(self):
+        return self.L.ft_context_stream(self.h)
+
+    def set_use_graph(self, enable):
+        self._ck(self.L.ft_set_use_graph(self.h, int(enable)))
+
+    def launch_counts(self):
+        v = [C.c_int() for _ in range(3)]
+        self._ck(self.L.ft_launch_counts(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    # ---- diagnostics ----
+    def level_dims(self, level):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.L.ft_debug_level_dims(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level_image(self, eye, level, blurred=False):
+        w, h = self.level_dims(level)
+        out = np.zeros((h, w), np.uint8)
+        self._ck(self.L.ft_debug_level_image(self.h, eye, level, int(blurred), _ptr(out)))
+        return out
+
+    def level_candidates(self, eye, level):
+        n = C.c_int()
+        self._ck(self.L.ft_debug_level_candidates(self.h, eye, level, 0, None, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3), np.float32)
+        self._ck(self.L.ft_debug_level_candidates(self.h, eye, level, n.value, _ptr(out), C.byref(n)))
+        return out[: n.value]
+
+    def track(self, M):
+        ti = np.zeros((max(M, 1), 4), np.int32); tf = np.zeros((max(M, 1), 9), np.float32)
+        self._ck(self.L.ft_debug_track(self.h, M, _ptr(ti), _ptr(tf)))
+        return ti[:M], tf[:M]
+
+    def grid(self, right=False):
+        counts = np.zeros(64 * 48, np.int32)
+        idx = np.zeros(2 * self.cap, np.int32)
+        n = C.c_int()
+        self._ck(self.L.ft_debug_grid(self.h, int(right), _ptr(counts), _ptr(idx), C.byref(n)))
+        return counts, idx[: n.value].copy()
+
+    def stats(self):
+        s = np.zeros(8, np.int64)
+        self._ck(self.L.ft_debug_stats(self.h, _ptr(s), 8))
+        names = ["cand_left", "cand_right", "kp_left", "kp_right", "stereo_tested", "stereo_refined", "sbp_candidates",
+                 "sbp_rounds"]
+        return dict(zip(names, [int(x) for x in s]))
+
+
+def keypoints_as_array(kps):
+    """structured ft_keypoint array -> float32 [n,6] (x,y,size,angle,response,octave), the oracle's layout"""
+    out = np.zeros((len(kps), 6), np.float32)
+    for i, k in enumerate(("x", "y", "size", "angle", "response")):
+        out[:, i] = kps[k]
+    out[:, 5] = kps["octave"]
+    return out

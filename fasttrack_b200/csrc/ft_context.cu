@@ -1,0 +1,693 @@
+// ft_context.cu -- C ABI of the front-end (include/fasttrack_b200.h): context, device memory,
+// coefficient tables, CUDA-graph capture of the per-frame launch chain, host<->device transfers.
+//
+// Host-side constants are computed exactly the way ORBextractor's constructor does
+// (reference src/ORBextractor.cc:393-499): running float32 scale products, cvRound'ed level
+// sizes and per-level quotas, umax.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ft_internal.h"
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return FT_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct ft_context {
+  ft_config cfg;
+  FtParams P;
+  FtBuffers B;
+  FtStereoBuffers S;
+  FtGridBuffers G;
+  FtSbpBuffers Q;
+  FtCamera cam1, cam2;
+  FtPose pose;
+  float mbf, mb;
+  float minX, maxX, minY, maxY, gridWInv, gridHInv, logScale;
+  int fisheye;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> quota;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr;
+  uint8_t* dIn[2] = {nullptr, nullptr};     // device staging for the input images
+  uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
+  int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
+  cudaGraphExec_t gExtract = nullptr, gStereo = nullptr;
+  int useGraph = 1;
+  bool extracted = false, stereoDone = false, countsValid = false;
+  int lastM = 0;
+  int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
+  long long pyrBytes = 0;
+};
+
+extern "C" const char* ft_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ft_version(void) { return "fasttrack_b200 0.1 (sm_100a)"; }
+
+template <typename T>
+static cudaError_t dalloc(ft_context* c, T** p, size_t n) {
+  void* v = nullptr;
+  cudaError_t e = cudaMalloc(&v, n * sizeof(T) + 256);
+  if (e == cudaSuccess) { c->allocs.push_back(v); *p = (T*)v; cudaMemset(v, 0, n * sizeof(T) + 256); }
+  return e;
+}
+
+static ft_status build_params(ft_context* c) {
+  const ft_config& cfg = c->cfg;
+  FtParams& P = c->P;
+  memset(&P, 0, sizeof(P));
+  const int nl = cfg.nlevels;
+  if (nl < 1 || nl > FT_MAX_LEVELS || cfg.width < 64 || cfg.height < 64 || cfg.width > 4000 || cfg.height > 4000 ||
+      cfg.nfeatures < 1 || cfg.nfeatures > 10000 || cfg.scale_factor <= 1.0f || cfg.min_th_fast < 1 ||
+      cfg.ini_th_fast < cfg.min_th_fast || cfg.ini_th_fast > 254) {
+    set_err("ft_context_create: unsupported configuration");
+    return FT_ERR_INVALID;
+  }
+  P.nlevels = nl; P.width = cfg.width; P.height = cfg.height; P.nfeatures = cfg.nfeatures;
+  P.iniTh = cfg.ini_th_fast; P.minTh = cfg.min_th_fast; P.camType = cfg.camera_type;
+  P.lap[0][0] = cfg.lap_left[0]; P.lap[0][1] = cfg.lap_left[1];
+  P.lap[1][0] = cfg.lap_right[0]; P.lap[1][1] = cfg.lap_right[1];
+  // scale tables (ORBextractor.cc:398-411,444-450); scaleFactor is held as double there
+  const double sfD = (double)cfg.scale_factor;
+  c->scale.assign(nl, 1.f); c->sigma2.assign(nl, 1.f); c->invScale.assign(nl, 1.f); c->invSigma2.assign(nl, 1.f);
+  for (int i = 1; i < nl; i++) {
+    c->scale[i] = (float)(c->scale[i - 1] * sfD);
+    c->sigma2[i] = c->scale[i] * c->scale[i];
+  }
+  for (int i = 0; i < nl; i++) { c->invScale[i] = 1.0f / c->scale[i]; c->invSigma2[i] = 1.0f / c->sigma2[i]; }
+  for (int i = 0; i < nl; i++) { P.scale[i] = c->scale[i]; P.invScale[i] = c->invScale[i]; P.sigma2[i] = c->sigma2[i]; }
+  // quotas (:454-465)
+  c->quota.assign(nl, 0);
+  {
+    const float factor = (float)(1.0f / sfD);
+    float nDesired = cfg.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+      c->quota[l] = cv_round_f(nDesired);
+      sum += c->quota[l];
+      nDesired *= factor;
+    }
+    c->quota[nl - 1] = std::max(cfg.nfeatures - sum, 0);
+  }
+  // umax (:478-493)
+  {
+    int umax[FT_HALF_PATCH + 2] = {0};
+    const int vmax = (int)std::floor(FT_HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(FT_HALF_PATCH * std::sqrt(2.f) / 2);
+    const double hp2 = FT_HALF_PATCH * FT_HALF_PATCH;
+    int v, v0;
+    for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(std::sqrt(hp2 - v * v));
+    for (v = FT_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+      while (umax[v0] == umax[v0 + 1]) ++v0;
+      umax[v] = v0;
+      ++v0;
+    }
+    for (int i = 0; i < 16; i++) P.umax[i] = umax[i];
+  }
+  int off = 0, cellBase = 0, cellKp = 0, cand = 0, lvlKp = 0, xt = 0, yt = 0, tiles = 0;
+  for (int l = 0; l < nl; l++) {
+    FtLevel& L = P.lv[l];
+    L.w = cv_round_f((float)cfg.width * c->invScale[l]);     // (:1500)
+    L.h = cv_round_f((float)cfg.height * c->invScale[l]);
+    L.pitch = align_up(L.w, 64);
+    L.offset = off;
+    off += align_up(L.pitch * L.h, 256);
+    L.maxBorderX = L.w - FT_EDGE_THRESHOLD + 3;
+    L.maxBorderY = L.h - FT_EDGE_THRESHOLD + 3;
+    const float width = (float)(L.maxBorderX - FT_MIN_BORDER), height = (float)(L.maxBorderY - FT_MIN_BORDER);
+    L.nCols = (int)(width / 35.f);
+    L.nRows = (int)(height / 35.f);
+    if (L.nCols < 1 || L.nRows < 1) {
+      set_err("ft_context_create: image too small for the requested number of pyramid levels");
+      return FT_ERR_INVALID;
+    }
+    L.wCell = (int)std::ceil(width / L.nCols);
+    L.hCell = (int)std::ceil(height / L.nRows);
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+    L.cellKpBase = cellKp;
+    cellKp += L.nCols * L.nRows * L.cellCap;
+    L.candBase = cand;
+    L.candCap = std::min(L.nCols * L.nRows * L.cellCap, 0xFFFFF);
+    cand += L.candCap;
+    L.quota = c->quota[l];
+    L.nIni = (int)std::round((float)(L.maxBorderX - FT_MIN_BORDER) / (L.maxBorderY - FT_MIN_BORDER));   // (:664)
+    if (L.nIni < 1) {
+      set_err("ft_context_create: aspect ratio below 1:2 is not supported (the reference indexes an empty vector)");
+      return FT_ERR_INVALID;
+    }
+    L.hX = (float)(L.maxBorderX - FT_MIN_BORDER) / L.nIni;
+    L.nodeCap = L.quota + 4 * L.nIni + 8;
+    L.lvlKpBase = lvlKp;
+    L.lvlKpCap = L.nodeCap;
+    lvlKp += L.lvlKpCap;
+    L.xTab = xt; L.yTab = yt;
+    xt += L.w; yt += L.h;
+    L.blurTileBase = tiles;
+    L.blurTilesX = (L.w + 63) / 64;
+    tiles += L.blurTilesX * ((L.h + 31) / 32);
+  }
+  P.totalCells = cellBase;
+  P.totalBlurTiles = tiles;
+  P.maxKp = align_up(lvlKp, 8);
+  if (P.maxKp > 65535) { set_err("ft_context_create: too many keypoints"); return FT_ERR_INVALID; }
+  c->pyrBytes = off;
+  return FT_OK;
+}
+
+static ft_status build_tables(ft_context* c, int cellKpTotal, int candTotal, int lvlKpTotal) {
+  const FtParams& P = c->P;
+  (void)cellKpTotal; (void)candTotal; (void)lvlKpTotal;
+  int xt = 0, yt = 0;
+  for (int l = 0; l < P.nlevels; l++) { xt += P.lv[l].w; yt += P.lv[l].h; }
+  std::vector<int2> xTab(xt), yTab(yt);
+  for (int l = 1; l < P.nlevels; l++) {
+    const FtLevel& L = P.lv[l];
+    const FtLevel& S = P.lv[l - 1];
+    // cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp)
+    const double scale_x = 1. / ((double)L.w / S.w), scale_y = 1. / ((double)L.h / S.h);
+    for (int dx = 0; dx < L.w; dx++) {
+      float fx = (float)((dx + 0.5) * scale_x - 0.5);
+      int sx = (int)std::floor(fx);
+      fx -= sx;
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+      const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
+      xTab[L.xTab + dx] = make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16)));
+    }
+    for (int dy = 0; dy < L.h; dy++) {
+      float fy = (float)((dy + 0.5) * scale_y - 0.5);
+      int sy = (int)std::floor(fy);
+      fy -= sy;
+      const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
+      const int y0 = std::min(std::max(sy, 0), S.h - 1), y1 = std::min(std::max(sy + 1, 0), S.h - 1);
+      yTab[L.yTab + dy] = make_int2(y0 | (y1 << 16), (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16)));
+    }
+  }
+  int2 *dx = nullptr, *dy = nullptr;
+  CK(dalloc(c, &dx, xTab.size()));
+  CK(dalloc(c, &dy, yTab.size()));
+  CK(cudaMemcpy(dx, xTab.data(), xTab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dy, yTab.data(), yTab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  c->B.xTab = dx; c->B.yTab = dy;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
+  if (!cfg || !out) { set_err("ft_context_create: null argument"); return FT_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("ft_context_create: no CUDA device available (this library has no CPU fallback)");
+    return FT_ERR_CUDA;
+  }
+  if (cfg->device_id < 0 || cfg->device_id >= ndev) { set_err("ft_context_create: bad device_id"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(cfg->device_id));
+  ft_context* c = new ft_context();
+  c->cfg = *cfg;
+  ft_status st = build_params(c);
+  if (st != FT_OK) { delete c; return st; }
+  FtParams& P = c->P;
+  c->fisheye = cfg->camera_type == FT_CAM_KB8;
+  c->cam1.type = c->cam2.type = cfg->camera_type;
+  memcpy(c->cam1.p, cfg->cam1, 32); memcpy(c->cam2.p, cfg->cam2, 32);
+  c->mbf = cfg->bf;
+  c->mb = cfg->bf / cfg->cam1[0];            // mb = mbf/fx (Frame.cc:199)
+  c->minX = 0.f; c->maxX = (float)cfg->width; c->minY = 0.f; c->maxY = (float)cfg->height;   // ComputeImageBounds, no distortion
+  c->gridWInv = (float)FT_GRID_COLS / (c->maxX - c->minX);
+  c->gridHInv = (float)FT_GRID_ROWS / (c->maxY - c->minY);
+  c->logScale = (float)std::log((double)cfg->scale_factor);   // mfLogScaleFactor = log(mfScaleFactor) (Frame.cc:112-113)
+  // pose defaults to identity; rig extrinsics from Tlr
+  memset(&c->pose, 0, sizeof(c->pose));
+  for (int i = 0; i < 3; i++) { c->pose.Rcw[4 * i] = 1; c->pose.Rwc[4 * i] = 1; c->pose.Rlr[4 * i] = 1; c->pose.Rrl[4 * i] = 1; }
+  if (c->fisheye) {
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) c->pose.Rlr[3 * i + j] = cfg->Tlr[4 * i + j];
+      c->pose.tlr[i] = cfg->Tlr[4 * i + 3];
+    }
+    // Trl = Tlr^-1
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c->pose.Rrl[3 * i + j] = c->pose.Rlr[3 * j + i];
+    for (int i = 0; i < 3; i++)
+      c->pose.trl[i] = -(c->pose.Rrl[3 * i] * c->pose.tlr[0] + c->pose.Rrl[3 * i + 1] * c->pose.tlr[1] + c->pose.Rrl[3 * i + 2] * c->pose.tlr[2]);
+  }
+
+  int cellKpTotal = 0, candTotal = 0, lvlKpTotal = 0;
+  for (int l = 0; l < P.nlevels; l++) {
+    cellKpTotal += P.lv[l].nCols * P.lv[l].nRows * P.lv[l].cellCap;
+    candTotal += P.lv[l].candCap;
+    lvlKpTotal += P.lv[l].lvlKpCap;
+  }
+  auto fail = [&](ft_status s) { ft_context_destroy(c); return s; };
+#define CKF(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return fail(FT_ERR_CUDA);                                                                    \
+    }                                                                                              \
+  } while (0)
+  for (int e = 0; e < 2; e++) {
+    FtEye& E = c->B.eye[e];
+    CKF(dalloc(c, &E.pyr, (size_t)c->pyrBytes));
+    CKF(dalloc(c, &E.blur, (size_t)c->pyrBytes));
+    CKF(dalloc(c, &E.cellKp, (size_t)cellKpTotal));
+    CKF(dalloc(c, &E.cellCount, (size_t)P.totalCells));
+    CKF(dalloc(c, &E.cand, (size_t)candTotal));
+    CKF(dalloc(c, &E.candNode, (size_t)candTotal));
+    CKF(dalloc(c, &E.lvlCandCount, (size_t)FT_MAX_LEVELS));
+    CKF(dalloc(c, &E.lvlKp, (size_t)lvlKpTotal));
+    CKF(dalloc(c, &E.lvlKpCount, (size_t)FT_MAX_LEVELS));
+    CKF(dalloc(c, &E.kps, (size_t)P.maxKp));
+    CKF(dalloc(c, &E.desc, (size_t)P.maxKp * 32));
+    CKF(dalloc(c, &E.counts, (size_t)4));
+    CKF(dalloc(c, &c->dIn[e], (size_t)cfg->width * cfg->height));
+    CKF(cudaMallocHost((void**)&c->hIn[e], (size_t)cfg->width * cfg->height));
+  }
+  CKF(dalloc(c, &c->B.status, (size_t)4));
+  if (build_tables(c, cellKpTotal, candTotal, lvlKpTotal) != FT_OK) return fail(FT_ERR_CUDA);
+  // stereo
+  CKF(dalloc(c, &c->S.uRight, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.depth, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.bestIdxR, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.sad, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.l2r, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.r2l, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.p3d, (size_t)P.maxKp * 3));
+  CKF(dalloc(c, &c->S.code, (size_t)P.maxKp));
+  CKF(dalloc(c, &c->S.stats, (size_t)8));
+  // grid
+  CKF(dalloc(c, &c->G.cellStart, (size_t)2 * (FT_GRID_COLS * FT_GRID_ROWS + 1)));
+  CKF(dalloc(c, &c->G.cellIdx, (size_t)2 * P.maxKp));
+  // projection search
+  const int MM = cfg->max_map_points > 0 ? cfg->max_map_points : 25000;
+  c->cfg.max_map_points = MM;
+  FtSbpBuffers& Q = c->Q;
+  CKF(dalloc(c, &Q.pos, (size_t)MM * 3));
+  CKF(dalloc(c, &Q.normal, (size_t)MM * 3));
+  CKF(dalloc(c, &Q.minmax, (size_t)MM * 2));
+  CKF(dalloc(c, &Q.desc, (size_t)MM * 32));
+  CKF(dalloc(c, &Q.flags, (size_t)MM));
+  CKF(dalloc(c, &Q.trI, (size_t)MM * 4));
+  CKF(dalloc(c, &Q.trF, (size_t)MM * 9));
+  CKF(dalloc(c, &Q.listOff, (size_t)MM * 2));
+  CKF(dalloc(c, &Q.listLen, (size_t)MM * 2));
+  Q.poolCap = MM * 96;
+  CKF(dalloc(c, &Q.pool, (size_t)Q.poolCap));
+  CKF(dalloc(c, &Q.cursor, (size_t)8));
+  CKF(dalloc(c, &Q.sel, (size_t)MM * 2));
+  CKF(dalloc(c, &Q.holder, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.holderObs, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.minKey, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
+  CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
+  memset(c->hCounts, 0, 64 * sizeof(int));
+  CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CKF(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->evFork2, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
+  CKF(ft_launch_extract_setup(P));
+  *out = c;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_context_destroy(ft_context* c) {
+  if (!c) return FT_OK;
+  cudaSetDevice(c->cfg.device_id);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->gExtract) cudaGraphExecDestroy(c->gExtract);
+  if (c->gStereo) cudaGraphExecDestroy(c->gStereo);
+  for (void* p : c->allocs) cudaFree(p);
+  for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
+  if (c->hCounts) cudaFreeHost(c->hCounts);
+  if (c->evFork) cudaEventDestroy(c->evFork);
+  if (c->evJoin) cudaEventDestroy(c->evJoin);
+  if (c->evFork2) cudaEventDestroy(c->evFork2);
+  if (c->evJoin2) cudaEventDestroy(c->evJoin2);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  delete c;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_get_scale_tables(ft_context* c, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                                         int* features_per_level) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  for (int i = 0; i < c->P.nlevels; i++) {
+    if (scale) scale[i] = c->scale[i];
+    if (inv_scale) inv_scale[i] = c->invScale[i];
+    if (sigma2) sigma2[i] = c->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = c->invSigma2[i];
+    if (features_per_level) features_per_level[i] = c->quota[i];
+  }
+  return FT_OK;
+}
+
+// The per-frame extraction chain. Enqueued on c->stream with the blur forked onto c->stream2;
+// identical whether it is being captured into a graph or launched directly.
+static int enqueue_extract(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+  const FtParams& P = c->P;
+  int n = 0;
+  cudaStream_t s = c->stream, s2 = c->stream2;
+  ft_launch_copy_level0(P, c->B, dL, stepL, dR, stepR, s); n++;
+  for (int l = 1; l < P.nlevels; l++) { ft_launch_resize(P, c->B, l, s); n++; }
+  cudaEventRecord(c->evFork, s);
+  cudaStreamWaitEvent(s2, c->evFork, 0);
+  ft_launch_blur(P, c->B, 0, P.nlevels, s2); n++;
+  cudaEventRecord(c->evJoin, s2);
+  ft_launch_fast(P, c->B, 0, P.nlevels, s); n++;
+  ft_launch_octree(P, c->B, 0, P.nlevels, s); n++;
+  cudaStreamWaitEvent(s, c->evJoin, 0);
+  ft_launch_orient_desc(P, c->B, s); n++;
+  ft_launch_grid(P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s); n++;
+  return n;
+}
+
+static ft_status run_extract(ft_context* c) {
+  // inputs are in c->dIn[0/1] with pitch == width
+  const int w = c->cfg.width;
+  if (c->useGraph) {
+    if (!c->gExtract) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      c->nLaunchExtract = enqueue_extract(c, c->dIn[0], w, c->dIn[1], w);
+      CK(cudaStreamEndCapture(c->stream, &g));
+      CK(cudaGraphInstantiate(&c->gExtract, g, 0));
+      cudaGraphDestroy(g);
+    }
+    CK(cudaGraphLaunch(c->gExtract, c->stream));
+  } else {
+    c->nLaunchExtract = enqueue_extract(c, c->dIn[0], w, c->dIn[1], w);
+    CK(cudaGetLastError());
+  }
+  c->extracted = true; c->stereoDone = false; c->countsValid = false;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
+  if (!c || !imgL || !imgR) { set_err("ft_extract_stereo: null argument (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  if (stepL < w || stepR < w) { set_err("ft_extract_stereo: step smaller than width"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  const uint8_t* src[2] = {imgL, imgR};
+  const int step[2] = {stepL, stepR};
+  for (int e = 0; e < 2; e++) {
+    cudaPointerAttributes at;
+    bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      CK(cudaMemcpy2DAsync(c->dIn[e], w, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      // pageable memory: stage through the context's pinned buffer so the copy stays asynchronous
+      CK(cudaStreamSynchronize(c->stream));   // previous frame may still be reading the staging buffer
+      for (int y = 0; y < h; y++) memcpy(c->hIn[e] + (size_t)y * w, src[e] + (size_t)y * step[e], w);
+      CK(cudaMemcpyAsync(c->dIn[e], c->hIn[e], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  return run_extract(c);
+}
+
+extern "C" ft_status ft_extract_stereo_device(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+  if (!c || !dL || !dR) { set_err("ft_extract_stereo_device: null argument"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaMemcpy2DAsync(c->dIn[0], w, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpy2DAsync(c->dIn[1], w, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  return run_extract(c);
+}
+
+extern "C" ft_status ft_stereo_match(ft_context* c) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_stereo_match: no extracted frame"); return FT_ERR_STATE; }
+  if (c->fisheye) { set_err("ft_stereo_match: context is a KannalaBrandt8 rig; call ft_stereo_match_fisheye"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  if (c->useGraph) {
+    if (!c->gStereo) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
+      ft_launch_stereo(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
+      CK(cudaStreamEndCapture(c->stream, &g));
+      CK(cudaGraphInstantiate(&c->gStereo, g, 0));
+      cudaGraphDestroy(g);
+    }
+    CK(cudaGraphLaunch(c->gStereo, c->stream));
+  } else {
+    CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
+    ft_launch_stereo(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
+    CK(cudaGetLastError());
+  }
+  c->nLaunchStereo = 2;
+  c->stereoDone = true;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_stereo_match_fisheye(ft_context* c) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_stereo_match_fisheye: no extracted frame"); return FT_ERR_STATE; }
+  if (!c->fisheye) { set_err("ft_stereo_match_fisheye: context is a pinhole rig"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
+  ft_launch_fisheye(c->P, c->B, c->S, c->cam1, c->cam2, c->pose, c->stream);
+  CK(cudaGetLastError());
+  c->nLaunchStereo = 2;
+  c->stereoDone = true;
+  return FT_OK;
+}
+
+static ft_status check_device_status(ft_context* c, int status) {
+  if (!status) return FT_OK;
+  char buf[256];
+  snprintf(buf, sizeof(buf), "device buffer bound exceeded (status 0x%x:%s%s%s%s%s%s)", status,
+           status & FT_ST_CELL_OVERFLOW ? " fast-cell" : "", status & FT_ST_NODE_OVERFLOW ? " octree-node" : "",
+           status & FT_ST_KP_OVERFLOW ? " keypoints" : "", status & FT_ST_CAND_OVERFLOW ? " candidates" : "",
+           status & FT_ST_SBP_POOL_OVERFLOW ? " search-pool" : "", status & FT_ST_RESOLVE_NOCONV ? " resolve" : "");
+  set_err(buf);
+  cudaMemsetAsync(c->B.status, 0, sizeof(int), c->stream);
+  return FT_ERR_CAPACITY;
+}
+
+static ft_status fetch_counts(ft_context* c) {
+  if (c->countsValid) return FT_OK;
+  CK(cudaMemcpyAsync(c->hCounts, c->B.eye[0].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->hCounts + 2, c->B.eye[1].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->countsValid = true;
+  return check_device_status(c, c->hCounts[4]);
+}
+
+extern "C" ft_status ft_frame_counts(ft_context* c, int* nL, int* nR, int* monoL, int* monoR) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_frame_counts: no extracted frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  if (nL) *nL = c->hCounts[0];
+  if (monoL) *monoL = c->hCounts[1];
+  if (nR) *nR = c->hCounts[2];
+  if (monoR) *monoR = c->hCounts[3];
+  return FT_OK;
+}
+
+extern "C" ft_status ft_frame_download(ft_context* c, int eye, int cap, ft_keypoint* kps, uint8_t* desc, int* n,
+                                       int* mono_index, float* u_right, float* depth, int* l2r, int* r2l, float* p3d) {
+  if (!c || eye < 0 || eye > 1) { set_err("ft_frame_download: bad argument"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_frame_download: no extracted frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int cnt = c->hCounts[2 * eye], nLeft = c->hCounts[0], nRight = c->hCounts[2];
+  if (n) *n = cnt;
+  if (mono_index) *mono_index = c->hCounts[2 * eye + 1];
+  if ((kps || desc) && cap < cnt) { set_err("ft_frame_download: capacity smaller than keypoint count"); return FT_ERR_INVALID; }
+  const FtEye& E = c->B.eye[eye];
+  if (kps && cnt) CK(cudaMemcpyAsync(kps, E.kps, sizeof(ft_keypoint) * cnt, cudaMemcpyDeviceToHost, c->stream));
+  if (desc && cnt) CK(cudaMemcpyAsync(desc, E.desc, 32 * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream));
+  if ((u_right || depth || l2r || r2l || p3d) && !c->stereoDone) { set_err("ft_frame_download: stereo results requested before stereo matching"); return FT_ERR_STATE; }
+  if (u_right && nLeft) CK(cudaMemcpyAsync(u_right, c->S.uRight, sizeof(float) * nLeft, cudaMemcpyDeviceToHost, c->stream));
+  if (depth && nLeft) CK(cudaMemcpyAsync(depth, c->S.depth, sizeof(float) * nLeft, cudaMemcpyDeviceToHost, c->stream));
+  if (l2r && nLeft) CK(cudaMemcpyAsync(l2r, c->S.l2r, sizeof(int) * nLeft, cudaMemcpyDeviceToHost, c->stream));
+  if (r2l && nRight) CK(cudaMemcpyAsync(r2l, c->S.r2l, sizeof(int) * nRight, cudaMemcpyDeviceToHost, c->stream));
+  if (p3d && nLeft) CK(cudaMemcpyAsync(p3d, c->S.p3d, sizeof(float) * 3 * nLeft, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_set_pose(ft_context* c, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow) {
+  if (!c || !Rcw || !tcw) { set_err("ft_set_pose: null argument"); return FT_ERR_INVALID; }
+  memcpy(c->pose.Rcw, Rcw, 36); memcpy(c->pose.tcw, tcw, 12);
+  if (Rwc) memcpy(c->pose.Rwc, Rwc, 36);
+  else for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c->pose.Rwc[3 * i + j] = Rcw[3 * j + i];
+  if (Ow) memcpy(c->pose.Ow, Ow, 12);
+  else for (int i = 0; i < 3; i++)
+    c->pose.Ow[i] = -(c->pose.Rwc[3 * i] * tcw[0] + c->pose.Rwc[3 * i + 1] * tcw[1] + c->pose.Rwc[3 * i + 2] * tcw[2]);
+  return FT_OK;
+}
+
+extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* pos, const float* normal,
+                                            const float* minmax, const uint8_t* desc, const int* flags, float th,
+                                            int bFar, float thFar, float nnratio, int* holder, uint8_t* holderObs,
+                                            int* best_idx, int* nmatches) {
+  if (!c || M < 0 || (M > 0 && (!pos || !normal || !minmax || !desc || !flags)) || !holder || !holderObs) {
+    set_err("ft_search_local_points: null argument"); return FT_ERR_INVALID;
+  }
+  if (!c->extracted) { set_err("ft_search_local_points: no extracted frame"); return FT_ERR_STATE; }
+  if (!c->fisheye && !c->stereoDone) { set_err("ft_search_local_points: stereo matching has not run (mvuRight is read)"); return FT_ERR_STATE; }
+  if (c->fisheye && !c->stereoDone) { set_err("ft_search_local_points: fisheye stereo matching has not run (match tables are read)"); return FT_ERR_STATE; }
+  if (M > c->cfg.max_map_points) {
+    set_err("ft_search_local_points: more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)");
+    return FT_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int nLeft = c->hCounts[0], nRight = c->hCounts[2];
+  const int N = c->fisheye ? nLeft + nRight : nLeft;
+  if (nmatches) *nmatches = 0;
+  c->lastM = M;
+  c->nLaunchSearch = 0;
+  if (M == 0 || N == 0) return FT_OK;
+  FtSbpBuffers& Q = c->Q;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(Q.pos, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.normal, normal, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.minmax, minmax, sizeof(float) * 2 * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.desc, desc, (size_t)32 * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.flags, flags, sizeof(int) * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.holder, holder, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(Q.holderObs, holderObs, (size_t)N, cudaMemcpyHostToDevice, s));
+  FtFrustumArgs fa;
+  fa.cam1 = c->cam1; fa.cam2 = c->cam2; fa.pose = c->pose;
+  fa.minX = c->minX; fa.maxX = c->maxX; fa.minY = c->minY; fa.maxY = c->maxY;
+  fa.mbf = c->mbf; fa.logScale = c->logScale; fa.nlevels = c->P.nlevels; fa.fisheye = c->fisheye;
+  fa.viewCosLimit = 0.5f;   // Tracking.cc:3512
+  FtGatherArgs ga;
+  ga.minX = c->minX; ga.minY = c->minY; ga.gridWInv = c->gridWInv; ga.gridHInv = c->gridHInv;
+  ga.th = th; ga.bFactor = (th != 1.0f); ga.bFar = bFar; ga.thFar = thFar; ga.fisheye = c->fisheye;
+  ft_launch_frustum_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s);
+  FtResolveArgs ra;
+  ra.M = M; ra.nLeft = nLeft; ra.nSlots = N; ra.fisheye = c->fisheye; ra.nnratio = nnratio;
+  ft_launch_resolve(c->B, Q, c->S, ra, s);
+  c->nLaunchSearch = 4 + (c->fisheye ? 1 : 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(holder, Q.holder, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(holderObs, Q.holderObs, (size_t)N, cudaMemcpyDeviceToHost, s));
+  if (best_idx) CK(cudaMemcpyAsync(best_idx, Q.sel, sizeof(int) * 2 * M, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->hCounts + 8, Q.cursor, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (nmatches) *nmatches = c->hCounts[9];
+  return check_device_status(c, c->hCounts[4]);
+}
+
+extern "C" ft_status ft_synchronize(ft_context* c) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  return FT_OK;
+}
+
+extern "C" void* ft_context_stream(ft_context* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" ft_status ft_set_use_graph(ft_context* c, int enable) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  c->useGraph = enable;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_launch_counts(ft_context* c, int* extract, int* stereo, int* search) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (extract) *extract = c->nLaunchExtract;
+  if (stereo) *stereo = c->nLaunchStereo;
+  if (search) *search = c->nLaunchSearch;
+  return FT_OK;
+}
+
+// ---- diagnostics --------------------------------------------------------------------------
+extern "C" ft_status ft_debug_level_dims(ft_context* c, int level, int* w, int* h) {
+  if (!c || level < 0 || level >= c->P.nlevels) { set_err("bad level"); return FT_ERR_INVALID; }
+  *w = c->P.lv[level].w; *h = c->P.lv[level].h;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_level_image(ft_context* c, int eye, int level, int blurred, uint8_t* out) {
+  if (!c || level < 0 || level >= c->P.nlevels || eye < 0 || eye > 1 || !out) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  const FtLevel& L = c->P.lv[level];
+  const uint8_t* src = (blurred ? c->B.eye[eye].blur : c->B.eye[eye].pyr) + L.offset;
+  CK(cudaMemcpy2DAsync(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_level_candidates(ft_context* c, int eye, int level, int cap, float* xyr, int* n) {
+  if (!c || level < 0 || level >= c->P.nlevels || eye < 0 || eye > 1 || !n) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  const FtLevel& L = c->P.lv[level];
+  int cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, c->B.eye[eye].lvlCandCount + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = cnt;
+  if (!xyr || cap < cnt || cnt == 0) return FT_OK;
+  std::vector<uint32_t> tmp(cnt);
+  CK(cudaMemcpy(tmp.data(), c->B.eye[eye].cand + L.candBase, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < cnt; i++) { xyr[3 * i] = (float)ft_px(tmp[i]); xyr[3 * i + 1] = (float)ft_py(tmp[i]); xyr[3 * i + 2] = (float)ft_ps(tmp[i]); }
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_track(ft_context* c, int M, int* track_i, float* track_f) {
+  if (!c || M > c->lastM) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  if (track_i) CK(cudaMemcpy(track_i, c->Q.trI, sizeof(int) * 4 * M, cudaMemcpyDeviceToHost));
+  if (track_f) CK(cudaMemcpy(track_f, c->Q.trF, sizeof(float) * 9 * M, cudaMemcpyDeviceToHost));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_grid(ft_context* c, int right, int* counts, int* indices, int* n) {
+  if (!c || !counts || !indices || !n) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  const int cells = FT_GRID_COLS * FT_GRID_ROWS;
+  std::vector<int> start(cells + 1);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(start.data(), c->G.cellStart + (right ? cells + 1 : 0), sizeof(int) * (cells + 1), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < cells; i++) counts[i] = start[i + 1] - start[i];
+  *n = start[cells];
+  if (*n) CK(cudaMemcpy(indices, c->G.cellIdx + (right ? c->P.maxKp : 0), sizeof(int) * (*n), cudaMemcpyDeviceToHost));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_stats(ft_context* c, long long* stats, int n) {
+  if (!c || !stats || n < 8) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  int cand[2][FT_MAX_LEVELS], kp[2][FT_MAX_LEVELS];
+  for (int e = 0; e < 2; e++) {
+    CK(cudaMemcpy(cand[e], c->B.eye[e].lvlCandCount, sizeof(int) * FT_MAX_LEVELS, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(kp[e], c->B.eye[e].lvlKpCount, sizeof(int) * FT_MAX_LEVELS, cudaMemcpyDeviceToHost));
+  }
+  unsigned long long st[8];
+  CK(cudaMemcpy(st, c->S.stats, sizeof(st), cudaMemcpyDeviceToHost));
+  int cur[4];
+  CK(cudaMemcpy(cur, c->Q.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; i++) stats[i] = 0;
+  for (int l = 0; l < c->P.nlevels; l++) { stats[0] += cand[0][l]; stats[1] += cand[1][l]; stats[2] += kp[0][l]; stats[3] += kp[1][l]; }
+  stats[4] = (long long)st[0]; stats[5] = (long long)st[1]; stats[6] = cur[0]; stats[7] = cur[2];
+  return FT_OK;
+}

@@ -1,0 +1,170 @@
+// ft_device.cuh -- device-side data layout shared by all kernels of the front-end.
+//
+// Everything a frame needs lives in HBM for the lifetime of the context ("FrameDevice"):
+// both eyes' pyramids and blurred pyramids (one slab each, 64-byte row pitch, 256-byte
+// level alignment), FAST per-cell candidate slabs, per-level octree outputs, the final
+// keypoint/descriptor arrays, stereo results, the 64x48 frame grid and the map-point
+// snapshot + candidate lists of the projection search. Kernels receive the geometry as a
+// __grid_constant__ FtParams (by value, so it is baked into CUDA-graph nodes).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fasttrack_b200.h"
+
+#define FT_EDGE_THRESHOLD 19   // reference include/ORBextractor.h:31
+#define FT_HALF_PATCH 15       // :30
+#define FT_PATCH 31            // :29
+#define FT_MIN_BORDER 16       // EDGE_THRESHOLD-3 (ORBextractor.cc:1120)
+
+struct FtLevel {
+  int w, h;               // level size (cvRound(width * invScale))
+  int pitch;              // bytes per row in the slab
+  int offset;             // byte offset of the level in the slab
+  int nCols, nRows;       // FAST cell grid (ORBextractor.cc:1131-1134)
+  int wCell, hCell;
+  int maxBorderX, maxBorderY;
+  int cellBase;           // first cell id of this level (per eye)
+  int cellCap;            // candidate capacity per cell
+  int cellKpBase;         // entry offset of this level's cell slab
+  int candBase;           // entry offset of this level's flat candidate list
+  int candCap;            // capacity of the flat list (worst case NMS survivors)
+  int quota;              // mnFeaturesPerLevel
+  int nodeCap;            // octree list capacity
+  int lvlKpBase;          // entry offset of this level's kept keypoints
+  int lvlKpCap;
+  int nIni;               // octree roots
+  float hX;
+  int xTab, yTab;         // offsets into the resize coefficient tables
+  int blurTileBase;       // first blur tile id
+  int blurTilesX;
+  int pad;
+};
+
+struct FtParams {
+  int nlevels, width, height, nfeatures;
+  int iniTh, minTh;
+  int totalCells, totalBlurTiles;
+  int maxKp;              // capacity of the final per-eye keypoint arrays
+  int camType;
+  int lap[2][2];
+  int umax[16];
+  float scale[FT_MAX_LEVELS], invScale[FT_MAX_LEVELS], sigma2[FT_MAX_LEVELS];
+  FtLevel lv[FT_MAX_LEVELS];
+};
+
+// Per-eye device buffers.
+struct FtEye {
+  uint8_t* pyr;            // pyramid slab
+  uint8_t* blur;           // blurred pyramid slab
+  uint32_t* cellKp;        // per-cell candidates: x:12 | y:12 | score:8 (relative to minBorder)
+  int* cellCount;          // [totalCells]
+  uint32_t* cand;          // flat per-level candidate lists in canonical order (same packing)
+  uint16_t* candNode;      // octree scratch: node code per candidate
+  int* lvlCandCount;       // [nlevels]
+  uint32_t* lvlKp;         // kept keypoints per level after the octree (level coords, absolute): x:12|y:12|score:8
+  int* lvlKpCount;         // [nlevels]
+  ft_keypoint* kps;        // final keypoints [maxKp]
+  uint8_t* desc;           // final descriptors [maxKp][32]
+  int* counts;             // [0]=n, [1]=monoIndex
+};
+
+struct FtBuffers {
+  FtEye eye[2];
+  const int2* xTab;        // per level, per dst column: {sx, a0 | a1<<16}
+  const int2* yTab;        // per level, per dst row:    {sy0 | sy1<<16, b0 | b1<<16}
+  int* status;             // device-side status word (capacity overflow flags)
+};
+
+// status bits
+#define FT_ST_CELL_OVERFLOW 1
+#define FT_ST_NODE_OVERFLOW 2
+#define FT_ST_KP_OVERFLOW 4
+#define FT_ST_CAND_OVERFLOW 8
+#define FT_ST_SBP_POOL_OVERFLOW 16
+#define FT_ST_RESOLVE_NOCONV 32
+
+__host__ __device__ __forceinline__ uint32_t ft_pack_xys(int x, int y, int s) {
+  return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+}
+__host__ __device__ __forceinline__ int ft_px(uint32_t p) { return (int)(p & 0xFFFu); }
+__host__ __device__ __forceinline__ int ft_py(uint32_t p) { return (int)((p >> 12) & 0xFFFu); }
+__host__ __device__ __forceinline__ int ft_ps(uint32_t p) { return (int)(p >> 24); }
+
+// 256-bit Hamming distance: __popc over the eight 32-bit words of two uint4 pairs
+// (reference ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:2256-2273, computes the same sum).
+__device__ __forceinline__ int ft_hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---- stereo / projection-search buffers ----
+struct FtStereoBuffers {
+  float* uRight;           // [maxKp]
+  float* depth;            // [maxKp]
+  int* bestIdxR;           // coarse match (diagnostic)
+  int* sad;                // best SAD per accepted match, -1 otherwise
+  int* l2r;                // fisheye [maxKp]
+  int* r2l;                // fisheye [maxKp]
+  float* p3d;              // fisheye [maxKp][3]
+  int* code;               // fisheye per-left code
+  unsigned long long* stats;  // [8] counters
+};
+
+struct FtCamera {
+  int type;
+  float p[8];
+};
+
+struct FtPose {
+  float Rcw[9], tcw[3], Rwc[9], Ow[3];
+  float Rlr[9], tlr[3], Rrl[9], trl[3];   // fisheye rig extrinsics (Tlr = T_c1_c2 and its inverse)
+};
+
+struct FtGridBuffers {
+  int* cellStart;          // [2][64*48+1] (left, right)
+  int* cellIdx;            // [2][maxKp]
+};
+
+// Map-point snapshot, frustum scratch, candidate lists and claim tables of the projection search.
+struct FtSbpBuffers {
+  float* pos;              // [M][3]
+  float* normal;           // [M][3]
+  float* minmax;           // [M][2] raw mfMinDistance, mfMaxDistance
+  uint8_t* desc;           // [M][32]
+  int* flags;              // [M] bit0 skip, bit1 Observations()>0
+  int* trI;                // [M][4] inView, inViewR, level, levelR
+  float* trF;              // [M][9] projX, projY, projXR, depth, viewCos, projXR_r, projYR_r, depthR, viewCosR
+  int* listOff;            // [M][2]
+  int* listLen;            // [M][2]
+  uint32_t* pool;          // candidate entries idx:16 | dist:9 | octave:4
+  int poolCap;
+  int* cursor;             // [0] pool cursor, [1] nmatches, [2] rounds, [3] non-blocking searched map points
+  int* sel;                // [M][2] selected keypoint per branch, -1 none
+  int* holder;             // [2*maxKp] in/out
+  uint8_t* holderObs;      // [2*maxKp]
+  int* minKey;             // [2*maxKp]
+  int* lastKey;            // [2*maxKp]
+};
+
+// ---- projection-search kernel arguments ----
+struct FtFrustumArgs {
+  FtCamera cam1, cam2;
+  FtPose pose;
+  float minX, maxX, minY, maxY;
+  float mbf, logScale;
+  int nlevels, fisheye;
+  float viewCosLimit;
+};
+
+struct FtGatherArgs {
+  float minX, minY, gridWInv, gridHInv;
+  float th; int bFactor; int bFar; float thFar;
+  int fisheye;
+};
+
+struct FtResolveArgs {
+  int M, nLeft, nSlots, fisheye;
+  float nnratio;
+};
+

@@ -1,0 +1,855 @@
+// ft_extract.cu -- ORB extraction kernels for sm_100a (both eyes per launch).
+//
+// Stage map (reference = CPU branch of src/ORBextractor.cc; results are bit-exact):
+//   k_resize        ComputePyramid               (:1495-1520)  cv::resize INTER_LINEAR, 11-bit fixed point
+//   k_blur          GaussianBlur 7x7 sigma 2     (:1456-1457)  8.8 / 16.16 fixed point, reflect-101
+//   k_fast_cells    per-cell cv::FAST + fallback (:1131-1203)  one CTA per cell, smem tile, ordered compaction
+//   k_octree        DistributeOctTree            (:660-884)    one CTA per (eye, level), node list in smem
+//   k_orient_desc   IC_Angle + rBRIEF + tail     (:39-108, :1392-1492) one warp per keypoint
+#include "ft_device.cuh"
+#include "ft_sort.h"
+
+__constant__ __align__(16) int8_t c_pattern[1024] = {
+#include "../../include/ft_orb_pattern.inc"
+};
+
+// ------------------------------------------------------------------------------------
+// Pyramid: level l from level l-1. 4 destination pixels per thread, uchar4 store.
+// Coefficients come from tables built once on the host (they depend on sizes only).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                int level) {
+  const FtLevel& L = p.lv[level];
+  const FtLevel& S = p.lv[level - 1];
+  const int eye = blockIdx.z;
+  const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int dy = blockIdx.y * 8 + threadIdx.y;
+  if (dx0 >= L.w || dy >= L.h) return;
+  const uint8_t* src = b.eye[eye].pyr + S.offset;
+  uint8_t* dst = b.eye[eye].pyr + L.offset;
+  const int2 yt = b.yTab[L.yTab + dy];
+  const int sy0 = yt.x & 0xFFFF, sy1 = yt.x >> 16;
+  const int b0 = (short)(yt.y & 0xFFFF), b1 = (short)(yt.y >> 16);
+  const uint8_t* r0 = src + (size_t)sy0 * S.pitch;
+  const uint8_t* r1 = src + (size_t)sy1 * S.pitch;
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int dx = dx0 + k;
+    if (dx < L.w) {
+      const int2 xt = b.xTab[L.xTab + dx];
+      const int sx = xt.x;
+      const int sx1 = min(sx + 1, S.w - 1);
+      const int a0 = (short)(xt.y & 0xFFFF), a1 = (short)(xt.y >> 16);
+      const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+      const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      out |= (uint32_t)(v & 0xFF) << (8 * k);
+    }
+  }
+  *reinterpret_cast<uint32_t*>(dst + (size_t)dy * L.pitch + dx0) = out;
+}
+
+// Level 0: copy the caller's image (arbitrary pitch) into the slab.
+__global__ void __launch_bounds__(256) k_copy_level0(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                     const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
+  const FtLevel& L = p.lv[0];
+  const int eye = blockIdx.z;
+  const uint8_t* src = eye ? imgR : imgL;
+  const int step = eye ? stepR : stepL;
+  const int x = (blockIdx.x * 64 + threadIdx.x) * 4;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  if (x >= L.w || y >= L.h) return;
+  const uint8_t* s = src + (size_t)y * step + x;
+  uint32_t v = 0;
+  if (x + 3 < L.w && ((reinterpret_cast<uintptr_t>(s) & 3) == 0)) {
+    v = *reinterpret_cast<const uint32_t*>(s);
+  } else {
+    for (int k = 0; k < 4 && x + k < L.w; k++) v |= (uint32_t)s[k] << (8 * k);
+  }
+  *reinterpret_cast<uint32_t*>(b.eye[eye].pyr + L.offset + (size_t)y * L.pitch + x) = v;
+}
+
+// ------------------------------------------------------------------------------------
+// Gaussian blur, all levels of both eyes in one launch. Tile = 64 x 32 outputs per CTA.
+// ------------------------------------------------------------------------------------
+#define BLUR_TW 64
+#define BLUR_TH 32
+__device__ __forceinline__ int ft_reflect101(int q, int n) {
+  if (n == 1) return 0;
+  while (q < 0 || q >= n) q = q < 0 ? -q : 2 * (n - 1) - q;
+  return q;
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                              int levelBegin, int levelEnd) {
+  __shared__ uint8_t sIn[BLUR_TH + 6][BLUR_TW + 8];
+  __shared__ uint16_t sH[BLUR_TH + 6][BLUR_TW];
+  const int eye = blockIdx.y;
+  int level = levelBegin;
+  const int tile = blockIdx.x + p.lv[levelBegin].blurTileBase;
+  while (level + 1 < levelEnd && tile >= p.lv[level + 1].blurTileBase) level++;
+  const FtLevel& L = p.lv[level];
+  const int t = tile - L.blurTileBase;
+  const int tx = (t % L.blurTilesX) * BLUR_TW, ty = (t / L.blurTilesX) * BLUR_TH;
+  const uint8_t* src = b.eye[eye].pyr + L.offset;
+  uint8_t* dst = b.eye[eye].blur + L.offset;
+  const int tid = threadIdx.x;
+  // stage (TH+6) x (TW+6) input pixels with reflect-101 addressing
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+    const int ry = i / (BLUR_TW + 6), rx = i % (BLUR_TW + 6);
+    const int gy = ft_reflect101(ty + ry - 3, L.h), gx = ft_reflect101(tx + rx - 3, L.w);
+    sIn[ry][rx] = src[(size_t)gy * L.pitch + gx];
+  }
+  __syncthreads();
+  for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+    const int ry = i / BLUR_TW, rx = i % BLUR_TW;
+    const uint8_t* s = &sIn[ry][rx];
+    const unsigned acc = 18u * (s[0] + s[6]) + 34u * (s[1] + s[5]) + 48u * (s[2] + s[4]) + 56u * s[3];
+    sH[ry][rx] = (uint16_t)acc;
+  }
+  __syncthreads();
+  {
+    const int x = tid % BLUR_TW;
+    const int yg = (tid / BLUR_TW) * 8;   // 4 groups of 8 rows
+    const int gx = tx + x;
+    if (gx < L.w) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int y = yg + k;
+        const int gy = ty + y;
+        if (gy < L.h) {
+          const unsigned v = 18u * ((unsigned)sH[y][x] + sH[y + 6][x]) + 34u * ((unsigned)sH[y + 1][x] + sH[y + 5][x]) +
+                             48u * ((unsigned)sH[y + 2][x] + sH[y + 4][x]) + 56u * (unsigned)sH[y + 3][x];
+          dst[(size_t)gy * L.pitch + gx] = (uint8_t)((v + 32768u) >> 16);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// FAST-9/16 per cell. One CTA (128 threads) per cell of one eye.
+// score(p) = max over the 16 arcs of 9 contiguous ring pixels of min(+-diff) - 1; corner(th) <=> score >= th.
+// The cell first tries iniThFAST; when no pixel survives NMS it falls back to minThFAST
+// (ORBextractor.cc:1157-1177). NMS only sees scores inside the cell's interior, as cv::FAST on a ROI does.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int ft_fast_score(const uint8_t* c, int stride) {
+  // ring order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+  const int v = c[0];
+  int d[16];
+  d[0] = v - c[3 * stride];      d[1] = v - c[3 * stride + 1];  d[2] = v - c[2 * stride + 2];  d[3] = v - c[stride + 3];
+  d[4] = v - c[3];               d[5] = v - c[-stride + 3];     d[6] = v - c[-2 * stride + 2]; d[7] = v - c[-3 * stride + 1];
+  d[8] = v - c[-3 * stride];     d[9] = v - c[-3 * stride - 1]; d[10] = v - c[-2 * stride - 2]; d[11] = v - c[-stride - 3];
+  d[12] = v - c[-3];             d[13] = v - c[stride - 3];     d[14] = v - c[2 * stride - 2]; d[15] = v - c[3 * stride - 1];
+  // two signed 16-bit lanes per word: low = d (bright-centre arcs), high = -d (dark-centre arcs)
+  unsigned x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = ((unsigned)d[i] & 0xFFFFu) | ((unsigned)(-d[i]) << 16);
+  unsigned m2[16], m4[16], m8[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) m2[i] = __vmins2(x[i], x[(i + 1) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) m4[i] = __vmins2(m2[i], m2[(i + 2) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) m8[i] = __vmins2(m4[i], m4[(i + 4) & 15]);
+  unsigned best = __vmins2(m8[0], x[8]);
+#pragma unroll
+  for (int i = 1; i < 16; i++) best = __vmaxs2(best, __vmins2(m8[i], x[(i + 8) & 15]));
+  const int pos = (short)(best & 0xFFFFu), neg = (short)(best >> 16);
+  return max(pos, neg) - 1;
+}
+
+__global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                    int levelBegin, int levelEnd) {
+  extern __shared__ uint8_t smem[];
+  __shared__ int sWarp[4];
+  __shared__ int sAny;
+  const int eye = blockIdx.y;
+  const int cell = blockIdx.x + p.lv[levelBegin].cellBase;
+  int level = levelBegin;
+  while (level + 1 < levelEnd && cell >= p.lv[level + 1].cellBase) level++;
+  const FtLevel& L = p.lv[level];
+  const int ci = (cell - L.cellBase) / L.nCols, cj = (cell - L.cellBase) % L.nCols;
+  const FtEye& E = b.eye[eye];
+  const int tid = threadIdx.x;
+  // cell window (ORBextractor.cc:1136-1153); all quantities are integers held in floats there
+  const int iniY = FT_MIN_BORDER + ci * L.hCell, iniX = FT_MIN_BORDER + cj * L.wCell;
+  int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
+  const bool skip = (iniY >= L.maxBorderY - 3) || (iniX >= L.maxBorderX - 6);
+  if (maxY > L.maxBorderY) maxY = L.maxBorderY;
+  if (maxX > L.maxBorderX) maxX = L.maxBorderX;
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  if (skip || rw < 7 || rh < 7) {
+    if (tid == 0) E.cellCount[cell] = 0;
+    return;
+  }
+  const int iw = rw - 6, ih = rh - 6;
+  const int rwPad = (rw + 3) & ~3;
+  uint8_t* sImg = smem;                         // [rh][rwPad]
+  uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // [ih][iw] score (0 below minTh), then NMS survivors
+  uint8_t* sMx = sSc + ((iw * ih + 15) & ~15);
+  const uint8_t* src = E.pyr + L.offset + (size_t)iniY * L.pitch + iniX;
+  for (int i = tid; i < rh * rw; i += 128) {
+    const int y = i / rw, x = i - y * rw;
+    sImg[y * rwPad + x] = src[(size_t)y * L.pitch + x];
+  }
+  if (tid == 0) sAny = 0;
+  __syncthreads();
+  const int total = iw * ih;
+  for (int i = tid; i < total; i += 128) {
+    const int y = i / iw, x = i - y * iw;
+    const uint8_t* c = &sImg[(y + 3) * rwPad + (x + 3)];
+    // quick reject at minTh: every 9-arc holds one pixel of each opposite ring pair
+    const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
+    const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
+    const bool dark = (t0 < lo || t8 < lo) && (t4 < lo || t12 < lo);
+    const bool bright = (t0 > hi || t8 > hi) && (t4 > hi || t12 > hi);
+    int s = 0;
+    if (dark || bright) {
+      s = ft_fast_score(c, rwPad);
+      if (s < p.minTh) s = 0;
+    }
+    sSc[i] = (uint8_t)s;
+  }
+  __syncthreads();
+  // 3x3 strict-maximum NMS inside the interior
+  bool any20 = false;
+  for (int i = tid; i < total; i += 128) {
+    const int y = i / iw, x = i - y * iw;
+    const int s = sSc[i];
+    int keep = 0;
+    if (s) {
+      int m = 0;
+      const bool up = y > 0, dn = y < ih - 1, lf = x > 0, rt = x < iw - 1;
+      if (lf) m = max(m, (int)sSc[i - 1]);
+      if (rt) m = max(m, (int)sSc[i + 1]);
+      if (up) {
+        m = max(m, (int)sSc[i - iw]);
+        if (lf) m = max(m, (int)sSc[i - iw - 1]);
+        if (rt) m = max(m, (int)sSc[i - iw + 1]);
+      }
+      if (dn) {
+        m = max(m, (int)sSc[i + iw]);
+        if (lf) m = max(m, (int)sSc[i + iw - 1]);
+        if (rt) m = max(m, (int)sSc[i + iw + 1]);
+      }
+      if (s > m) keep = s;
+    }
+    sMx[i] = (uint8_t)keep;
+    any20 |= keep >= p.iniTh;
+  }
+  if (any20) sAny = 1;
+  __syncthreads();
+  const int th = sAny ? p.iniTh : p.minTh;
+  // ordered compaction: thread t owns the contiguous pixel range [t*seg, (t+1)*seg) in row-major order
+  const int seg = (total + 127) / 128;
+  const int beg = min(tid * seg, total), end = min(beg + seg, total);
+  int cnt = 0;
+  for (int i = beg; i < end; i++) cnt += sMx[i] >= th && sMx[i] > 0;
+  // block exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((tid & 31) >= o) incl += n;
+  }
+  if ((tid & 31) == 31) sWarp[tid >> 5] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < (tid >> 5); w++) base += sWarp[w];
+  const int totalKp = sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
+  int pos = base + incl - cnt;
+  uint32_t* out = E.cellKp + L.cellKpBase + (size_t)(cell - L.cellBase) * L.cellCap;
+  for (int i = beg; i < end; i++) {
+    const int s = sMx[i];
+    if (s >= th && s > 0) {
+      const int y = i / iw, x = i - y * iw;
+      if (pos < L.cellCap) out[pos] = ft_pack_xys(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, s);
+      pos++;
+    }
+  }
+  if (tid == 0) {
+    E.cellCount[cell] = min(totalKp, L.cellCap);
+    if (totalKp > L.cellCap) atomicOr(b.status, FT_ST_CELL_OVERFLOW);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Octree distribution. One CTA per (eye, level). The std::list of nodes becomes an array in
+// list order that is rebuilt every pass; a node's keypoints are not moved: every candidate
+// carries a 16-bit code (node slot * 4 + quadrant) that is remapped through a table.
+// ------------------------------------------------------------------------------------
+#define OCT_THREADS 512
+
+struct OctSmem {
+  // carved from dynamic shared memory, all arrays sized nodeCap
+  short4* bnd[2];      // ULx, ULy, BRx, BRy  (ping-pong)
+  int* cnt[2];         // keypoints per node
+  int* ccnt;           // [cap][4] child counts of the pass
+  int* posA;           // scan scratch
+  int* posB;
+  int* posC;
+  int* map;            // [cap*4] code -> node index in the current list
+  unsigned long long* vec[2];  // expandable nodes (key<<32 | node index), ping-pong
+  int* vecPos;         // node index -> position in processing order, -1 when not in vec
+};
+
+// exclusive scans of three per-node quantities by warp 0; returns totals through smem
+__device__ void oct_scan3(int n, const int* a, const int* b3, const int* c3, int* oa, int* ob, int* oc, int* totals,
+                          bool reverseA) {
+  // reverseA: oa[i] = sum of a[j] for j > i (children of later nodes go in front of earlier ones)
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int ra = 0, rb = 0, rc = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int ia = reverseA ? (n - 1 - i) : i;
+      int va = (i < n) ? a[ia] : 0, vb = (i < n) ? b3[i] : 0, vc = (i < n) ? c3[i] : 0;
+      int sa = va, sb = vb, sc = vc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o),
+                  tc = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+        if (lane >= o) { sa += ta; sb += tb; sc += tc; }
+      }
+      if (i < n) { oa[ia] = ra + sa - va; ob[i] = rb + sb - vb; oc[i] = rc + sc - vc; }
+      ra += __shfl_sync(0xFFFFFFFFu, sa, 31); rb += __shfl_sync(0xFFFFFFFFu, sb, 31); rc += __shfl_sync(0xFFFFFFFFu, sc, 31);
+    }
+    if (lane == 0) { totals[0] = ra; totals[1] = rb; totals[2] = rc; }
+  }
+}
+
+__device__ __forceinline__ void oct_child_bounds(short4 bd, int q, short4& out) {
+  // DivideNode (ORBextractor.cc:510-538): halfX = ceil((UR.x-UL.x)/2.f), halfY = ceil((BR.y-UL.y)/2.f)
+  const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
+  const int mx = bd.x + halfX, my = bd.y + halfY;
+  out.x = (q & 1) ? mx : bd.x;
+  out.z = (q & 1) ? bd.z : mx;
+  out.y = (q & 2) ? my : bd.y;
+  out.w = (q & 2) ? bd.w : my;
+}
+
+__global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                        int levelBegin) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  __shared__ int sTot[4];
+  __shared__ int sN, sMode, sVecN, sP, sCellTot;
+  const int level = levelBegin + blockIdx.x;
+  const int eye = blockIdx.y;
+  const FtLevel& L = p.lv[level];
+  const FtEye& E = b.eye[eye];
+  const int tid = threadIdx.x;
+  const int cap = L.nodeCap;
+  const int N = L.quota;
+
+  OctSmem S;
+  {
+    uint8_t* q = smemRaw;
+    S.vec[0] = (unsigned long long*)q; q += sizeof(unsigned long long) * cap;
+    S.vec[1] = (unsigned long long*)q; q += sizeof(unsigned long long) * cap;
+    S.bnd[0] = (short4*)q; q += sizeof(short4) * cap;
+    S.bnd[1] = (short4*)q; q += sizeof(short4) * cap;
+    S.cnt[0] = (int*)q; q += 4 * cap;
+    S.cnt[1] = (int*)q; q += 4 * cap;
+    S.ccnt = (int*)q; q += 16 * cap;
+    S.posA = (int*)q; q += 4 * cap;
+    S.posB = (int*)q; q += 4 * cap;
+    S.posC = (int*)q; q += 4 * cap;
+    S.map = (int*)q; q += 16 * cap;
+    S.vecPos = (int*)q; q += 4 * cap;
+  }
+
+  // ---- gather the per-cell lists into the flat canonical order (cell row-major, then row-major in cell) ----
+  const int nCells = L.nCols * L.nRows;
+  uint32_t* cand = E.cand + L.candBase;
+  uint16_t* code = E.candNode + L.candBase;
+  {
+    // running offset over cells, 512 cells per round
+    __shared__ int sScan[OCT_THREADS / 32];
+    __shared__ int sBase;
+    if (tid == 0) sBase = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < nCells; c0 += OCT_THREADS) {
+      const int c = c0 + tid;
+      const int cnt = c < nCells ? E.cellCount[L.cellBase + c] : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += n;
+      }
+      if ((tid & 31) == 31) sScan[tid >> 5] = incl;
+      __syncthreads();
+      int off = sBase;
+      for (int w = 0; w < (tid >> 5); w++) off += sScan[w];
+      off += incl - cnt;
+      const uint32_t* src = E.cellKp + L.cellKpBase + (size_t)c * L.cellCap;
+      for (int k = 0; k < cnt; k++)
+        if (off + k < L.candCap) cand[off + k] = src[k];
+      __syncthreads();
+      if (tid == OCT_THREADS - 1) sBase = off + cnt;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int C = sBase;
+      if (C > L.candCap) { C = L.candCap; atomicOr(b.status, FT_ST_CAND_OVERFLOW); }
+      sCellTot = C;
+      E.lvlCandCount[level] = C;
+    }
+    __syncthreads();
+  }
+  const int C = sCellTot;
+  uint32_t* outKp = E.lvlKp + L.lvlKpBase;
+  if (C == 0) {
+    if (tid == 0) E.lvlKpCount[level] = 0;
+    return;
+  }
+
+  // ---- roots (ORBextractor.cc:664-706) ----
+  int cur = 0;  // ping-pong index of the current list
+  const int nIni = L.nIni;
+  const float hX = L.hX;
+  const int H = L.maxBorderY - FT_MIN_BORDER;
+  for (int i = tid; i < nIni; i += OCT_THREADS) {
+    short4 bd;
+    bd.x = (short)(int)__fmul_rn(hX, (float)i);
+    bd.z = (short)(int)__fmul_rn(hX, (float)(i + 1));
+    bd.y = 0; bd.w = (short)H;
+    S.bnd[0][i] = bd;
+    S.cnt[0][i] = 0;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += OCT_THREADS) {
+    const uint32_t pk = cand[c];
+    int r = (int)__fdiv_rn((float)ft_px(pk), hX);
+    if (r >= nIni) r = nIni - 1;
+    atomicAdd(&S.cnt[0][r], 1);
+    code[c] = (uint16_t)(r * 4);
+  }
+  __syncthreads();
+  // drop empty roots
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < nIni; i++) {
+      if (S.cnt[0][i] > 0) {
+        S.bnd[1][n] = S.bnd[0][i]; S.cnt[1][n] = S.cnt[0][i];
+        for (int q = 0; q < 4; q++) S.map[i * 4 + q] = n;
+        n++;
+      } else {
+        for (int q = 0; q < 4; q++) S.map[i * 4 + q] = -1;
+      }
+    }
+    sN = n; sMode = 0; sVecN = 0;
+  }
+  cur = 1;
+  __syncthreads();
+
+  // ---- main loop ----
+  // sMode: 0 = normal pass, 1 = careful pass (largest-first with early break), 2 = finished
+  int vcur = 0;  // ping-pong of the expandable-node vector
+  for (int iter = 0; iter < 64; iter++) {
+    const int n = sN;
+    const int mode = sMode;
+    if (mode == 2) break;
+    short4* bnd = S.bnd[cur]; int* cnt = S.cnt[cur];
+    short4* bnd2 = S.bnd[cur ^ 1]; int* cnt2 = S.cnt[cur ^ 1];
+    const int m = sVecN;                 // size of the vector entering a careful pass
+    unsigned long long* vecPrev = S.vec[vcur];
+    unsigned long long* vecNew = S.vec[vcur ^ 1];
+
+    // which nodes are split (speculatively, in careful mode) this pass
+    for (int i = tid; i < n; i += OCT_THREADS) {
+      S.vecPos[i] = -1;
+      S.ccnt[4 * i] = 0; S.ccnt[4 * i + 1] = 0; S.ccnt[4 * i + 2] = 0; S.ccnt[4 * i + 3] = 0;
+    }
+    __syncthreads();
+    if (mode == 1) {
+      if (tid == 0) ftsort::sort(vecPrev, m);   // std::sort(..., compareNodes) (ORBextractor.cc:805)
+      __syncthreads();
+      // processing order r = 0..m-1 walks the sorted vector from the back (:806)
+      for (int r = tid; r < m; r += OCT_THREADS) S.vecPos[(int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu)] = r;
+      __syncthreads();
+    }
+    // candidates: remap code -> node, count children of nodes being split
+    for (int c = tid; c < C; c += OCT_THREADS) {
+      const int node = S.map[code[c]];
+      const bool split = (mode == 0) ? (cnt[node] > 1) : (S.vecPos[node] >= 0);
+      int q = 0;
+      if (split) {
+        const uint32_t pk = cand[c];
+        const short4 bd = bnd[node];
+        const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
+        q = (ft_px(pk) < bd.x + halfX ? 0 : 1) | (ft_py(pk) < bd.y + halfY ? 0 : 2);
+        atomicAdd(&S.ccnt[4 * node + q], 1);
+      }
+      code[c] = (uint16_t)(node * 4 + q);
+    }
+    __syncthreads();
+
+    if (mode == 0) {
+      // per node: k = non-empty children, e = children with more than one keypoint
+      for (int i = tid; i < n; i += OCT_THREADS) {
+        int k = 0, e = 0, nm = 0;
+        if (cnt[i] > 1) {
+          for (int q = 0; q < 4; q++) { k += S.ccnt[4 * i + q] > 0; e += S.ccnt[4 * i + q] > 1; }
+        } else nm = 1;
+        S.posA[i] = k; S.posB[i] = nm; S.posC[i] = e;
+      }
+      __syncthreads();
+      // posA <- children of later nodes (they end up in front), posB <- noMore nodes before i, posC <- vec offset
+      oct_scan3(n, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, true);
+      __syncthreads();
+      const int totalChildren = sTot[0], nNew = sTot[0] + sTot[1], nToExpand = sTot[2];
+      if (nNew > cap) {  // cannot happen (list <= N+3, roots*4); guarded so a logic slip cannot corrupt memory
+        if (tid == 0) { atomicOr(b.status, FT_ST_NODE_OVERFLOW); E.lvlKpCount[level] = 0; }
+        return;
+      }
+      for (int i = tid; i < n; i += OCT_THREADS) {
+        if (cnt[i] > 1) {
+          const short4 bd = bnd[i];
+          int after = 0;   // non-empty children with a higher quadrant index are pushed later => sit in front
+          int vpos = S.posC[i];
+          int pos[4];
+          for (int q = 3; q >= 0; q--) { pos[q] = S.posA[i] + after; after += S.ccnt[4 * i + q] > 0; }
+          for (int q = 0; q < 4; q++) {
+            const int cc = S.ccnt[4 * i + q];
+            if (cc > 0) {
+              short4 cb; oct_child_bounds(bd, q, cb);
+              bnd2[pos[q]] = cb; cnt2[pos[q]] = cc;
+              S.map[4 * i + q] = pos[q];
+              if (cc > 1) vecNew[vpos++] = ((unsigned long long)(((unsigned)cc << 12) | (unsigned)cb.x) << 32) | (unsigned)pos[q];
+            } else S.map[4 * i + q] = -1;
+          }
+        } else {
+          const int np = totalChildren + S.posB[i];
+          bnd2[np] = bnd[i]; cnt2[np] = cnt[i];
+          S.map[4 * i] = np; S.map[4 * i + 1] = np; S.map[4 * i + 2] = np; S.map[4 * i + 3] = np;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        sN = nNew; sVecN = nToExpand;
+        if (nNew >= N || nNew == n) sMode = 2;                 // (:790)
+        else if (nNew + nToExpand * 3 > N) sMode = 1;          // (:794)
+      }
+      cur ^= 1; vcur ^= 1;
+      __syncthreads();
+    } else {
+      // careful pass: nodes of the sorted vector are split from the back until the list reaches N (:806-853)
+      // posA[r] = growth of the r-th processed node (non-empty children - 1), inclusive prefix decides the cut
+      for (int r = tid; r < m; r += OCT_THREADS) {
+        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
+        int k = 0, e = 0;
+        for (int q = 0; q < 4; q++) { k += S.ccnt[4 * node + q] > 0; e += S.ccnt[4 * node + q] > 1; }
+        S.posA[r] = k; S.posB[r] = k - 1; S.posC[r] = e;
+      }
+      __syncthreads();
+      // exclusive prefix over processing order: posA -> children before r, posB -> growth before r, posC -> vec offset
+      oct_scan3(m, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, false);
+      __syncthreads();
+      // number processed P: first r with n + growthBefore(r) + growth(r) >= N, else m
+      if (tid == 0) sP = m;
+      __syncthreads();
+      for (int r = tid; r < m; r += OCT_THREADS) {
+        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
+        int k = 0;
+        for (int q = 0; q < 4; q++) k += S.ccnt[4 * node + q] > 0;
+        if (n + S.posB[r] + (k - 1) >= N) atomicMin(&sP, r + 1);
+      }
+      __syncthreads();
+      const int P = sP;
+      // totals restricted to the processed prefix
+      __shared__ int sChildP, sGrowP, sVecP;
+      if (tid == 0) {
+        if (P == m) { sChildP = sTot[0]; sGrowP = sTot[1]; sVecP = sTot[2]; }
+        else { sChildP = S.posA[P]; sGrowP = S.posB[P]; sVecP = S.posC[P]; }
+      }
+      __syncthreads();
+      const int childP = sChildP, nNew = n + sGrowP, vecP = sVecP;
+      if (nNew > cap) {
+        if (tid == 0) { atomicOr(b.status, FT_ST_NODE_OVERFLOW); E.lvlKpCount[level] = 0; }
+        return;
+      }
+      // processed nodes: children go to the front, later-processed first
+      for (int r = tid; r < P; r += OCT_THREADS) {
+        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
+        const short4 bd = bnd[node];
+        int k = 0;
+        for (int q = 0; q < 4; q++) k += S.ccnt[4 * node + q] > 0;
+        const int start = childP - S.posA[r] - k;   // children of nodes processed after r sit in front
+        int after = 0, vpos = S.posC[r];
+        int pos[4];
+        for (int q = 3; q >= 0; q--) { pos[q] = start + after; after += S.ccnt[4 * node + q] > 0; }
+        for (int q = 0; q < 4; q++) {
+          const int cc = S.ccnt[4 * node + q];
+          if (cc > 0) {
+            short4 cb; oct_child_bounds(bd, q, cb);
+            bnd2[pos[q]] = cb; cnt2[pos[q]] = cc;
+            S.map[4 * node + q] = pos[q];
+            if (cc > 1) vecNew[vpos++] = ((unsigned long long)(((unsigned)cc << 12) | (unsigned)cb.x) << 32) | (unsigned)pos[q];
+          } else S.map[4 * node + q] = -1;
+        }
+      }
+      // surviving old nodes keep their relative order behind the new children
+      for (int i = tid; i < n; i += OCT_THREADS) {
+        const int r = S.vecPos[i];
+        S.posB[i] = (r >= 0 && r < P) ? 0 : 1;   // reuse posB as "survives" flag (m <= n so no overlap hazard after sync)
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // exclusive scan of the survive flags into posA
+        const int lane = tid;
+        int run = 0;
+        for (int base = 0; base < n; base += 32) {
+          const int i = base + lane;
+          const int v = i < n ? S.posB[i] : 0;
+          int s = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += t; }
+          if (i < n) S.posA[i] = run + s - v;
+          run += __shfl_sync(0xFFFFFFFFu, s, 31);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += OCT_THREADS) {
+        if (S.posB[i]) {
+          const int np = childP + S.posA[i];
+          bnd2[np] = bnd[i]; cnt2[np] = cnt[i];
+          S.map[4 * i] = np; S.map[4 * i + 1] = np; S.map[4 * i + 2] = np; S.map[4 * i + 3] = np;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        sN = nNew; sVecN = vecP;
+        if (nNew >= N || nNew == n) sMode = 2;   // (:855)
+      }
+      cur ^= 1; vcur ^= 1;
+      __syncthreads();
+    }
+  }
+
+  // ---- best keypoint per node: highest response, first in input order wins ties (:862-881) ----
+  const int n = sN;
+  unsigned* best = (unsigned*)S.posA;
+  for (int i = tid; i < n; i += OCT_THREADS) best[i] = 0;
+  __syncthreads();
+  for (int c = tid; c < C; c += OCT_THREADS) {
+    const int node = S.map[code[c]];
+    const unsigned key = ((unsigned)ft_ps(cand[c]) << 20) | (unsigned)(0xFFFFF - c);
+    atomicMax(&best[node], key);
+  }
+  __syncthreads();
+  if (n > L.lvlKpCap) {
+    if (tid == 0) { atomicOr(b.status, FT_ST_KP_OVERFLOW); E.lvlKpCount[level] = 0; }
+    return;
+  }
+  for (int i = tid; i < n; i += OCT_THREADS) {
+    const int c = 0xFFFFF - (int)(best[i] & 0xFFFFFu);
+    const uint32_t pk = cand[c];
+    outKp[i] = ft_pack_xys(ft_px(pk) + FT_MIN_BORDER, ft_py(pk) + FT_MIN_BORDER, ft_ps(pk));
+  }
+  if (tid == 0) E.lvlKpCount[level] = n;
+}
+
+// ------------------------------------------------------------------------------------
+// Orientation + descriptor + final ordering. One warp per kept keypoint.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float ft_fast_atan2(float y, float x) {
+  // cv::fastAtan2 scalar path; every operation individually rounded (no FMA contraction)
+  const float sc = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * sc, p3 = -0.3258083974640975f * sc, p5 = 0.1555786518463281f * sc,
+              p7 = -0.04432655554792128f * sc;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float eps = (float)2.2204460492503131e-16;
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+#define OD_WARPS 8
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_constant__ FtParams p,
+                                                               const __grid_constant__ FtBuffers b) {
+  __shared__ int sLvlOff[FT_MAX_LEVELS + 1];
+  __shared__ int sScan[OD_WARPS];
+  __shared__ int sMonoBefore;   // mono (non-lapping) keypoints before this block's first keypoint
+  __shared__ int sMonoTotal;
+  __shared__ int sPat[256];     // rBRIEF pattern staged from constant memory (lanes read different rows)
+  const int eye = blockIdx.y;
+  const FtEye& E = b.eye[eye];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  sPat[tid] = reinterpret_cast<const int*>(c_pattern)[tid];
+  if (tid == 0) {
+    int o = 0;
+    for (int l = 0; l < p.nlevels; l++) { sLvlOff[l] = o; o += E.lvlKpCount[l]; }
+    sLvlOff[p.nlevels] = o;
+    sMonoBefore = 0; sMonoTotal = 0;
+  }
+  __syncthreads();
+  const int total = sLvlOff[p.nlevels];
+  const int lap0 = p.lap[eye][0], lap1 = p.lap[eye][1];
+  const int first = blockIdx.x * OD_WARPS;   // first global keypoint order index of this block
+  if (blockIdx.x == 0 && tid == 0) {
+    E.counts[0] = min(total, p.maxKp);
+    if (total > p.maxKp) atomicOr(b.status, FT_ST_KP_OVERFLOW);
+  }
+  if (first >= total || total > p.maxKp) {
+    // block 0 still has to publish monoIndex when there are no keypoints
+    if (blockIdx.x == 0 && tid == 0) E.counts[1] = 0;
+    return;
+  }
+  // count non-lapping keypoints (a) before `first`, (b) in total: each thread strides over all keypoints
+  {
+    int before = 0, all = 0;
+    for (int g = tid; g < total; g += OD_WARPS * 32) {
+      int l = 0;
+      while (g >= sLvlOff[l + 1]) l++;
+      const uint32_t pk = E.lvlKp[p.lv[l].lvlKpBase + (g - sLvlOff[l])];
+      float x = (float)ft_px(pk);
+      if (l != 0) x = __fmul_rn(x, p.scale[l]);
+      const bool inLap = (x >= (float)lap0) && (x <= (float)lap1);
+      if (!inLap) { all++; if (g < first) before++; }
+    }
+    atomicAdd(&sMonoBefore, before);
+    atomicAdd(&sMonoTotal, all);
+  }
+  __syncthreads();
+  const int g = first + warp;
+  // in-block order: lapping flags of the (up to) OD_WARPS keypoints of this block
+  int l = 0;
+  bool valid = g < total;
+  uint32_t pk = 0;
+  if (valid) {
+    while (g >= sLvlOff[l + 1]) l++;
+    pk = E.lvlKp[p.lv[l].lvlKpBase + (g - sLvlOff[l])];
+  }
+  const int kx = ft_px(pk), ky = ft_py(pk);
+  float fxs = (float)kx, fys = (float)ky;
+  if (l != 0) { fxs = __fmul_rn(fxs, p.scale[l]); fys = __fmul_rn(fys, p.scale[l]); }
+  const bool inLap = valid && (fxs >= (float)lap0) && (fxs <= (float)lap1);
+  if (lane == 0) sScan[warp] = (valid && !inLap) ? 1 : 0;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) E.counts[1] = sMonoTotal;
+  if (!valid) return;
+  int monoBefore = sMonoBefore;
+  for (int w = 0; w < warp; w++) monoBefore += sScan[w];
+  // destination index (ORBextractor.cc:1408,1476-1486): lapping points fill from the end backwards
+  const int dstIdx = inLap ? (total - 1 - (g - monoBefore)) : monoBefore;
+
+  const FtLevel& L = p.lv[l];
+  const uint8_t* img = E.pyr + L.offset;
+  const uint8_t* center = img + (size_t)ky * L.pitch + kx;
+  // IC_Angle (ORBextractor.cc:39-66): integer moments over the 749-px disc; lanes span u = -15..15
+  int m01 = 0, m10 = 0;
+  {
+    const int u = lane - 15;
+    if (lane < 31) {
+#pragma unroll 1
+      for (int v = -FT_HALF_PATCH; v <= FT_HALF_PATCH; v++) {
+        const int d = p.umax[v < 0 ? -v : v];
+        if (u >= -d && u <= d) {
+          const int val = center[v * L.pitch + u];
+          m10 += u * val;
+          m01 += v * val;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+      m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+    }
+  }
+  const float angle = ft_fast_atan2((float)m01, (float)m10);
+  // computeOrbDescriptor (ORBextractor.cc:68-108)
+  const float factorPI = (float)(3.14159265358979323846 / 180.f);
+  const float ang = __fmul_rn(angle, factorPI);
+  // correctly-rounded-in-practice float cos/sin via double (glibc cosf/sinf are < 1 ulp)
+  const float a = (float)cos((double)ang), bb = (float)sin((double)ang);
+  const uint8_t* bimg = E.blur + L.offset;
+  const uint8_t* bc = bimg + (size_t)ky * L.pitch + kx;
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int pw = sPat[lane * 8 + k];
+    const int x0 = (int8_t)(pw & 0xFF), y0 = (int8_t)((pw >> 8) & 0xFF), x1 = (int8_t)((pw >> 16) & 0xFF), y1 = (int8_t)(pw >> 24);
+    const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn((float)x0, bb), __fmul_rn((float)y0, a)));
+    const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn((float)x0, a), __fmul_rn((float)y0, bb)));
+    const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn((float)x1, bb), __fmul_rn((float)y1, a)));
+    const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn((float)x1, a), __fmul_rn((float)y1, bb)));
+    const int t0 = bc[ry0 * L.pitch + rx0], t1 = bc[ry1 * L.pitch + rx1];
+    val |= (t0 < t1) << k;
+  }
+  E.desc[(size_t)dstIdx * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    ft_keypoint kp;
+    kp.x = fxs; kp.y = fys;
+    kp.size = (float)(int)__fmul_rn((float)FT_PATCH, p.scale[l]);
+    kp.angle = angle;
+    kp.response = (float)ft_ps(pk);
+    kp.octave = l;
+    E.kps[dstIdx] = kp;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+size_t ft_fast_smem_bytes(const FtParams& p) {
+  size_t mx = 0;
+  for (int l = 0; l < p.nlevels; l++) {
+    const FtLevel& L = p.lv[l];
+    const int rw = L.wCell + 6, rh = L.hCell + 6;
+    const int rwPad = (rw + 3) & ~3;
+    size_t s = ((rh * rwPad + 15) & ~15) + 2 * ((L.wCell * L.hCell + 15) & ~15);
+    if (s > mx) mx = s;
+  }
+  return mx;
+}
+size_t ft_octree_smem_bytes(const FtParams& p, int level) {
+  return (size_t)p.lv[level].nodeCap * (8 + 8 + 8 + 8 + 4 + 4 + 16 + 4 + 4 + 4 + 16 + 4) + 64;
+}
+
+cudaError_t ft_launch_extract_setup(const FtParams& p) {
+  size_t mx = 0;
+  for (int l = 0; l < p.nlevels; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
+  cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_fast_smem_bytes(p));
+}
+
+void ft_launch_copy_level0(const FtParams& p, const FtBuffers& b, const uint8_t* imgL, int stepL, const uint8_t* imgR,
+                           int stepR, cudaStream_t st) {
+  dim3 blk(64, 4), grd((p.lv[0].w + 255) / 256, (p.lv[0].h + 3) / 4, 2);
+  k_copy_level0<<<grd, blk, 0, st>>>(p, b, imgL, stepL, imgR, stepR);
+}
+void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
+  dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, 2);
+  k_resize<<<grd, blk, 0, st>>>(p, b, level);
+}
+void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
+  const int tiles = (l1 < p.nlevels ? p.lv[l1].blurTileBase : p.totalBlurTiles) - p.lv[l0].blurTileBase;
+  k_blur<<<dim3(tiles, 2), 256, 0, st>>>(p, b, l0, l1);
+}
+void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
+  const int cells = (l1 < p.nlevels ? p.lv[l1].cellBase : p.totalCells) - p.lv[l0].cellBase;
+  k_fast_cells<<<dim3(cells, 2), 128, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
+}
+void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
+  size_t mx = 0;
+  for (int l = l0; l < l1; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
+  k_octree<<<dim3(l1 - l0, 2), OCT_THREADS, mx, st>>>(p, b, l0);
+}
+void ft_launch_orient_desc(const FtParams& p, const FtBuffers& b, cudaStream_t st) {
+  k_orient_desc<<<dim3((p.maxKp + OD_WARPS - 1) / OD_WARPS, 2), OD_WARPS * 32, 0, st>>>(p, b);
+}

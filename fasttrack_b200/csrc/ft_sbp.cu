@@ -1,0 +1,467 @@
+// ft_sbp.cu -- Tracking::SearchLocalPoints on the device-resident frame (sm_100a).
+//
+//   k_grid_build   Frame::AssignFeaturesToGrid + PosInGrid          (reference src/Frame.cc:409-440,749-759)
+//   k_frustum      Frame::isInFrustum / isInFrustumChecks + MapPoint::PredictScale
+//                  (src/Frame.cc:536-598,1308-1382; src/MapPoint.cc:502-546)
+//   k_gather       Frame::GetFeaturesInArea in its traversal order + Hamming distance per candidate
+//                  (src/Frame.cc:681-747; src/ORBmatcher.cc:85-114)
+//   k_resolve      the best / second-best scan and the loop-carried keypoint claims of
+//                  ORBmatcher::SearchByProjection (src/ORBmatcher.cc:57-225), solved as a fix-point
+//   k_resolve_seq  the same loop executed in order by one thread: only used for fisheye rigs when a searched
+//                  map point has Observations()==0 (its mirrored write can un-block a keypoint)
+//
+// Claims. In the reference a keypoint taken by map point i (with Observations()>0) is invisible to every j>i.
+// Every read/write gets a time stamp: left search of map point j = 2j, right search = 2j+1. A slot is blocked
+// at time t iff it was blocked on entry or some blocking write has a stamp < t. Given the decisions of all
+// map points the per-slot minimum stamp is an atomicMin; given the stamps every decision is independent. A
+// decision only depends on decisions with smaller stamps, so iterating the two steps reaches the unique
+// sequential result; each round finalises at least the next undecided map point and in practice the depth
+// of the longest chain of displaced matches (reported as `rounds`).
+#include "ft_device.cuh"
+#include "ft_camera.cuh"
+
+#define GRID_CELLS (FT_GRID_COLS * FT_GRID_ROWS)
+
+// ---- frame grid -------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                     const __grid_constant__ FtGridBuffers g, int fisheye, float minX,
+                                                     float minY, float gridWInv, float gridHInv) {
+  __shared__ int sCnt[GRID_CELLS];
+  __shared__ int sStart[GRID_CELLS + 1];
+  __shared__ int sWarp[32];
+  const int tid = threadIdx.x;
+  const int nEyes = fisheye ? 2 : 1;
+  for (int eye = 0; eye < nEyes; eye++) {
+    const FtEye& E = b.eye[eye];
+    const int n = E.counts[0];
+    int* cellStart = g.cellStart + eye * (GRID_CELLS + 1);
+    int* cellIdx = g.cellIdx + eye * p.maxKp;
+    for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+      const ft_keypoint kp = E.kps[i];
+      const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), gridWInv));
+      const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), gridHInv));
+      if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
+      atomicAdd(&sCnt[px * FT_GRID_ROWS + py], 1);
+    }
+    __syncthreads();
+    // exclusive scan over 3072 cells: 3 per thread
+    {
+      const int c0 = tid * 3;
+      const int a0 = sCnt[c0], a1 = sCnt[c0 + 1], a2 = sCnt[c0 + 2];
+      const int sum = a0 + a1 + a2;
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+      }
+      if ((tid & 31) == 31) sWarp[tid >> 5] = incl;
+      __syncthreads();
+      if (tid < 32) {
+        int w = sWarp[tid];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+          if (tid >= o) wi += t;
+        }
+        sWarp[tid] = wi - w;
+      }
+      __syncthreads();
+      const int base = sWarp[tid >> 5] + incl - sum;
+      sStart[c0] = base; sStart[c0 + 1] = base + a0; sStart[c0 + 2] = base + a0 + a1;
+      if (tid == 1023) sStart[GRID_CELLS] = base + sum;
+    }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+      const ft_keypoint kp = E.kps[i];
+      const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), gridWInv));
+      const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), gridHInv));
+      if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
+      const int c = px * FT_GRID_ROWS + py;
+      cellIdx[sStart[c] + atomicAdd(&sCnt[c], 1)] = i;
+    }
+    __syncthreads();
+    // cells list keypoints in ascending index (insertion order of the reference's push_back loop)
+    for (int c = tid; c < GRID_CELLS; c += 1024) {
+      const int s0 = sStart[c], s1 = sStart[c + 1];
+      for (int i = s0 + 1; i < s1; i++) {
+        const int v = cellIdx[i];
+        int j = i - 1;
+        while (j >= s0 && cellIdx[j] > v) { cellIdx[j + 1] = cellIdx[j]; j--; }
+        cellIdx[j + 1] = v;
+      }
+    }
+    for (int c = tid; c <= GRID_CELLS; c += 1024) cellStart[c] = sStart[c];
+    __syncthreads();
+  }
+}
+
+// ---- frustum ----------------------------------------------------------------------------
+
+__device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const float* Pn, float minDistRaw,
+                                  float maxDistRaw, bool right, bool pinholeMode, float& u, float& v, float& xr,
+                                  float& depth, float& viewCosOut, int& level) {
+  float mR[9], mt[3], twc[3];
+  if (right) {
+    // mR = Rrl * Rcw; mt = Rrl * tcw + trl; twc = Rwc * tlr + Ow (Frame.cc:1314-1320)
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        mR[3 * i + j] = __fadd_rn(__fadd_rn(__fmul_rn(a.pose.Rrl[3 * i], a.pose.Rcw[j]), __fmul_rn(a.pose.Rrl[3 * i + 1], a.pose.Rcw[3 + j])),
+                                  __fmul_rn(a.pose.Rrl[3 * i + 2], a.pose.Rcw[6 + j]));
+    float Rt[3], Rw[3];
+    ft_mat3_vec(a.pose.Rrl, a.pose.tcw, Rt);
+    ft_mat3_vec(a.pose.Rwc, a.pose.tlr, Rw);
+    for (int i = 0; i < 3; i++) { mt[i] = __fadd_rn(Rt[i], a.pose.trl[i]); twc[i] = __fadd_rn(Rw[i], a.pose.Ow[i]); }
+  } else {
+    for (int i = 0; i < 9; i++) mR[i] = a.pose.Rcw[i];
+    for (int i = 0; i < 3; i++) { mt[i] = a.pose.tcw[i]; twc[i] = a.pose.Ow[i]; }
+  }
+  float Pc[3];
+  ft_mat3_vec(mR, P, Pc);
+  for (int i = 0; i < 3; i++) Pc[i] = __fadd_rn(Pc[i], mt[i]);
+  const float PcDist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1])), __fmul_rn(Pc[2], Pc[2])));
+  const float PcZ = Pc[2];
+  if (PcZ < 0.0f) return false;
+  float uv[2];
+  ft_cam_project(right ? a.cam2 : a.cam1, Pc, uv);
+  if (uv[0] < a.minX || uv[0] > a.maxX) return false;
+  if (uv[1] < a.minY || uv[1] > a.maxY) return false;
+  if (pinholeMode) { u = uv[0]; v = uv[1]; }   // mTrackProjX/Y are written before the distance checks (Frame.cc:563-564)
+  const float maxDistance = __fmul_rn(1.2f, maxDistRaw), minDistance = __fmul_rn(0.8f, minDistRaw);
+  const float PO[3] = {__fsub_rn(P[0], twc[0]), __fsub_rn(P[1], twc[1]), __fsub_rn(P[2], twc[2])};
+  const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+  if (dist < minDistance || dist > maxDistance) return false;
+  const float viewCos = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1])), __fmul_rn(PO[2], Pn[2])), dist);
+  if (viewCos < a.viewCosLimit) return false;
+  // MapPoint::PredictScale (MapPoint.cc:531-546): ceil(log(maxDistRaw/dist)/logScale), float log via double
+  const float ratio = __fdiv_rn(maxDistRaw, dist);
+  const float q = __fdiv_rn((float)log((double)ratio), a.logScale);
+  int nScale = (int)ceilf(q);
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= a.nlevels) nScale = a.nlevels - 1;
+  u = uv[0]; v = uv[1];
+  xr = pinholeMode ? __fsub_rn(uv[0], __fmul_rn(a.mbf, __fdiv_rn(1.0f, PcZ))) : 0.f;
+  depth = PcDist; viewCosOut = viewCos; level = nScale;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_frustum(const __grid_constant__ FtSbpBuffers s, const __grid_constant__ FtFrustumArgs a,
+                                                 int M) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= M) return;
+  int inView = 0, inViewR = 0, level = -1, levelR = -1;
+  float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (!(s.flags[i] & 1)) {
+    const float P[3] = {s.pos[3 * i], s.pos[3 * i + 1], s.pos[3 * i + 2]};
+    const float Pn[3] = {s.normal[3 * i], s.normal[3 * i + 1], s.normal[3 * i + 2]};
+    const float mn = s.minmax[2 * i], mx = s.minmax[2 * i + 1];
+    if (!a.fisheye) {
+      float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
+      const bool ok = ft_frustum_checks(a, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
+      f[0] = u; f[1] = v;
+      if (ok) { inView = 1; f[2] = xr; f[3] = d; f[4] = vc; level = lv; }
+    } else {
+      float u = 0, v = 0, xr = 0, d = 0, vc = 0; int lv = -1;
+      if (ft_frustum_checks(a, P, Pn, mn, mx, false, false, u, v, xr, d, vc, lv)) {
+        inView = 1; f[0] = u; f[1] = v; f[3] = d; f[4] = vc; level = lv;
+      }
+      if (ft_frustum_checks(a, P, Pn, mn, mx, true, false, u, v, xr, d, vc, lv)) {
+        inViewR = 1; f[5] = u; f[6] = v; f[7] = d; f[8] = vc; levelR = lv;
+      }
+    }
+  }
+  s.trI[4 * i] = inView; s.trI[4 * i + 1] = inViewR; s.trI[4 * i + 2] = level; s.trI[4 * i + 3] = levelR;
+#pragma unroll
+  for (int k = 0; k < 9; k++) s.trF[9 * i + k] = f[k];
+}
+
+// ---- candidate gathering ------------------------------------------------------------------
+
+#define GA_WARPS 8
+__global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                          const __grid_constant__ FtGridBuffers g,
+                                                          const __grid_constant__ FtStereoBuffers st,
+                                                          const __grid_constant__ FtSbpBuffers s,
+                                                          const __grid_constant__ FtGatherArgs a, int M) {
+  const int lane = threadIdx.x & 31;
+  const int mp = blockIdx.x * GA_WARPS + (threadIdx.x >> 5);
+  if (mp >= M) return;
+  const int flags = s.flags[mp];
+  const int inView = s.trI[4 * mp], inViewR = s.trI[4 * mp + 1];
+  bool searched = (inView || inViewR) && !(flags & 1);
+  if (a.bFar && s.trF[9 * mp + 3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
+  if (lane == 0) {
+    s.sel[2 * mp] = -1; s.sel[2 * mp + 1] = -1;
+    if (searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
+  }
+  const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
+  const uint4 md0 = md[0], md1 = md[1];
+  const int nBranches = a.fisheye ? 2 : 1;
+  for (int br = 0; br < nBranches; br++) {
+    int len = 0, off = 0;
+    const bool active = searched && (br == 0 ? inView : inViewR) && (br == 0 || s.trI[4 * mp + 3] != -1);
+    if (active) {
+      const int lvl = s.trI[4 * mp + 2 + br];
+      const float x = br == 0 ? s.trF[9 * mp] : s.trF[9 * mp + 5];
+      const float y = br == 0 ? s.trF[9 * mp + 1] : s.trF[9 * mp + 6];
+      const float viewCos = br == 0 ? s.trF[9 * mp + 4] : s.trF[9 * mp + 8];
+      float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos (ORBmatcher.cc:314-320)
+      if (br == 0 && a.bFactor) r = __fmul_rn(r, a.th);
+      const float rr = __fmul_rn(r, p.scale[lvl]);
+      const int minLevel = lvl - 1, maxLevel = lvl;
+      // GetFeaturesInArea cell window (Frame.cc:689-707)
+      const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
+      const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
+      const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
+      const int cy1 = min(FT_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
+      if (cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0) {
+        const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
+        const int* cellStart = g.cellStart + br * (GRID_CELLS + 1);
+        const int* cellIdx = g.cellIdx + br * p.maxKp;
+        const FtEye& E = b.eye[br];
+        const float projXR = s.trF[9 * mp + 2];
+        auto passes = [&](int idx) -> bool {
+          const ft_keypoint kp = E.kps[idx];
+          if (kp.octave < minLevel) return false;
+          if (maxLevel >= 0 && kp.octave > maxLevel) return false;
+          const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+          if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
+          if (!a.fisheye) {
+            const float ur = st.uRight[idx];
+            if (ur > 0) {
+              const float er = fabsf(__fsub_rn(projXR, ur));
+              if (er > rr) return false;                       // stereo consistency (ORBmatcher.cc:105-110)
+            }
+          }
+          return true;
+        };
+        // pass 1: count
+        int cnt = 0;
+        for (int c = lane; c < nc; c += 32) {
+          const int cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
+          for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) cnt += passes(cellIdx[k]);
+        }
+        int total = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        if (total > 0) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s.cursor[0], total);
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          if (base + total > s.poolCap) {
+            if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
+          } else {
+            // pass 2: ordered fill (ix outer, iy inner, cell insertion order)
+            int run = 0;
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+              const int c = c0 + lane;
+              int mine = 0, cell = 0;
+              if (c < nc) {
+                cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
+                for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) mine += passes(cellIdx[k]);
+              }
+              int incl = mine;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+              }
+              int w = base + run + incl - mine;
+              if (c < nc && mine) {
+                for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) {
+                  const int idx = cellIdx[k];
+                  if (passes(idx)) s.pool[w++] = (uint32_t)idx;
+                }
+              }
+              run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            __syncwarp();
+            // pass 3: Hamming distance + octave per candidate
+            for (int k = lane; k < total; k += 32) {
+              const int idx = (int)s.pool[base + k];
+              const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
+              const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
+              s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)E.kps[idx].octave << 25);
+            }
+            len = total; off = base;
+          }
+        }
+      }
+    }
+    if (lane == 0) { s.listOff[2 * mp + br] = off; s.listLen[2 * mp + br] = len; }
+  }
+}
+
+// ---- claim resolution ---------------------------------------------------------------------
+
+// best / second-best scan of one candidate list (ORBmatcher.cc:88-141). Returns the accepted keypoint or -1;
+// *cont is set when the reference executes `continue` (ratio test failed on same-level neighbours).
+template <typename BlockedFn>
+__device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float nnratio, BlockedFn blocked, bool* cont) {
+  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+  for (int k = 0; k < len; k++) {
+    const uint32_t e = list[k];
+    const int idx = (int)(e & 0xFFFFu);
+    if (blocked(idx)) continue;
+    const int dist = (int)((e >> 16) & 0x1FFu), oct = (int)(e >> 25);
+    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+  }
+  *cont = false;
+  if (bestDist <= 100) {   // TH_HIGH
+    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
+    return bestIdx;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(1024) k_resolve(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
+                                                  const __grid_constant__ FtStereoBuffers st,
+                                                  const __grid_constant__ FtResolveArgs a0) {
+  __shared__ int sChanged;
+  const int tid = threadIdx.x;
+  FtResolveArgs a = a0;
+  a.nLeft = b.eye[0].counts[0];
+  a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
+  int* status = b.status;
+  const int M = a.M, nS = a.nSlots;
+  if (a.fisheye && s.cursor[3] > 0) return;   // k_resolve_seq handles this frame
+  int rounds = 0;
+  for (;;) {
+    for (int i = tid; i < nS; i += 1024) s.minKey[i] = 0x7FFFFFFF;
+    if (tid == 0) sChanged = 0;
+    __syncthreads();
+    for (int mp = tid; mp < M; mp += 1024) {
+      if (!(s.flags[mp] & 2)) continue;   // writes of map points without observations never block
+      const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
+      if (sl >= 0) {
+        atomicMin(&s.minKey[sl], 2 * mp);
+        if (a.fisheye && st.l2r[sl] != -1) atomicMin(&s.minKey[st.l2r[sl] + a.nLeft], 2 * mp);
+      }
+      if (sr >= 0) {
+        atomicMin(&s.minKey[sr + a.nLeft], 2 * mp + 1);
+        if (st.r2l[sr] != -1) atomicMin(&s.minKey[st.r2l[sr]], 2 * mp + 1);
+      }
+    }
+    __syncthreads();
+    int changed = 0;
+    for (int mp = tid; mp < M; mp += 1024) {
+      const int lenL = s.listLen[2 * mp], lenR = s.listLen[2 * mp + 1];
+      if (lenL == 0 && lenR == 0) continue;
+      const bool blocking = (s.flags[mp] & 2) != 0;
+      int newL = -1, newR = -1;
+      bool cont = false;
+      if (lenL > 0) {
+        const int t = 2 * mp;
+        newL = ft_scan_list(s.pool + s.listOff[2 * mp], lenL, a.nnratio,
+                            [&](int idx) { return (s.holder[idx] != -1 && s.holderObs[idx]) || s.minKey[idx] < t; }, &cont);
+      }
+      if (lenR > 0 && !cont) {
+        const int t = 2 * mp;   // own left writes (stamp 2mp) are handled explicitly, older stamps through minKey
+        const int ownMirror = (blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
+        bool contR = false;
+        newR = ft_scan_list(s.pool + s.listOff[2 * mp + 1], lenR, a.nnratio,
+                            [&](int idx) {
+                              const int slot = idx + a.nLeft;
+                              return (s.holder[slot] != -1 && s.holderObs[slot]) || s.minKey[slot] < t || idx == ownMirror;
+                            }, &contR);
+      }
+      if (newL != s.sel[2 * mp] || newR != s.sel[2 * mp + 1]) changed = 1;
+      s.sel[2 * mp] = newL; s.sel[2 * mp + 1] = newR;
+    }
+    if (changed) sChanged = 1;
+    __syncthreads();
+    rounds++;
+    const int ch = sChanged;
+    __syncthreads();
+    if (!ch) break;
+    if (rounds > M + 2) { if (tid == 0) atomicOr(status, FT_ST_RESOLVE_NOCONV); break; }
+  }
+  // final holders: the write with the highest stamp wins each slot; count matches (ORBmatcher.cc:142-155,207-222)
+  for (int i = tid; i < nS; i += 1024) s.lastKey[i] = -1;
+  __syncthreads();
+  int nm = 0;
+  for (int mp = tid; mp < M; mp += 1024) {
+    const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
+    if (sl >= 0) {
+      atomicMax(&s.lastKey[sl], 2 * mp); nm++;
+      if (a.fisheye && st.l2r[sl] != -1) { atomicMax(&s.lastKey[st.l2r[sl] + a.nLeft], 2 * mp); nm++; }
+    }
+    if (sr >= 0) {
+      atomicMax(&s.lastKey[sr + a.nLeft], 2 * mp + 1); nm++;
+      if (st.r2l[sr] != -1) { atomicMax(&s.lastKey[st.r2l[sr]], 2 * mp + 1); nm++; }
+    }
+  }
+  if (nm) atomicAdd(&s.cursor[1], nm);
+  __syncthreads();
+  for (int i = tid; i < nS; i += 1024) {
+    const int k = s.lastKey[i];
+    if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
+  }
+  if (tid == 0) s.cursor[2] = rounds;
+}
+
+// In-order execution by one thread (fisheye rigs with non-blocking map points only).
+__global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
+                              const __grid_constant__ FtStereoBuffers st, const __grid_constant__ FtResolveArgs a0) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  FtResolveArgs a = a0;
+  a.nLeft = b.eye[0].counts[0];
+  a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
+  if (!(a.fisheye && s.cursor[3] > 0)) return;   // the fix-point kernel handles this frame
+  int nm = 0;
+  for (int mp = 0; mp < a.M; mp++) {
+    const int lenL = s.listLen[2 * mp], lenR = s.listLen[2 * mp + 1];
+    s.sel[2 * mp] = -1; s.sel[2 * mp + 1] = -1;
+    if (lenL == 0 && lenR == 0) continue;
+    const uint8_t obs = (uint8_t)((s.flags[mp] >> 1) & 1);
+    bool cont = false;
+    if (lenL > 0) {
+      const int sl = ft_scan_list(s.pool + s.listOff[2 * mp], lenL, a.nnratio,
+                                  [&](int idx) { return s.holder[idx] != -1 && s.holderObs[idx]; }, &cont);
+      if (sl >= 0) {
+        s.sel[2 * mp] = sl;
+        s.holder[sl] = mp; s.holderObs[sl] = obs; nm++;
+        if (a.fisheye && st.l2r[sl] != -1) { s.holder[st.l2r[sl] + a.nLeft] = mp; s.holderObs[st.l2r[sl] + a.nLeft] = obs; nm++; }
+      }
+    }
+    if (lenR > 0 && !cont) {
+      bool contR = false;
+      const int sr = ft_scan_list(s.pool + s.listOff[2 * mp + 1], lenR, a.nnratio,
+                                  [&](int idx) { return s.holder[idx + a.nLeft] != -1 && s.holderObs[idx + a.nLeft]; }, &contR);
+      if (sr >= 0) {
+        s.sel[2 * mp + 1] = sr;
+        if (st.r2l[sr] != -1) { s.holder[st.r2l[sr]] = mp; s.holderObs[st.r2l[sr]] = obs; nm++; }
+        s.holder[sr + a.nLeft] = mp; s.holderObs[sr + a.nLeft] = obs; nm++;
+      }
+    }
+  }
+  s.cursor[1] = nm; s.cursor[2] = 0;
+}
+
+__global__ void k_sbp_reset(const __grid_constant__ FtSbpBuffers s) {
+  if (threadIdx.x < 4) s.cursor[threadIdx.x] = 0;
+}
+
+// ---- host launchers -----------------------------------------------------------------------
+void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
+                    float gridWInv, float gridHInv, cudaStream_t st) {
+  k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv);
+}
+void ft_launch_frustum_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
+                              const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M,
+                              cudaStream_t st) {
+  k_sbp_reset<<<1, 32, 0, st>>>(s);
+  k_frustum<<<(M + 255) / 256, 256, 0, st>>>(s, fa, M);
+  k_gather<<<(M + GA_WARPS - 1) / GA_WARPS, GA_WARPS * 32, 0, st>>>(p, b, g, stb, s, ga, M);
+}
+void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
+                       cudaStream_t st) {
+  k_resolve<<<1, 1024, 0, st>>>(b, s, stb, ra);
+  if (ra.fisheye) k_resolve_seq<<<1, 32, 0, st>>>(b, s, stb, ra);   // exits immediately unless it is needed
+}

@@ -1,0 +1,157 @@
+/* fasttrack_b200.h -- C ABI of the B200-native stereo tracking front-end.
+ *
+ * Drop-in boundary for the hot path of sfu-rsl/FastTrack (ORB-SLAM3 + CUDA): ORB
+ * extraction (L+R), stereo matching and SearchByProjection of local MapPoints.
+ * Plain C: opaque handle, POD structs, raw pointers and sizes. Every entry point
+ * returns an ft_status (0 = ok) and never exits/aborts; ft_last_error() gives the text.
+ * One context per (GPU, camera rig, sequence); calls on one context are single-threaded,
+ * contexts on different GPUs are independent (no NCCL, no peer access).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   ft_context_create / destroy   <- KernelController::initializeKernels / shutdownKernels
+ *                                    (include/Kernels/KernelController.h:27-29),
+ *                                    CudaUtils::loadSetting (src/Kernels/CudaUtils.cu:24-40),
+ *                                    ORBextractor ctor/dtor device setup (src/ORBextractor.cc:416-442,1546-1564)
+ *   ft_extract_stereo             <- ORBextractor::operator() x2 as driven by Frame::ExtractORB on two
+ *                                    threads (include/ORBextractor.h:113-115, src/Frame.cc:127-130,442-449)
+ *   ft_stereo_match               <- Frame::ComputeStereoMatches / KernelController::launchStereoMatchKernel
+ *                                    (src/Frame.cc:835-1005, KernelController.h:33-39)
+ *   ft_stereo_match_fisheye       <- Frame::ComputeStereoFishEyeMatches / launchFisheyeStereoMatchKernel
+ *                                    (src/Frame.cc:1231-1271, KernelController.h:41)
+ *   ft_frame_download             <- the host vectors those operators fill (mvKeys, mDescriptors, mvuRight,
+ *                                    mvDepth, mvLeftToRightMatch, mvRightToLeftMatch, mvStereo3Dpoints)
+ *   ft_set_pose                   <- Frame::SetPose / UpdatePoseMatrices (src/Frame.cc:345-372)
+ *   ft_search_local_points        <- Frame::isInFrustum loop of Tracking::SearchLocalPoints
+ *                                    (src/Tracking.cc:3504-3522) + ORBmatcher::SearchByProjection #1
+ *                                    (src/ORBmatcher.cc:49-312) / launchSearchLocalPointsKernel
+ *                                    (KernelController.h:43-45)
+ */
+#ifndef FASTTRACK_B200_H
+#define FASTTRACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FT_MAX_LEVELS 16
+#define FT_GRID_COLS 64 /* FRAME_GRID_COLS, include/Frame.h:47 */
+#define FT_GRID_ROWS 48 /* FRAME_GRID_ROWS, include/Frame.h:46 */
+
+typedef enum {
+  FT_OK = 0,
+  FT_ERR_INVALID = 1,   /* bad argument / unsupported configuration */
+  FT_ERR_CUDA = 2,      /* CUDA runtime error (text in ft_last_error) */
+  FT_ERR_CAPACITY = 3,  /* a device-side buffer bound was exceeded; nothing was truncated silently */
+  FT_ERR_STATE = 4      /* call out of order (e.g. stereo match before extract) */
+} ft_status;
+
+typedef enum { FT_CAM_PINHOLE = 0, FT_CAM_KB8 = 1 } ft_camera_type;
+
+/* Settings the reference reads from YAML (src/Settings.cc) plus the rig geometry. */
+typedef struct {
+  int device_id;
+  int width, height;        /* Camera.width / Camera.height */
+  int nfeatures;            /* ORBextractor.nFeatures */
+  int nlevels;              /* ORBextractor.nLevels (<= FT_MAX_LEVELS) */
+  float scale_factor;       /* ORBextractor.scaleFactor */
+  int ini_th_fast;          /* ORBextractor.iniThFAST */
+  int min_th_fast;          /* ORBextractor.minThFAST */
+  int camera_type;          /* ft_camera_type */
+  float cam1[8];            /* fx fy cx cy [k1 k2 k3 k4] (KB8) */
+  float cam2[8];
+  int lap_left[2];          /* KannalaBrandt8::mvLappingArea of camera 1 ({0,0} for pinhole) */
+  int lap_right[2];
+  float bf;                 /* mbf = baseline * fx */
+  float Tlr[12];            /* 3x4 row-major T_c1_c2 (fisheye rigs); ignored for pinhole */
+  int max_map_points;       /* capacity of one ft_search_local_points call (reference: 25000) */
+} ft_config;
+
+/* cv::KeyPoint without class_id (always -1 in the reference): 24 bytes. */
+typedef struct {
+  float x, y;      /* pt, level-0 coordinates */
+  float size;      /* float(int(31*scale[octave])) */
+  float angle;     /* degrees [0,360) */
+  float response;  /* FAST score */
+  int octave;
+} ft_keypoint;
+
+typedef struct ft_context ft_context;
+
+const char* ft_last_error(void);
+const char* ft_version(void);
+
+ft_status ft_context_create(const ft_config* cfg, ft_context** out);
+ft_status ft_context_destroy(ft_context* ctx);
+
+/* Scale tables exactly as ORBextractor exposes them (GetScaleFactors etc., ORBextractor.h:117-146). */
+ft_status ft_get_scale_tables(ft_context* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                              int* features_per_level);
+
+/* Extract both eyes. imgL/imgR: HOST pointers to 8-bit grayscale, row pitch stepL/stepR bytes.
+ * Uploads, builds both pyramids, FAST + octree + orientation + rBRIEF; results stay on the device.
+ * Asynchronous w.r.t. the host: returns once the work is enqueued. */
+ft_status ft_extract_stereo(ft_context* ctx, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR);
+
+/* Same, for images already resident in device memory (tight pitch == width not required). */
+ft_status ft_extract_stereo_device(ft_context* ctx, const uint8_t* d_imgL, int stepL, const uint8_t* d_imgR, int stepR);
+
+/* Frame::ComputeStereoMatches on the device-resident frame (pinhole / rectified rigs). */
+ft_status ft_stereo_match(ft_context* ctx);
+/* Frame::ComputeStereoFishEyeMatches (KannalaBrandt8 rigs). */
+ft_status ft_stereo_match_fisheye(ft_context* ctx);
+
+/* Number of keypoints per eye and monoIndex (operator()'s return value). Synchronises. */
+ft_status ft_frame_counts(ft_context* ctx, int* n_left, int* n_right, int* mono_left, int* mono_right);
+
+/* Copy one eye's result to host buffers (any pointer may be NULL). kps/desc capacity = cap entries.
+ * u_right/depth (left eye only, length n_left), l2r (n_left) / r2l (n_right) / p3d (n_left*3) for fisheye. */
+ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps, uint8_t* desc, int* n, int* mono_index,
+                            float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
+
+/* Pose of the current frame: Rcw (row-major 3x3), tcw; Rwc/Ow may be NULL (then Rwc = Rcw^T, Ow = -Rwc*tcw). */
+ft_status ft_set_pose(ft_context* ctx, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow);
+
+/* Tracking::SearchLocalPoints, loop 2 + SearchByProjection. All pointers are HOST memory.
+ *   pos/normal [M][3], minmax [M][2] = raw {mfMinDistance, mfMaxDistance}, desc [M][32],
+ *   flags [M]: bit0 = skip (isBad() or mnLastFrameSeen == frame id), bit1 = Observations() > 0.
+ *   holder [N] in/out  : F.mvpMapPoints as indices: -1 none, -2 a map point that is not in this call,
+ *                        >= 0 index into this call's arrays.  N = n_left (pinhole) or n_left+n_right (fisheye).
+ *   holder_obs [N] in/out: 1 when the holder has Observations() > 0.
+ *   best_idx [M][2] out (may be NULL): keypoint chosen by the left / right search of each map point, -1 none.
+ *   nmatches out: the function's return value in the reference. */
+ft_status ft_search_local_points(ft_context* ctx, int M, const float* pos, const float* normal, const float* minmax,
+                                 const uint8_t* desc, const int* flags, float th, int b_far_points,
+                                 float th_far_points, float nnratio, int* holder, uint8_t* holder_obs, int* best_idx,
+                                 int* nmatches);
+
+/* Block until everything enqueued on this context has finished. */
+ft_status ft_synchronize(ft_context* ctx);
+
+/* ---- diagnostics used by the parity tests (device -> host copies of intermediate stages) ---- */
+ft_status ft_debug_level_dims(ft_context* ctx, int level, int* w, int* h);
+ft_status ft_debug_level_image(ft_context* ctx, int eye, int level, int blurred, uint8_t* out /* w*h tight */);
+/* pre-octree FAST candidates of one level in canonical order: xyr[n][3], returns count in *n */
+ft_status ft_debug_level_candidates(ft_context* ctx, int eye, int level, int cap, float* xyr, int* n);
+/* frustum scratch of the last ft_search_local_points: track_i[M][4] = inView,inViewR,level,levelR;
+ * track_f[M][9] = projX,projY,projXR,depth,viewCos,projXR_r,projYR_r,depthR,viewCosR */
+ft_status ft_debug_track(ft_context* ctx, int M, int* track_i, float* track_f);
+/* frame grid: counts[64*48] (ix*48+iy) and the concatenated keypoint indices */
+ft_status ft_debug_grid(ft_context* ctx, int right, int* counts, int* indices, int* n);
+/* measured counts of the last frame for the roofline arithmetic (bench.py):
+ * stats[0..] = C_left, C_right (FAST candidates), K_left, K_right, stereo candidates tested, coarse matches
+ * refined, projection-search candidates, resolve rounds */
+ft_status ft_debug_stats(ft_context* ctx, long long* stats, int n);
+
+/* The CUDA stream the context enqueues on (cudaStream_t as void*), for event timing by the caller. */
+void* ft_context_stream(ft_context* ctx);
+/* Enable/disable replay of the captured CUDA graph for the per-frame chain (default on). */
+ft_status ft_set_use_graph(ft_context* ctx, int enable);
+/* Number of kernel launches the last ft_extract_stereo + ft_stereo_match + ft_search_local_points issued. */
+ft_status ft_launch_counts(ft_context* ctx, int* extract, int* stereo, int* search);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTTRACK_B200_H */
