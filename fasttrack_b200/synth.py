@@ -119,9 +119,56 @@ class StereoScene:
         return (40.0 * np.sin(2 * np.pi * t / 200.0), 12.0 * np.sin(2 * np.pi * t / 130.0))
 
 
+def kb8_project(cam, P):
+    """KannalaBrandt8::project, vectorised (float64)"""
+    x, y, z = P[..., 0], P[..., 1], P[..., 2]
+    theta = np.arctan2(np.sqrt(x * x + y * y), z)
+    psi = np.arctan2(y, x)
+    t2 = theta * theta
+    r = theta * (1 + t2 * (cam[4] + t2 * (cam[5] + t2 * (cam[6] + t2 * cam[7]))))
+    return cam[0] * r * np.cos(psi) + cam[2], cam[1] * r * np.sin(psi) + cam[3]
+
+
+def kb8_unproject(cam, u, v):
+    """KannalaBrandt8::unproject, vectorised Newton iteration (float64); returns rays with z = 1"""
+    px, py = (u - cam[2]) / cam[0], (v - cam[3]) / cam[1]
+    td = np.clip(np.sqrt(px * px + py * py), 1e-9, np.pi / 2)
+    th = td.copy()
+    for _ in range(12):
+        t2 = th * th
+        f = th * (1 + t2 * (cam[4] + t2 * (cam[5] + t2 * (cam[6] + t2 * cam[7])))) - td
+        df = 1 + t2 * (3 * cam[4] + t2 * (5 * cam[5] + t2 * (7 * cam[6] + t2 * 9 * cam[7])))
+        th = th - f / df
+    sc = np.tan(th) / td
+    return np.stack([px * sc, py * sc, np.ones_like(px)], -1)
+
+
 def fisheye_pair(seed=3, size=512):
-    sc = StereoScene(seed=seed, width=size, height=size, dmin=1.0, dmax=40.0)
-    return sc.pair()
+    """Config-3 pair, geometrically consistent with the TUM-VI KannalaBrandt8 rig: the left image is a config-1
+    texture; the right image is rendered by casting every right pixel's ray onto a piecewise-constant depth map
+    (0.6-5 m blocks, defined in the right camera frame), moving the point into the left camera with T_c1_c2 and
+    sampling the left image bilinearly at its KB8 projection."""
+    rng = np.random.default_rng(seed)
+    left = texture(size, size, seed * 1000 + 1).astype(np.float64)
+    depth = np.full((size, size), 3.0)
+    for _ in range(40):
+        bw, bh = rng.integers(60, 200), rng.integers(60, 200)
+        x0, y0 = rng.integers(0, size - 30), rng.integers(0, size - 30)
+        depth[y0:y0 + bh, x0:x0 + bw] = rng.uniform(0.6, 5.0)
+    cam1 = np.asarray(TUMVI["cam1"], np.float64); cam2 = np.asarray(TUMVI["cam2"], np.float64)
+    Rlr, tlr, _, _ = tumvi_extrinsics()
+    vv, uu = np.mgrid[0:size, 0:size].astype(np.float64)
+    ray2 = kb8_unproject(cam2, uu, vv)
+    P2 = ray2 * depth[..., None]
+    P1 = P2 @ Rlr.astype(np.float64).T + tlr.astype(np.float64)
+    u1, v1 = kb8_project(cam1, P1)
+    x0 = np.clip(np.floor(u1).astype(np.int64), 0, size - 2); y0 = np.clip(np.floor(v1).astype(np.int64), 0, size - 2)
+    fx = np.clip(u1 - x0, 0, 1); fy = np.clip(v1 - y0, 0, 1)
+    right = (left[y0, x0] * (1 - fx) * (1 - fy) + left[y0, x0 + 1] * fx * (1 - fy) + left[y0 + 1, x0] * (1 - fx) * fy +
+             left[y0 + 1, x0 + 1] * fx * fy)
+    right = right + rng.integers(-2, 3, right.shape)
+    f = lambda a: np.ascontiguousarray(np.clip(np.rint(a), 0, 255).astype(np.uint8))
+    return f(left), f(right)
 
 
 def mappoints(keys, desc, scale_factors, M, seed=4, width=752, height=480, fx=458.654, fy=457.296, cx=367.215,

@@ -1,0 +1,73 @@
+"""The C-ABI library must load and export every symbol include/fasttrack_b200.h declares (no compute here)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    from fasttrack_b200 import build as b
+    if b.needs_build():
+        g.build()
+    import fasttrack_b200
+    return fasttrack_b200.load_library()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "fasttrack_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ft_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+
+
+def test_python_binding_lists_the_same_exports(lib):
+    import fasttrack_b200
+    hdr = open(os.path.join(ROOT, "include", "fasttrack_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ft_[a-z0-9_]+)\s*\(", hdr))
+    assert names == set(fasttrack_b200.EXPORTS)
+
+
+def test_config_struct_layout_matches_header():
+    import fasttrack_b200
+    # 9 ints + 1 float + ... : the ctypes mirror must have the C struct's size (all 4-byte members, no padding)
+    assert ctypes.sizeof(fasttrack_b200.Config) == 4 * (9 + 8 + 8 + 2 + 2 + 1 + 12 + 1)
+    assert fasttrack_b200.KEYPOINT_DTYPE.itemsize == 24
+
+
+def test_version_and_error_strings(lib):
+    assert b"sm_100a" in lib.ft_version()
+    assert isinstance(lib.ft_last_error(), bytes)
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    """No CPU fallback: on a box without a CUDA device context creation returns FT_ERR_CUDA."""
+    import fasttrack_b200
+    from conftest import _has_gpu
+    if _has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(fasttrack_b200.FtError) as e:
+        fasttrack_b200.Context(752, 480)
+    assert e.value.status == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_pattern_table_pinned():
+    txt = open(os.path.join(ROOT, "include", "ft_orb_pattern.inc")).read()
+    nums = [int(x) for x in re.findall(r"-?\d+", re.sub(r"//.*", "", txt))]
+    assert len(nums) == 1024
+    digest = hashlib.sha256(bytes([(n + 256) % 256 for n in nums])).hexdigest()
+    assert digest == "2164181aea6ff9ac426ca512d5130d15e1f6e3cd47b1cbdd568bbe1e55d49023"
+    ref = "/root/reference/src/ORBextractor.cc"
+    if os.path.exists(ref):   # only in the build container; the GPU box has no reference tree
+        src = "\n".join(open(ref).read().split("\n")[133:391])
+        refnums = [int(x) for x in re.findall(r"-?\d+", re.sub(r"/\*.*?\*/", "", src))]
+        assert refnums == nums

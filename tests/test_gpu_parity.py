@@ -1,0 +1,263 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs and against the committed golden vectors. Bit-exact for keypoints, octaves, descriptors, match
+indices; stereo uRight/depth compared exactly (north_star tolerance: 1e-3 px)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+import fasttrack_b200 as ft
+from fasttrack_b200 import synth
+
+E = synth.EUROC
+
+
+def _ctx(c, **kw):
+    mbf = np.float32(c["fx"] * c["baseline"])
+    return ft.Context(c["width"], c["height"], nfeatures=c.get("nfeatures", 1200), nlevels=c.get("nlevels", 8),
+                      cam1=[c["fx"], c["fy"], c["cx"], c["cy"]], bf=float(mbf), **kw), mbf, np.float32(mbf / np.float32(c["fx"]))
+
+
+def _oracle_pair(L, R, nf, nl):
+    exL, exR = oracle.Extractor(nf, 1.2, nl), oracle.Extractor(nf, 1.2, nl)
+    monoL, kL, dL = exL.extract(L); monoR, kR, dR = exR.extract(R)
+    return exL, exR, (monoL, kL, dL), (monoR, kR, dR)
+
+
+@pytest.fixture(scope="module")
+def euroc(euroc_pair):
+    L, R = euroc_pair
+    ctx, mbf, mb = _ctx(E)
+    ctx.extract_stereo(L, R)
+    ctx.stereo_match()
+    exL, exR, oL, oR = _oracle_pair(L, R, 1200, 8)
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    yield dict(ctx=ctx, mbf=mbf, mb=mb, exL=exL, exR=exR, oL=oL, oR=oR, st=st, L=L, R=R)
+    ctx.close()
+
+
+def test_scale_tables_match_oracle(euroc):
+    t = euroc["ctx"].scale_tables()
+    ex = euroc["exL"]
+    assert np.array_equal(t["scale"], ex.scale) and np.array_equal(t["inv_scale"], ex.inv_scale)
+    assert np.array_equal(t["sigma2"], ex.sigma2) and np.array_equal(t["inv_sigma2"], ex.inv_sigma2)
+    assert np.array_equal(t["features_per_level"], ex.features_per_level)
+
+
+def test_pyramid_blur_candidates_bit_exact(euroc):
+    ctx = euroc["ctx"]
+    for eye, ex in ((0, euroc["exL"]), (1, euroc["exR"])):
+        for l in range(8):
+            assert np.array_equal(ctx.level_image(eye, l), ex.level_image(l)), "pyramid eye %d level %d" % (eye, l)
+            assert np.array_equal(ctx.level_image(eye, l, True), ex.level_image(l, True)), "blur eye %d level %d" % (eye, l)
+            assert np.array_equal(ctx.level_candidates(eye, l), ex.level_candidates(l)), "FAST eye %d level %d" % (eye, l)
+
+
+def test_keypoints_and_descriptors_bit_exact(euroc):
+    ctx = euroc["ctx"]
+    for eye, (mono, k, d) in ((0, euroc["oL"]), (1, euroc["oR"])):
+        g = ctx.download(eye)
+        assert g["n"] == len(k) and g["mono_index"] == mono
+        assert np.array_equal(ft.keypoints_as_array(g["kps"]), k)
+        differing = int((g["desc"] != d).any(axis=1).sum())
+        # north_star: descriptors may differ only where a rotated sample sits within 1e-4 of a rounding boundary
+        borderline = (euroc["exL"] if eye == 0 else euroc["exR"]).desc_borderline()
+        assert differing <= borderline
+        assert differing == 0, "descriptor rows differ: %d (borderline samples %d)" % (differing, borderline)
+
+
+def test_stereo_bit_exact(euroc):
+    g = euroc["ctx"].download(0, stereo=True)
+    st = euroc["st"]
+    assert int((st["depth"] > 0).sum()) > 200
+    assert np.array_equal(g["u_right"], st["uRight"])
+    assert np.abs(g["u_right"] - st["uRight"]).max() <= 1e-3      # the stated tolerance; exact in practice
+    assert np.array_equal(g["depth"], st["depth"])
+
+
+@pytest.mark.parametrize("M,th", [(5000, 1.0), (10000, 2.0), (20000, 6.0), (20000, 10.0)])
+def test_search_by_projection_bit_exact(euroc, M, th):
+    ctx = euroc["ctx"]
+    _, kL, dL = euroc["oL"]
+    mp = synth.mappoints(kL, dL, euroc["exL"].scale, M, seed=4 + M)
+    F = oracle.Frame(kL, dL, euroc["exL"].scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                     mbf=float(euroc["mbf"]), u_right=euroc["st"]["uRight"])
+    n_o, h_o, ho_o, ti, tf = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], th,
+                                                   mp["holder"], mp["holder_obs"])
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n_g, h_g, ho_g, best = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], th,
+                                                   mp["holder"], mp["holder_obs"])
+    gi, gf = ctx.track(M)
+    clean = ti[:, 4] == 0          # decisions within 1e-5 of a float boundary are counted, not compared
+    assert (~clean).sum() < 0.002 * M + 5
+    assert np.array_equal(gi[clean, 0], ti[clean, 0]) and np.array_equal(gi[clean, 2], ti[clean, 2])
+    assert np.array_equal(gf[clean, :5], tf[clean, :5])
+    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
+        assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    assert n_o > 100
+
+
+def test_search_by_projection_moved_pose(euroc):
+    """non-identity pose: rotate/translate the camera and the map together, results must not change class"""
+    ctx = euroc["ctx"]
+    _, kL, dL = euroc["oL"]
+    M = 8000
+    mp = synth.mappoints(kL, dL, euroc["exL"].scale, M, seed=77)
+    a = 0.3
+    Rwc = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    Ow = np.array([0.5, -0.2, 1.0], np.float32)
+    pos = (Rwc @ mp["pos"].T).T + Ow
+    nrm = (Rwc @ mp["normal"].T).T
+    Rcw = np.ascontiguousarray(Rwc.T); tcw = -(Rcw @ Ow)
+    F = oracle.Frame(kL, dL, euroc["exL"].scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                     mbf=float(euroc["mbf"]), u_right=euroc["st"]["uRight"], Rcw=Rcw, tcw=tcw)
+    n_o, h_o, ho_o, ti, tf = F.search_local_points(pos, nrm, mp["minmax"], mp["desc"], mp["flags"], 3.0, mp["holder"], mp["holder_obs"])
+    ctx.set_pose(Rcw, tcw, F.Rwc, F.Ow)
+    n_g, h_g, ho_g, _ = ctx.search_local_points(pos, nrm, mp["minmax"], mp["desc"], mp["flags"], 3.0, mp["holder"], mp["holder_obs"])
+    gi, gf = ctx.track(M)
+    clean = ti[:, 4] == 0
+    assert np.array_equal(gi[clean, 0], ti[clean, 0]) and np.array_equal(gi[clean, 2], ti[clean, 2])
+    assert np.array_equal(gf[clean, :5], tf[clean, :5])
+    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
+        assert n_g == n_o and np.array_equal(h_g, h_o)
+
+
+def test_grid_matches_oracle(euroc):
+    _, kL, dL = euroc["oL"]
+    F = oracle.Frame(kL, dL, euroc["exL"].scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0])
+    co, io = F.grid()
+    cg, ig = euroc["ctx"].grid()
+    assert np.array_equal(co, cg) and np.array_equal(io, ig)
+
+
+def test_golden_mini_pipeline(mini_golden, mini_cfg):
+    """CUDA path against committed vectors (no live oracle involved)."""
+    g = mini_golden
+    ctx, mbf, mb = _ctx(mini_cfg, max_map_points=4000)
+    ctx.extract_stereo(g["imgL"], g["imgR"])
+    ctx.stereo_match()
+    l, r = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(l["kps"]), g["kL"]) and np.array_equal(l["desc"], g["dL"])
+    assert np.array_equal(ft.keypoints_as_array(r["kps"]), g["kR"]) and np.array_equal(r["desc"], g["dR"])
+    assert np.array_equal(l["u_right"], g["uRight"]) and np.array_equal(l["depth"], g["depth"])
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n, holder, hobs, _ = ctx.search_local_points(g["mp_pos"], g["mp_normal"], g["mp_minmax"], g["mp_desc"], g["mp_flags"], 3.0,
+                                                 g["mp_holder"], g["mp_holder_obs"])
+    assert n == int(g["sbp_n"]) and np.array_equal(holder, g["sbp_holder"]) and np.array_equal(hobs, g["sbp_holder_obs"])
+    ctx.close()
+
+
+def test_graph_and_direct_launch_agree(euroc_pair):
+    L, R = euroc_pair
+    ctx, _, _ = _ctx(E)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    a = ctx.download(0, stereo=True)
+    ctx.set_use_graph(False)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    b = ctx.download(0, stereo=True)
+    assert np.array_equal(a["kps"], b["kps"]) and np.array_equal(a["desc"], b["desc"]) and np.array_equal(a["u_right"], b["u_right"])
+    ctx.close()
+
+
+def test_repeated_frames_are_deterministic_and_independent(euroc_pair):
+    """frame t+1 must not see state of frame t: extract A, B, A again -> identical results for A"""
+    L, R = euroc_pair
+    sc = synth.StereoScene(seed=5)
+    L2, R2 = sc.pair(pan=(10, 3), noise_seed=1)
+    ctx, _, _ = _ctx(E)
+    ctx.extract_stereo(L, R); ctx.stereo_match(); a = ctx.download(0, stereo=True)
+    ctx.extract_stereo(L2, R2); ctx.stereo_match(); b = ctx.download(0, stereo=True)
+    ctx.extract_stereo(L, R); ctx.stereo_match(); c = ctx.download(0, stereo=True)
+    assert np.array_equal(a["kps"], c["kps"]) and np.array_equal(a["desc"], c["desc"]) and np.array_equal(a["depth"], c["depth"])
+    assert not np.array_equal(a["kps"], b["kps"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["flat", "noise", "half_flat", "strided"])
+def test_edge_images(kind):
+    """empty result, saturated candidate counts, cells that need the minThFAST fallback, non-tight row pitch"""
+    c = dict(E, nfeatures=500)
+    rng = np.random.default_rng(11)
+    if kind == "flat":
+        L = np.full((480, 752), 90, np.uint8); R = L.copy()
+    elif kind == "noise":
+        L = rng.integers(0, 256, (480, 752), dtype=np.uint8); R = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+    elif kind == "half_flat":
+        L = synth.texture(480, 752, 21); L[:, 376:] = (L[:, 376:] // 16 + 100).astype(np.uint8); R = np.roll(L, -7, axis=1)
+    else:
+        big = synth.texture(480, 800, 22)
+        L = big[:, 13:765]; R = big[:, 5:757]
+        assert L.strides[0] == 800
+    ctx, mbf, mb = _ctx(c)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR, oL, oR = _oracle_pair(np.ascontiguousarray(L), np.ascontiguousarray(R), 500, 8)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    assert np.array_equal(gl["u_right"], st["uRight"]) and np.array_equal(gl["depth"], st["depth"])
+    if kind == "flat":
+        assert gl["n"] == 0
+    for l in range(8):
+        assert np.array_equal(ctx.level_candidates(0, l), exL.level_candidates(l))
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape,nf,nl", [((480, 640), 1000, 8), ((376, 1241), 2000, 8), ((512, 512), 1000, 8), ((240, 376), 300, 5)])
+def test_other_resolutions(shape, nf, nl):
+    h, w = shape
+    sc = synth.StereoScene(seed=31 + h, width=w, height=h, dmin=1.0, dmax=30.0, margin_x=96, margin_y=8)
+    L, R = sc.pair()
+    c = dict(width=w, height=h, nfeatures=nf, nlevels=nl, fx=400.0, fy=400.0, cx=w / 2.0, cy=h / 2.0, baseline=0.1)
+    ctx, mbf, mb = _ctx(c)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR, oL, oR = _oracle_pair(L, R, nf, nl)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    assert np.array_equal(gl["u_right"], st["uRight"]) and np.array_equal(gl["depth"], st["depth"])
+    ctx.close()
+
+
+def test_octree_fuzz_many_seeds():
+    """the order-sensitive octree (incl. the std::sort tie order) on many different textures / quotas"""
+    for seed in range(12):
+        nf = [150, 400, 800, 1200, 2000, 3000][seed % 6]
+        img = synth.texture(480, 752, 100 + seed, n_rect=2000 + 700 * seed, n_disc=500 * (seed % 4))
+        R = np.roll(img, -5, axis=1)
+        c = dict(E, nfeatures=nf)
+        ctx, _, _ = _ctx(c)
+        ctx.extract_stereo(img, R)
+        ex = oracle.Extractor(nf, 1.2, 8)
+        mono, k, d = ex.extract(img)
+        g = ctx.download(0)
+        assert np.array_equal(ft.keypoints_as_array(g["kps"]), k), "seed %d nfeatures %d" % (seed, nf)
+        assert np.array_equal(g["desc"], d)
+        ctx.close()
+
+
+def test_api_errors():
+    ctx, _, _ = _ctx(E)
+    with pytest.raises(ft.FtError) as e:
+        ctx.stereo_match()
+    assert e.value.status == 4
+    with pytest.raises(ft.FtError) as e:
+        ft.Context(32, 32)
+    assert e.value.status == 1
+    with pytest.raises(ft.FtError) as e:
+        ft.Context(752, 480, nlevels=14)       # top levels smaller than one FAST cell: the reference divides by zero
+    assert e.value.status == 1
+    L = synth.texture(480, 752, 1)
+    ctx.extract_stereo(L, L); ctx.stereo_match()
+    n = ctx.counts()["n_left"]
+    M = 30000
+    z = np.zeros
+    with pytest.raises(ft.FtError) as e:       # reference: raise(SIGSEGV) beyond 25000 map points
+        ctx.search_local_points(z((M, 3)), z((M, 3)), z((M, 2)), z((M, 32), np.uint8), z(M, np.int32), 1.0, np.full(n, -1), z(n, np.uint8))
+    assert e.value.status == 3
+    nm, holder, _, _ = ctx.search_local_points(z((0, 3)), z((0, 3)), z((0, 2)), z((0, 32), np.uint8), z(0, np.int32), 1.0,
+                                               np.full(n, -1), z(n, np.uint8))
+    assert nm == 0 and np.all(holder == -1)
+    ctx.close()

@@ -1,0 +1,72 @@
+"""Differential tests oracle-vs-cv2 on fresh random inputs. Skipped where cv2 is not importable; the committed
+vectors in tests/golden/ carry the same pin everywhere else."""
+import math
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+import oracle
+from fasttrack_b200 import synth
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (512, 512), (376, 1241)])
+def test_pyramid_chain_and_blur(shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    ex = oracle.Extractor()
+    cur = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    for l in range(1, 8):
+        dw = oracle.cv_round(np.float32(w) * ex.inv_scale[l]); dh = oracle.cv_round(np.float32(h) * ex.inv_scale[l])
+        ref = cv2.resize(cur, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(oracle.resize(cur, dw, dh), ref)
+        assert np.array_equal(oracle.blur(ref), cv2.GaussianBlur(ref, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+        cur = ref
+
+
+def test_extractor_stages_against_cv2_driven_pipeline():
+    """ComputePyramid + per-cell FAST with threshold fallback (ORBextractor.cc:1112-1203) rebuilt from cv2 calls."""
+    img = synth.texture(240, 376, 5)
+    ex = oracle.Extractor(400, 1.2, 6)
+    ex.extract(img)
+    for l in range(6):
+        im = ex.level_image(l)
+        w, h = ex.level_dims(l)
+        if l > 0:
+            assert np.array_equal(cv2.resize(ex.level_image(l - 1), (w, h), interpolation=cv2.INTER_LINEAR), im)
+        mb, mxx, mxy = 16, w - 16, h - 16
+        width, height = np.float32(mxx - mb), np.float32(mxy - mb)
+        ncols, nrows = int(width / np.float32(35)), int(height / np.float32(35))
+        wc, hc = math.ceil(width / ncols), math.ceil(height / nrows)
+        out = []
+        for i in range(nrows):
+            iy, my = mb + i * hc, min(mb + i * hc + hc + 6, mxy)
+            if iy >= mxy - 3:
+                continue
+            for j in range(ncols):
+                ix, mx = mb + j * wc, min(mb + j * wc + wc + 6, mxx)
+                if ix >= mxx - 6:
+                    continue
+                roi = np.ascontiguousarray(im[iy:my, ix:mx])
+                k = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True).detect(roi)
+                if not k:
+                    k = cv2.FastFeatureDetector_create(threshold=7, nonmaxSuppression=True).detect(roi)
+                out += [(p.pt[0] + j * wc, p.pt[1] + i * hc, p.response) for p in k]
+        assert np.array_equal(np.array(out, np.float32).reshape(-1, 3), ex.level_candidates(l))
+        b = ex.level_image(l, True)
+        if b is not None:
+            assert np.array_equal(b, cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+
+
+def test_fast_random_rois():
+    rng = np.random.default_rng(3)
+    img = synth.texture(200, 300, 9)
+    for _ in range(30):
+        x0, y0 = int(rng.integers(0, 250)), int(rng.integers(0, 150))
+        w, h = int(rng.integers(7, 50)), int(rng.integers(7, 50))
+        roi = img[y0:y0 + h, x0:x0 + w]
+        th = int(rng.choice([7, 20, 35]))
+        k = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=True).detect(np.ascontiguousarray(roi))
+        ref = np.array([[p.pt[0], p.pt[1], p.response] for p in k], np.float32).reshape(-1, 3)
+        assert np.array_equal(oracle.fast(roi, th), ref)

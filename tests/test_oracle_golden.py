@@ -1,0 +1,54 @@
+"""Pins the CPU oracle's primitives against vectors produced by OpenCV (tests/golden/cv2_primitives.npz,
+made by tools/make_cv2_golden.py with cv2 4.13.0). These are the un-vendored third-party calls on the
+reference's path: cv::resize (ORBextractor.cc:1508), GaussianBlur (:1457), cv::FAST (:1157,1176),
+fastAtan2 (:65), BFMatcher::knnMatch (Frame.cc:1249)."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+@pytest.mark.parametrize("name", ["tex", "noise"])
+def test_resize_chain_matches_cv2(cv2_golden, name):
+    cur = cv2_golden["img_" + name]
+    for l in range(3):
+        ref = cv2_golden["resize_%s_%d" % (name, l)]
+        mine = oracle.resize(cur, ref.shape[1], ref.shape[0])
+        assert np.array_equal(mine, ref), "level %d" % l
+        cur = ref
+
+
+def test_resize_odd_shape(cv2_golden):
+    ref = cv2_golden["resize_odd"]
+    assert np.array_equal(oracle.resize(cv2_golden["img_odd"], ref.shape[1], ref.shape[0]), ref)
+
+
+@pytest.mark.parametrize("name", ["tex", "noise"])
+def test_blur_matches_cv2(cv2_golden, name):
+    assert np.array_equal(oracle.blur(cv2_golden["img_" + name]), cv2_golden["blur_" + name])
+
+
+@pytest.mark.parametrize("name", ["tex", "noise"])
+@pytest.mark.parametrize("th", [20, 7])
+def test_fast_matches_cv2(cv2_golden, name, th):
+    img = cv2_golden["img_" + name]
+    assert np.array_equal(oracle.fast(img, th), cv2_golden["fast_%s_%d" % (name, th)])
+    roi = img[10:52, 20:64]   # strided view, like the reference's rowRange/colRange cells
+    assert np.array_equal(oracle.fast(roi, th), cv2_golden["fastroi_%s_%d" % (name, th)])
+
+
+def test_fast_atan2_matches_cv2(cv2_golden):
+    yx, ref = cv2_golden["atan_yx"], cv2_golden["atan_deg"]
+    mine = np.array([oracle.fast_atan2(y, x) for y, x in yx], np.float32)
+    assert np.array_equal(mine, ref)
+
+
+def test_knn_matches_cv2(cv2_golden):
+    idx, dist = oracle.knn2(cv2_golden["knn_q"], cv2_golden["knn_t"])
+    assert np.array_equal(idx, cv2_golden["knn_idx"])
+    assert np.array_equal(dist, cv2_golden["knn_dist"])
+
+
+def test_cv_round_half_even():
+    for v, r in [(0.5, 0), (1.5, 2), (2.5, 2), (-0.5, 0), (-1.5, -2), (-2.5, -2), (3.4999, 3), (3.5001, 4)]:
+        assert oracle.cv_round(v) == r
