@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- stereo front-end throughput on B200 (contract in the task brief).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = one synthetic EuRoC-shaped stereo frame (752x480, 1200 features, 8 levels, x1.2) through
+extract(L,R) -> ComputeStereoMatches -> SearchLocalPoints(M map points). One independent sequence per GPU
+(no collective on the data path; torch.distributed is only used for the barrier and the max-over-ranks time).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fasttrack_b200 import synth  # noqa: E402
+
+E = synth.EUROC
+N_FRAMES = 12            # distinct pre-generated frames per rank, cycled
+M_POINTS = 8000          # local map size per frame
+TH = 3.0
+WORKLOAD = ("euroc_752x480_stereo_sequence: extract(L,R; 1200 features, 8 levels, x1.2) + ComputeStereoMatches + "
+            "SearchLocalPoints(M=%d, th=%g)" % (M_POINTS, TH))
+METRIC = "frames/sec (ORB extract L+R + stereo match + projection search)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_frames(seed, n):
+    sc = synth.StereoScene(seed=seed)
+    out = []
+    for t in range(n):
+        out.append(sc.pair(pan=sc.sequence_pan(7 * t), noise_seed=seed * 100 + t))
+    return out
+
+
+def fast_mappoints(keys, desc, scale_factors, M, seed):
+    """vectorised variant of synth.mappoints for bench setup (same distribution, no per-point Python loop)"""
+    rng = np.random.default_rng(seed)
+    N = len(keys); nl = len(scale_factors)
+    fx, fy, cx, cy = E["fx"], E["fy"], E["cx"], E["cy"]
+    inside = rng.random(M) < 0.7
+    anchored = (rng.random(M) < 0.5) & inside & (N > 0)
+    z = rng.uniform(0.4, 25.0, M)
+    lvl = rng.integers(0, nl, M)
+    k = rng.integers(0, max(N, 1), M)
+    u = rng.uniform(0, E["width"], M); v = rng.uniform(0, E["height"], M)
+    d = rng.integers(0, 256, (M, 32), dtype=np.uint8)
+    if N:
+        lvl = np.where(anchored, keys[k, 5].astype(np.int64), lvl)
+        jit = 1.5 * scale_factors[lvl]
+        u = np.where(anchored, keys[k, 0] + rng.uniform(-1, 1, M) * jit, u)
+        v = np.where(anchored, keys[k, 1] + rng.uniform(-1, 1, M) * jit, v)
+        bits = np.unpackbits(desc[k], axis=1)
+        nflip = rng.integers(0, 49, M)
+        flip = rng.random((M, 256)).argsort(axis=1) < nflip[:, None]
+        d = np.where(anchored[:, None], np.packbits(bits ^ flip.astype(np.uint8), axis=1), d)
+    P = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    dist = np.linalg.norm(P, axis=1)
+    n = P / dist[:, None] + 0.26 * rng.standard_normal((M, 3))
+    n /= np.linalg.norm(n, axis=1)[:, None]
+    maxd = dist * scale_factors[lvl] * 0.95
+    mode = rng.integers(0, 4, M)
+    out_ = ~inside
+    P[out_ & (mode == 0), 2] *= -1
+    P[out_ & (mode == 1), 0] += (2.0 * E["width"] / fx) * z[out_ & (mode == 1)]
+    maxd = np.where(out_ & (mode == 2), dist * 0.3, maxd)
+    n[out_ & (mode == 3)] *= -1
+    mind = maxd / scale_factors[nl - 1]
+    flags = np.full(M, 2, np.int32)
+    flags[rng.random(M) < 0.02] |= 1
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    return dict(pos=f32(P), normal=f32(n), minmax=f32(np.stack([mind, maxd], 1)), desc=np.ascontiguousarray(d), flags=flags)
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, restated (oracle port), on the box's host cores with
+    the reference's threading: two threads for L/R extraction (Frame.cc:127-130), everything else on one."""
+    if rank != 0:
+        return
+    import oracle
+    frames = make_frames(5, min(N_FRAMES, 6))
+    mbf = np.float32(E["fx"] * E["baseline"]); mb = np.float32(mbf / np.float32(E["fx"]))
+    exL, exR = oracle.Extractor(), oracle.Extractor()
+    maps = []
+    for (L, R) in frames:
+        _, kL, dL = exL.extract(L)
+        maps.append(fast_mappoints(kL, dL, exL.scale, M_POINTS, 99))
+    def step(i):
+        k = i % len(frames)
+        L, R = frames[k]
+        # Frame ctor: two extractor threads, then ComputeStereoMatches (timed inside the oracle in C++)
+        ms, nl, nr, ns = oracle.time_stereo_frame(exL, exR, L, R, float(mbf), float(mb), two_threads=True)
+        # Tracking::SearchLocalPoints on that frame (frame model incl. AssignFeaturesToGrid is rebuilt per step)
+        _, kL, dL = pre[k]
+        t0 = time.perf_counter()
+        F = oracle.Frame(kL, dL, exL.scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                         mbf=float(mbf), u_right=pre_ur[k])
+        mp = maps[k]
+        F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], TH,
+                              np.full(len(kL), -1, np.int32), np.zeros(len(kL), np.uint8))
+        return ms + (time.perf_counter() - t0) * 1e3
+    pre, pre_ur = [], []
+    for (L, R) in frames:
+        mL, kL, dL = exL.extract(L); mR, kR, dR = exR.extract(R)
+        pre.append((mL, kL, dL))
+        pre_ur.append(oracle.stereo(exL, exR, kL, dL, kR, dR, float(mbf), float(mb))["uRight"])
+    for i in range(args.warmup):
+        step(i)
+    t = [step(i) for i in range(args.steps)]
+    ms = float(np.mean(t))
+    val = 1000.0 / ms
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": 2, "kind": "port",
+                             "sample": "%d frames of the bench workload; L/R extraction on 2 threads as Frame.cc:127-130, "
+                                       "stereo + SearchLocalPoints on 1; host has %d cores" % (args.steps, os.cpu_count())},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fasttrack_b200 as ft
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    mbf = np.float32(E["fx"] * E["baseline"])
+    ctx = ft.Context(E["width"], E["height"], nfeatures=E["nfeatures"], nlevels=E["nlevels"], scale_factor=E["scale"],
+                     cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), max_map_points=25000, device_id=local)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    scale = ctx.scale_tables()["scale"]
+
+    # ---- inputs: one independent synthetic sequence per GPU (seed = 5 + rank), prepared outside the timed region ----
+    frames = make_frames(5 + rank, N_FRAMES)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hL = [pin(L) for L, R in frames]; hR = [pin(R) for L, R in frames]
+    dL = [t.cuda(non_blocking=False) for t in hL]; dR = [t.cuda(non_blocking=False) for t in hR]
+    maps, hmaps = [], []
+    for i in range(N_FRAMES):
+        ctx.extract_stereo(frames[i][0], frames[i][1])
+        g = ctx.download(0)
+        mp = fast_mappoints(ft.keypoints_as_array(g["kps"]), g["desc"], scale, M_POINTS, 1000 * rank + i)
+        maps.append(mp)
+        hmaps.append({k: pin(v) for k, v in mp.items()})
+    cap = ctx.cap
+    out_kps = [torch.empty(cap * 24, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    out_desc = [torch.empty(cap * 32, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    out_ur = torch.empty(cap, dtype=torch.float32).pin_memory(); out_dp = torch.empty(cap, dtype=torch.float32).pin_memory()
+    holder = torch.empty(cap, dtype=torch.int32).pin_memory(); hobs = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    best = torch.empty(M_POINTS * 2, dtype=torch.int32).pin_memory()
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    import ctypes as C
+    L_ = ctx.L
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush_buf.add_(1)
+
+    # ---- step variants ----
+    def step_resident(i):
+        """inputs already in HBM: images (device), map-point snapshot (device); results stay on the device"""
+        k = i % N_FRAMES
+        ctx.extract_stereo_ptr(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"], device=True)
+        ctx.stereo_match()
+        ctx.search_resident(TH)
+
+    def step_e2e(i):
+        """the user-facing call sequence with HOST buffers: H2D of images and map points, D2H of every result"""
+        k = i % N_FRAMES
+        ctx.extract_stereo_ptr(hL[k].data_ptr(), E["width"], hR[k].data_ptr(), E["width"], device=False)
+        ctx.stereo_match()
+        n, mono = C.c_int(), C.c_int()
+        ctx._ck(L_.ft_frame_download(ctx.h, 0, cap, out_kps[0].data_ptr(), out_desc[0].data_ptr(), C.byref(n), C.byref(mono),
+                                     out_ur.data_ptr(), out_dp.data_ptr(), None, None, None))
+        nl = n.value
+        ctx._ck(L_.ft_frame_download(ctx.h, 1, cap, out_kps[1].data_ptr(), out_desc[1].data_ptr(), C.byref(n), C.byref(mono),
+                                     None, None, None, None, None))
+        nr = n.value
+        holder[:nl] = -1; hobs[:nl] = 0
+        m = hmaps[k]
+        ctx.search_local_points_raw(M_POINTS, m["pos"].data_ptr(), m["normal"].data_ptr(), m["minmax"].data_ptr(),
+                                    m["desc"].data_ptr(), m["flags"].data_ptr(), TH, holder.data_ptr(), hobs.data_ptr(),
+                                    best.data_ptr())
+        return nl, nr
+
+    # resident leg: upload one snapshot per frame index lazily is not "resident"; keep ONE pool resident and
+    # re-upload outside the timed region whenever the frame changes -> the pool of frame k is uploaded before its step
+    def prep_resident(i):
+        k = i % N_FRAMES
+        m = maps[k]
+        ctx.upload_map_points(m["pos"], m["normal"], m["minmax"], m["desc"], m["flags"])
+        ctx.upload_holders(None, None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for i in range(max(args.warmup, 3)):
+        prep_resident(i); step_resident(i); ctx.synchronize()
+    for i in range(3):
+        step_e2e(i)
+
+    # ---- timed region 1: device-resident inputs, CUDA events per step on the context's stream, L2 flushed between ----
+    sampler = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        prep_resident(i)
+        flush_l2()
+        ev[i][0].record(stream)
+        step_resident(i)
+        ev[i][1].record(stream)
+    barrier()
+    wall1 = time.perf_counter()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    dev_ms_total = float(step_ms.sum())
+    ext_l, st_l, se_l = ctx.launch_counts()
+    launches_per_step = ext_l + st_l + se_l
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        nl, nr = step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + nl * 5
+    d2h = (nl + nr) * (24 + 32) + nl * 8 + nl * 5 + M_POINTS * 8 + 9 * 4
+
+    # ---- per-kernel pass: CUDA events around every kernel (direct launches), same inputs ----
+    ctx.set_stage_timing(True)
+    acc = {}
+    for i in range(args.profile_steps):
+        prep_resident(i); flush_l2(); step_resident(i)
+        for k_, v in ctx.stage_times().items():
+            acc.setdefault(k_, []).append(v)
+    ctx.set_stage_timing(False)
+    stage_ms = {k_: float(np.mean(v)) for k_, v in acc.items()}
+    st = ctx.stats()
+
+    # ---- reductions over ranks (max time) ----
+    tt = torch.tensor([dev_ms_total, e2e_s, wall1 - wall0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_total, e2e_s, wall_s = [float(x) for x in tt.tolist()]
+    ms_per_step = dev_ms_total / args.steps
+    value = world * args.steps / (dev_ms_total / 1e3)
+    e2e_value = world * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (SURVEY.md 8d byte formulas with the measured counts) ----
+    pk, pk_kind = peaks()
+    lv = [ctx.level_dims(l) for l in range(E["nlevels"])]
+    sumP = sum(w * h for w, h in lv)
+    C_ = st["cand_left"] + st["cand_right"]; K_ = st["kp_left"] + st["kp_right"]
+    alg_bytes = {
+        "copy_level0": 2 * 2 * lv[0][0] * lv[0][1],
+        "resize": 2 * (sum(w * h for w, h in lv[:-1]) + sum(w * h for w, h in lv[1:])),
+        "blur": 2 * 2 * sumP,
+        "fast_cells": 2 * sumP + 16 * C_,
+        "octree": 16 * C_ + 20 * K_,
+        "orient_desc": (749 + 4 + 512 + 32) * K_,
+        "stereo_match": 44 * K_ + 44 * st["stereo_tested"] + 352 * st["stereo_refined"] + 12 * st["kp_left"],
+        "gather": 68 * M_POINTS + 52 * st["sbp_candidates"],
+        "resolve": 4 * st["sbp_candidates"] * max(st["sbp_rounds"], 1) + 8 * M_POINTS,
+    }
+    top = max((k_ for k_ in stage_ms if k_ in alg_bytes), key=lambda k_: stage_ms[k_])
+    ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                "algorithmic_bytes_per_launch": alg_bytes[top], "launch_ms": stage_ms[top]}
+    frame_bytes = sum(alg_bytes.values())
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write)", "frames_cycled": N_FRAMES,
+                       "sequences": world, "parallelism": "independent sequence per GPU, no collective"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": roofline,
+            "stages_ms": stage_ms,
+            "frame_algorithmic_bytes": int(frame_bytes),
+            "frame_hbm_roofline_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "counts": st,
+            "wall_s_resident_loop": wall_s,
+            "step_ms_p50_p95": [float(np.percentile(step_ms, 50)), float(np.percentile(step_ms, 95))]}
+
+    # ---- CPU baseline beside it (rank 0, N == 1): the oracle port on a bounded sample of the same workload ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        exL, exR = oracle.Extractor(), oracle.Extractor()
+        mb = np.float32(mbf / np.float32(E["fx"]))
+        nsample = 30
+        t_cpu = []
+        for i in range(nsample + 2):
+            L, R = frames[i % N_FRAMES]
+            ms, _, _, _ = oracle.time_stereo_frame(exL, exR, L, R, float(mbf), float(mb), two_threads=True)
+            _, kL, dLd = exL.extract(L) if i < 2 else (0, None, None)
+            if i >= 2:
+                t_cpu.append(ms)
+        # projection search of the oracle on 6 frames
+        sbp = []
+        for i in range(6):
+            L, R = frames[i]
+            _, kL, dLd = exL.extract(L); _, kR, dRd = exR.extract(R)
+            so = oracle.stereo(exL, exR, kL, dLd, kR, dRd, float(mbf), float(mb))
+            F = oracle.Frame(kL, dLd, exL.scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                             mbf=float(mbf), u_right=so["uRight"])
+            mp = maps[i]
+            t0 = time.perf_counter()
+            F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], TH,
+                                  np.full(len(kL), -1, np.int32), np.zeros(len(kL), np.uint8))
+            sbp.append((time.perf_counter() - t0) * 1e3)
+        cpu_ms = float(np.mean(t_cpu) + np.mean(sbp))
+        line["cpu_baseline"] = {"value": 1000.0 / cpu_ms, "unit": "frames/s", "cores": 2, "kind": "port",
+                                "ms_per_frame": cpu_ms,
+                                "sample": "%d frames (extract L/R on 2 threads + stereo) + 6 frames SearchLocalPoints "
+                                          "of the same workload; host has %d cores" % (nsample, os.cpu_count())}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

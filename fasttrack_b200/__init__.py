@@ -21,8 +21,12 @@ EXPORTS = [
     "ft_extract_stereo", "ft_extract_stereo_device", "ft_stereo_match", "ft_stereo_match_fisheye", "ft_frame_counts",
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
-    "ft_context_stream", "ft_set_use_graph", "ft_launch_counts",
+    "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times",
 ]
+
+STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
+          "stereo_outliers", "frustum", "gather", "resolve"]
 
 
 class FtError(RuntimeError):
@@ -82,6 +86,12 @@ def load_library():
     L.ft_context_stream.argtypes = [vp]
     L.ft_set_use_graph.argtypes = [vp, C.c_int]
     L.ft_launch_counts.argtypes = [vp, ip, ip, ip]
+    L.ft_upload_map_points.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.ft_upload_holders.argtypes = [vp, C.c_int, vp, vp]
+    L.ft_search_resident.argtypes = [vp, C.c_float, C.c_int, C.c_float, C.c_float]
+    L.ft_search_download.argtypes = [vp, vp, vp, vp, ip]
+    L.ft_set_stage_timing.argtypes = [vp, C.c_int]
+    L.ft_get_stage_times.argtypes = [vp, vp, C.c_int]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
             getattr(L, name).restype = C.c_int
@@ -217,6 +227,40 @@ class Context:
         self._ck(self.L.ft_search_local_points(self.h, M, pos, normal, minmax, desc, flags, th, int(b_far), th_far,
                                                nnratio, holder, holder_obs, best, C.byref(nm)))
         return nm.value
+
+    # ---- resident projection search (map-point snapshot stays on the device) ----
+    def upload_map_points(self, pos, normal, minmax, desc, flags):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        self._mp_keep = (f(pos), f(normal), f(minmax), np.ascontiguousarray(desc, np.uint8),
+                         np.ascontiguousarray(flags, np.int32))
+        self._ck(self.L.ft_upload_map_points(self.h, len(self._mp_keep[0]), *[_ptr(a) for a in self._mp_keep]))
+
+    def upload_holders(self, holder=None, holder_obs=None):
+        if holder is None:
+            self._ck(self.L.ft_upload_holders(self.h, 0, None, None))
+            return
+        self._h_keep = (np.ascontiguousarray(holder, np.int32), np.ascontiguousarray(holder_obs, np.uint8))
+        self._ck(self.L.ft_upload_holders(self.h, len(self._h_keep[0]), _ptr(self._h_keep[0]), _ptr(self._h_keep[1])))
+
+    def search_resident(self, th, b_far=False, th_far=50.0, nnratio=0.8):
+        self._ck(self.L.ft_search_resident(self.h, th, int(b_far), th_far, nnratio))
+
+    def search_download(self, M):
+        c = self.counts()
+        N = c["n_left"] + (c["n_right"] if self.fisheye else 0)
+        holder = np.zeros(max(N, 1), np.int32); hobs = np.zeros(max(N, 1), np.uint8)
+        best = np.full((max(M, 1), 2), -1, np.int32)
+        nm = C.c_int()
+        self._ck(self.L.ft_search_download(self.h, _ptr(holder), _ptr(hobs), _ptr(best), C.byref(nm)))
+        return nm.value, holder[:N], hobs[:N], best[:M]
+
+    def set_stage_timing(self, enable):
+        self._ck(self.L.ft_set_stage_timing(self.h, int(enable)))
+
+    def stage_times(self):
+        ms = np.zeros(len(STAGES), np.float32)
+        self._ck(self.L.ft_get_stage_times(self.h, _ptr(ms), len(STAGES)))
+        return {k: float(v) for k, v in zip(STAGES, ms) if v >= 0}
 
     def synchronize(self):
         self._ck(self.L.ft_synchronize(self.h))

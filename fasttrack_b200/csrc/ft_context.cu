@@ -53,6 +53,22 @@ struct ft_context {
   int lastM = 0;
   int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
   long long pyrBytes = 0;
+  // resident map-point snapshot + initial holders for ft_search_resident
+  int residentM = 0;
+  int* holderInit = nullptr;
+  uint8_t* holderObsInit = nullptr;
+  // per-stage CUDA-event timing (direct-launch mode only)
+  int timing = 0;
+  cudaEvent_t evA[FT_STAGE_COUNT] = {}, evB[FT_STAGE_COUNT] = {};
+  bool stageUsed[FT_STAGE_COUNT] = {};
+};
+
+struct StageScope {
+  ft_context* c; int id; cudaStream_t s;
+  StageScope(ft_context* c_, int id_, cudaStream_t s_) : c(c_), id(id_), s(s_) {
+    if (c->timing) { cudaEventRecord(c->evA[id], s); c->stageUsed[id] = true; }
+  }
+  ~StageScope() { if (c->timing) cudaEventRecord(c->evB[id], s); }
 };
 
 extern "C" const char* ft_last_error(void) { return g_err.c_str(); }
@@ -314,6 +330,8 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &Q.holderObs, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &Q.minKey, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &c->holderInit, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &c->holderObsInit, (size_t)2 * P.maxKp));
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -336,6 +354,7 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
   if (c->hCounts) cudaFreeHost(c->hCounts);
+  for (int i = 0; i < FT_STAGE_COUNT; i++) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoin) cudaEventDestroy(c->evJoin);
   if (c->evFork2) cudaEventDestroy(c->evFork2);
@@ -365,24 +384,24 @@ static int enqueue_extract(ft_context* c, const uint8_t* dL, int stepL, const ui
   const FtParams& P = c->P;
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2;
-  ft_launch_copy_level0(P, c->B, dL, stepL, dR, stepR, s); n++;
-  for (int l = 1; l < P.nlevels; l++) { ft_launch_resize(P, c->B, l, s); n++; }
+  { StageScope t(c, FT_STAGE_COPY0, s); ft_launch_copy_level0(P, c->B, dL, stepL, dR, stepR, s); n++; }
+  { StageScope t(c, FT_STAGE_RESIZE, s); for (int l = 1; l < P.nlevels; l++) { ft_launch_resize(P, c->B, l, s); n++; } }
   cudaEventRecord(c->evFork, s);
   cudaStreamWaitEvent(s2, c->evFork, 0);
-  ft_launch_blur(P, c->B, 0, P.nlevels, s2); n++;
+  { StageScope t(c, FT_STAGE_BLUR, s2); ft_launch_blur(P, c->B, 0, P.nlevels, s2); n++; }
   cudaEventRecord(c->evJoin, s2);
-  ft_launch_fast(P, c->B, 0, P.nlevels, s); n++;
-  ft_launch_octree(P, c->B, 0, P.nlevels, s); n++;
+  { StageScope t(c, FT_STAGE_FAST, s); ft_launch_fast(P, c->B, 0, P.nlevels, s); n++; }
+  { StageScope t(c, FT_STAGE_OCTREE, s); ft_launch_octree(P, c->B, 0, P.nlevels, s); n++; }
   cudaStreamWaitEvent(s, c->evJoin, 0);
-  ft_launch_orient_desc(P, c->B, s); n++;
-  ft_launch_grid(P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s); n++;
+  { StageScope t(c, FT_STAGE_ORIENT, s); ft_launch_orient_desc(P, c->B, s); n++; }
+  { StageScope t(c, FT_STAGE_GRID, s); ft_launch_grid(P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s); n++; }
   return n;
 }
 
 static ft_status run_extract(ft_context* c) {
   // inputs are in c->dIn[0/1] with pitch == width
   const int w = c->cfg.width;
-  if (c->useGraph) {
+  if (c->useGraph && !c->timing) {
     if (!c->gExtract) {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -437,12 +456,13 @@ extern "C" ft_status ft_stereo_match(ft_context* c) {
   if (!c->extracted) { set_err("ft_stereo_match: no extracted frame"); return FT_ERR_STATE; }
   if (c->fisheye) { set_err("ft_stereo_match: context is a KannalaBrandt8 rig; call ft_stereo_match_fisheye"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
-  if (c->useGraph) {
+  if (c->useGraph && !c->timing) {
     if (!c->gStereo) {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
-      ft_launch_stereo(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
+      ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
+      ft_launch_stereo_outliers(c->P, c->B, c->S, c->stream);
       CK(cudaStreamEndCapture(c->stream, &g));
       CK(cudaGraphInstantiate(&c->gStereo, g, 0));
       cudaGraphDestroy(g);
@@ -450,7 +470,8 @@ extern "C" ft_status ft_stereo_match(ft_context* c) {
     CK(cudaGraphLaunch(c->gStereo, c->stream));
   } else {
     CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
-    ft_launch_stereo(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
+    { StageScope t(c, FT_STAGE_STEREO, c->stream); ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, c->stream); }
+    { StageScope t(c, FT_STAGE_OUTLIER, c->stream); ft_launch_stereo_outliers(c->P, c->B, c->S, c->stream); }
     CK(cudaGetLastError());
   }
   c->nLaunchStereo = 2;
@@ -541,38 +562,55 @@ extern "C" ft_status ft_set_pose(ft_context* c, const float* Rcw, const float* t
   return FT_OK;
 }
 
-extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* pos, const float* normal,
-                                            const float* minmax, const uint8_t* desc, const int* flags, float th,
-                                            int bFar, float thFar, float nnratio, int* holder, uint8_t* holderObs,
-                                            int* best_idx, int* nmatches) {
-  if (!c || M < 0 || (M > 0 && (!pos || !normal || !minmax || !desc || !flags)) || !holder || !holderObs) {
-    set_err("ft_search_local_points: null argument"); return FT_ERR_INVALID;
-  }
-  if (!c->extracted) { set_err("ft_search_local_points: no extracted frame"); return FT_ERR_STATE; }
-  if (!c->fisheye && !c->stereoDone) { set_err("ft_search_local_points: stereo matching has not run (mvuRight is read)"); return FT_ERR_STATE; }
-  if (c->fisheye && !c->stereoDone) { set_err("ft_search_local_points: fisheye stereo matching has not run (match tables are read)"); return FT_ERR_STATE; }
+extern "C" ft_status ft_upload_map_points(ft_context* c, int M, const float* pos, const float* normal,
+                                          const float* minmax, const uint8_t* desc, const int* flags) {
+  if (!c || M < 0 || (M > 0 && (!pos || !normal || !minmax || !desc || !flags))) { set_err("ft_upload_map_points: null argument"); return FT_ERR_INVALID; }
   if (M > c->cfg.max_map_points) {
-    set_err("ft_search_local_points: more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)");
+    set_err("ft_upload_map_points: more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)");
     return FT_ERR_CAPACITY;
   }
   CK(cudaSetDevice(c->cfg.device_id));
-  ft_status st = fetch_counts(c);
-  if (st != FT_OK) return st;
-  const int nLeft = c->hCounts[0], nRight = c->hCounts[2];
-  const int N = c->fisheye ? nLeft + nRight : nLeft;
-  if (nmatches) *nmatches = 0;
-  c->lastM = M;
-  c->nLaunchSearch = 0;
-  if (M == 0 || N == 0) return FT_OK;
   FtSbpBuffers& Q = c->Q;
   cudaStream_t s = c->stream;
+  c->residentM = M;
+  if (M == 0) return FT_OK;
   CK(cudaMemcpyAsync(Q.pos, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(Q.normal, normal, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(Q.minmax, minmax, sizeof(float) * 2 * M, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(Q.desc, desc, (size_t)32 * M, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(Q.flags, flags, sizeof(int) * M, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.holder, holder, sizeof(int) * N, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.holderObs, holderObs, (size_t)N, cudaMemcpyHostToDevice, s));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_upload_holders(ft_context* c, int N, const int* holder, const uint8_t* holderObs) {
+  if (!c || N < 0 || N > 2 * c->P.maxKp) { set_err("ft_upload_holders: bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  cudaStream_t s = c->stream;
+  if (!holder || !holderObs) {   // F.mvpMapPoints all NULL, as right after the Frame constructor (Frame.cc:173)
+    CK(cudaMemsetAsync(c->holderInit, 0xFF, sizeof(int) * 2 * c->P.maxKp, s));
+    CK(cudaMemsetAsync(c->holderObsInit, 0, (size_t)2 * c->P.maxKp, s));
+    return FT_OK;
+  }
+  CK(cudaMemcpyAsync(c->holderInit, holder, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->holderObsInit, holderObs, (size_t)N, cudaMemcpyHostToDevice, s));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float thFar, float nnratio) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_search_resident: no extracted frame"); return FT_ERR_STATE; }
+  if (!c->stereoDone) { set_err("ft_search_resident: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  FtSbpBuffers& Q = c->Q;
+  cudaStream_t s = c->stream;
+  const int M = c->residentM;
+  c->lastM = M;
+  c->nLaunchSearch = 0;
+  CK(cudaMemcpyAsync(Q.holder, c->holderInit, sizeof(int) * 2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(Q.holderObs, c->holderObsInit, (size_t)2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
+  ft_launch_sbp_reset(Q, s);
+  c->nLaunchSearch = 1;
+  if (M == 0) return FT_OK;
   FtFrustumArgs fa;
   fa.cam1 = c->cam1; fa.cam2 = c->cam2; fa.pose = c->pose;
   fa.minX = c->minX; fa.maxX = c->maxX; fa.minY = c->minY; fa.maxY = c->maxY;
@@ -581,20 +619,77 @@ extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* p
   FtGatherArgs ga;
   ga.minX = c->minX; ga.minY = c->minY; ga.gridWInv = c->gridWInv; ga.gridHInv = c->gridHInv;
   ga.th = th; ga.bFactor = (th != 1.0f); ga.bFar = bFar; ga.thFar = thFar; ga.fisheye = c->fisheye;
-  ft_launch_frustum_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s);
   FtResolveArgs ra;
-  ra.M = M; ra.nLeft = nLeft; ra.nSlots = N; ra.fisheye = c->fisheye; ra.nnratio = nnratio;
-  ft_launch_resolve(c->B, Q, c->S, ra, s);
+  ra.M = M; ra.nLeft = 0; ra.nSlots = 0; ra.fisheye = c->fisheye; ra.nnratio = nnratio;
+  { StageScope t(c, FT_STAGE_FRUSTUM, s); ft_launch_frustum(Q, fa, M, s); }
+  { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, ga, M, s); }
+  { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
   c->nLaunchSearch = 4 + (c->fisheye ? 1 : 0);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(holder, Q.holder, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(holderObs, Q.holderObs, (size_t)N, cudaMemcpyDeviceToHost, s));
-  if (best_idx) CK(cudaMemcpyAsync(best_idx, Q.sel, sizeof(int) * 2 * M, cudaMemcpyDeviceToHost, s));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_search_download(ft_context* c, int* holder, uint8_t* holderObs, int* best_idx, int* nmatches) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
+  FtSbpBuffers& Q = c->Q;
+  cudaStream_t s = c->stream;
+  if (holder && N) CK(cudaMemcpyAsync(holder, Q.holder, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  if (holderObs && N) CK(cudaMemcpyAsync(holderObs, Q.holderObs, (size_t)N, cudaMemcpyDeviceToHost, s));
+  if (best_idx && c->lastM) CK(cudaMemcpyAsync(best_idx, Q.sel, sizeof(int) * 2 * c->lastM, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(c->hCounts + 8, Q.cursor, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (nmatches) *nmatches = c->hCounts[9];
   return check_device_status(c, c->hCounts[4]);
+}
+
+extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* pos, const float* normal,
+                                            const float* minmax, const uint8_t* desc, const int* flags, float th,
+                                            int bFar, float thFar, float nnratio, int* holder, uint8_t* holderObs,
+                                            int* best_idx, int* nmatches) {
+  if (!c || !holder || !holderObs) { set_err("ft_search_local_points: null argument"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_search_local_points: no extracted frame"); return FT_ERR_STATE; }
+  if (!c->stereoDone) { set_err("ft_search_local_points: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
+  if (nmatches) *nmatches = 0;
+  st = ft_upload_map_points(c, M, pos, normal, minmax, desc, flags);
+  if (st != FT_OK) return st;
+  if (M == 0 || N == 0) { c->lastM = 0; return FT_OK; }
+  st = ft_upload_holders(c, N, holder, holderObs);
+  if (st != FT_OK) return st;
+  st = ft_search_resident(c, th, bFar, thFar, nnratio);
+  if (st != FT_OK) return st;
+  return ft_search_download(c, holder, holderObs, best_idx, nmatches);
+}
+
+extern "C" ft_status ft_set_stage_timing(ft_context* c, int enable) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  if (enable && !c->evA[0]) {
+    for (int i = 0; i < FT_STAGE_COUNT; i++) { CK(cudaEventCreate(&c->evA[i])); CK(cudaEventCreate(&c->evB[i])); }
+  }
+  c->timing = enable;
+  for (int i = 0; i < FT_STAGE_COUNT; i++) c->stageUsed[i] = false;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_get_stage_times(ft_context* c, float* ms, int n) {
+  if (!c || !ms || n < FT_STAGE_COUNT) { set_err("ft_get_stage_times: bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->stream2));
+  for (int i = 0; i < FT_STAGE_COUNT; i++) {
+    ms[i] = -1.f;
+    if (c->timing && c->stageUsed[i]) CK(cudaEventElapsedTime(&ms[i], c->evA[i], c->evB[i]));
+  }
+  return FT_OK;
 }
 
 extern "C" ft_status ft_synchronize(ft_context* c) {

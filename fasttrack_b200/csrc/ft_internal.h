@@ -11,14 +11,16 @@ void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaS
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);
 void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);
 void ft_launch_orient_desc(const FtParams& p, const FtBuffers& b, cudaStream_t st);
-void ft_launch_stereo(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
-                      cudaStream_t st);
+void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
+                            cudaStream_t st);
+void ft_launch_stereo_outliers(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, cudaStream_t st);
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
                     float gridWInv, float gridHInv, cudaStream_t st);
-void ft_launch_frustum_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
-                              const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M,
-                              cudaStream_t st);
+void ft_launch_sbp_reset(const FtSbpBuffers& s, cudaStream_t st);
+void ft_launch_frustum(const FtSbpBuffers& s, const FtFrustumArgs& fa, int M, cudaStream_t st);
+void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
+                      const FtSbpBuffers& s, const FtGatherArgs& ga, int M, cudaStream_t st);
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st);

@@ -453,11 +453,12 @@ void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& 
                     float gridWInv, float gridHInv, cudaStream_t st) {
   k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv);
 }
-void ft_launch_frustum_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
-                              const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M,
-                              cudaStream_t st) {
-  k_sbp_reset<<<1, 32, 0, st>>>(s);
+void ft_launch_sbp_reset(const FtSbpBuffers& s, cudaStream_t st) { k_sbp_reset<<<1, 32, 0, st>>>(s); }
+void ft_launch_frustum(const FtSbpBuffers& s, const FtFrustumArgs& fa, int M, cudaStream_t st) {
   k_frustum<<<(M + 255) / 256, 256, 0, st>>>(s, fa, M);
+}
+void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
+                      const FtSbpBuffers& s, const FtGatherArgs& ga, int M, cudaStream_t st) {
   k_gather<<<(M + GA_WARPS - 1) / GA_WARPS, GA_WARPS * 32, 0, st>>>(p, b, g, stb, s, ga, M);
 }
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,

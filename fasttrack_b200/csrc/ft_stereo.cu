@@ -333,9 +333,11 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_fisheye_match(const __grid_co
   }
 }
 
-void ft_launch_stereo(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
-                      cudaStream_t st) {
+void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
+                            cudaStream_t st) {
   k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, 0, st>>>(p, b, s, mbf, mb);
+}
+void ft_launch_stereo_outliers(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, cudaStream_t st) {
   k_stereo_outliers<<<1, 1024, sizeof(int) * p.maxKp, st>>>(p, b, s);
 }
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,

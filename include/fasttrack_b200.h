@@ -126,6 +126,18 @@ ft_status ft_search_local_points(ft_context* ctx, int M, const float* pos, const
                                  float th_far_points, float nnratio, int* holder, uint8_t* holder_obs, int* best_idx,
                                  int* nmatches);
 
+/* The same search in three separable steps, so that the map-point snapshot can stay resident on the device
+ * between frames (the reference re-marshals all map points on every call, SearchLocalPointsKernel.cu:368-409):
+ *   ft_upload_map_points  H2D of the snapshot (asynchronous),
+ *   ft_upload_holders     H2D of F.mvpMapPoints as indices (NULL pointers = all empty, as after the Frame ctor),
+ *   ft_search_resident    frustum + candidate gathering + claim resolution, asynchronous, results stay on the device,
+ *   ft_search_download    D2H of the results; synchronises. */
+ft_status ft_upload_map_points(ft_context* ctx, int M, const float* pos, const float* normal, const float* minmax,
+                               const uint8_t* desc, const int* flags);
+ft_status ft_upload_holders(ft_context* ctx, int N, const int* holder, const uint8_t* holder_obs);
+ft_status ft_search_resident(ft_context* ctx, float th, int b_far_points, float th_far_points, float nnratio);
+ft_status ft_search_download(ft_context* ctx, int* holder, uint8_t* holder_obs, int* best_idx, int* nmatches);
+
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
 
@@ -143,6 +155,24 @@ ft_status ft_debug_grid(ft_context* ctx, int right, int* counts, int* indices, i
  * stats[0..] = C_left, C_right (FAST candidates), K_left, K_right, stereo candidates tested, coarse matches
  * refined, projection-search candidates, resolve rounds */
 ft_status ft_debug_stats(ft_context* ctx, long long* stats, int n);
+
+/* Per-stage device timing with CUDA events recorded around every kernel on the stream it is launched on.
+ * Enabling it switches the context to direct launches (events cannot be read out of a replayed graph). */
+#define FT_STAGE_COPY0 0
+#define FT_STAGE_RESIZE 1
+#define FT_STAGE_BLUR 2
+#define FT_STAGE_FAST 3
+#define FT_STAGE_OCTREE 4
+#define FT_STAGE_ORIENT 5
+#define FT_STAGE_GRID 6
+#define FT_STAGE_STEREO 7
+#define FT_STAGE_OUTLIER 8
+#define FT_STAGE_FRUSTUM 9
+#define FT_STAGE_GATHER 10
+#define FT_STAGE_RESOLVE 11
+#define FT_STAGE_COUNT 12
+ft_status ft_set_stage_timing(ft_context* ctx, int enable);
+ft_status ft_get_stage_times(ft_context* ctx, float* ms /* [FT_STAGE_COUNT], -1 = not run */, int n);
 
 /* The CUDA stream the context enqueues on (cudaStream_t as void*), for event timing by the caller. */
 void* ft_context_stream(ft_context* ctx);
