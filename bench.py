@@ -335,18 +335,27 @@ def main():
     # ---- roofline of the dominant kernel (SURVEY.md 8d byte formulas with the measured counts) ----
     pk, pk_kind = peaks()
     lv = [ctx.level_dims(l) for l in range(E["nlevels"])]
-    sumP = sum(w * h for w, h in lv)
+    px = [w * h for w, h in lv]
+    sumP = sum(px)
+    cL, kLv = ctx.level_counts(0); cR, kRv = ctx.level_counts(1)
+    C0, K0 = int(cL[0] + cR[0]), int(kLv[0] + kRv[0])
     C_ = st["cand_left"] + st["cand_right"]; K_ = st["kp_left"] + st["kp_right"]
+    # per launch (both eyes): bytes each kernel has to move at minimum (SURVEY.md 8d formulas, measured counts)
     alg_bytes = {
-        "copy_level0": 2 * 2 * lv[0][0] * lv[0][1],
-        "resize": 2 * (sum(w * h for w, h in lv[:-1]) + sum(w * h for w, h in lv[1:])),
-        "blur": 2 * 2 * sumP,
-        "fast_cells": 2 * sumP + 16 * C_,
-        "octree": 16 * C_ + 20 * K_,
+        "copy_level0": 2 * 2 * px[0],
+        "resize": 2 * (sum(px[:-1]) + sum(px[1:])),
+        "blur_l0": 2 * 2 * px[0],
+        "blur": 2 * 2 * (sumP - px[0]),
+        "fast_cells_l0": 2 * px[0] + 16 * C0,
+        "fast_cells": 2 * (sumP - px[0]) + 16 * (C_ - C0),
+        "octree_l0": 16 * C0 + 20 * K0,
+        "octree": 16 * (C_ - C0) + 20 * (K_ - K0),
         "orient_desc": (749 + 4 + 512 + 32) * K_,
+        "grid": 24 * st["kp_left"] + 4 * st["kp_left"] + 4 * 3073,
         "stereo_match": 44 * K_ + 44 * st["stereo_tested"] + 352 * st["stereo_refined"] + 12 * st["kp_left"],
+        "frustum": (12 + 12 + 8 + 4 + 52) * M_POINTS,
         "gather": 68 * M_POINTS + 52 * st["sbp_candidates"],
-        "resolve": 4 * st["sbp_candidates"] * max(st["sbp_rounds"], 1) + 8 * M_POINTS,
+        "resolve": 4 * st["sbp_candidates"] + 8 * M_POINTS,
     }
     top = max((k_ for k_ in stage_ms if k_ in alg_bytes), key=lambda k_: stage_ms[k_])
     ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9

@@ -22,11 +22,11 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
-          "stereo_outliers", "frustum", "gather", "resolve"]
+          "stereo_outliers", "frustum", "gather", "resolve", "fast_cells_l0", "octree_l0", "blur_l0"]
 
 
 class FtError(RuntimeError):
@@ -92,6 +92,8 @@ def load_library():
     L.ft_search_download.argtypes = [vp, vp, vp, vp, ip]
     L.ft_set_stage_timing.argtypes = [vp, C.c_int]
     L.ft_get_stage_times.argtypes = [vp, vp, C.c_int]
+    L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
+    L.ft_debug_sort.argtypes = [vp, C.c_int]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
             getattr(L, name).restype = C.c_int
@@ -307,6 +309,11 @@ class Context:
         self._ck(self.L.ft_debug_grid(self.h, int(right), _ptr(counts), _ptr(idx), C.byref(n)))
         return counts, idx[: n.value].copy()
 
+    def level_counts(self, eye):
+        cand = np.zeros(self.nlevels, np.int32); kp = np.zeros(self.nlevels, np.int32)
+        self._ck(self.L.ft_debug_level_counts(self.h, eye, _ptr(cand), _ptr(kp)))
+        return cand, kp
+
     def stats(self):
         s = np.zeros(8, np.int64)
         self._ck(self.L.ft_debug_stats(self.h, _ptr(s), 8))
@@ -322,3 +329,12 @@ def keypoints_as_array(kps):
         out[:, i] = kps[k]
     out[:, 5] = kps["octave"]
     return out
+
+
+def device_sort(words):
+    """test hook: sort uint64 words by their high 32 bits with the device introsort"""
+    a = np.ascontiguousarray(words, np.uint64).copy()
+    st = load_library().ft_debug_sort(a.ctypes.data, len(a))
+    if st != 0:
+        raise FtError(st, "ft_debug_sort failed")
+    return a

@@ -42,8 +42,8 @@ struct ft_context {
   std::vector<float> scale, invScale, sigma2, invSigma2;
   std::vector<int> quota;
   std::vector<void*> allocs;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evPyr = nullptr, evJoin3 = nullptr;
   uint8_t* dIn[2] = {nullptr, nullptr};     // device staging for the input images
   uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
   int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
@@ -326,9 +326,10 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &Q.pool, (size_t)Q.poolCap));
   CKF(dalloc(c, &Q.cursor, (size_t)8));
   CKF(dalloc(c, &Q.sel, (size_t)MM * 2));
+  CKF(dalloc(c, &Q.active, (size_t)MM));
   CKF(dalloc(c, &Q.holder, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &Q.holderObs, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.minKey, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.minKey, (size_t)2 * 2 * P.maxKp));   // two buffers used alternately by k_resolve
   CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &c->holderInit, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &c->holderObsInit, (size_t)2 * P.maxKp));
@@ -336,11 +337,15 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   memset(c->hCounts, 0, 64 * sizeof(int));
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CKF(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   CKF(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evFork2, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->evJoin3, cudaEventDisableTiming));
   CKF(ft_launch_extract_setup(P));
+  CKF(ft_launch_sbp_setup(P));
   *out = c;
   return FT_OK;
 }
@@ -359,8 +364,11 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->evJoin) cudaEventDestroy(c->evJoin);
   if (c->evFork2) cudaEventDestroy(c->evFork2);
   if (c->evJoin2) cudaEventDestroy(c->evJoin2);
+  if (c->evPyr) cudaEventDestroy(c->evPyr);
+  if (c->evJoin3) cudaEventDestroy(c->evJoin3);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   delete c;
   return FT_OK;
 }
@@ -381,21 +389,50 @@ extern "C" ft_status ft_get_scale_tables(ft_context* c, float* scale, float* inv
 // The per-frame extraction chain. Enqueued on c->stream with the blur forked onto c->stream2;
 // identical whether it is being captured into a graph or launched directly.
 static int enqueue_extract(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+  // Launch topology (captured as-is into the CUDA graph): level 0 needs no resize, and its octree is the longest
+  // single dependency of the frame, so it gets its own branch that starts right after the input copy.
+  //   s : copy0 -> resize 1..n-1 -> FAST 1..n-1 -> octree 1..n-1 ----+
+  //   s3: (after copy0) FAST 0 -> octree 0 --------------------------+-> orient+descriptors
+  //   s2: (after copy0) blur 0, (after resizes) blur 1..n-1 ---------+
   const FtParams& P = c->P;
+  const int nl = P.nlevels;
   int n = 0;
-  cudaStream_t s = c->stream, s2 = c->stream2;
+  cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
   { StageScope t(c, FT_STAGE_COPY0, s); ft_launch_copy_level0(P, c->B, dL, stepL, dR, stepR, s); n++; }
-  { StageScope t(c, FT_STAGE_RESIZE, s); for (int l = 1; l < P.nlevels; l++) { ft_launch_resize(P, c->B, l, s); n++; } }
   cudaEventRecord(c->evFork, s);
+  cudaStreamWaitEvent(s3, c->evFork, 0);
   cudaStreamWaitEvent(s2, c->evFork, 0);
-  { StageScope t(c, FT_STAGE_BLUR, s2); ft_launch_blur(P, c->B, 0, P.nlevels, s2); n++; }
+  { StageScope t(c, FT_STAGE_FAST_L0, s3); ft_launch_fast(P, c->B, 0, 1, s3); n++; }
+  { StageScope t(c, FT_STAGE_OCTREE_L0, s3); ft_launch_octree(P, c->B, 0, 1, s3); n++; }
+  cudaEventRecord(c->evJoin3, s3);
+  { StageScope t(c, FT_STAGE_BLUR_L0, s2); ft_launch_blur(P, c->B, 0, 1, s2); n++; }
+  if (nl > 1) {
+    { StageScope t(c, FT_STAGE_RESIZE, s); for (int l = 1; l < nl; l++) { ft_launch_resize(P, c->B, l, s); n++; } }
+    cudaEventRecord(c->evPyr, s);
+    cudaStreamWaitEvent(s2, c->evPyr, 0);
+    { StageScope t(c, FT_STAGE_BLUR, s2); ft_launch_blur(P, c->B, 1, nl, s2); n++; }
+    { StageScope t(c, FT_STAGE_FAST, s); ft_launch_fast(P, c->B, 1, nl, s); n++; }
+    { StageScope t(c, FT_STAGE_OCTREE, s); ft_launch_octree(P, c->B, 1, nl, s); n++; }
+  }
   cudaEventRecord(c->evJoin, s2);
-  { StageScope t(c, FT_STAGE_FAST, s); ft_launch_fast(P, c->B, 0, P.nlevels, s); n++; }
-  { StageScope t(c, FT_STAGE_OCTREE, s); ft_launch_octree(P, c->B, 0, P.nlevels, s); n++; }
   cudaStreamWaitEvent(s, c->evJoin, 0);
+  cudaStreamWaitEvent(s, c->evJoin3, 0);
   { StageScope t(c, FT_STAGE_ORIENT, s); ft_launch_orient_desc(P, c->B, s); n++; }
-  { StageScope t(c, FT_STAGE_GRID, s); ft_launch_grid(P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s); n++; }
   return n;
+}
+
+// Stereo matching with the frame grid (only read by the projection search) built on a parallel branch.
+static int enqueue_stereo(ft_context* c) {
+  cudaStream_t s = c->stream, s2 = c->stream2;
+  cudaMemsetAsync(c->S.stats, 0, 7 * sizeof(unsigned long long), s);
+  cudaEventRecord(c->evFork2, s);
+  cudaStreamWaitEvent(s2, c->evFork2, 0);
+  { StageScope t(c, FT_STAGE_GRID, s2); ft_launch_grid(c->P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s2); }
+  cudaEventRecord(c->evJoin2, s2);
+  if (c->fisheye) { StageScope t(c, FT_STAGE_STEREO, s); ft_launch_fisheye(c->P, c->B, c->S, c->cam1, c->cam2, c->pose, s); }
+  else { StageScope t(c, FT_STAGE_STEREO, s); ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, s); }
+  cudaStreamWaitEvent(s, c->evJoin2, 0);
+  return c->fisheye ? 3 : 2;
 }
 
 static ft_status run_extract(ft_context* c) {
@@ -451,45 +488,38 @@ extern "C" ft_status ft_extract_stereo_device(ft_context* c, const uint8_t* dL, 
   return run_extract(c);
 }
 
-extern "C" ft_status ft_stereo_match(ft_context* c) {
-  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
-  if (!c->extracted) { set_err("ft_stereo_match: no extracted frame"); return FT_ERR_STATE; }
-  if (c->fisheye) { set_err("ft_stereo_match: context is a KannalaBrandt8 rig; call ft_stereo_match_fisheye"); return FT_ERR_INVALID; }
+static ft_status run_stereo(ft_context* c) {
   CK(cudaSetDevice(c->cfg.device_id));
   if (c->useGraph && !c->timing) {
     if (!c->gStereo) {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
-      ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, c->stream);
-      ft_launch_stereo_outliers(c->P, c->B, c->S, c->stream);
+      c->nLaunchStereo = enqueue_stereo(c);
       CK(cudaStreamEndCapture(c->stream, &g));
       CK(cudaGraphInstantiate(&c->gStereo, g, 0));
       cudaGraphDestroy(g);
     }
     CK(cudaGraphLaunch(c->gStereo, c->stream));
   } else {
-    CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
-    { StageScope t(c, FT_STAGE_STEREO, c->stream); ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, c->stream); }
-    { StageScope t(c, FT_STAGE_OUTLIER, c->stream); ft_launch_stereo_outliers(c->P, c->B, c->S, c->stream); }
+    c->nLaunchStereo = enqueue_stereo(c);
     CK(cudaGetLastError());
   }
-  c->nLaunchStereo = 2;
   c->stereoDone = true;
   return FT_OK;
+}
+
+extern "C" ft_status ft_stereo_match(ft_context* c) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_stereo_match: no extracted frame"); return FT_ERR_STATE; }
+  if (c->fisheye) { set_err("ft_stereo_match: context is a KannalaBrandt8 rig; call ft_stereo_match_fisheye"); return FT_ERR_INVALID; }
+  return run_stereo(c);
 }
 
 extern "C" ft_status ft_stereo_match_fisheye(ft_context* c) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   if (!c->extracted) { set_err("ft_stereo_match_fisheye: no extracted frame"); return FT_ERR_STATE; }
   if (!c->fisheye) { set_err("ft_stereo_match_fisheye: context is a pinhole rig"); return FT_ERR_INVALID; }
-  CK(cudaSetDevice(c->cfg.device_id));
-  CK(cudaMemsetAsync(c->S.stats, 0, 8 * sizeof(unsigned long long), c->stream));
-  ft_launch_fisheye(c->P, c->B, c->S, c->cam1, c->cam2, c->pose, c->stream);
-  CK(cudaGetLastError());
-  c->nLaunchStereo = 2;
-  c->stereoDone = true;
-  return FT_OK;
+  return run_stereo(c);
 }
 
 static ft_status check_device_status(ft_context* c, int status) {
@@ -620,7 +650,7 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   ga.minX = c->minX; ga.minY = c->minY; ga.gridWInv = c->gridWInv; ga.gridHInv = c->gridHInv;
   ga.th = th; ga.bFactor = (th != 1.0f); ga.bFar = bFar; ga.thFar = thFar; ga.fisheye = c->fisheye;
   FtResolveArgs ra;
-  ra.M = M; ra.nLeft = 0; ra.nSlots = 0; ra.fisheye = c->fisheye; ra.nnratio = nnratio;
+  ra.M = M; ra.nLeft = 0; ra.nSlots = 2 * c->P.maxKp; ra.fisheye = c->fisheye; ra.nnratio = nnratio;   // nSlots: smem sizing bound
   { StageScope t(c, FT_STAGE_FRUSTUM, s); ft_launch_frustum(Q, fa, M, s); }
   { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, ga, M, s); }
   { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
@@ -784,5 +814,14 @@ extern "C" ft_status ft_debug_stats(ft_context* c, long long* stats, int n) {
   for (int i = 0; i < 8; i++) stats[i] = 0;
   for (int l = 0; l < c->P.nlevels; l++) { stats[0] += cand[0][l]; stats[1] += cand[1][l]; stats[2] += kp[0][l]; stats[3] += kp[1][l]; }
   stats[4] = (long long)st[0]; stats[5] = (long long)st[1]; stats[6] = cur[0]; stats[7] = cur[2];
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_level_counts(ft_context* c, int eye, int* cand, int* kp) {
+  if (!c || eye < 0 || eye > 1 || !cand || !kp) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(cand, c->B.eye[eye].lvlCandCount, sizeof(int) * c->P.nlevels, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(kp, c->B.eye[eye].lvlKpCount, sizeof(int) * c->P.nlevels, cudaMemcpyDeviceToHost));
   return FT_OK;
 }

@@ -139,7 +139,8 @@ struct FtSbpBuffers {
   int* listLen;            // [M][2]
   uint32_t* pool;          // candidate entries idx:16 | dist:9 | octave:4
   int poolCap;
-  int* cursor;             // [0] pool cursor, [1] nmatches, [2] rounds, [3] non-blocking searched map points
+  int* cursor;             // [0] pool cursor, [1] nmatches, [2] rounds, [3] non-blocking searched map points, [4] active count
+  int* active;             // [M] map points with a non-empty candidate list (order irrelevant)
   int* sel;                // [M][2] selected keypoint per branch, -1 none
   int* holder;             // [2*maxKp] in/out
   uint8_t* holderObs;      // [2*maxKp]

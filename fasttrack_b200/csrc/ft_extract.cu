@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtPa
 // carries a 16-bit code (node slot * 4 + quadrant) that is remapped through a table.
 // ------------------------------------------------------------------------------------
 #define OCT_THREADS 512
+#define OCT_SMEM_CANDS 16384   // candidates of one level held in shared memory (6 B each); larger levels use HBM scratch
 
 struct OctSmem {
   // carved from dynamic shared memory, all arrays sized nodeCap
@@ -335,6 +336,8 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ int sTot[4];
   __shared__ int sN, sMode, sVecN, sP, sCellTot;
+  __shared__ int sScan[OCT_THREADS / 32];
+  __shared__ int sChildP, sGrowP, sVecP;
   const int level = levelBegin + blockIdx.x;
   const int eye = blockIdx.y;
   const FtLevel& L = p.lv[level];
@@ -342,8 +345,12 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   const int tid = threadIdx.x;
   const int cap = L.nodeCap;
   const int N = L.quota;
+  const int nCells = L.nCols * L.nRows;
 
   OctSmem S;
+  int* cellOff;          // [nCells + 1] exclusive prefix of the per-cell candidate counts
+  uint32_t* candS;       // [OCT_SMEM_CANDS]
+  uint16_t* codeS;       // [OCT_SMEM_CANDS]
   {
     uint8_t* q = smemRaw;
     S.vec[0] = (unsigned long long*)q; q += sizeof(unsigned long long) * cap;
@@ -358,18 +365,17 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     S.posC = (int*)q; q += 4 * cap;
     S.map = (int*)q; q += 16 * cap;
     S.vecPos = (int*)q; q += 4 * cap;
+    cellOff = (int*)q; q += 4 * (nCells + 1);
+    q = (uint8_t*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    candS = (uint32_t*)q; q += 4 * OCT_SMEM_CANDS;
+    codeS = (uint16_t*)q;
   }
 
-  // ---- gather the per-cell lists into the flat canonical order (cell row-major, then row-major in cell) ----
-  const int nCells = L.nCols * L.nRows;
-  uint32_t* cand = E.cand + L.candBase;
-  uint16_t* code = E.candNode + L.candBase;
+  // ---- flat canonical order (cell row-major, then row-major inside the cell) ----
+  // exclusive scan of the per-cell counts, then every candidate finds its cell by binary search: the copy out of
+  // the per-cell slabs is one coalesced pass instead of a per-cell serial loop.
   {
-    // running offset over cells, 512 cells per round
-    __shared__ int sScan[OCT_THREADS / 32];
-    __shared__ int sBase;
-    if (tid == 0) sBase = 0;
-    __syncthreads();
+    int running = 0;
     for (int c0 = 0; c0 < nCells; c0 += OCT_THREADS) {
       const int c = c0 + tid;
       const int cnt = c < nCells ? E.cellCount[L.cellBase + c] : 0;
@@ -381,18 +387,17 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       }
       if ((tid & 31) == 31) sScan[tid >> 5] = incl;
       __syncthreads();
-      int off = sBase;
+      int off = running;
       for (int w = 0; w < (tid >> 5); w++) off += sScan[w];
-      off += incl - cnt;
-      const uint32_t* src = E.cellKp + L.cellKpBase + (size_t)c * L.cellCap;
-      for (int k = 0; k < cnt; k++)
-        if (off + k < L.candCap) cand[off + k] = src[k];
-      __syncthreads();
-      if (tid == OCT_THREADS - 1) sBase = off + cnt;
+      if (c < nCells) cellOff[c] = off + incl - cnt;
+      int tot = 0;
+      for (int w = 0; w < OCT_THREADS / 32; w++) tot += sScan[w];
+      running += tot;
       __syncthreads();
     }
     if (tid == 0) {
-      int C = sBase;
+      int C = running;
+      cellOff[nCells] = C;
       if (C > L.candCap) { C = L.candCap; atomicOr(b.status, FT_ST_CAND_OVERFLOW); }
       sCellTot = C;
       E.lvlCandCount[level] = C;
@@ -404,6 +409,17 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   if (C == 0) {
     if (tid == 0) E.lvlKpCount[level] = 0;
     return;
+  }
+  uint32_t* candG = E.cand + L.candBase;          // global copy: read back by ft_debug_level_candidates
+  const bool inSmem = C <= OCT_SMEM_CANDS;
+  uint32_t* cand = inSmem ? candS : candG;
+  uint16_t* code = inSmem ? codeS : (E.candNode + L.candBase);
+  for (int c = tid; c < C; c += OCT_THREADS) {
+    int lo = 0, hi = nCells;                      // largest cell with cellOff[cell] <= c
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cellOff[mid] <= c) lo = mid; else hi = mid; }
+    const uint32_t v = E.cellKp[L.cellKpBase + (size_t)lo * L.cellCap + (c - cellOff[lo])];
+    candG[c] = v;
+    if (inSmem) candS[c] = v;
   }
 
   // ---- roots (ORBextractor.cc:664-706) ----
@@ -463,14 +479,21 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       S.vecPos[i] = -1;
       S.ccnt[4 * i] = 0; S.ccnt[4 * i + 1] = 0; S.ccnt[4 * i + 2] = 0; S.ccnt[4 * i + 3] = 0;
     }
-    __syncthreads();
     if (mode == 1) {
-      if (tid == 0) ftsort::sort(vecPrev, m);   // std::sort(..., compareNodes) (ORBextractor.cc:805)
+      // std::sort(..., compareNodes) (ORBextractor.cc:805): warp 0 replays libstdc++'s introsort loop, then the
+      // final insertion sort (= stable sort of what the loop leaves) is a parallel rank computation
+      if (tid < 32) ftsort::warp_introsort_loop(vecPrev, m, S.posA, S.posB);
+      __syncthreads();
+      ftsort::stable_rank(vecPrev, vecNew, m, tid, OCT_THREADS);
       __syncthreads();
       // processing order r = 0..m-1 walks the sorted vector from the back (:806)
-      for (int r = tid; r < m; r += OCT_THREADS) S.vecPos[(int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu)] = r;
-      __syncthreads();
+      for (int r = tid; r < m; r += OCT_THREADS) {
+        const unsigned long long e = vecNew[m - 1 - r];
+        vecPrev[m - 1 - r] = e;
+        S.vecPos[(int)(e & 0xFFFFFFFFu)] = r;
+      }
     }
+    __syncthreads();
     // candidates: remap code -> node, count children of nodes being split
     for (int c = tid; c < C; c += OCT_THREADS) {
       const int node = S.map[code[c]];
@@ -537,20 +560,19 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       __syncthreads();
     } else {
       // careful pass: nodes of the sorted vector are split from the back until the list reaches N (:806-853)
-      // posA[r] = growth of the r-th processed node (non-empty children - 1), inclusive prefix decides the cut
+      // posA[r] = non-empty children of the r-th processed node, posB[r] = growth (children - 1), posC[r] = expandable
       for (int r = tid; r < m; r += OCT_THREADS) {
         const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
         int k = 0, e = 0;
         for (int q = 0; q < 4; q++) { k += S.ccnt[4 * node + q] > 0; e += S.ccnt[4 * node + q] > 1; }
         S.posA[r] = k; S.posB[r] = k - 1; S.posC[r] = e;
       }
+      if (tid == 0) sP = m;
       __syncthreads();
       // exclusive prefix over processing order: posA -> children before r, posB -> growth before r, posC -> vec offset
       oct_scan3(m, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, false);
       __syncthreads();
       // number processed P: first r with n + growthBefore(r) + growth(r) >= N, else m
-      if (tid == 0) sP = m;
-      __syncthreads();
       for (int r = tid; r < m; r += OCT_THREADS) {
         const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
         int k = 0;
@@ -560,7 +582,6 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       __syncthreads();
       const int P = sP;
       // totals restricted to the processed prefix
-      __shared__ int sChildP, sGrowP, sVecP;
       if (tid == 0) {
         if (P == m) { sChildP = sTot[0]; sGrowP = sTot[1]; sVecP = sTot[2]; }
         else { sChildP = S.posA[P]; sGrowP = S.posB[P]; sVecP = S.posC[P]; }
@@ -591,10 +612,11 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
           } else S.map[4 * node + q] = -1;
         }
       }
+      __syncthreads();   // posA/posB of the processed prefix are consumed; they are reused below
       // surviving old nodes keep their relative order behind the new children
       for (int i = tid; i < n; i += OCT_THREADS) {
         const int r = S.vecPos[i];
-        S.posB[i] = (r >= 0 && r < P) ? 0 : 1;   // reuse posB as "survives" flag (m <= n so no overlap hazard after sync)
+        S.posB[i] = (r >= 0 && r < P) ? 0 : 1;
       }
       __syncthreads();
       if (tid < 32) {
@@ -754,7 +776,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   {
     const int u = lane - 15;
     if (lane < 31) {
-#pragma unroll 1
+#pragma unroll
       for (int v = -FT_HALF_PATCH; v <= FT_HALF_PATCH; v++) {
         const int d = p.umax[v < 0 ? -v : v];
         if (u >= -d && u <= d) {
@@ -802,6 +824,37 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   }
 }
 
+// Test hook: the device sort on its own (tests/test_gpu_sort.py fuzzes it against std::sort).
+__global__ void __launch_bounds__(OCT_THREADS) k_debug_sort(unsigned long long* data, int n) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  unsigned long long* a = (unsigned long long*)smemRaw;
+  unsigned long long* o = a + n;
+  int* posA = (int*)(o + n);
+  int* posB = posA + n;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += OCT_THREADS) a[i] = data[i];
+  __syncthreads();
+  if (tid < 32) ftsort::warp_introsort_loop(a, n, posA, posB);
+  __syncthreads();
+  ftsort::stable_rank(a, o, n, tid, OCT_THREADS);
+  __syncthreads();
+  for (int i = tid; i < n; i += OCT_THREADS) data[i] = o[i];
+}
+
+extern "C" int ft_debug_sort(unsigned long long* keys_inout, int n) {
+  if (!keys_inout || n < 0 || n > 4096) return FT_ERR_INVALID;
+  if (n == 0) return FT_OK;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, sizeof(unsigned long long) * n) != cudaSuccess) return FT_ERR_CUDA;
+  cudaMemcpy(d, keys_inout, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)n * 24;
+  cudaFuncSetAttribute(k_debug_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_debug_sort<<<1, OCT_THREADS, smem>>>(d, n);
+  cudaError_t e = cudaMemcpy(keys_inout, d, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? FT_OK : FT_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
@@ -817,7 +870,9 @@ size_t ft_fast_smem_bytes(const FtParams& p) {
   return mx;
 }
 size_t ft_octree_smem_bytes(const FtParams& p, int level) {
-  return (size_t)p.lv[level].nodeCap * (8 + 8 + 8 + 8 + 4 + 4 + 16 + 4 + 4 + 4 + 16 + 4) + 64;
+  const FtLevel& L = p.lv[level];
+  return (size_t)L.nodeCap * (8 + 8 + 8 + 8 + 4 + 4 + 16 + 4 + 4 + 4 + 16 + 4) + 4 * (size_t)(L.nCols * L.nRows + 1) + 16 +
+         (size_t)OCT_SMEM_CANDS * 6 + 64;
 }
 
 cudaError_t ft_launch_extract_setup(const FtParams& p) {

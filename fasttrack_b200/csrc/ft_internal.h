@@ -4,6 +4,7 @@
 
 
 cudaError_t ft_launch_extract_setup(const FtParams& p);
+cudaError_t ft_launch_sbp_setup(const FtParams& p);
 void ft_launch_copy_level0(const FtParams& p, const FtBuffers& b, const uint8_t* imgL, int stepL, const uint8_t* imgR,
                            int stepR, cudaStream_t st);
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st);
@@ -13,7 +14,6 @@ void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cud
 void ft_launch_orient_desc(const FtParams& p, const FtBuffers& b, cudaStream_t st);
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
                             cudaStream_t st);
-void ft_launch_stereo_outliers(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, cudaStream_t st);
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,

@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
   const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
   const uint4 md0 = md[0], md1 = md[1];
   const int nBranches = a.fisheye ? 2 : 1;
+  int anyLen = 0;
+  if (lane == 0 && !a.fisheye) { s.listOff[2 * mp + 1] = 0; s.listLen[2 * mp + 1] = 0; }
   for (int br = 0; br < nBranches; br++) {
     int len = 0, off = 0;
     const bool active = searched && (br == 0 ? inView : inViewR) && (br == 0 || s.trI[4 * mp + 3] != -1);
@@ -294,7 +296,9 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
       }
     }
     if (lane == 0) { s.listOff[2 * mp + br] = off; s.listLen[2 * mp + br] = len; }
+    anyLen |= len;
   }
+  if (lane == 0 && anyLen) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
 }
 
 // ---- claim resolution ---------------------------------------------------------------------
@@ -305,7 +309,7 @@ template <typename BlockedFn>
 __device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float nnratio, BlockedFn blocked, bool* cont) {
   int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
   for (int k = 0; k < len; k++) {
-    const uint32_t e = list[k];
+    const uint32_t e = __ldg(list + k);
     const int idx = (int)(e & 0xFFFFu);
     if (blocked(idx)) continue;
     const int dist = (int)((e >> 16) & 0x1FFu), oct = (int)(e >> 25);
@@ -320,73 +324,92 @@ __device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float
   return -1;
 }
 
+// One thread-block cluster (8 or 16 CTAs, co-scheduled on one GPC) so that the best/second-best scans of all
+// candidate lists issue from several SMs at once: the rounds are instruction-bound, not bandwidth-bound. The
+// pre-blocked flags are replicated into every CTA's shared memory; the per-slot minimum stamps live in global
+// memory (atomicMin at L2, read back with ld.global.cg) in two buffers used alternately, so a round needs only
+// two cluster barriers: scatter | evaluate (+ reset of the other buffer). Only map points with a non-empty
+// candidate list are visited (compact list written by k_gather).
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 __global__ void __launch_bounds__(1024) k_resolve(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
                                                   const __grid_constant__ FtStereoBuffers st,
                                                   const __grid_constant__ FtResolveArgs a0) {
-  __shared__ int sChanged;
-  const int tid = threadIdx.x;
+  extern __shared__ int sMem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nThreads = gridDim.x * 1024;
+  const int gtid = blockIdx.x * 1024 + threadIdx.x;
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
-  int* status = b.status;
-  const int M = a.M, nS = a.nSlots;
-  if (a.fisheye && s.cursor[3] > 0) return;   // k_resolve_seq handles this frame
+  if (a.fisheye && s.cursor[3] > 0) return;   // k_resolve_seq handles this frame (uniform over the cluster)
+  const int nS = a.nSlots;
+  const int nA = s.cursor[4];
+  const int stride = a0.nSlots;               // a0.nSlots = capacity bound (2*maxKp): offset of the second buffer
+  uint8_t* pre = reinterpret_cast<uint8_t*>(sMem);
+  for (int i = threadIdx.x; i < nS; i += 1024) pre[i] = (s.holder[i] != -1 && s.holderObs[i]) ? 1 : 0;
+  for (int i = gtid; i < nS; i += nThreads) { s.minKey[i] = 0x7FFFFFFF; s.minKey[stride + i] = 0x7FFFFFFF; }
+  if (gtid < 2) s.cursor[5 + gtid] = 0;
+  cluster.sync();
   int rounds = 0;
   for (;;) {
-    for (int i = tid; i < nS; i += 1024) s.minKey[i] = 0x7FFFFFFF;
-    if (tid == 0) sChanged = 0;
-    __syncthreads();
-    for (int mp = tid; mp < M; mp += 1024) {
-      if (!(s.flags[mp] & 2)) continue;   // writes of map points without observations never block
+    int* mk = s.minKey + (rounds & 1) * stride;
+    int* mkNext = s.minKey + ((rounds + 1) & 1) * stride;
+    for (int k = gtid; k < nA; k += nThreads) {
+      const int mp = __ldg(&s.active[k]);
+      if (!(__ldg(&s.flags[mp]) & 2)) continue;   // writes of map points without observations never block
       const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
       if (sl >= 0) {
-        atomicMin(&s.minKey[sl], 2 * mp);
-        if (a.fisheye && st.l2r[sl] != -1) atomicMin(&s.minKey[st.l2r[sl] + a.nLeft], 2 * mp);
+        atomicMin(&mk[sl], 2 * mp);
+        if (a.fisheye && st.l2r[sl] != -1) atomicMin(&mk[st.l2r[sl] + a.nLeft], 2 * mp);
       }
       if (sr >= 0) {
-        atomicMin(&s.minKey[sr + a.nLeft], 2 * mp + 1);
-        if (st.r2l[sr] != -1) atomicMin(&s.minKey[st.r2l[sr]], 2 * mp + 1);
+        atomicMin(&mk[sr + a.nLeft], 2 * mp + 1);
+        if (st.r2l[sr] != -1) atomicMin(&mk[st.r2l[sr]], 2 * mp + 1);
       }
     }
-    __syncthreads();
+    cluster.sync();
     int changed = 0;
-    for (int mp = tid; mp < M; mp += 1024) {
-      const int lenL = s.listLen[2 * mp], lenR = s.listLen[2 * mp + 1];
-      if (lenL == 0 && lenR == 0) continue;
-      const bool blocking = (s.flags[mp] & 2) != 0;
+    for (int k = gtid; k < nA; k += nThreads) {
+      const int mp = __ldg(&s.active[k]);
+      const int2 off = __ldg(reinterpret_cast<const int2*>(s.listOff) + mp);
+      const int2 len = __ldg(reinterpret_cast<const int2*>(s.listLen) + mp);
+      const bool blocking = (__ldg(&s.flags[mp]) & 2) != 0;
       int newL = -1, newR = -1;
       bool cont = false;
-      if (lenL > 0) {
-        const int t = 2 * mp;
-        newL = ft_scan_list(s.pool + s.listOff[2 * mp], lenL, a.nnratio,
-                            [&](int idx) { return (s.holder[idx] != -1 && s.holderObs[idx]) || s.minKey[idx] < t; }, &cont);
+      const int t = 2 * mp;
+      if (len.x > 0) {
+        const uint32_t* list = s.pool + off.x;
+        newL = ft_scan_list(list, len.x, a.nnratio, [&](int idx) { return pre[idx] || __ldcg(&mk[idx]) < t; }, &cont);
       }
-      if (lenR > 0 && !cont) {
-        const int t = 2 * mp;   // own left writes (stamp 2mp) are handled explicitly, older stamps through minKey
+      if (len.y > 0 && !cont) {
+        // own left writes (stamp 2mp) are handled explicitly, older stamps through the table
         const int ownMirror = (blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
         bool contR = false;
-        newR = ft_scan_list(s.pool + s.listOff[2 * mp + 1], lenR, a.nnratio,
-                            [&](int idx) {
-                              const int slot = idx + a.nLeft;
-                              return (s.holder[slot] != -1 && s.holderObs[slot]) || s.minKey[slot] < t || idx == ownMirror;
-                            }, &contR);
+        const uint32_t* list = s.pool + off.y;
+        newR = ft_scan_list(list, len.y, a.nnratio,
+                            [&](int idx) { const int slot = idx + a.nLeft; return pre[slot] || __ldcg(&mk[slot]) < t || idx == ownMirror; },
+                            &contR);
       }
-      if (newL != s.sel[2 * mp] || newR != s.sel[2 * mp + 1]) changed = 1;
-      s.sel[2 * mp] = newL; s.sel[2 * mp + 1] = newR;
+      const int2 old = *reinterpret_cast<const int2*>(s.sel + 2 * mp);
+      if (newL != old.x || newR != old.y) { changed = 1; *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(newL, newR); }
     }
-    if (changed) sChanged = 1;
-    __syncthreads();
+    if (changed) s.cursor[5 + (rounds & 1)] = 1;
+    for (int i = gtid; i < nS; i += nThreads) mkNext[i] = 0x7FFFFFFF;
+    if (gtid == 0) s.cursor[5 + ((rounds + 1) & 1)] = 0;
+    cluster.sync();
+    const int ch = __ldcg(&s.cursor[5 + (rounds & 1)]);
     rounds++;
-    const int ch = sChanged;
-    __syncthreads();
     if (!ch) break;
-    if (rounds > M + 2) { if (tid == 0) atomicOr(status, FT_ST_RESOLVE_NOCONV); break; }
+    if (rounds > a.M + 2) { if (gtid == 0) atomicOr(b.status, FT_ST_RESOLVE_NOCONV); break; }
   }
   // final holders: the write with the highest stamp wins each slot; count matches (ORBmatcher.cc:142-155,207-222)
-  for (int i = tid; i < nS; i += 1024) s.lastKey[i] = -1;
-  __syncthreads();
+  for (int i = gtid; i < nS; i += nThreads) s.lastKey[i] = -1;
+  cluster.sync();
   int nm = 0;
-  for (int mp = tid; mp < M; mp += 1024) {
+  for (int k = gtid; k < nA; k += nThreads) {
+    const int mp = __ldg(&s.active[k]);
     const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
     if (sl >= 0) {
       atomicMax(&s.lastKey[sl], 2 * mp); nm++;
@@ -398,12 +421,12 @@ __global__ void __launch_bounds__(1024) k_resolve(const __grid_constant__ FtBuff
     }
   }
   if (nm) atomicAdd(&s.cursor[1], nm);
-  __syncthreads();
-  for (int i = tid; i < nS; i += 1024) {
-    const int k = s.lastKey[i];
+  cluster.sync();
+  for (int i = gtid; i < nS; i += nThreads) {
+    const int k = __ldcg(&s.lastKey[i]);
     if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
   }
-  if (tid == 0) s.cursor[2] = rounds;
+  if (gtid == 0) s.cursor[2] = rounds;
 }
 
 // In-order execution by one thread (fisheye rigs with non-blocking map points only).
@@ -445,10 +468,29 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
 }
 
 __global__ void k_sbp_reset(const __grid_constant__ FtSbpBuffers s) {
-  if (threadIdx.x < 4) s.cursor[threadIdx.x] = 0;
+  if (threadIdx.x < 8) s.cursor[threadIdx.x] = 0;
 }
 
 // ---- host launchers -----------------------------------------------------------------------
+static int g_resolveCluster = 8;
+cudaError_t ft_launch_sbp_setup(const FtParams& p) {
+  cudaError_t e = cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * p.maxKp + 16);
+  if (e != cudaSuccess) return e;
+  // 16-CTA clusters are a non-portable size: opt in, and fall back to the portable 8 when the device cannot place one
+  g_resolveCluster = 8;
+  if (cudaFuncSetAttribute(k_resolve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 2 * p.maxKp + 16;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nClusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nClusters, k_resolve, &cfg) == cudaSuccess && nClusters >= 1) g_resolveCluster = 16;
+  }
+  cudaGetLastError();
+  return cudaSuccess;
+}
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
                     float gridWInv, float gridHInv, cudaStream_t st) {
   k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv);
@@ -463,6 +505,12 @@ void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers
 }
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st) {
-  k_resolve<<<1, 1024, 0, st>>>(b, s, stb, ra);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = (size_t)ra.nSlots + 16; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = g_resolveCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_resolve, b, s, stb, ra);
   if (ra.fisheye) k_resolve_seq<<<1, 32, 0, st>>>(b, s, stb, ra);   // exits immediately unless it is needed
 }

@@ -160,4 +160,96 @@ FT_HD void sort(elem_t* base, int n) {
   }
 }
 
+#ifdef __CUDACC__
+// ---- warp-cooperative version (device only) -----------------------------------------------------------
+// Same element movement as sort() above, executed by one full warp:
+//  * __unguarded_partition is data-parallel. Let A be the ascending positions in (first, last) whose element is
+//    not less than the pivot (where the left scan stops) and B the descending positions in [first, last) whose
+//    element is not greater (where the right scan stops; the pivot at `first` is the sentinel). Positions strictly
+//    between two stops are never touched, so iteration k of the sequential loop stops at
+//        i_k = (k == 0) ? A[0] : min(A[k], B[k-1]),   j_k = (k == 0) ? B[0] : max(B[k], A[k-1])
+//    (the min/max account for the elements the previous swap put at B[k-1] / A[k-1]); it swaps while i_k < j_k,
+//    and when the loop continues i_k = A[k], j_k = B[k]. The number of swaps K is the first k with !(i_k < j_k),
+//    the returned cut is i_K, and the K swaps A[k] <-> B[k] touch disjoint positions.
+//  * __final_insertion_sort is an insertion sort of the whole array, i.e. a stable sort of the arrangement the
+//    introsort loop leaves; stable_rank() computes that permutation in parallel.
+__device__ __forceinline__ int warp_partition(elem_t* base, int first, int last, int* posA, int* posB, int lane) {
+  const uint32_t p = (uint32_t)(base[first] >> 32);
+  const unsigned lt = (1u << lane) - 1u;
+  int nA = 0, nB = 0;
+  for (int c0 = first; c0 < last; c0 += 32) {
+    const int i = c0 + lane;
+    const bool in = i < last;
+    const uint32_t k = in ? (uint32_t)(base[i] >> 32) : 0u;
+    const bool fa = in && i > first && k >= p;
+    const bool fb = in && k <= p;
+    const unsigned ma = __ballot_sync(0xFFFFFFFFu, fa), mb = __ballot_sync(0xFFFFFFFFu, fb);
+    if (fa) posA[nA + __popc(ma & lt)] = i;
+    if (fb) posB[nB + __popc(mb & lt)] = i;
+    nA += __popc(ma); nB += __popc(mb);
+  }
+  __syncwarp();
+  int K = -1, cut = first + 1;
+  for (int k0 = 0; K < 0; k0 += 32) {
+    const int k = k0 + lane;
+    const int Ak = k < nA ? posA[k] : 0x7FFFFFFF;
+    const int Bk = k < nB ? posB[nB - 1 - k] : -1;
+    int ik = Ak, jk = Bk;
+    if (k > 0) {
+      const int Bp = (k - 1) < nB ? posB[nB - k] : -1;
+      const int Ap = (k - 1) < nA ? posA[k - 1] : 0x7FFFFFFF;
+      ik = min(Ak, Bp); jk = max(Bk, Ap);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, !(ik < jk));
+    if (m) { const int l = __ffs(m) - 1; K = k0 + l; cut = __shfl_sync(0xFFFFFFFFu, ik, l); }
+  }
+  for (int k = lane; k < K; k += 32) swp(&base[posA[k]], &base[posB[nB - 1 - k]]);
+  __syncwarp();
+  return cut;
+}
+
+// introsort loop only (no final insertion sort); posA/posB: scratch of n ints each. Call with a full warp.
+__device__ __forceinline__ void warp_introsort_loop(elem_t* base, int n, int* posA, int* posB) {
+  if (n <= 16) return;
+  const int lane = threadIdx.x & 31;
+  int stackFirst[64], stackLast[64], stackDepth[64];
+  int sp = 1;
+  stackFirst[0] = 0; stackLast[0] = n; stackDepth[0] = 2 * floor_log2(n);
+  while (sp > 0) {
+    --sp;
+    int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
+    while (last - first > 16) {
+      if (depth == 0) {
+        if (lane == 0) heap_sort(base + first, last - first);
+        __syncwarp();
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      if (lane == 0) move_median_to_first(&base[first], &base[first + 1], &base[mid], &base[last - 1]);
+      __syncwarp();
+      const int cut = warp_partition(base, first, last, posA, posB, lane);
+      stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth;
+      ++sp;
+      last = cut;
+    }
+  }
+}
+
+// out[rank] = in[i] with rank = #(smaller keys) + #(equal keys before i): the stable sort an insertion sort yields.
+// Call with `nthreads` cooperating threads (tid in [0, nthreads)); caller synchronises before and after.
+__device__ __forceinline__ void stable_rank(const elem_t* in, elem_t* out, int n, int tid, int nthreads) {
+  for (int i = tid; i < n; i += nthreads) {
+    const elem_t e = in[i];
+    const uint32_t k = (uint32_t)(e >> 32);
+    int r = 0;
+    for (int j = 0; j < n; j++) {
+      const uint32_t kj = (uint32_t)(in[j] >> 32);
+      r += (kj < k) || (kj == k && j < i);
+    }
+    out[r] = e;
+  }
+}
+#endif
+
 }  // namespace ftsort

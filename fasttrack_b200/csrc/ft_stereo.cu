@@ -4,7 +4,7 @@
 //                      one warp per left keypoint; row-band + octave + disparity filter over the right
 //                      keypoints, Hamming argmin with __popc over uint4 descriptor words, then 11x11 SAD
 //                      over 11 shifts on the left keypoint's pyramid level and the parabola fit.
-//   k_stereo_outliers  the (SAD, iL) median filter at the end of the same function (:991-1004).
+//                      The (SAD, iL) median filter at the end of the same function (:991-1004) runs in the last CTA.
 //   k_fisheye_match    Frame::ComputeStereoFishEyeMatches (:1231-1271): brute-force 2-NN Hamming with Lowe
 //                      ratio, then KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:306-406).
 #include "ft_device.cuh"
@@ -12,16 +12,12 @@
 
 #define ST_WARPS 8
 
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ FtParams p,
-                                                                const __grid_constant__ FtBuffers b,
-                                                                const __grid_constant__ FtStereoBuffers s, float mbf,
-                                                                float mb) {
+// per-warp body of k_stereo_match: one left keypoint
+__device__ __forceinline__ void ft_stereo_one(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf,
+                                              float mb, int iL, int lane) {
   const FtEye& EL = b.eye[0];
   const FtEye& ER = b.eye[1];
-  const int lane = threadIdx.x & 31;
-  const int iL = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
-  const int nL = EL.counts[0], nR = ER.counts[0];
-  if (iL >= nL) return;
+  const int nR = ER.counts[0];
   if (lane == 0) { s.uRight[iL] = -1.0f; s.depth[iL] = -1.0f; s.bestIdxR[iL] = -1; s.sad[iL] = -1; }
   const ft_keypoint kpL = EL.kps[iL];
   const int levelL = kpL.octave;
@@ -79,12 +75,16 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   int sum[11];
 #pragma unroll
   for (int k = 0; k < 11; k++) sum[k] = 0;
-  for (int i = lane; i < 121; i += 32) {
-    const int yy = i / 11 - w, xx = i % 11 - w;
-    const int a = IL[(size_t)(cy + yy) * LV.pitch + cxl + xx];
-    const uint8_t* rr = IR + (size_t)(cy + yy) * LV.pitch + cxr + xx - Lw;
 #pragma unroll
-    for (int k = 0; k < 11; k++) sum[k] += abs(a - (int)rr[k]);
+  for (int it = 0; it < 4; it++) {
+    const int i = lane + 32 * it;
+    if (i < 121) {
+      const int yy = i / 11 - w, xx = i % 11 - w;
+      const int a = IL[(size_t)(cy + yy) * LV.pitch + cxl + xx];
+      const uint8_t* rr = IR + (size_t)(cy + yy) * LV.pitch + cxr + xx - Lw;
+#pragma unroll
+      for (int k = 0; k < 11; k++) sum[k] += abs(a - (int)rr[k]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 11; k++) {
@@ -118,41 +118,78 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   }
 }
 
-// Median filter over the accepted matches: sort (SAD, iL), median = element size/2, drop SAD >= 2.1*median.
-__global__ void __launch_bounds__(1024) k_stereo_outliers(const __grid_constant__ FtParams p,
-                                                          const __grid_constant__ FtBuffers b,
-                                                          const __grid_constant__ FtStereoBuffers s) {
-  extern __shared__ int sSad[];   // [maxKp]
-  __shared__ int sCount, sMedian;
+// Stereo matching with the outlier filter fused in: the last CTA to finish (ticket counter) runs the
+// (SAD, iL) median filter of Frame.cc:991-1004. The reference sorts the pairs and reads element size/2; only
+// that element's SAD is used, so a two-pass 8+7-bit radix select over shared-memory histograms gives the same
+// value (SAD <= 121*255 < 2^15) without sorting.
+__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ FtParams p,
+                                                                const __grid_constant__ FtBuffers b,
+                                                                const __grid_constant__ FtStereoBuffers s, float mbf,
+                                                                float mb) {
+  __shared__ int sHist[256];
+  __shared__ int sLast, sCount, sBin, sBefore, sMedian;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nL = b.eye[0].counts[0];
-  const int tid = threadIdx.x;
-  if (tid == 0) { sCount = 0; sMedian = -1; }
+  const int iL = blockIdx.x * ST_WARPS + (tid >> 5);
+  if (iL < nL) ft_stereo_one(p, b, s, mbf, mb, iL, lane);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(&s.stats[7]), 1u);
+    sLast = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  // ---- outlier filter, 256 threads ----
+  sHist[tid] = 0;
+  if (tid == 0) { sCount = 0; reinterpret_cast<unsigned*>(&s.stats[7])[0] = 0; }
   __syncthreads();
   int local = 0;
-  for (int i = tid; i < nL; i += 1024) {
-    const int v = s.sad[i];
-    sSad[i] = v;
-    local += v >= 0;
+  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+    const int v = __ldcg(&s.sad[i]);
+    if (v >= 0) { local++; atomicAdd(&sHist[v >> 7], 1); }
   }
   if (local) atomicAdd(&sCount, local);
   __syncthreads();
   const int cnt = sCount;
   if (cnt == 0) return;
-  const int target = cnt / 2;
-  for (int i = tid; i < nL; i += 1024) {
-    const int v = sSad[i];
-    if (v < 0) continue;
-    int rank = 0;
-    for (int j = 0; j < nL; j++) {
-      const int u = sSad[j];
-      rank += (u >= 0) && (u < v || (u == v && j < i));
+  const int target = cnt / 2;   // vDistIdx[vDistIdx.size()/2]
+  if (tid < 32) {
+    // 8 bins per lane, find the bin holding rank `target`
+    int c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { c[k] = sHist[tid * 8 + k]; sum += c[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (tid >= o) incl += t; }
+    int before = incl - sum;
+    if (target >= before && target < incl) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (target >= before && target < before + c[k]) { sBin = tid * 8 + k; sBefore = before; }
+        before += c[k];
+      }
     }
-    if (rank == target) sMedian = v;
+  }
+  __syncthreads();
+  const int bin = sBin, rem = target - sBefore;
+  if (tid < 128) sHist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+    const int v = __ldcg(&s.sad[i]);
+    if (v >= 0 && (v >> 7) == bin) atomicAdd(&sHist[v & 127], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, lo = 0;
+    for (int k = 0; k < 128; k++) { if (rem >= acc && rem < acc + sHist[k]) { lo = k; break; } acc += sHist[k]; }
+    sMedian = (bin << 7) | lo;
   }
   __syncthreads();
   const float thDist = __fmul_rn(1.5f * 1.4f, (float)sMedian);
-  for (int i = tid; i < nL; i += 1024) {
-    const int v = sSad[i];
+  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+    const int v = __ldcg(&s.sad[i]);
     if (v >= 0 && !((float)v < thDist)) { s.uRight[i] = -1.0f; s.depth[i] = -1.0f; }
   }
 }
@@ -336,9 +373,6 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_fisheye_match(const __grid_co
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
                             cudaStream_t st) {
   k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, 0, st>>>(p, b, s, mbf, mb);
-}
-void ft_launch_stereo_outliers(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, cudaStream_t st) {
-  k_stereo_outliers<<<1, 1024, sizeof(int) * p.maxKp, st>>>(p, b, s);
 }
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st) {

@@ -146,6 +146,11 @@ ft_status ft_debug_level_dims(ft_context* ctx, int level, int* w, int* h);
 ft_status ft_debug_level_image(ft_context* ctx, int eye, int level, int blurred, uint8_t* out /* w*h tight */);
 /* pre-octree FAST candidates of one level in canonical order: xyr[n][3], returns count in *n */
 ft_status ft_debug_level_candidates(ft_context* ctx, int eye, int level, int cap, float* xyr, int* n);
+/* the device introsort used by the octree, on its own: sorts n <= 4096 words by their high 32 bits exactly as
+ * libstdc++ std::sort would arrange them (test hook) */
+int ft_debug_sort(unsigned long long* keys_inout, int n);
+/* per-level FAST candidate and kept-keypoint counts of one eye (arrays of nlevels) */
+ft_status ft_debug_level_counts(ft_context* ctx, int eye, int* cand, int* kp);
 /* frustum scratch of the last ft_search_local_points: track_i[M][4] = inView,inViewR,level,levelR;
  * track_f[M][9] = projX,projY,projXR,depth,viewCos,projXR_r,projYR_r,depthR,viewCosR */
 ft_status ft_debug_track(ft_context* ctx, int M, int* track_i, float* track_f);
@@ -170,7 +175,10 @@ ft_status ft_debug_stats(ft_context* ctx, long long* stats, int n);
 #define FT_STAGE_FRUSTUM 9
 #define FT_STAGE_GATHER 10
 #define FT_STAGE_RESOLVE 11
-#define FT_STAGE_COUNT 12
+#define FT_STAGE_FAST_L0 12   /* level 0 has its own branch of the launch graph */
+#define FT_STAGE_OCTREE_L0 13
+#define FT_STAGE_BLUR_L0 14
+#define FT_STAGE_COUNT 15
 ft_status ft_set_stage_timing(ft_context* ctx, int enable);
 ft_status ft_get_stage_times(ft_context* ctx, float* ms /* [FT_STAGE_COUNT], -1 = not run */, int n);
 
