@@ -44,7 +44,6 @@ struct ft_context {
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evPyr = nullptr, evJoin3 = nullptr;
-  uint8_t* dIn[2] = {nullptr, nullptr};     // device staging for the input images
   uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
   int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
   cudaGraphExec_t gExtract = nullptr, gStereo = nullptr;
@@ -291,7 +290,6 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
     CKF(dalloc(c, &E.kps, (size_t)P.maxKp));
     CKF(dalloc(c, &E.desc, (size_t)P.maxKp * 32));
     CKF(dalloc(c, &E.counts, (size_t)4));
-    CKF(dalloc(c, &c->dIn[e], (size_t)cfg->width * cfg->height));
     CKF(cudaMallocHost((void**)&c->hIn[e], (size_t)cfg->width * cfg->height));
   }
   CKF(dalloc(c, &c->B.status, (size_t)4));
@@ -329,10 +327,11 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &Q.active, (size_t)MM));
   CKF(dalloc(c, &Q.holder, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &Q.holderObs, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.minKey, (size_t)2 * 2 * P.maxKp));   // two buffers used alternately by k_resolve
+  CKF(dalloc(c, &Q.minKey, (size_t)3 * 2 * P.maxKp));   // three stamp buffers rotated by k_resolve
   CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &c->holderInit, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &c->holderObsInit, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.holderInit, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.holderObsInit, (size_t)2 * P.maxKp));
+  c->holderInit = Q.holderInit; c->holderObsInit = Q.holderObsInit;
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -388,17 +387,17 @@ extern "C" ft_status ft_get_scale_tables(ft_context* c, float* scale, float* inv
 
 // The per-frame extraction chain. Enqueued on c->stream with the blur forked onto c->stream2;
 // identical whether it is being captured into a graph or launched directly.
-static int enqueue_extract(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+static int enqueue_extract(ft_context* c) {
   // Launch topology (captured as-is into the CUDA graph): level 0 needs no resize, and its octree is the longest
   // single dependency of the frame, so it gets its own branch that starts right after the input copy.
-  //   s : copy0 -> resize 1..n-1 -> FAST 1..n-1 -> octree 1..n-1 ----+
-  //   s3: (after copy0) FAST 0 -> octree 0 --------------------------+-> orient+descriptors
-  //   s2: (after copy0) blur 0, (after resizes) blur 1..n-1 ---------+
+  // The input images have already been copied straight into the level-0 slabs of the two pyramids.
+  //   s : resize 1..n-1 -> FAST 1..n-1 -> octree 1..n-1 ----+
+  //   s3: FAST 0 -> octree 0 --------------------------------+-> orient+descriptors
+  //   s2: blur 0, (after resizes) blur 1..n-1 ---------------+
   const FtParams& P = c->P;
   const int nl = P.nlevels;
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
-  { StageScope t(c, FT_STAGE_COPY0, s); ft_launch_copy_level0(P, c->B, dL, stepL, dR, stepR, s); n++; }
   cudaEventRecord(c->evFork, s);
   cudaStreamWaitEvent(s3, c->evFork, 0);
   cudaStreamWaitEvent(s2, c->evFork, 0);
@@ -436,20 +435,19 @@ static int enqueue_stereo(ft_context* c) {
 }
 
 static ft_status run_extract(ft_context* c) {
-  // inputs are in c->dIn[0/1] with pitch == width
-  const int w = c->cfg.width;
+  // inputs are already in the level-0 slabs
   if (c->useGraph && !c->timing) {
     if (!c->gExtract) {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      c->nLaunchExtract = enqueue_extract(c, c->dIn[0], w, c->dIn[1], w);
+      c->nLaunchExtract = enqueue_extract(c);
       CK(cudaStreamEndCapture(c->stream, &g));
       CK(cudaGraphInstantiate(&c->gExtract, g, 0));
       cudaGraphDestroy(g);
     }
     CK(cudaGraphLaunch(c->gExtract, c->stream));
   } else {
-    c->nLaunchExtract = enqueue_extract(c, c->dIn[0], w, c->dIn[1], w);
+    c->nLaunchExtract = enqueue_extract(c);
     CK(cudaGetLastError());
   }
   c->extracted = true; c->stereoDone = false; c->countsValid = false;
@@ -468,12 +466,12 @@ extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int s
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned) {
-      CK(cudaMemcpy2DAsync(c->dIn[e], w, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(c->B.eye[e].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
     } else {
       // pageable memory: stage through the context's pinned buffer so the copy stays asynchronous
       CK(cudaStreamSynchronize(c->stream));   // previous frame may still be reading the staging buffer
       for (int y = 0; y < h; y++) memcpy(c->hIn[e] + (size_t)y * w, src[e] + (size_t)y * step[e], w);
-      CK(cudaMemcpyAsync(c->dIn[e], c->hIn[e], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(c->B.eye[e].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, c->hIn[e], w, w, h, cudaMemcpyHostToDevice, c->stream));
     }
   }
   return run_extract(c);
@@ -483,8 +481,8 @@ extern "C" ft_status ft_extract_stereo_device(ft_context* c, const uint8_t* dL, 
   if (!c || !dL || !dR) { set_err("ft_extract_stereo_device: null argument"); return FT_ERR_INVALID; }
   const int w = c->cfg.width, h = c->cfg.height;
   CK(cudaSetDevice(c->cfg.device_id));
-  CK(cudaMemcpy2DAsync(c->dIn[0], w, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
-  CK(cudaMemcpy2DAsync(c->dIn[1], w, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpy2DAsync(c->B.eye[0].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpy2DAsync(c->B.eye[1].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
   return run_extract(c);
 }
 
@@ -636,11 +634,12 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   const int M = c->residentM;
   c->lastM = M;
   c->nLaunchSearch = 0;
-  CK(cudaMemcpyAsync(Q.holder, c->holderInit, sizeof(int) * 2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(Q.holderObs, c->holderObsInit, (size_t)2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
-  ft_launch_sbp_reset(Q, s);
-  c->nLaunchSearch = 1;
-  if (M == 0) return FT_OK;
+  if (M == 0) {   // nothing to project: the holders come back unchanged
+    CK(cudaMemcpyAsync(Q.holder, c->holderInit, sizeof(int) * 2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(Q.holderObs, c->holderObsInit, (size_t)2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemsetAsync(Q.cursor, 0, 8 * sizeof(int), s));
+    return FT_OK;
+  }
   FtFrustumArgs fa;
   fa.cam1 = c->cam1; fa.cam2 = c->cam2; fa.pose = c->pose;
   fa.minX = c->minX; fa.maxX = c->maxX; fa.minY = c->minY; fa.maxY = c->maxY;
@@ -651,10 +650,9 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   ga.th = th; ga.bFactor = (th != 1.0f); ga.bFar = bFar; ga.thFar = thFar; ga.fisheye = c->fisheye;
   FtResolveArgs ra;
   ra.M = M; ra.nLeft = 0; ra.nSlots = 2 * c->P.maxKp; ra.fisheye = c->fisheye; ra.nnratio = nnratio;   // nSlots: smem sizing bound
-  { StageScope t(c, FT_STAGE_FRUSTUM, s); ft_launch_frustum(Q, fa, M, s); }
-  { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, ga, M, s); }
+  { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s); }
   { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
-  c->nLaunchSearch = 4 + (c->fisheye ? 1 : 0);
+  c->nLaunchSearch = 2 + (c->fisheye ? 1 : 0);
   CK(cudaGetLastError());
   return FT_OK;
 }
@@ -670,7 +668,7 @@ extern "C" ft_status ft_search_download(ft_context* c, int* holder, uint8_t* hol
   if (holder && N) CK(cudaMemcpyAsync(holder, Q.holder, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
   if (holderObs && N) CK(cudaMemcpyAsync(holderObs, Q.holderObs, (size_t)N, cudaMemcpyDeviceToHost, s));
   if (best_idx && c->lastM) CK(cudaMemcpyAsync(best_idx, Q.sel, sizeof(int) * 2 * c->lastM, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->hCounts + 8, Q.cursor, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->hCounts + 8, Q.cursor, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (nmatches) *nmatches = c->hCounts[9];
@@ -809,11 +807,11 @@ extern "C" ft_status ft_debug_stats(ft_context* c, long long* stats, int n) {
   }
   unsigned long long st[8];
   CK(cudaMemcpy(st, c->S.stats, sizeof(st), cudaMemcpyDeviceToHost));
-  int cur[4];
+  int cur[8];
   CK(cudaMemcpy(cur, c->Q.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; i++) stats[i] = 0;
   for (int l = 0; l < c->P.nlevels; l++) { stats[0] += cand[0][l]; stats[1] += cand[1][l]; stats[2] += kp[0][l]; stats[3] += kp[1][l]; }
-  stats[4] = (long long)st[0]; stats[5] = (long long)st[1]; stats[6] = cur[0]; stats[7] = cur[2];
+  stats[4] = (long long)st[0]; stats[5] = (long long)st[1]; stats[6] = cur[7]; stats[7] = cur[2];
   return FT_OK;
 }
 

@@ -139,10 +139,13 @@ struct FtSbpBuffers {
   int* listLen;            // [M][2]
   uint32_t* pool;          // candidate entries idx:16 | dist:9 | octave:4
   int poolCap;
-  int* cursor;             // [0] pool cursor, [1] nmatches, [2] rounds, [3] non-blocking searched map points, [4] active count
+  int* cursor;             // [0] pool cursor, [1] nmatches, [2] rounds, [3] non-blocking searched map points, [4] active count,
+                           // [5..6..7->5,6 + 7] round flags / pool usage of the last search
   int* active;             // [M] map points with a non-empty candidate list (order irrelevant)
   int* sel;                // [M][2] selected keypoint per branch, -1 none
-  int* holder;             // [2*maxKp] in/out
+  int* holderInit;         // [2*maxKp] F.mvpMapPoints on entry (indices), uploaded by the caller
+  uint8_t* holderObsInit;  // [2*maxKp]
+  int* holder;             // [2*maxKp] result
   uint8_t* holderObs;      // [2*maxKp]
   int* minKey;             // [2*maxKp]
   int* lastKey;            // [2*maxKp]

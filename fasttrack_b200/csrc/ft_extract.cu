@@ -50,26 +50,6 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams
   *reinterpret_cast<uint32_t*>(dst + (size_t)dy * L.pitch + dx0) = out;
 }
 
-// Level 0: copy the caller's image (arbitrary pitch) into the slab.
-__global__ void __launch_bounds__(256) k_copy_level0(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
-                                                     const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
-  const FtLevel& L = p.lv[0];
-  const int eye = blockIdx.z;
-  const uint8_t* src = eye ? imgR : imgL;
-  const int step = eye ? stepR : stepL;
-  const int x = (blockIdx.x * 64 + threadIdx.x) * 4;
-  const int y = blockIdx.y * 4 + threadIdx.y;
-  if (x >= L.w || y >= L.h) return;
-  const uint8_t* s = src + (size_t)y * step + x;
-  uint32_t v = 0;
-  if (x + 3 < L.w && ((reinterpret_cast<uintptr_t>(s) & 3) == 0)) {
-    v = *reinterpret_cast<const uint32_t*>(s);
-  } else {
-    for (int k = 0; k < 4 && x + k < L.w; k++) v |= (uint32_t)s[k] << (8 * k);
-  }
-  *reinterpret_cast<uint32_t*>(b.eye[eye].pyr + L.offset + (size_t)y * L.pitch + x) = v;
-}
-
 // ------------------------------------------------------------------------------------
 // Gaussian blur, all levels of both eyes in one launch. Tile = 64 x 32 outputs per CTA.
 // ------------------------------------------------------------------------------------
@@ -129,7 +109,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FtParams p
 }
 
 // ------------------------------------------------------------------------------------
-// FAST-9/16 per cell. One CTA (128 threads) per cell of one eye.
+// FAST-9/16 per cell. One CTA (FAST_THREADS threads) per cell of one eye.
 // score(p) = max over the 16 arcs of 9 contiguous ring pixels of min(+-diff) - 1; corner(th) <=> score >= th.
 // The cell first tries iniThFAST; when no pixel survives NMS it falls back to minThFAST
 // (ORBextractor.cc:1157-1177). NMS only sees scores inside the cell's interior, as cv::FAST on a ROI does.
@@ -160,10 +140,11 @@ __device__ __forceinline__ int ft_fast_score(const uint8_t* c, int stride) {
   return max(pos, neg) - 1;
 }
 
-__global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+#define FAST_THREADS 256
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                     int levelBegin, int levelEnd) {
   extern __shared__ uint8_t smem[];
-  __shared__ int sWarp[4];
+  __shared__ int sWarp[FAST_THREADS / 32];
   __shared__ int sAny;
   const int eye = blockIdx.y;
   const int cell = blockIdx.x + p.lv[levelBegin].cellBase;
@@ -190,14 +171,14 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtPa
   uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // [ih][iw] score (0 below minTh), then NMS survivors
   uint8_t* sMx = sSc + ((iw * ih + 15) & ~15);
   const uint8_t* src = E.pyr + L.offset + (size_t)iniY * L.pitch + iniX;
-  for (int i = tid; i < rh * rw; i += 128) {
+  for (int i = tid; i < rh * rw; i += FAST_THREADS) {
     const int y = i / rw, x = i - y * rw;
     sImg[y * rwPad + x] = src[(size_t)y * L.pitch + x];
   }
   if (tid == 0) sAny = 0;
   __syncthreads();
   const int total = iw * ih;
-  for (int i = tid; i < total; i += 128) {
+  for (int i = tid; i < total; i += FAST_THREADS) {
     const int y = i / iw, x = i - y * iw;
     const uint8_t* c = &sImg[(y + 3) * rwPad + (x + 3)];
     // quick reject at minTh: every 9-arc holds one pixel of each opposite ring pair
@@ -215,7 +196,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtPa
   __syncthreads();
   // 3x3 strict-maximum NMS inside the interior
   bool any20 = false;
-  for (int i = tid; i < total; i += 128) {
+  for (int i = tid; i < total; i += FAST_THREADS) {
     const int y = i / iw, x = i - y * iw;
     const int s = sSc[i];
     int keep = 0;
@@ -243,7 +224,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtPa
   __syncthreads();
   const int th = sAny ? p.iniTh : p.minTh;
   // ordered compaction: thread t owns the contiguous pixel range [t*seg, (t+1)*seg) in row-major order
-  const int seg = (total + 127) / 128;
+  const int seg = (total + FAST_THREADS - 1) / FAST_THREADS;
   const int beg = min(tid * seg, total), end = min(beg + seg, total);
   int cnt = 0;
   for (int i = beg; i < end; i++) cnt += sMx[i] >= th && sMx[i] > 0;
@@ -258,7 +239,8 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ FtPa
   __syncthreads();
   int base = 0;
   for (int w = 0; w < (tid >> 5); w++) base += sWarp[w];
-  const int totalKp = sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
+  int totalKp = 0;
+  for (int w = 0; w < FAST_THREADS / 32; w++) totalKp += sWarp[w];
   int pos = base + incl - cnt;
   uint32_t* out = E.cellKp + L.cellKpBase + (size_t)(cell - L.cellBase) * L.cellCap;
   for (int i = beg; i < end; i++) {
@@ -883,11 +865,6 @@ cudaError_t ft_launch_extract_setup(const FtParams& p) {
   return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_fast_smem_bytes(p));
 }
 
-void ft_launch_copy_level0(const FtParams& p, const FtBuffers& b, const uint8_t* imgL, int stepL, const uint8_t* imgR,
-                           int stepR, cudaStream_t st) {
-  dim3 blk(64, 4), grd((p.lv[0].w + 255) / 256, (p.lv[0].h + 3) / 4, 2);
-  k_copy_level0<<<grd, blk, 0, st>>>(p, b, imgL, stepL, imgR, stepR);
-}
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
   dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, 2);
   k_resize<<<grd, blk, 0, st>>>(p, b, level);
@@ -898,7 +875,7 @@ void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaS
 }
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   const int cells = (l1 < p.nlevels ? p.lv[l1].cellBase : p.totalCells) - p.lv[l0].cellBase;
-  k_fast_cells<<<dim3(cells, 2), 128, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
+  k_fast_cells<<<dim3(cells, 2), FAST_THREADS, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
 }
 void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   size_t mx = 0;

@@ -5,8 +5,6 @@
 
 cudaError_t ft_launch_extract_setup(const FtParams& p);
 cudaError_t ft_launch_sbp_setup(const FtParams& p);
-void ft_launch_copy_level0(const FtParams& p, const FtBuffers& b, const uint8_t* imgL, int stepL, const uint8_t* imgR,
-                           int stepR, cudaStream_t st);
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st);
 void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);
@@ -18,9 +16,7 @@ void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuff
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
                     float gridWInv, float gridHInv, cudaStream_t st);
-void ft_launch_sbp_reset(const FtSbpBuffers& s, cudaStream_t st);
-void ft_launch_frustum(const FtSbpBuffers& s, const FtFrustumArgs& fa, int M, cudaStream_t st);
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
-                      const FtSbpBuffers& s, const FtGatherArgs& ga, int M, cudaStream_t st);
+                      const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st);
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st);

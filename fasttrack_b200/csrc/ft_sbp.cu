@@ -150,68 +150,68 @@ __device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const 
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_frustum(const __grid_constant__ FtSbpBuffers s, const __grid_constant__ FtFrustumArgs a,
-                                                 int M) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= M) return;
-  int inView = 0, inViewR = 0, level = -1, levelR = -1;
-  float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (!(s.flags[i] & 1)) {
-    const float P[3] = {s.pos[3 * i], s.pos[3 * i + 1], s.pos[3 * i + 2]};
-    const float Pn[3] = {s.normal[3 * i], s.normal[3 * i + 1], s.normal[3 * i + 2]};
-    const float mn = s.minmax[2 * i], mx = s.minmax[2 * i + 1];
-    if (!a.fisheye) {
-      float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
-      const bool ok = ft_frustum_checks(a, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
-      f[0] = u; f[1] = v;
-      if (ok) { inView = 1; f[2] = xr; f[3] = d; f[4] = vc; level = lv; }
-    } else {
-      float u = 0, v = 0, xr = 0, d = 0, vc = 0; int lv = -1;
-      if (ft_frustum_checks(a, P, Pn, mn, mx, false, false, u, v, xr, d, vc, lv)) {
-        inView = 1; f[0] = u; f[1] = v; f[3] = d; f[4] = vc; level = lv;
-      }
-      if (ft_frustum_checks(a, P, Pn, mn, mx, true, false, u, v, xr, d, vc, lv)) {
-        inViewR = 1; f[5] = u; f[6] = v; f[7] = d; f[8] = vc; levelR = lv;
-      }
-    }
-  }
-  s.trI[4 * i] = inView; s.trI[4 * i + 1] = inViewR; s.trI[4 * i + 2] = level; s.trI[4 * i + 3] = levelR;
-#pragma unroll
-  for (int k = 0; k < 9; k++) s.trF[9 * i + k] = f[k];
-}
-
-// ---- candidate gathering ------------------------------------------------------------------
-
+// ---- frustum + candidate gathering, one warp per map point ---------------------------------------
+// All lanes evaluate the (cheap) frustum test redundantly from broadcast loads, so the scratch values never make
+// a round trip through memory; lane 0 stores them for the caller. In-view map points then walk their grid window
+// once: passing keypoints are collected in traversal order into a small per-warp shared-memory buffer
+// (GA_BUF entries; longer lists take a second walk straight into the pool), and the lanes finally split the
+// candidates evenly for the Hamming distances.
 #define GA_WARPS 8
+#define GA_BUF 96
 __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                           const __grid_constant__ FtGridBuffers g,
                                                           const __grid_constant__ FtStereoBuffers st,
                                                           const __grid_constant__ FtSbpBuffers s,
+                                                          const __grid_constant__ FtFrustumArgs fa,
                                                           const __grid_constant__ FtGatherArgs a, int M) {
-  const int lane = threadIdx.x & 31;
-  const int mp = blockIdx.x * GA_WARPS + (threadIdx.x >> 5);
+  __shared__ unsigned short sBuf[GA_WARPS][GA_BUF];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mp = blockIdx.x * GA_WARPS + warp;
+  // cursors [0] pool, [3] non-blocking count, [4] active count are accumulated here; they are zero on entry
+  // (cleared at allocation and by the resolve kernel of the previous search)
   if (mp >= M) return;
   const int flags = s.flags[mp];
-  const int inView = s.trI[4 * mp], inViewR = s.trI[4 * mp + 1];
-  bool searched = (inView || inViewR) && !(flags & 1);
-  if (a.bFar && s.trF[9 * mp + 3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
-  if (lane == 0) {
-    s.sel[2 * mp] = -1; s.sel[2 * mp + 1] = -1;
-    if (searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
+  int inView = 0, inViewR = 0, level = -1, levelR = -1;
+  float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (!(flags & 1)) {
+    const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
+    const float Pn[3] = {s.normal[3 * mp], s.normal[3 * mp + 1], s.normal[3 * mp + 2]};
+    const float mn = s.minmax[2 * mp], mx = s.minmax[2 * mp + 1];
+    if (!fa.fisheye) {
+      float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
+      const bool ok = ft_frustum_checks(fa, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
+      f[0] = u; f[1] = v;
+      if (ok) { inView = 1; f[2] = xr; f[3] = d; f[4] = vc; level = lv; }
+    } else {
+      float u = 0, v = 0, xr = 0, d = 0, vc = 0; int lv = -1;
+      if (ft_frustum_checks(fa, P, Pn, mn, mx, false, false, u, v, xr, d, vc, lv)) {
+        inView = 1; f[0] = u; f[1] = v; f[3] = d; f[4] = vc; level = lv;
+      }
+      if (ft_frustum_checks(fa, P, Pn, mn, mx, true, false, u, v, xr, d, vc, lv)) {
+        inViewR = 1; f[5] = u; f[6] = v; f[7] = d; f[8] = vc; levelR = lv;
+      }
+    }
   }
-  const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
-  const uint4 md0 = md[0], md1 = md[1];
-  const int nBranches = a.fisheye ? 2 : 1;
-  int anyLen = 0;
-  if (lane == 0 && !a.fisheye) { s.listOff[2 * mp + 1] = 0; s.listLen[2 * mp + 1] = 0; }
-  for (int br = 0; br < nBranches; br++) {
-    int len = 0, off = 0;
-    const bool active = searched && (br == 0 ? inView : inViewR) && (br == 0 || s.trI[4 * mp + 3] != -1);
-    if (active) {
-      const int lvl = s.trI[4 * mp + 2 + br];
-      const float x = br == 0 ? s.trF[9 * mp] : s.trF[9 * mp + 5];
-      const float y = br == 0 ? s.trF[9 * mp + 1] : s.trF[9 * mp + 6];
-      const float viewCos = br == 0 ? s.trF[9 * mp + 4] : s.trF[9 * mp + 8];
+  if (lane < 9) s.trF[9 * mp + lane] = f[lane];
+  if (lane == 0) {
+    *reinterpret_cast<int4*>(s.trI + 4 * mp) = make_int4(inView, inViewR, level, levelR);
+    *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(-1, -1);
+  }
+  bool searched = (inView || inViewR) && !(flags & 1);
+  if (a.bFar && f[3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
+  if (lane == 0 && searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
+  int2 lens = make_int2(0, 0), offs = make_int2(0, 0);
+  if (searched) {
+    const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
+    const uint4 md0 = md[0], md1 = md[1];
+    const int nBranches = a.fisheye ? 2 : 1;
+    for (int br = 0; br < nBranches; br++) {
+      const bool active = (br == 0 ? inView : inViewR) && (br == 0 || levelR != -1);
+      if (!active) continue;
+      const int lvl = br == 0 ? level : levelR;
+      const float x = br == 0 ? f[0] : f[5];
+      const float y = br == 0 ? f[1] : f[6];
+      const float viewCos = br == 0 ? f[4] : f[8];
       float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos (ORBmatcher.cc:314-320)
       if (br == 0 && a.bFactor) r = __fmul_rn(r, a.th);
       const float rr = __fmul_rn(r, p.scale[lvl]);
@@ -221,84 +221,86 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
       const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
       const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
       const int cy1 = min(FT_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
-      if (cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0) {
-        const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
-        const int* cellStart = g.cellStart + br * (GRID_CELLS + 1);
-        const int* cellIdx = g.cellIdx + br * p.maxKp;
-        const FtEye& E = b.eye[br];
-        const float projXR = s.trF[9 * mp + 2];
-        auto passes = [&](int idx) -> bool {
-          const ft_keypoint kp = E.kps[idx];
-          if (kp.octave < minLevel) return false;
-          if (maxLevel >= 0 && kp.octave > maxLevel) return false;
-          const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
-          if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
-          if (!a.fisheye) {
-            const float ur = st.uRight[idx];
-            if (ur > 0) {
-              const float er = fabsf(__fsub_rn(projXR, ur));
-              if (er > rr) return false;                       // stereo consistency (ORBmatcher.cc:105-110)
-            }
-          }
-          return true;
-        };
-        // pass 1: count
-        int cnt = 0;
-        for (int c = lane; c < nc; c += 32) {
-          const int cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
-          for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) cnt += passes(cellIdx[k]);
-        }
-        int total = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-        if (total > 0) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s.cursor[0], total);
-          base = __shfl_sync(0xFFFFFFFFu, base, 0);
-          if (base + total > s.poolCap) {
-            if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
-          } else {
-            // pass 2: ordered fill (ix outer, iy inner, cell insertion order)
-            int run = 0;
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-              const int c = c0 + lane;
-              int mine = 0, cell = 0;
-              if (c < nc) {
-                cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
-                for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) mine += passes(cellIdx[k]);
-              }
-              int incl = mine;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-              }
-              int w = base + run + incl - mine;
-              if (c < nc && mine) {
-                for (int k = cellStart[cell]; k < cellStart[cell + 1]; k++) {
-                  const int idx = cellIdx[k];
-                  if (passes(idx)) s.pool[w++] = (uint32_t)idx;
-                }
-              }
-              run += __shfl_sync(0xFFFFFFFFu, incl, 31);
-            }
-            __syncwarp();
-            // pass 3: Hamming distance + octave per candidate
-            for (int k = lane; k < total; k += 32) {
-              const int idx = (int)s.pool[base + k];
-              const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
-              const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
-              s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)E.kps[idx].octave << 25);
-            }
-            len = total; off = base;
+      if (!(cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0)) continue;
+      const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
+      const int* cellStart = g.cellStart + br * (GRID_CELLS + 1);
+      const int* cellIdx = g.cellIdx + br * p.maxKp;
+      const FtEye& E = b.eye[br];
+      const float projXR = f[2];
+      auto passes = [&](int idx) -> bool {
+        const ft_keypoint kp = E.kps[idx];
+        if (kp.octave < minLevel) return false;
+        if (maxLevel >= 0 && kp.octave > maxLevel) return false;
+        const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+        if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
+        if (!a.fisheye) {
+          const float ur = st.uRight[idx];
+          if (ur > 0) {
+            const float er = fabsf(__fsub_rn(projXR, ur));
+            if (er > rr) return false;                       // stereo consistency (ORBmatcher.cc:105-110)
           }
         }
+        return true;
+      };
+      // walk the window in traversal order (ix outer, iy inner, cell insertion order); dst == nullptr: into sBuf
+      auto walk = [&](uint32_t* dst) -> int {
+        int run = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int c = c0 + lane;
+          int mine = 0, k0 = 0, k1 = 0;
+          if (c < nc) {
+            const int cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
+            k0 = cellStart[cell]; k1 = cellStart[cell + 1];
+            for (int k = k0; k < k1; k++) mine += passes(cellIdx[k]);
+          }
+          int incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int w = run + incl - mine;
+          if (mine) {
+            for (int k = k0; k < k1; k++) {
+              const int idx = cellIdx[k];
+              if (passes(idx)) {
+                if (dst) dst[w] = (uint32_t)idx;
+                else if (w < GA_BUF) sBuf[warp][w] = (unsigned short)idx;
+                w++;
+              }
+            }
+          }
+          run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        return run;
+      };
+      const int total = walk(nullptr);
+      if (total == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s.cursor[0], total);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base + total > s.poolCap) {
+        if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
+        continue;
       }
+      if (total > GA_BUF) walk(s.pool + base);
+      __syncwarp();
+      // Hamming distance + octave per candidate
+      for (int k = lane; k < total; k += 32) {
+        const int idx = total > GA_BUF ? (int)s.pool[base + k] : (int)sBuf[warp][k];
+        const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
+        const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
+        s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)E.kps[idx].octave << 25);
+      }
+      __syncwarp();
+      if (br == 0) { lens.x = total; offs.x = base; } else { lens.y = total; offs.y = base; }
     }
-    if (lane == 0) { s.listOff[2 * mp + br] = off; s.listLen[2 * mp + br] = len; }
-    anyLen |= len;
   }
-  if (lane == 0 && anyLen) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
+  if (lane == 0) {
+    *reinterpret_cast<int2*>(s.listOff + 2 * mp) = offs;
+    *reinterpret_cast<int2*>(s.listLen + 2 * mp) = lens;
+    if (lens.x | lens.y) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
+  }
 }
 
 // ---- claim resolution ---------------------------------------------------------------------
@@ -333,84 +335,142 @@ __device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-__global__ void __launch_bounds__(1024) k_resolve(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
-                                                  const __grid_constant__ FtStereoBuffers st,
-                                                  const __grid_constant__ FtResolveArgs a0) {
+#define RS_THREADS 512
+#define RS_LCAP 12   // candidate entries per thread cached in shared memory (longer lists continue from L2)
+
+// best / second-best scan over a list whose first RS_LCAP entries sit in shared memory (column-major, one column
+// per thread) and the rest in global memory
+template <typename BlockedFn>
+__device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32_t* gList, int len, float nnratio,
+                                              BlockedFn blocked, bool* cont) {
+  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+  for (int k = 0; k < len; k++) {
+    const uint32_t e = k < RS_LCAP ? sEnt[k * RS_THREADS] : __ldg(gList + k);
+    const int idx = (int)(e & 0xFFFFu);
+    if (blocked(idx)) continue;
+    const int dist = (int)((e >> 16) & 0x1FFu), oct = (int)(e >> 25);
+    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+  }
+  *cont = false;
+  if (bestDist <= 100) {
+    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
+    return bestIdx;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
+                                                           const __grid_constant__ FtStereoBuffers st,
+                                                           const __grid_constant__ FtResolveArgs a0) {
   extern __shared__ int sMem[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int nThreads = gridDim.x * 1024;
-  const int gtid = blockIdx.x * 1024 + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int nThreads = gridDim.x * RS_THREADS;
+  const int gtid = blockIdx.x * RS_THREADS + tid;
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
-  if (a.fisheye && s.cursor[3] > 0) return;   // k_resolve_seq handles this frame (uniform over the cluster)
   const int nS = a.nSlots;
   const int nA = s.cursor[4];
-  const int stride = a0.nSlots;               // a0.nSlots = capacity bound (2*maxKp): offset of the second buffer
-  uint8_t* pre = reinterpret_cast<uint8_t*>(sMem);
-  for (int i = threadIdx.x; i < nS; i += 1024) pre[i] = (s.holder[i] != -1 && s.holderObs[i]) ? 1 : 0;
-  for (int i = gtid; i < nS; i += nThreads) { s.minKey[i] = 0x7FFFFFFF; s.minKey[stride + i] = 0x7FFFFFFF; }
-  if (gtid < 2) s.cursor[5 + gtid] = 0;
+  const bool seqMode = a.fisheye && s.cursor[3] > 0;   // k_resolve_seq resolves this frame (uniform over the cluster)
+  const int stride = a0.nSlots;               // a0.nSlots = capacity bound (2*maxKp): distance between stamp buffers
+  // shared memory: mkS[cap] int (this round's stamps), pre[cap] u8, entL / entR [RS_LCAP][RS_THREADS] u32
+  int* mkS = sMem;
+  uint8_t* pre = reinterpret_cast<uint8_t*>(sMem + a0.nSlots);
+  uint32_t* entL = reinterpret_cast<uint32_t*>(sMem + a0.nSlots + (a0.nSlots + 3) / 4);
+  uint32_t* entR = entL + RS_LCAP * RS_THREADS;
+  // working holders start from the caller's (F.mvpMapPoints on entry)
+  for (int i = gtid; i < nS; i += nThreads) { s.holder[i] = s.holderInit[i]; s.holderObs[i] = s.holderObsInit[i]; }
+  if (seqMode) return;
+  for (int i = tid; i < nS; i += RS_THREADS) pre[i] = (s.holderInit[i] != -1 && s.holderObsInit[i]) ? 1 : 0;
+  for (int i = gtid; i < nS; i += nThreads) {
+    s.minKey[i] = 0x7FFFFFFF; s.minKey[stride + i] = 0x7FFFFFFF; s.minKey[2 * stride + i] = 0x7FFFFFFF;
+    s.lastKey[i] = -1;
+  }
+  if (gtid < 3) s.cursor[5 + gtid] = 0;
+  if (gtid == 3) s.cursor[1] = 0;
+  // this thread's first map point: list heads cached in shared memory, decision kept in registers
+  int myMp = -1, myFlags = 0;
+  int2 myOff = make_int2(0, 0), myLen = make_int2(0, 0);
+  int selL = -1, selR = -1;
+  if (gtid < nA) {
+    myMp = __ldg(&s.active[gtid]);
+    myFlags = __ldg(&s.flags[myMp]);
+    myOff = __ldg(reinterpret_cast<const int2*>(s.listOff) + myMp);
+    myLen = __ldg(reinterpret_cast<const int2*>(s.listLen) + myMp);
+#pragma unroll
+    for (int k = 0; k < RS_LCAP; k++) {
+      if (k < myLen.x) entL[k * RS_THREADS + tid] = __ldg(s.pool + myOff.x + k);
+      if (k < myLen.y) entR[k * RS_THREADS + tid] = __ldg(s.pool + myOff.y + k);
+    }
+  }
   cluster.sync();
+  // Round r reads the stamps of buffer r%3 (all empty in round 0), scatters the decisions it makes into buffer
+  // (r+1)%3 and clears buffer (r+2)%3: one cluster barrier per round.
   int rounds = 0;
   for (;;) {
-    int* mk = s.minKey + (rounds & 1) * stride;
-    int* mkNext = s.minKey + ((rounds + 1) & 1) * stride;
-    for (int k = gtid; k < nA; k += nThreads) {
-      const int mp = __ldg(&s.active[k]);
-      if (!(__ldg(&s.flags[mp]) & 2)) continue;   // writes of map points without observations never block
-      const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
-      if (sl >= 0) {
-        atomicMin(&mk[sl], 2 * mp);
-        if (a.fisheye && st.l2r[sl] != -1) atomicMin(&mk[st.l2r[sl] + a.nLeft], 2 * mp);
-      }
-      if (sr >= 0) {
-        atomicMin(&mk[sr + a.nLeft], 2 * mp + 1);
-        if (st.r2l[sr] != -1) atomicMin(&mk[st.r2l[sr]], 2 * mp + 1);
-      }
-    }
-    cluster.sync();
+    int* mk = s.minKey + (rounds % 3) * stride;
+    int* mkNext = s.minKey + ((rounds + 1) % 3) * stride;
+    int* mkClear = s.minKey + ((rounds + 2) % 3) * stride;
+    for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = __ldcg(&mk[i]);
+    __syncthreads();
+    for (int i = gtid; i < nS; i += nThreads) mkClear[i] = 0x7FFFFFFF;
+    if (gtid == 0) s.cursor[5 + ((rounds + 2) % 3)] = 0;
     int changed = 0;
     for (int k = gtid; k < nA; k += nThreads) {
-      const int mp = __ldg(&s.active[k]);
-      const int2 off = __ldg(reinterpret_cast<const int2*>(s.listOff) + mp);
-      const int2 len = __ldg(reinterpret_cast<const int2*>(s.listLen) + mp);
-      const bool blocking = (__ldg(&s.flags[mp]) & 2) != 0;
+      const bool mine = (k == gtid);
+      const int mp = mine ? myMp : __ldg(&s.active[k]);
+      const int2 off = mine ? myOff : __ldg(reinterpret_cast<const int2*>(s.listOff) + mp);
+      const int2 len = mine ? myLen : __ldg(reinterpret_cast<const int2*>(s.listLen) + mp);
+      const bool blocking = ((mine ? myFlags : __ldg(&s.flags[mp])) & 2) != 0;
       int newL = -1, newR = -1;
       bool cont = false;
       const int t = 2 * mp;
       if (len.x > 0) {
-        const uint32_t* list = s.pool + off.x;
-        newL = ft_scan_list(list, len.x, a.nnratio, [&](int idx) { return pre[idx] || __ldcg(&mk[idx]) < t; }, &cont);
+        auto blk = [&](int idx) { return pre[idx] || mkS[idx] < t; };
+        newL = mine ? ft_scan_cached(entL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont)
+                    : ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont);
       }
       if (len.y > 0 && !cont) {
         // own left writes (stamp 2mp) are handled explicitly, older stamps through the table
         const int ownMirror = (blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
         bool contR = false;
-        const uint32_t* list = s.pool + off.y;
-        newR = ft_scan_list(list, len.y, a.nnratio,
-                            [&](int idx) { const int slot = idx + a.nLeft; return pre[slot] || __ldcg(&mk[slot]) < t || idx == ownMirror; },
-                            &contR);
+        auto blk = [&](int idx) { const int slot = idx + a.nLeft; return pre[slot] || mkS[slot] < t || idx == ownMirror; };
+        newR = mine ? ft_scan_cached(entR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR)
+                    : ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR);
       }
-      const int2 old = *reinterpret_cast<const int2*>(s.sel + 2 * mp);
-      if (newL != old.x || newR != old.y) { changed = 1; *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(newL, newR); }
+      if (mine) {
+        if (newL != selL || newR != selR) { changed = 1; selL = newL; selR = newR; }
+      } else {
+        const int2 old = make_int2(__ldcg(&s.sel[2 * mp]), __ldcg(&s.sel[2 * mp + 1]));
+        if (newL != old.x || newR != old.y) { changed = 1; *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(newL, newR); }
+      }
+      if (blocking) {   // stamps the next round reads (writes of map points without observations never block)
+        if (newL >= 0) {
+          atomicMin(&mkNext[newL], 2 * mp);
+          if (a.fisheye && st.l2r[newL] != -1) atomicMin(&mkNext[st.l2r[newL] + a.nLeft], 2 * mp);
+        }
+        if (newR >= 0) {
+          atomicMin(&mkNext[newR + a.nLeft], 2 * mp + 1);
+          if (st.r2l[newR] != -1) atomicMin(&mkNext[st.r2l[newR]], 2 * mp + 1);
+        }
+      }
     }
-    if (changed) s.cursor[5 + (rounds & 1)] = 1;
-    for (int i = gtid; i < nS; i += nThreads) mkNext[i] = 0x7FFFFFFF;
-    if (gtid == 0) s.cursor[5 + ((rounds + 1) & 1)] = 0;
+    if (changed) s.cursor[5 + (rounds % 3)] = 1;
     cluster.sync();
-    const int ch = __ldcg(&s.cursor[5 + (rounds & 1)]);
+    const int ch = __ldcg(&s.cursor[5 + (rounds % 3)]);
     rounds++;
     if (!ch) break;
     if (rounds > a.M + 2) { if (gtid == 0) atomicOr(b.status, FT_ST_RESOLVE_NOCONV); break; }
   }
   // final holders: the write with the highest stamp wins each slot; count matches (ORBmatcher.cc:142-155,207-222)
-  for (int i = gtid; i < nS; i += nThreads) s.lastKey[i] = -1;
-  cluster.sync();
   int nm = 0;
   for (int k = gtid; k < nA; k += nThreads) {
-    const int mp = __ldg(&s.active[k]);
-    const int sl = s.sel[2 * mp], sr = s.sel[2 * mp + 1];
+    const bool mine = (k == gtid);
+    const int mp = mine ? myMp : __ldg(&s.active[k]);
+    const int sl = mine ? selL : __ldcg(&s.sel[2 * mp]), sr = mine ? selR : __ldcg(&s.sel[2 * mp + 1]);
+    if (mine) *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(sl, sr);
     if (sl >= 0) {
       atomicMax(&s.lastKey[sl], 2 * mp); nm++;
       if (a.fisheye && st.l2r[sl] != -1) { atomicMax(&s.lastKey[st.l2r[sl] + a.nLeft], 2 * mp); nm++; }
@@ -426,7 +486,7 @@ __global__ void __launch_bounds__(1024) k_resolve(const __grid_constant__ FtBuff
     const int k = __ldcg(&s.lastKey[i]);
     if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
   }
-  if (gtid == 0) s.cursor[2] = rounds;
+  if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; }
 }
 
 // In-order execution by one thread (fisheye rigs with non-blocking map points only).
@@ -464,23 +524,20 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
       }
     }
   }
-  s.cursor[1] = nm; s.cursor[2] = 0;
-}
-
-__global__ void k_sbp_reset(const __grid_constant__ FtSbpBuffers s) {
-  if (threadIdx.x < 8) s.cursor[threadIdx.x] = 0;
+  s.cursor[1] = nm; s.cursor[2] = 0; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0;
 }
 
 // ---- host launchers -----------------------------------------------------------------------
 static int g_resolveCluster = 8;
+static size_t ft_resolve_smem(int slotCap) { return (size_t)slotCap * 4 + (size_t)((slotCap + 3) / 4) * 4 + 2 * RS_LCAP * RS_THREADS * 4 + 16; }
 cudaError_t ft_launch_sbp_setup(const FtParams& p) {
-  cudaError_t e = cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * p.maxKp + 16);
+  cudaError_t e = cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_resolve_smem(2 * p.maxKp));
   if (e != cudaSuccess) return e;
   // 16-CTA clusters are a non-portable size: opt in, and fall back to the portable 8 when the device cannot place one
   g_resolveCluster = 8;
   if (cudaFuncSetAttribute(k_resolve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(16); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 2 * p.maxKp + 16;
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(2 * p.maxKp);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -495,18 +552,14 @@ void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& 
                     float gridWInv, float gridHInv, cudaStream_t st) {
   k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv);
 }
-void ft_launch_sbp_reset(const FtSbpBuffers& s, cudaStream_t st) { k_sbp_reset<<<1, 32, 0, st>>>(s); }
-void ft_launch_frustum(const FtSbpBuffers& s, const FtFrustumArgs& fa, int M, cudaStream_t st) {
-  k_frustum<<<(M + 255) / 256, 256, 0, st>>>(s, fa, M);
-}
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
-                      const FtSbpBuffers& s, const FtGatherArgs& ga, int M, cudaStream_t st) {
-  k_gather<<<(M + GA_WARPS - 1) / GA_WARPS, GA_WARPS * 32, 0, st>>>(p, b, g, stb, s, ga, M);
+                      const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st) {
+  k_gather<<<(M + GA_WARPS - 1) / GA_WARPS, GA_WARPS * 32, 0, st>>>(p, b, g, stb, s, fa, ga, M);
 }
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = (size_t)ra.nSlots + 16; cfg.stream = st;
+  cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(ra.nSlots); cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = g_resolveCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -13,8 +13,14 @@
 #define ST_WARPS 8
 
 // per-warp body of k_stereo_match: one left keypoint
+struct FtRightKp {   // right keypoint as the row-band scan needs it (staged in shared memory once per CTA)
+  float x;
+  short minr, maxr;
+  int octave;
+};
+
 __device__ __forceinline__ void ft_stereo_one(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf,
-                                              float mb, int iL, int lane) {
+                                              float mb, int iL, int lane, const FtRightKp* sR) {
   const FtEye& EL = b.eye[0];
   const FtEye& ER = b.eye[1];
   const int nR = ER.counts[0];
@@ -30,15 +36,12 @@ __device__ __forceinline__ void ft_stereo_one(const FtParams& p, const FtBuffers
   if (maxU < 0) return;
   const uint4* dl = reinterpret_cast<const uint4*>(EL.desc + (size_t)iL * 32);
   const uint4 dl0 = dl[0], dl1 = dl[1];
-  // row band of a right keypoint: rows floor(y-r) .. ceil(y+r), r = 2*scale[octave] (:852-862);
   // the row table lists candidates in ascending iR and the scan keeps the first minimum (:897-917)
   unsigned best = (100u << 16) | 0xFFFFu;   // TH_HIGH = 100, strict <
   int tested = 0;
   for (int iR = lane; iR < nR; iR += 32) {
-    const ft_keypoint kpR = ER.kps[iR];
-    const float r = __fmul_rn(2.0f, p.scale[kpR.octave]);
-    const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
-    if (rowi < minr || rowi > maxr) continue;
+    const FtRightKp kpR = sR[iR];
+    if (rowi < kpR.minr || rowi > kpR.maxr) continue;
     if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
     if (kpR.x >= minU && kpR.x <= maxU) {
       const uint4* dr = reinterpret_cast<const uint4*>(ER.desc + (size_t)iR * 32);
@@ -126,12 +129,26 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
                                                                 const __grid_constant__ FtBuffers b,
                                                                 const __grid_constant__ FtStereoBuffers s, float mbf,
                                                                 float mb) {
+  extern __shared__ __align__(16) uint8_t sDyn[];
+  FtRightKp* sR = reinterpret_cast<FtRightKp*>(sDyn);
   __shared__ int sHist[256];
   __shared__ int sLast, sCount, sBin, sBefore, sMedian;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nL = b.eye[0].counts[0];
+  const int nL = b.eye[0].counts[0], nR = b.eye[1].counts[0];
   const int iL = blockIdx.x * ST_WARPS + (tid >> 5);
-  if (iL < nL) ft_stereo_one(p, b, s, mbf, mb, iL, lane);
+  if (blockIdx.x * ST_WARPS < nL) {
+    // row band of every right keypoint: rows floor(y-r) .. ceil(y+r), r = 2*scale[octave] (Frame.cc:852-862)
+    for (int i = tid; i < nR; i += ST_WARPS * 32) {
+      const ft_keypoint k = b.eye[1].kps[i];
+      const float r = __fmul_rn(2.0f, p.scale[k.octave]);
+      FtRightKp o;
+      o.x = k.x; o.octave = k.octave;
+      o.maxr = (short)(int)ceilf(__fadd_rn(k.y, r)); o.minr = (short)(int)floorf(__fsub_rn(k.y, r));
+      sR[i] = o;
+    }
+  }
+  __syncthreads();
+  if (iL < nL) ft_stereo_one(p, b, s, mbf, mb, iL, lane, sR);
   __syncthreads();
   if (tid == 0) {
     __threadfence();
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_fisheye_match(const __grid_co
 
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
                             cudaStream_t st) {
-  k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, 0, st>>>(p, b, s, mbf, mb);
+  k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, sizeof(FtRightKp) * p.maxKp, st>>>(p, b, s, mbf, mb);
 }
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st) {
