@@ -13,7 +13,7 @@ HEADERS = ["ft_device.cuh", "ft_camera.cuh", "ft_internal.h", "ft_sort.h",
            os.path.join("..", "..", "include", "ft_orb_pattern.inc")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # every float op on this path must round like the reference's scalar C++: no FMA contraction
-              "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("FT_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

@@ -290,6 +290,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
     CKF(dalloc(c, &E.kps, (size_t)P.maxKp));
     CKF(dalloc(c, &E.desc, (size_t)P.maxKp * 32));
     CKF(dalloc(c, &E.counts, (size_t)4));
+    CKF(dalloc(c, &E.octClock, (size_t)2 * FT_MAX_LEVELS * 64));
     CKF(cudaMallocHost((void**)&c->hIn[e], (size_t)cfg->width * cfg->height));
   }
   CKF(dalloc(c, &c->B.status, (size_t)4));
@@ -821,5 +822,13 @@ extern "C" ft_status ft_debug_level_counts(ft_context* c, int eye, int* cand, in
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(cand, c->B.eye[eye].lvlCandCount, sizeof(int) * c->P.nlevels, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(kp, c->B.eye[eye].lvlKpCount, sizeof(int) * c->P.nlevels, cudaMemcpyDeviceToHost));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_debug_oct_clock(ft_context* c, long long* out /* [2][FT_MAX_LEVELS][64] */) {
+  if (!c || !out) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out, c->B.eye[0].octClock, sizeof(long long) * 2 * FT_MAX_LEVELS * 64, cudaMemcpyDeviceToHost));
   return FT_OK;
 }

@@ -67,6 +67,7 @@ struct FtEye {
   ft_keypoint* kps;        // final keypoints [maxKp]
   uint8_t* desc;           // final descriptors [maxKp][32]
   int* counts;             // [0]=n, [1]=monoIndex
+  long long* octClock;     // debug: clock64 stamps of the octree phases (only with -DFT_OCT_CLOCK)
 };
 
 struct FtBuffers {

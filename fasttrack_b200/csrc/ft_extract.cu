@@ -6,6 +6,9 @@
 //   k_fast_cells    per-cell cv::FAST + fallback (:1131-1203)  one CTA per cell, smem tile, ordered compaction
 //   k_octree        DistributeOctTree            (:660-884)    one CTA per (eye, level), node list in smem
 //   k_orient_desc   IC_Angle + rBRIEF + tail     (:39-108, :1392-1492) one warp per keypoint
+#include <cstdio>
+#include <cstdlib>
+
 #include "ft_device.cuh"
 #include "ft_sort.h"
 
@@ -263,6 +266,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 // carries a 16-bit code (node slot * 4 + quadrant) that is remapped through a table.
 // ------------------------------------------------------------------------------------
 #define OCT_THREADS 512
+#ifdef FT_OCT_CLOCK
+#define OCT_TICK(slot) do { if (tid == 0 && E.octClock && (slot) < 64) E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + (slot)] = clock64(); } while (0)
+#else
+#define OCT_TICK(slot) do {} while (0)
+#endif
 #define OCT_SMEM_CANDS 16384   // candidates of one level held in shared memory (6 B each); larger levels use HBM scratch
 
 struct OctSmem {
@@ -303,6 +311,26 @@ __device__ void oct_scan3(int n, const int* a, const int* b3, const int* c3, int
   }
 }
 
+// Counter increments of the candidate loops. While a pass has at most OCT_PRIV counters (the first passes funnel
+// thousands of candidates into a handful of counters and same-address shared atomics serialise) every warp
+// counts into its own private copy; oct_count_flush folds the copies into the real counters.
+#define OCT_PRIV 64
+__device__ __forceinline__ void oct_count(int* counters, int* priv, bool usePriv, int key) {
+  if (usePriv) atomicAdd(&priv[(threadIdx.x >> 5) * OCT_PRIV + key], 1);
+  else atomicAdd(&counters[key], 1);
+}
+__device__ __forceinline__ void oct_priv_clear(int* priv) {
+  for (int i = threadIdx.x; i < (OCT_THREADS / 32) * OCT_PRIV; i += OCT_THREADS) priv[i] = 0;
+}
+__device__ __forceinline__ void oct_count_flush(int* counters, const int* priv, int nCounters) {
+  for (int k = threadIdx.x; k < nCounters; k += OCT_THREADS) {
+    int sum = 0;
+#pragma unroll
+    for (int w = 0; w < OCT_THREADS / 32; w++) sum += priv[w * OCT_PRIV + k];
+    counters[k] += sum;
+  }
+}
+
 __device__ __forceinline__ void oct_child_bounds(short4 bd, int q, short4& out) {
   // DivideNode (ORBextractor.cc:510-538): halfX = ceil((UR.x-UL.x)/2.f), halfY = ceil((BR.y-UL.y)/2.f)
   const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
@@ -320,6 +348,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   __shared__ int sN, sMode, sVecN, sP, sCellTot;
   __shared__ int sScan[OCT_THREADS / 32];
   __shared__ int sChildP, sGrowP, sVecP;
+  __shared__ int sPriv[(OCT_THREADS / 32) * OCT_PRIV];
   const int level = levelBegin + blockIdx.x;
   const int eye = blockIdx.y;
   const FtLevel& L = p.lv[level];
@@ -353,6 +382,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     codeS = (uint16_t*)q;
   }
 
+  OCT_TICK(0);
   // ---- flat canonical order (cell row-major, then row-major inside the cell) ----
   // exclusive scan of the per-cell counts, then every candidate finds its cell by binary search: the copy out of
   // the per-cell slabs is one coalesced pass instead of a per-cell serial loop.
@@ -387,6 +417,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     __syncthreads();
   }
   const int C = sCellTot;
+  OCT_TICK(1);
   uint32_t* outKp = E.lvlKp + L.lvlKpBase;
   if (C == 0) {
     if (tid == 0) E.lvlKpCount[level] = 0;
@@ -396,14 +427,32 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   const bool inSmem = C <= OCT_SMEM_CANDS;
   uint32_t* cand = inSmem ? candS : candG;
   uint16_t* code = inSmem ? codeS : (E.candNode + L.candBase);
-  for (int c = tid; c < C; c += OCT_THREADS) {
-    int lo = 0, hi = nCells;                      // largest cell with cellOff[cell] <= c
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cellOff[mid] <= c) lo = mid; else hi = mid; }
-    const uint32_t v = E.cellKp[L.cellKpBase + (size_t)lo * L.cellCap + (c - cellOff[lo])];
-    candG[c] = v;
-    if (inSmem) candS[c] = v;
+  {
+    // one warp per cell, four cells in flight per warp so the slab reads overlap
+    const int lane = tid & 31, warp = tid >> 5, nWarps = OCT_THREADS / 32;
+    for (int cell0 = warp * 4; cell0 < nCells; cell0 += nWarps * 4) {
+      uint32_t v[4]; int off[4], cnt[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int cell = cell0 + u;
+        off[u] = 0; cnt[u] = 0; v[u] = 0;
+        if (cell < nCells) {
+          off[u] = cellOff[cell]; cnt[u] = min(cellOff[cell + 1], C) - off[u];
+          if (lane < cnt[u]) v[u] = E.cellKp[L.cellKpBase + (size_t)cell * L.cellCap + lane];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (lane < cnt[u]) { candG[off[u] + lane] = v[u]; if (inSmem) candS[off[u] + lane] = v[u]; }
+        for (int k = 32 + lane; k < cnt[u]; k += 32) {   // rare: more than 32 survivors in one cell
+          const uint32_t w = E.cellKp[L.cellKpBase + (size_t)(cell0 + u) * L.cellCap + k];
+          candG[off[u] + k] = w; if (inSmem) candS[off[u] + k] = w;
+        }
+      }
+    }
   }
 
+  OCT_TICK(2);
   // ---- roots (ORBextractor.cc:664-706) ----
   int cur = 0;  // ping-pong index of the current list
   const int nIni = L.nIni;
@@ -417,15 +466,18 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     S.bnd[0][i] = bd;
     S.cnt[0][i] = 0;
   }
+  const bool privRoots = nIni <= OCT_PRIV;
+  if (privRoots) oct_priv_clear(sPriv);
   __syncthreads();
   for (int c = tid; c < C; c += OCT_THREADS) {
     const uint32_t pk = cand[c];
     int r = (int)__fdiv_rn((float)ft_px(pk), hX);
     if (r >= nIni) r = nIni - 1;
-    atomicAdd(&S.cnt[0][r], 1);
     code[c] = (uint16_t)(r * 4);
+    oct_count(S.cnt[0], sPriv, privRoots, r);
   }
   __syncthreads();
+  if (privRoots) { oct_count_flush(S.cnt[0], sPriv, nIni); __syncthreads(); }
   // drop empty roots
   if (tid == 0) {
     int n = 0;
@@ -443,6 +495,8 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
   cur = 1;
   __syncthreads();
 
+  OCT_TICK(3);
+  int tick = 4;
   // ---- main loop ----
   // sMode: 0 = normal pass, 1 = careful pass (largest-first with early break), 2 = finished
   int vcur = 0;  // ping-pong of the expandable-node vector
@@ -450,12 +504,16 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     const int n = sN;
     const int mode = sMode;
     if (mode == 2) break;
+    OCT_TICK(tick); tick++;
+    if (tid == 0 && E.octClock && tick < 60) E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + 40 + (tick - 5)] = mode * 100000 + n;
     short4* bnd = S.bnd[cur]; int* cnt = S.cnt[cur];
     short4* bnd2 = S.bnd[cur ^ 1]; int* cnt2 = S.cnt[cur ^ 1];
     const int m = sVecN;                 // size of the vector entering a careful pass
     unsigned long long* vecPrev = S.vec[vcur];
     unsigned long long* vecNew = S.vec[vcur ^ 1];
 
+    const bool usePriv = 4 * n <= OCT_PRIV;
+    if (usePriv) oct_priv_clear(sPriv);
     // which nodes are split (speculatively, in careful mode) this pass
     for (int i = tid; i < n; i += OCT_THREADS) {
       S.vecPos[i] = -1;
@@ -464,8 +522,10 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     if (mode == 1) {
       // std::sort(..., compareNodes) (ORBextractor.cc:805): warp 0 replays libstdc++'s introsort loop, then the
       // final insertion sort (= stable sort of what the loop leaves) is a parallel rank computation
+      OCT_TICK(20);
       if (tid < 32) ftsort::warp_introsort_loop(vecPrev, m, S.posA, S.posB);
       __syncthreads();
+      OCT_TICK(21);
       ftsort::stable_rank(vecPrev, vecNew, m, tid, OCT_THREADS);
       __syncthreads();
       // processing order r = 0..m-1 walks the sorted vector from the back (:806)
@@ -476,6 +536,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       }
     }
     __syncthreads();
+    if (mode == 1) OCT_TICK(22);
     // candidates: remap code -> node, count children of nodes being split
     for (int c = tid; c < C; c += OCT_THREADS) {
       const int node = S.map[code[c]];
@@ -486,12 +547,14 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         const short4 bd = bnd[node];
         const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
         q = (ft_px(pk) < bd.x + halfX ? 0 : 1) | (ft_py(pk) < bd.y + halfY ? 0 : 2);
-        atomicAdd(&S.ccnt[4 * node + q], 1);
+        oct_count(S.ccnt, sPriv, usePriv, 4 * node + q);
       }
       code[c] = (uint16_t)(node * 4 + q);
     }
     __syncthreads();
+    if (usePriv) { oct_count_flush(S.ccnt, sPriv, 4 * n); __syncthreads(); }
 
+    if (mode == 1) OCT_TICK(23);
     if (mode == 0) {
       // per node: k = non-empty children, e = children with more than one keypoint
       for (int i = tid; i < n; i += OCT_THREADS) {
@@ -563,6 +626,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       }
       __syncthreads();
       const int P = sP;
+      OCT_TICK(24);
       // totals restricted to the processed prefix
       if (tid == 0) {
         if (P == m) { sChildP = sTot[0]; sGrowP = sTot[1]; sVecP = sTot[2]; }
@@ -595,6 +659,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         }
       }
       __syncthreads();   // posA/posB of the processed prefix are consumed; they are reused below
+      OCT_TICK(25);
       // surviving old nodes keep their relative order behind the new children
       for (int i = tid; i < n; i += OCT_THREADS) {
         const int r = S.vecPos[i];
@@ -624,8 +689,9 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         }
       }
       __syncthreads();
+      OCT_TICK(26);
       if (tid == 0) {
-        sN = nNew; sVecN = vecP;
+        sN = nNew; sVecN = vecP; E.octClock ? (void)(E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + 63] = m) : (void)0;
         if (nNew >= N || nNew == n) sMode = 2;   // (:855)
       }
       cur ^= 1; vcur ^= 1;
@@ -633,6 +699,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     }
   }
 
+  OCT_TICK(tick); tick++;
   // ---- best keypoint per node: highest response, first in input order wins ties (:862-881) ----
   const int n = sN;
   unsigned* best = (unsigned*)S.posA;
@@ -654,6 +721,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     outKp[i] = ft_pack_xys(ft_px(pk) + FT_MIN_BORDER, ft_py(pk) + FT_MIN_BORDER, ft_ps(pk));
   }
   if (tid == 0) E.lvlKpCount[level] = n;
+  OCT_TICK(tick);
 }
 
 // ------------------------------------------------------------------------------------
@@ -816,23 +884,28 @@ __global__ void __launch_bounds__(OCT_THREADS) k_debug_sort(unsigned long long* 
   const int tid = threadIdx.x;
   for (int i = tid; i < n; i += OCT_THREADS) a[i] = data[i];
   __syncthreads();
+  const long long t0 = clock64();
   if (tid < 32) ftsort::warp_introsort_loop(a, n, posA, posB);
   __syncthreads();
+  const long long t1 = clock64();
   ftsort::stable_rank(a, o, n, tid, OCT_THREADS);
   __syncthreads();
+  const long long t2 = clock64();
   for (int i = tid; i < n; i += OCT_THREADS) data[i] = o[i];
+  if (tid == 0) { data[n] = (unsigned long long)(t1 - t0); data[n + 1] = (unsigned long long)(t2 - t1); }
 }
 
 extern "C" int ft_debug_sort(unsigned long long* keys_inout, int n) {
   if (!keys_inout || n < 0 || n > 4096) return FT_ERR_INVALID;
   if (n == 0) return FT_OK;
   unsigned long long* d = nullptr;
-  if (cudaMalloc(&d, sizeof(unsigned long long) * n) != cudaSuccess) return FT_ERR_CUDA;
+  if (cudaMalloc(&d, sizeof(unsigned long long) * (n + 2)) != cudaSuccess) return FT_ERR_CUDA;
   cudaMemcpy(d, keys_inout, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice);
   const size_t smem = (size_t)n * 24;
   cudaFuncSetAttribute(k_debug_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_debug_sort<<<1, OCT_THREADS, smem>>>(d, n);
   cudaError_t e = cudaMemcpy(keys_inout, d, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+  if (getenv("FT_SORT_CLOCK")) { unsigned long long t[2]; cudaMemcpy(t, d + n, 16, cudaMemcpyDeviceToHost); fprintf(stderr, "ft_debug_sort n=%d loop=%llu rank=%llu cycles\n", n, t[0], t[1]); }
   cudaFree(d);
   return e == cudaSuccess ? FT_OK : FT_ERR_CUDA;
 }

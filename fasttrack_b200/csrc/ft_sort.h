@@ -209,15 +209,16 @@ __device__ __forceinline__ int warp_partition(elem_t* base, int first, int last,
 }
 
 // introsort loop only (no final insertion sort); posA/posB: scratch of n ints each. Call with a full warp.
+// The explicit stack of pending right-hand ranges lives in registers, one entry per lane (its depth is bounded by
+// the depth limit 2*floor(log2 n) < 32), so the loop touches no local memory.
 __device__ __forceinline__ void warp_introsort_loop(elem_t* base, int n, int* posA, int* posB) {
   if (n <= 16) return;
   const int lane = threadIdx.x & 31;
-  int stackFirst[64], stackLast[64], stackDepth[64];
-  int sp = 1;
-  stackFirst[0] = 0; stackLast[0] = n; stackDepth[0] = 2 * floor_log2(n);
-  while (sp > 0) {
-    --sp;
-    int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
+  int myFirst = 0, myLast = 0, myDepth = 0;     // stack entry held by this lane
+  int sp = 0;
+  int first = 0, last = n, depth = 2 * floor_log2(n);
+  bool have = true;
+  while (have) {
     while (last - first > 16) {
       if (depth == 0) {
         if (lane == 0) heap_sort(base + first, last - first);
@@ -229,9 +230,17 @@ __device__ __forceinline__ void warp_introsort_loop(elem_t* base, int n, int* po
       if (lane == 0) move_median_to_first(&base[first], &base[first + 1], &base[mid], &base[last - 1]);
       __syncwarp();
       const int cut = warp_partition(base, first, last, posA, posB, lane);
-      stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth;
+      if (lane == sp) { myFirst = cut; myLast = last; myDepth = depth; }   // push the right-hand range
       ++sp;
       last = cut;
+    }
+    if (sp > 0) {
+      --sp;
+      first = __shfl_sync(0xFFFFFFFFu, myFirst, sp);
+      last = __shfl_sync(0xFFFFFFFFu, myLast, sp);
+      depth = __shfl_sync(0xFFFFFFFFu, myDepth, sp);
+    } else {
+      have = false;
     }
   }
 }
