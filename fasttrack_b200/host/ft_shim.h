@@ -1,0 +1,286 @@
+// ft_shim.h -- host-side mirror of the reference's operator surface over the C ABI (header-only, C++17).
+//
+// Same names, argument meaning and return values as the reference classes on this path, so host code written
+// against ORB-SLAM3 / FastTrack keeps compiling:
+//   ORB_SLAM3::ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+//                                              (reference include/ORBextractor.h:113-115, src/ORBextractor.cc:1356-1493)
+//   ORB_SLAM3::Frame::ComputeStereoMatches / ComputeStereoFishEyeMatches / AssignFeaturesToGrid
+//                                              (src/Frame.cc:835-1005, 1231-1271, 409-440)
+//   ORB_SLAM3::ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+//                                              (include/ORBmatcher.h:47, src/ORBmatcher.cc:49-312), including the
+//                                              isInFrustum pass of Tracking::SearchLocalPoints (src/Tracking.cc:3504-3522)
+// Everything is computed on the GPU by libfasttrack_b200; there is no CPU branch here. When the library is
+// compiled into a tree that has OpenCV, define FT_SHIM_USE_OPENCV and the cv:: types are used directly;
+// otherwise the minimal ftcv:: stand-ins below carry the same fields.
+#pragma once
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fasttrack_b200.h"
+
+#ifdef FT_SHIM_USE_OPENCV
+#include <opencv2/core/core.hpp>
+namespace ftcv = cv;
+#else
+namespace ftcv {
+struct Point2f { float x = 0, y = 0; };
+struct KeyPoint {           // cv::KeyPoint
+  Point2f pt;
+  float size = 0, angle = -1, response = 0;
+  int octave = 0, class_id = -1;
+};
+class Mat {                 // 8-bit single-channel subset of cv::Mat
+ public:
+  int rows = 0, cols = 0;
+  size_t step = 0;
+  unsigned char* data = nullptr;
+  Mat() {}
+  Mat(int r, int c, unsigned char* d, size_t s) : rows(r), cols(c), step(s), data(d) {}
+  void create(int r, int c) { own_ = std::make_shared<std::vector<unsigned char>>((size_t)r * c); rows = r; cols = c; step = c; data = own_->data(); }
+  void release() { own_.reset(); rows = cols = 0; step = 0; data = nullptr; }
+  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+  unsigned char* ptr(int r) { return data + (size_t)r * step; }
+  const unsigned char* ptr(int r) const { return data + (size_t)r * step; }
+ private:
+  std::shared_ptr<std::vector<unsigned char>> own_;
+};
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
+}  // namespace ftcv
+#endif
+
+namespace ORB_SLAM3 {
+
+class FtError : public std::runtime_error {
+ public:
+  FtError(int st, const std::string& m) : std::runtime_error("fasttrack_b200 status " + std::to_string(st) + ": " + m), status(st) {}
+  int status;
+};
+inline void ft_check(ft_status st) { if (st != FT_OK) throw FtError((int)st, ft_last_error()); }
+
+// One GPU context shared by the two extractors of a stereo rig and by the Frame / ORBmatcher mirrors.
+// Replaces KernelController's static singletons (reference include/Kernels/KernelController.h).
+class FrontEndContext {
+ public:
+  explicit FrontEndContext(const ft_config& cfg) : cfg_(cfg) { ft_check(ft_context_create(&cfg_, &ctx_)); }
+  ~FrontEndContext() { ft_context_destroy(ctx_); }
+  FrontEndContext(const FrontEndContext&) = delete;
+  ft_context* get() const { return ctx_; }
+  const ft_config& config() const { return cfg_; }
+
+  // Frame::ExtractORB runs the two extractors on two std::threads (src/Frame.cc:127-130). The first eye to
+  // arrive parks its image; the second one launches the stereo extraction for both and wakes the first.
+  void submit(int eye, const unsigned char* img, int step) {
+    std::unique_lock<std::mutex> lk(mu_);
+    img_[eye] = img; step_[eye] = step;
+    const unsigned gen = gen_;
+    if (++arrived_ == 2) {
+      ft_status st = ft_extract_stereo(ctx_, img_[0], step_[0], img_[1], step_[1]);
+      if (st == FT_OK) st = ft_synchronize(ctx_);
+      status_ = st; err_ = st == FT_OK ? "" : ft_last_error();
+      arrived_ = 0; ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lk, [&] { return gen_ != gen; });
+    }
+    if (status_ != FT_OK) throw FtError((int)status_, err_);
+  }
+
+ private:
+  ft_config cfg_;
+  ft_context* ctx_ = nullptr;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  const unsigned char* img_[2] = {nullptr, nullptr};
+  int step_[2] = {0, 0};
+  int arrived_ = 0;
+  unsigned gen_ = 0;
+  ft_status status_ = FT_OK;
+  std::string err_;
+};
+
+class ORBextractor {
+ public:
+  // same parameter list as the reference constructor plus the shared context and which eye this instance serves
+  ORBextractor(std::shared_ptr<FrontEndContext> fe, int eye) : fe_(fe), eye_(eye) {
+    const ft_config& c = fe_->config();
+    nfeatures = c.nfeatures; nlevels = c.nlevels; scaleFactor = c.scale_factor;
+    mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+    mnFeaturesPerLevel.resize(nlevels);
+    ft_check(ft_get_scale_tables(fe_->get(), mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                                 mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()));
+  }
+
+  // Compute the ORB features and descriptors on an image; returns monoIndex, -1 on an empty image.
+  int operator()(ftcv::InputArray image, ftcv::InputArray /*mask: ignored, as in the reference*/,
+                 std::vector<ftcv::KeyPoint>& keypoints, ftcv::OutputArray descriptors, std::vector<int>& vLappingArea) {
+    if (image.empty()) return -1;
+    const ft_config& c = fe_->config();
+    if (image.cols != c.width || image.rows != c.height) throw FtError(FT_ERR_INVALID, "image size differs from the configured camera");
+    const int* lap = eye_ == 0 ? c.lap_left : c.lap_right;
+    if (vLappingArea.size() != 2 || vLappingArea[0] != lap[0] || vLappingArea[1] != lap[1])
+      throw FtError(FT_ERR_INVALID, "vLappingArea differs from the rig configuration the context was created with");
+    fe_->submit(eye_, image.data, (int)image.step);
+    const int cap = c.nfeatures + 64 * c.nlevels;
+    std::vector<ft_keypoint> k(cap);
+    std::vector<unsigned char> d((size_t)cap * 32);
+    int n = 0, mono = 0;
+    ft_check(ft_frame_download(fe_->get(), eye_, cap, k.data(), d.data(), &n, &mono, nullptr, nullptr, nullptr, nullptr, nullptr));
+    keypoints.assign(n, ftcv::KeyPoint());
+    for (int i = 0; i < n; i++) {
+      ftcv::KeyPoint& o = keypoints[i];
+      o.pt.x = k[i].x; o.pt.y = k[i].y; o.size = k[i].size; o.angle = k[i].angle; o.response = k[i].response;
+      o.octave = k[i].octave; o.class_id = -1;
+    }
+    if (n == 0) descriptors.release();
+    else {
+      descriptors.create(n, 32);
+      for (int i = 0; i < n; i++) memcpy(descriptors.ptr(i), &d[(size_t)i * 32], 32);
+    }
+    return mono;
+  }
+
+  int GetLevels() { return nlevels; }
+  float GetScaleFactor() { return (float)scaleFactor; }
+  int GetNFeatures() { return nfeatures; }
+  std::vector<float> GetScaleFactors() { return mvScaleFactor; }
+  std::vector<float> GetInverseScaleFactors() { return mvInvScaleFactor; }
+  std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
+  std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+ protected:
+  std::shared_ptr<FrontEndContext> fe_;
+  int eye_;
+  int nfeatures, nlevels;
+  double scaleFactor;
+  std::vector<int> mnFeaturesPerLevel;
+  std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+};
+
+// The fields of MapPoint that the projection search reads or writes (reference include/MapPoint.h:170-181 and
+// the getters used in Frame::isInFrustum). A full MapPoint class can expose the same names.
+struct MapPoint {
+  float mWorldPos[3] = {0, 0, 0}, mNormalVector[3] = {0, 0, 1};
+  float mfMinDistance = 0, mfMaxDistance = 0;
+  unsigned char mDescriptor[32] = {0};
+  int nObs = 1;
+  bool mbBad = false;
+  unsigned long mnLastFrameSeen = ~0ul;
+  // tracking scratch written by the search
+  bool mbTrackInView = false, mbTrackInViewR = false;
+  float mTrackProjX = -1, mTrackProjY = -1, mTrackProjXR = 0, mTrackDepth = 0, mTrackViewCos = 0;
+  float mTrackProjXR_r = 0, mTrackProjYR = 0, mTrackDepthR = 0, mTrackViewCosR = 0;
+  int mnTrackScaleLevel = -1, mnTrackScaleLevelR = -1;
+  bool isBad() const { return mbBad; }
+  int Observations() const { return nObs; }
+};
+
+class Frame {
+ public:
+  Frame(std::shared_ptr<FrontEndContext> fe, unsigned long id) : mnId(id), fe_(fe) {}
+  std::shared_ptr<FrontEndContext> context() const { return fe_; }
+
+  // Frame::ComputeStereoMatches (src/Frame.cc:835-1005): fills mvuRight / mvDepth for the frame extracted last.
+  void ComputeStereoMatches() {
+    ft_check(ft_stereo_match(fe_->get()));
+    fetchStereo(false);
+  }
+  // Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1231-1271)
+  void ComputeStereoFishEyeMatches() {
+    ft_check(ft_stereo_match_fisheye(fe_->get()));
+    fetchStereo(true);
+  }
+  void SetPose(const float Rcw[9], const float tcw[3]) { ft_check(ft_set_pose(fe_->get(), Rcw, tcw, nullptr, nullptr)); }
+
+  unsigned long mnId;
+  int N = 0, Nleft = -1, Nright = -1;
+  std::vector<ftcv::KeyPoint> mvKeys, mvKeysRight;
+  ftcv::Mat mDescriptors, mDescriptorsRight;
+  std::vector<float> mvuRight, mvDepth;
+  std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+  std::vector<float> mvStereo3Dpoints;      // Nleft x 3
+  std::vector<MapPoint*> mvpMapPoints;
+
+ private:
+  void fetchStereo(bool fisheye) {
+    int nl = 0, nr = 0, ml = 0, mr = 0;
+    ft_check(ft_frame_counts(fe_->get(), &nl, &nr, &ml, &mr));
+    mvuRight.assign(nl, -1.f); mvDepth.assign(nl, -1.f);
+    if (fisheye) {
+      Nleft = nl; Nright = nr; N = nl + nr;
+      mvLeftToRightMatch.assign(nl, -1); mvRightToLeftMatch.assign(nr, -1); mvStereo3Dpoints.assign((size_t)nl * 3, 0.f);
+      ft_check(ft_frame_download(fe_->get(), 0, 0, nullptr, nullptr, nullptr, nullptr, mvuRight.data(), mvDepth.data(),
+                                 mvLeftToRightMatch.data(), mvRightToLeftMatch.data(), mvStereo3Dpoints.data()));
+    } else {
+      N = nl; Nleft = Nright = -1;
+      ft_check(ft_frame_download(fe_->get(), 0, 0, nullptr, nullptr, nullptr, nullptr, mvuRight.data(), mvDepth.data(),
+                                 nullptr, nullptr, nullptr));
+    }
+    mvpMapPoints.assign(N, nullptr);
+  }
+  std::shared_ptr<FrontEndContext> fe_;
+};
+
+class ORBmatcher {
+ public:
+  static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;
+  ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+  // Tracking::SearchLocalPoints loop 2 (isInFrustum, viewing-cos limit 0.5) + SearchByProjection #1.
+  // Map points are snapshotted at call time (the back-end threads mutate them concurrently in the reference);
+  // F.mvpMapPoints is updated in place and the function returns the reference's nmatches.
+  int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                         const float thFarPoints = 50.0f) {
+    const int M = (int)vpMapPoints.size(), N = F.N;
+    std::vector<float> pos((size_t)M * 3), nrm((size_t)M * 3), mm((size_t)M * 2);
+    std::vector<unsigned char> desc((size_t)M * 32);
+    std::vector<int> flags(M);
+    for (int i = 0; i < M; i++) {
+      const MapPoint* p = vpMapPoints[i];
+      memcpy(&pos[3 * (size_t)i], p->mWorldPos, 12); memcpy(&nrm[3 * (size_t)i], p->mNormalVector, 12);
+      mm[2 * (size_t)i] = p->mfMinDistance; mm[2 * (size_t)i + 1] = p->mfMaxDistance;
+      memcpy(&desc[32 * (size_t)i], p->mDescriptor, 32);
+      flags[i] = ((p->isBad() || p->mnLastFrameSeen == F.mnId) ? 1 : 0) | (p->Observations() > 0 ? 2 : 0);
+    }
+    // F.mvpMapPoints as indices: map points of this call by index, any other map point as -2
+    std::vector<int> holder(N, -1);
+    std::vector<unsigned char> hobs(N, 0);
+    std::vector<MapPoint*> foreign(N, nullptr);
+    for (int i = 0; i < N; i++) {
+      MapPoint* q = F.mvpMapPoints[i];
+      if (!q) continue;
+      foreign[i] = q; holder[i] = -2; hobs[i] = q->Observations() > 0;
+    }
+    std::vector<int> best((size_t)std::max(M, 1) * 2, -1);
+    int nmatches = 0;
+    ft_check(ft_search_local_points(F.context()->get(), M, pos.data(), nrm.data(), mm.data(), desc.data(), flags.data(), th,
+                                    bFarPoints ? 1 : 0, thFarPoints, mfNNratio, holder.data(), hobs.data(), best.data(),
+                                    &nmatches));
+    for (int i = 0; i < N; i++) F.mvpMapPoints[i] = holder[i] >= 0 ? vpMapPoints[holder[i]] : (holder[i] == -2 ? foreign[i] : nullptr);
+    if (M > 0) {   // the mTrack* scratch the reference leaves in every MapPoint
+      std::vector<int> ti((size_t)M * 4);
+      std::vector<float> tf((size_t)M * 9);
+      ft_check(ft_debug_track(F.context()->get(), M, ti.data(), tf.data()));
+      for (int i = 0; i < M; i++) {
+        MapPoint* p = vpMapPoints[i];
+        const float* f = &tf[9 * (size_t)i];
+        p->mbTrackInView = ti[4 * (size_t)i] != 0; p->mbTrackInViewR = ti[4 * (size_t)i + 1] != 0;
+        p->mnTrackScaleLevel = ti[4 * (size_t)i + 2]; p->mnTrackScaleLevelR = ti[4 * (size_t)i + 3];
+        p->mTrackProjX = f[0]; p->mTrackProjY = f[1]; p->mTrackProjXR = f[2]; p->mTrackDepth = f[3]; p->mTrackViewCos = f[4];
+        p->mTrackProjXR_r = f[5]; p->mTrackProjYR = f[6]; p->mTrackDepthR = f[7]; p->mTrackViewCosR = f[8];
+      }
+    }
+    return nmatches;
+  }
+
+ protected:
+  float mfNNratio;
+  bool mbCheckOrientation;
+};
+
+}  // namespace ORB_SLAM3
