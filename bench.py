@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from fasttrack_b200 import synth  # noqa: E402
+from fasttrack_b200 import replicas, synth  # noqa: E402
 
 E = synth.EUROC
 N_FRAMES = 12            # distinct pre-generated frames per rank, cycled
@@ -187,8 +187,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = replicas.env_rank()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -210,7 +209,7 @@ def main():
     scale = ctx.scale_tables()["scale"]
 
     # ---- inputs: one independent synthetic sequence per GPU (seed = 5 + rank), prepared outside the timed region ----
-    frames = make_frames(5 + rank, N_FRAMES)
+    frames = make_frames(replicas.sequence_seed(rank), N_FRAMES)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hL = [pin(L) for L, R in frames]; hR = [pin(R) for L, R in frames]
     dL = [t.cuda(non_blocking=False) for t in hL]; dR = [t.cuda(non_blocking=False) for t in hR]
@@ -324,13 +323,10 @@ def main():
     st = ctx.stats()
 
     # ---- reductions over ranks (max time) ----
-    tt = torch.tensor([dev_ms_total, e2e_s, wall1 - wall0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms_total, e2e_s, wall_s = [float(x) for x in tt.tolist()]
+    dev_ms_total, e2e_s, wall_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0], device="cuda")
     ms_per_step = dev_ms_total / args.steps
-    value = world * args.steps / (dev_ms_total / 1e3)
-    e2e_value = world * args.steps / e2e_s
+    value = replicas.aggregate_throughput(world, args.steps, dev_ms_total / 1e3)
+    e2e_value = replicas.aggregate_throughput(world, args.steps, e2e_s)
 
     # ---- roofline of the dominant kernel (SURVEY.md 8d byte formulas with the measured counts) ----
     pk, pk_kind = peaks()

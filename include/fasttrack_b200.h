@@ -20,7 +20,7 @@
  *                                    (src/Frame.cc:1231-1271, KernelController.h:41)
  *   ft_frame_download             <- the host vectors those operators fill (mvKeys, mDescriptors, mvuRight,
  *                                    mvDepth, mvLeftToRightMatch, mvRightToLeftMatch, mvStereo3Dpoints)
- *   ft_set_pose                   <- Frame::SetPose / UpdatePoseMatrices (src/Frame.cc:345-372)
+ *   ft_set_pose                   <- Frame::SetPose / UpdatePoseMatrices (src/Frame.cc:455-506)
  *   ft_search_local_points        <- Frame::isInFrustum loop of Tracking::SearchLocalPoints
  *                                    (src/Tracking.cc:3504-3522) + ORBmatcher::SearchByProjection #1
  *                                    (src/ORBmatcher.cc:49-312) / launchSearchLocalPointsKernel

@@ -13,6 +13,7 @@ using namespace ORB_SLAM3;
 template <typename T>
 static std::vector<T> rd(const std::string& p) {
   std::ifstream f(p, std::ios::binary | std::ios::ate);
+  if (!f) { fprintf(stderr, "shim_demo: cannot open %s\n", p.c_str()); exit(2); }
   std::vector<T> v((size_t)f.tellg() / sizeof(T));
   f.seekg(0); f.read((char*)v.data(), v.size() * sizeof(T));
   return v;
