@@ -221,11 +221,13 @@ def main():
         maps.append(mp)
         hmaps.append({k: pin(v) for k, v in mp.items()})
     cap = ctx.cap
+    cap_dev = int(ctx.L.ft_max_keypoints(ctx.h))
     out_kps = [torch.empty(cap * 24, dtype=torch.uint8).pin_memory() for _ in range(2)]
     out_desc = [torch.empty(cap * 32, dtype=torch.uint8).pin_memory() for _ in range(2)]
     out_ur = torch.empty(cap, dtype=torch.float32).pin_memory(); out_dp = torch.empty(cap, dtype=torch.float32).pin_memory()
     holder = torch.empty(cap, dtype=torch.int32).pin_memory(); hobs = torch.empty(cap, dtype=torch.uint8).pin_memory()
     best = torch.empty(M_POINTS * 2, dtype=torch.int32).pin_memory()
+    counts4 = torch.zeros(4, dtype=torch.int32).pin_memory()
     ctx.set_pose(np.eye(3), np.zeros(3))
     import ctypes as C
     L_ = ctx.L
@@ -244,17 +246,14 @@ def main():
         ctx.search_resident(TH)
 
     def step_e2e(i):
-        """the user-facing call sequence with HOST buffers: H2D of images and map points, D2H of every result"""
+        """the user-facing call sequence with HOST buffers: Frame construction (upload, extract, stereo, download of
+        every host vector) in one C-ABI call, then SearchLocalPoints (H2D of the map-point arrays, D2H of the result)"""
         k = i % N_FRAMES
-        ctx.extract_stereo_ptr(hL[k].data_ptr(), E["width"], hR[k].data_ptr(), E["width"], device=False)
-        ctx.stereo_match()
-        n, mono = C.c_int(), C.c_int()
-        ctx._ck(L_.ft_frame_download(ctx.h, 0, cap, out_kps[0].data_ptr(), out_desc[0].data_ptr(), C.byref(n), C.byref(mono),
-                                     out_ur.data_ptr(), out_dp.data_ptr(), None, None, None))
-        nl = n.value
-        ctx._ck(L_.ft_frame_download(ctx.h, 1, cap, out_kps[1].data_ptr(), out_desc[1].data_ptr(), C.byref(n), C.byref(mono),
-                                     None, None, None, None, None))
-        nr = n.value
+        ctx._ck(L_.ft_frame_construct(ctx.h, hL[k].data_ptr(), E["width"], hR[k].data_ptr(), E["width"],
+                                      out_kps[0].data_ptr(), out_desc[0].data_ptr(), out_kps[1].data_ptr(),
+                                      out_desc[1].data_ptr(), counts4.data_ptr(), out_ur.data_ptr(), out_dp.data_ptr(),
+                                      None, None, None))
+        nl, nr = int(counts4[0]), int(counts4[2])
         holder[:nl] = -1; hobs[:nl] = 0
         m = hmaps[k]
         ctx.search_local_points_raw(M_POINTS, m["pos"].data_ptr(), m["normal"].data_ptr(), m["minmax"].data_ptr(),
@@ -309,7 +308,7 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + nl * 5
-    d2h = (nl + nr) * (24 + 32) + nl * 8 + nl * 5 + M_POINTS * 8 + 9 * 4
+    d2h = 2 * cap_dev * (24 + 32) + cap_dev * 8 + nl * 5 + M_POINTS * 8 + 13 * 4
 
     # ---- per-kernel pass: CUDA events around every kernel (direct launches), same inputs ----
     ctx.set_stage_timing(True)

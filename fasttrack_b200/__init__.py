@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -94,6 +94,8 @@ def load_library():
     L.ft_get_stage_times.argtypes = [vp, vp, C.c_int]
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
+    L.ft_max_keypoints.argtypes = [vp]
+    L.ft_frame_construct.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
             getattr(L, name).restype = C.c_int
@@ -134,7 +136,7 @@ class Context:
         h = C.c_void_p()
         self._ck(self.L.ft_context_create(C.byref(cfg), C.byref(h)))
         self.h = h
-        self.cap = nfeatures + 64 * nlevels
+        self.cap = max(nfeatures + 64 * nlevels, int(self.L.ft_max_keypoints(self.h)))
 
     def _ck(self, st):
         if st != 0:
@@ -200,6 +202,26 @@ class Context:
             if self.fisheye:
                 out.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
         return out
+
+    def frame_construct(self, imgL, imgR):
+        """Frame constructor in one call: returns (left dict, right dict) like download()"""
+        cap = self.cap
+        kL = np.zeros(cap, KEYPOINT_DTYPE); kR = np.zeros(cap, KEYPOINT_DTYPE)
+        dL = np.zeros((cap, 32), np.uint8); dR = np.zeros((cap, 32), np.uint8)
+        ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32)
+        cnt = np.zeros(4, np.int32)
+        l2r = r2l = p3d = None
+        if self.fisheye:
+            l2r = np.zeros(cap, np.int32); r2l = np.zeros(cap, np.int32); p3d = np.zeros((cap, 3), np.float32)
+        self._ck(self.L.ft_frame_construct(self.h, imgL.ctypes.data, imgL.strides[0], imgR.ctypes.data, imgR.strides[0],
+                                           _ptr(kL), _ptr(dL), _ptr(kR), _ptr(dR), _ptr(cnt), _ptr(ur), _ptr(dp),
+                                           _ptr(l2r), _ptr(r2l), _ptr(p3d)))
+        nl, ml, nr, mr = [int(x) for x in cnt]
+        left = dict(kps=kL[:nl].copy(), desc=dL[:nl].copy(), n=nl, mono_index=ml, u_right=ur[:nl].copy(), depth=dp[:nl].copy())
+        right = dict(kps=kR[:nr].copy(), desc=dR[:nr].copy(), n=nr, mono_index=mr)
+        if self.fisheye:
+            left.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
+        return left, right
 
     def set_pose(self, Rcw, tcw, Rwc=None, Ow=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1)

@@ -580,6 +580,42 @@ extern "C" ft_status ft_frame_download(ft_context* c, int eye, int cap, ft_keypo
   return FT_OK;
 }
 
+extern "C" int ft_max_keypoints(ft_context* c) { return c ? c->P.maxKp : 0; }
+
+// Frame constructor in one call (reference src/Frame.cc:102-223 for pinhole rigs, :1115-1229 for fisheye):
+// upload both images, extract, stereo-match, and bring every host vector the constructor fills back with a
+// single synchronisation. Output arrays must hold ft_max_keypoints() entries.
+extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR,
+                                        ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR,
+                                        int* counts4 /* nL, monoL, nR, monoR */, float* u_right, float* depth,
+                                        int* l2r, int* r2l, float* p3d) {
+  if (!c || !counts4) { set_err("ft_frame_construct: null argument"); return FT_ERR_INVALID; }
+  ft_status st = ft_extract_stereo(c, imgL, stepL, imgR, stepR);
+  if (st != FT_OK) return st;
+  st = c->fisheye ? ft_stereo_match_fisheye(c) : ft_stereo_match(c);
+  if (st != FT_OK) return st;
+  cudaStream_t s = c->stream;
+  const int cap = c->P.maxKp;
+  CK(cudaMemcpyAsync(c->hCounts, c->B.eye[0].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->hCounts + 2, c->B.eye[1].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (kpsL) CK(cudaMemcpyAsync(kpsL, c->B.eye[0].kps, sizeof(ft_keypoint) * cap, cudaMemcpyDeviceToHost, s));
+  if (descL) CK(cudaMemcpyAsync(descL, c->B.eye[0].desc, (size_t)32 * cap, cudaMemcpyDeviceToHost, s));
+  if (kpsR) CK(cudaMemcpyAsync(kpsR, c->B.eye[1].kps, sizeof(ft_keypoint) * cap, cudaMemcpyDeviceToHost, s));
+  if (descR) CK(cudaMemcpyAsync(descR, c->B.eye[1].desc, (size_t)32 * cap, cudaMemcpyDeviceToHost, s));
+  if (u_right) CK(cudaMemcpyAsync(u_right, c->S.uRight, sizeof(float) * cap, cudaMemcpyDeviceToHost, s));
+  if (depth) CK(cudaMemcpyAsync(depth, c->S.depth, sizeof(float) * cap, cudaMemcpyDeviceToHost, s));
+  if (c->fisheye) {
+    if (l2r) CK(cudaMemcpyAsync(l2r, c->S.l2r, sizeof(int) * cap, cudaMemcpyDeviceToHost, s));
+    if (r2l) CK(cudaMemcpyAsync(r2l, c->S.r2l, sizeof(int) * cap, cudaMemcpyDeviceToHost, s));
+    if (p3d) CK(cudaMemcpyAsync(p3d, c->S.p3d, sizeof(float) * 3 * cap, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  c->countsValid = true;
+  for (int i = 0; i < 4; i++) counts4[i] = c->hCounts[i];
+  return check_device_status(c, c->hCounts[4]);
+}
+
 extern "C" ft_status ft_set_pose(ft_context* c, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow) {
   if (!c || !Rcw || !tcw) { set_err("ft_set_pose: null argument"); return FT_ERR_INVALID; }
   memcpy(c->pose.Rcw, Rcw, 36); memcpy(c->pose.tcw, tcw, 12);

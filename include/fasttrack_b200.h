@@ -110,6 +110,18 @@ ft_status ft_frame_counts(ft_context* ctx, int* n_left, int* n_right, int* mono_
 ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps, uint8_t* desc, int* n, int* mono_index,
                             float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
 
+/* Capacity (entries) of the per-eye keypoint arrays: nfeatures + a few per level (the octree may exceed a level
+ * quota by up to 3, reference sizes its buffers nfeatures+20, include/Kernels/CudaUtils.h:16). */
+int ft_max_keypoints(ft_context* ctx);
+
+/* The Frame constructor's front-end work in one call and one synchronisation (reference src/Frame.cc:102-223,
+ * 1115-1229): upload, extract both eyes, stereo-match (pinhole or fisheye according to the context), download.
+ * Every output array must hold ft_max_keypoints() entries (p3d: 3x); counts4 = {n_left, mono_left, n_right,
+ * mono_right}. Unused outputs may be NULL. */
+ft_status ft_frame_construct(ft_context* ctx, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR,
+                             ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR, int* counts4,
+                             float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
+
 /* Pose of the current frame: Rcw (row-major 3x3), tcw; Rwc/Ow may be NULL (then Rwc = Rcw^T, Ow = -Rwc*tcw). */
 ft_status ft_set_pose(ft_context* ctx, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow);
 

@@ -261,3 +261,30 @@ def test_api_errors():
                                                np.full(n, -1), z(n, np.uint8))
     assert nm == 0 and np.all(holder == -1)
     ctx.close()
+
+
+def test_frame_construct_one_call(euroc):
+    """ft_frame_construct == extract + stereo + downloads"""
+    ctx = euroc["ctx"]
+    left, right = ctx.frame_construct(euroc["L"], euroc["R"])
+    _, kL, dL = euroc["oL"]; _, kR, dR = euroc["oR"]
+    assert np.array_equal(ft.keypoints_as_array(left["kps"]), kL) and np.array_equal(left["desc"], dL)
+    assert np.array_equal(ft.keypoints_as_array(right["kps"]), kR) and np.array_equal(right["desc"], dR)
+    assert np.array_equal(left["u_right"], euroc["st"]["uRight"]) and np.array_equal(left["depth"], euroc["st"]["depth"])
+
+
+def test_resident_search_matches_host_call(euroc):
+    """ft_upload_map_points + ft_upload_holders + ft_search_resident + ft_search_download == ft_search_local_points"""
+    ctx = euroc["ctx"]
+    _, kL, dL = euroc["oL"]
+    M = 7000
+    mp = synth.mappoints(kL, dL, euroc["exL"].scale, M, seed=55)
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n1, h1, o1, b1 = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0,
+                                             mp["holder"], mp["holder_obs"])
+    ctx.upload_map_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"])
+    ctx.upload_holders(mp["holder"], mp["holder_obs"])
+    for _ in range(3):          # repeated searches over the resident snapshot start from the same holders
+        ctx.search_resident(3.0)
+        n2, h2, o2, b2 = ctx.search_download(M)
+        assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(o1, o2) and np.array_equal(b1, b2)
