@@ -241,8 +241,7 @@ def main():
     def step_resident(i):
         """inputs already in HBM: images (device), map-point snapshot (device); results stay on the device"""
         k = i % N_FRAMES
-        ctx.extract_stereo_ptr(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"], device=True)
-        ctx.stereo_match()
+        ctx.frame_enqueue_device(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"])
         ctx.search_resident(TH)
 
     def step_e2e(i):

@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -95,6 +95,7 @@ def load_library():
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
     L.ft_max_keypoints.argtypes = [vp]
+    L.ft_frame_enqueue_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_frame_construct.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
@@ -170,6 +171,9 @@ class Context:
     def extract_stereo_ptr(self, ptrL, stepL, ptrR, stepR, device=False):
         f = self.L.ft_extract_stereo_device if device else self.L.ft_extract_stereo
         self._ck(f(self.h, ptrL, stepL, ptrR, stepR))
+
+    def frame_enqueue_device(self, ptrL, stepL, ptrR, stepR):
+        self._ck(self.L.ft_frame_enqueue_device(self.h, ptrL, stepL, ptrR, stepR))
 
     def stereo_match(self):
         self._ck(self.L.ft_stereo_match_fisheye(self.h) if self.fisheye else self.L.ft_stereo_match(self.h))

@@ -46,7 +46,7 @@ struct ft_context {
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evPyr = nullptr, evJoin3 = nullptr;
   uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
   int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
-  cudaGraphExec_t gExtract = nullptr, gStereo = nullptr;
+  cudaGraphExec_t gExtract = nullptr, gStereo = nullptr, gFrame = nullptr;
   int useGraph = 1;
   bool extracted = false, stereoDone = false, countsValid = false;
   int lastM = 0;
@@ -305,9 +305,11 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &c->S.p3d, (size_t)P.maxKp * 3));
   CKF(dalloc(c, &c->S.code, (size_t)P.maxKp));
   CKF(dalloc(c, &c->S.stats, (size_t)8));
+  c->B.stereoStats = c->S.stats;
   // grid
   CKF(dalloc(c, &c->G.cellStart, (size_t)2 * (FT_GRID_COLS * FT_GRID_ROWS + 1)));
   CKF(dalloc(c, &c->G.cellIdx, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &c->G.rec, (size_t)2 * P.maxKp));
   // projection search
   const int MM = cfg->max_map_points > 0 ? cfg->max_map_points : 25000;
   c->cfg.max_map_points = MM;
@@ -356,6 +358,7 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->gExtract) cudaGraphExecDestroy(c->gExtract);
   if (c->gStereo) cudaGraphExecDestroy(c->gStereo);
+  if (c->gFrame) cudaGraphExecDestroy(c->gFrame);
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
   if (c->hCounts) cudaFreeHost(c->hCounts);
@@ -424,7 +427,6 @@ static int enqueue_extract(ft_context* c) {
 // Stereo matching with the frame grid (only read by the projection search) built on a parallel branch.
 static int enqueue_stereo(ft_context* c) {
   cudaStream_t s = c->stream, s2 = c->stream2;
-  cudaMemsetAsync(c->S.stats, 0, 7 * sizeof(unsigned long long), s);
   cudaEventRecord(c->evFork2, s);
   cudaStreamWaitEvent(s2, c->evFork2, 0);
   { StageScope t(c, FT_STAGE_GRID, s2); ft_launch_grid(c->P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s2); }
@@ -455,10 +457,10 @@ static ft_status run_extract(ft_context* c) {
   return FT_OK;
 }
 
-extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
-  if (!c || !imgL || !imgR) { set_err("ft_extract_stereo: null argument (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
+static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
+  if (!c || !imgL || !imgR) { set_err("null image (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
   const int w = c->cfg.width, h = c->cfg.height;
-  if (stepL < w || stepR < w) { set_err("ft_extract_stereo: step smaller than width"); return FT_ERR_INVALID; }
+  if (stepL < w || stepR < w) { set_err("image step smaller than width"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
   const uint8_t* src[2] = {imgL, imgR};
   const int step[2] = {stepL, stepR};
@@ -466,15 +468,22 @@ extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int s
     cudaPointerAttributes at;
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    uint8_t* dst = c->B.eye[e].pyr + c->P.lv[0].offset;   // straight into level 0 of the pyramid slab
     if (pinned) {
-      CK(cudaMemcpy2DAsync(c->B.eye[e].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
     } else {
       // pageable memory: stage through the context's pinned buffer so the copy stays asynchronous
       CK(cudaStreamSynchronize(c->stream));   // previous frame may still be reading the staging buffer
       for (int y = 0; y < h; y++) memcpy(c->hIn[e] + (size_t)y * w, src[e] + (size_t)y * step[e], w);
-      CK(cudaMemcpy2DAsync(c->B.eye[e].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, c->hIn[e], w, w, h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, c->hIn[e], w, w, h, cudaMemcpyHostToDevice, c->stream));
     }
   }
+  return FT_OK;
+}
+
+extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
+  ft_status st = upload_images(c, imgL, stepL, imgR, stepR);
+  if (st != FT_OK) return st;
   return run_extract(c);
 }
 
@@ -580,6 +589,37 @@ extern "C" ft_status ft_frame_download(ft_context* c, int eye, int cap, ft_keypo
   return FT_OK;
 }
 
+// extract + stereo as ONE captured graph (the Frame constructor does both back to back)
+static ft_status run_frame(ft_context* c) {
+  if (c->useGraph && !c->timing) {
+    if (!c->gFrame) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      c->nLaunchExtract = enqueue_extract(c);
+      c->nLaunchStereo = enqueue_stereo(c);
+      CK(cudaStreamEndCapture(c->stream, &g));
+      CK(cudaGraphInstantiate(&c->gFrame, g, 0));
+      cudaGraphDestroy(g);
+    }
+    CK(cudaGraphLaunch(c->gFrame, c->stream));
+    c->extracted = true; c->stereoDone = true; c->countsValid = false;
+    return FT_OK;
+  }
+  ft_status st = run_extract(c);
+  if (st != FT_OK) return st;
+  return run_stereo(c);
+}
+
+// Device-resident inputs: copy into the level-0 slabs, then extract + stereo-match as one graph; asynchronous.
+extern "C" ft_status ft_frame_enqueue_device(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+  if (!c || !dL || !dR) { set_err("ft_frame_enqueue_device: null argument"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaMemcpy2DAsync(c->B.eye[0].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpy2DAsync(c->B.eye[1].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  return run_frame(c);
+}
+
 extern "C" int ft_max_keypoints(ft_context* c) { return c ? c->P.maxKp : 0; }
 
 // Frame constructor in one call (reference src/Frame.cc:102-223 for pinhole rigs, :1115-1229 for fisheye):
@@ -590,9 +630,9 @@ extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int 
                                         int* counts4 /* nL, monoL, nR, monoR */, float* u_right, float* depth,
                                         int* l2r, int* r2l, float* p3d) {
   if (!c || !counts4) { set_err("ft_frame_construct: null argument"); return FT_ERR_INVALID; }
-  ft_status st = ft_extract_stereo(c, imgL, stepL, imgR, stepR);
+  ft_status st = upload_images(c, imgL, stepL, imgR, stepR);
   if (st != FT_OK) return st;
-  st = c->fisheye ? ft_stereo_match_fisheye(c) : ft_stereo_match(c);
+  st = run_frame(c);
   if (st != FT_OK) return st;
   cudaStream_t s = c->stream;
   const int cap = c->P.maxKp;

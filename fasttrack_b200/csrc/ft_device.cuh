@@ -75,6 +75,7 @@ struct FtBuffers {
   const int2* xTab;        // per level, per dst column: {sx, a0 | a1<<16}
   const int2* yTab;        // per level, per dst row:    {sy0 | sy1<<16, b0 | b1<<16}
   int* status;             // device-side status word (capacity overflow flags)
+  unsigned long long* stereoStats;   // FtStereoBuffers::stats (cleared by k_orient_desc for the stereo kernel)
 };
 
 // status bits
@@ -125,6 +126,7 @@ struct FtPose {
 struct FtGridBuffers {
   int* cellStart;          // [2][64*48+1] (left, right)
   int* cellIdx;            // [2][maxKp]
+  float4* rec;             // [2][maxKp] per keypoint {x, y, uRight (pinhole; -1 otherwise), octave as float bits}
 };
 
 // Map-point snapshot, frustum scratch, candidate lists and claim tables of the projection search.

@@ -169,21 +169,26 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     return;
   }
   const int iw = rw - 6, ih = rh - 6;
-  const int rwPad = (rw + 3) & ~3;
-  uint8_t* sImg = smem;                         // [rh][rwPad]
+  const int ax = iniX & 3;                      // the tile is staged with aligned 32-bit loads: ax bytes of slack in front
+  const int rwPad = (rw + 6) & ~3;              // >= ax + rw, multiple of 4
+  uint8_t* sImg = smem;                         // [rh][rwPad], cell pixel (y, x) at sImg[y*rwPad + ax + x]
   uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // [ih][iw] score (0 below minTh), then NMS survivors
   uint8_t* sMx = sSc + ((iw * ih + 15) & ~15);
-  const uint8_t* src = E.pyr + L.offset + (size_t)iniY * L.pitch + iniX;
-  for (int i = tid; i < rh * rw; i += FAST_THREADS) {
-    const int y = i / rw, x = i - y * rw;
-    sImg[y * rwPad + x] = src[(size_t)y * L.pitch + x];
+  {
+    const uint8_t* srcA = E.pyr + L.offset + (size_t)iniY * L.pitch + (iniX - ax);   // 4-byte aligned
+    const int wpr = (ax + rw + 3) >> 2;                                               // words per row
+    uint32_t* sW = reinterpret_cast<uint32_t*>(sImg);
+    for (int i = tid; i < rh * wpr; i += FAST_THREADS) {
+      const int y = i / wpr, wx = i - y * wpr;
+      sW[y * (rwPad >> 2) + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
+    }
   }
   if (tid == 0) sAny = 0;
   __syncthreads();
   const int total = iw * ih;
   for (int i = tid; i < total; i += FAST_THREADS) {
     const int y = i / iw, x = i - y * iw;
-    const uint8_t* c = &sImg[(y + 3) * rwPad + (x + 3)];
+    const uint8_t* c = &sImg[(y + 3) * rwPad + ax + (x + 3)];
     // quick reject at minTh: every 9-arc holds one pixel of each opposite ring pair
     const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
     const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
@@ -771,6 +776,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   const int total = sLvlOff[p.nlevels];
   const int lap0 = p.lap[eye][0], lap1 = p.lap[eye][1];
   const int first = blockIdx.x * OD_WARPS;   // first global keypoint order index of this block
+  if (blockIdx.x == 0 && eye == 0 && tid < 2 && b.stereoStats) b.stereoStats[tid] = 0ull;   // counters of the stereo kernel that follows
   if (blockIdx.x == 0 && tid == 0) {
     E.counts[0] = min(total, p.maxKp);
     if (total > p.maxKp) atomicOr(b.status, FT_ST_KP_OVERFLOW);
@@ -780,8 +786,13 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
     if (blockIdx.x == 0 && tid == 0) E.counts[1] = 0;
     return;
   }
-  // count non-lapping keypoints (a) before `first`, (b) in total: each thread strides over all keypoints
-  {
+  // count non-lapping keypoints (a) before `first`, (b) in total. Keypoints sit 19 px inside every level, so a
+  // lapping area left of x = 19 (pinhole rigs pass {0,0}) contains none of them and one spanning the image all.
+  if (lap1 < FT_EDGE_THRESHOLD) {
+    if (tid == 0) { sMonoBefore = first; sMonoTotal = total; }
+  } else if (lap0 <= FT_EDGE_THRESHOLD && lap1 >= p.width) {
+    // all lapping: nothing to count
+  } else {
     int before = 0, all = 0;
     for (int g = tid; g < total; g += OD_WARPS * 32) {
       int l = 0;
@@ -918,7 +929,7 @@ size_t ft_fast_smem_bytes(const FtParams& p) {
   for (int l = 0; l < p.nlevels; l++) {
     const FtLevel& L = p.lv[l];
     const int rw = L.wCell + 6, rh = L.hCell + 6;
-    const int rwPad = (rw + 3) & ~3;
+    const int rwPad = (rw + 6) & ~3;
     size_t s = ((rh * rwPad + 15) & ~15) + 2 * ((L.wCell * L.hCell + 15) & ~15);
     if (s > mx) mx = s;
   }

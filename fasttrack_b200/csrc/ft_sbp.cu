@@ -38,8 +38,10 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
     int* cellIdx = g.cellIdx + eye * p.maxKp;
     for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
     __syncthreads();
+    float4* rec = g.rec + eye * p.maxKp;
     for (int i = tid; i < n; i += 1024) {
       const ft_keypoint kp = E.kps[i];
+      rec[i] = make_float4(kp.x, kp.y, __int_as_float(kp.octave), 0.f);   // 16-byte search record read by k_gather
       const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), gridWInv));
       const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), gridHInv));
       if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
@@ -227,10 +229,12 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
       const int* cellIdx = g.cellIdx + br * p.maxKp;
       const FtEye& E = b.eye[br];
       const float projXR = f[2];
+      const float4* rec = g.rec + br * p.maxKp;
       auto passes = [&](int idx) -> bool {
-        const ft_keypoint kp = E.kps[idx];
-        if (kp.octave < minLevel) return false;
-        if (maxLevel >= 0 && kp.octave > maxLevel) return false;
+        const float4 kp = __ldg(rec + idx);
+        const int oct = __float_as_int(kp.z);
+        if (oct < minLevel) return false;
+        if (maxLevel >= 0 && oct > maxLevel) return false;
         const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
         if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
         if (!a.fisheye) {
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         const int idx = total > GA_BUF ? (int)s.pool[base + k] : (int)sBuf[warp][k];
         const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
         const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
-        s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)E.kps[idx].octave << 25);
+        s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)__float_as_int(__ldg(rec + idx).z) << 25);
       }
       __syncwarp();
       if (br == 0) { lens.x = total; offs.x = base; } else { lens.y = total; offs.y = base; }

@@ -122,6 +122,9 @@ ft_status ft_frame_construct(ft_context* ctx, const uint8_t* imgL, int stepL, co
                              ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR, int* counts4,
                              float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
 
+/* ft_frame_construct without the downloads, for images already in device memory; asynchronous. */
+ft_status ft_frame_enqueue_device(ft_context* ctx, const uint8_t* d_imgL, int stepL, const uint8_t* d_imgR, int stepR);
+
 /* Pose of the current frame: Rcw (row-major 3x3), tcw; Rwc/Ow may be NULL (then Rwc = Rcw^T, Ow = -Rwc*tcw). */
 ft_status ft_set_pose(ft_context* ctx, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow);
 

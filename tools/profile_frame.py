@@ -1,5 +1,5 @@
 """Small driver for ncu: W warm-up + K timed-shape frames of the bench workload (device-resident inputs).
-Kernel launches per frame: 13 (extract) + 2 (stereo) + 4 (search) = 19; setup issues 13 more before the loop."""
+Kernel launches per frame: 14 (extract) + 2 (stereo + grid) + 2 (search) = 18; setup issues 14 more before the loop."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,8 +21,7 @@ ctx.set_pose(np.eye(3), np.zeros(3))
 ctx.upload_map_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"])
 ctx.upload_holders(None, None)
 for i in range(W + K):
-    ctx.extract_stereo_ptr(dL.data_ptr(), E["width"], dR.data_ptr(), E["width"], device=True)
-    ctx.stereo_match()
+    ctx.frame_enqueue_device(dL.data_ptr(), E["width"], dR.data_ptr(), E["width"])
     ctx.search_resident(bench.TH)
     ctx.synchronize()
 print("profiled frames:", K, "launch counts", ctx.launch_counts(), ctx.stats())
