@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       // std::sort(..., compareNodes) (ORBextractor.cc:805): warp 0 replays libstdc++'s introsort loop, then the
       // final insertion sort (= stable sort of what the loop leaves) is a parallel rank computation
       OCT_TICK(20);
-      if (tid < 32) ftsort::warp_introsort_loop(vecPrev, m, S.posA, S.posB);
+      __syncthreads();   // the loop above initialises vecPos/ccnt; posC doubles as the range queue of the sort
+      ftsort::cta_introsort_loop(vecPrev, m, S.posA, S.posB, S.posC);
       __syncthreads();
       OCT_TICK(21);
       ftsort::stable_rank(vecPrev, vecNew, m, tid, OCT_THREADS);
@@ -896,7 +897,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_debug_sort(unsigned long long* 
   for (int i = tid; i < n; i += OCT_THREADS) a[i] = data[i];
   __syncthreads();
   const long long t0 = clock64();
-  if (tid < 32) ftsort::warp_introsort_loop(a, n, posA, posB);
+  ftsort::cta_introsort_loop(a, n, posA, posB, posB + n);
   __syncthreads();
   const long long t1 = clock64();
   ftsort::stable_rank(a, o, n, tid, OCT_THREADS);
@@ -912,7 +913,7 @@ extern "C" int ft_debug_sort(unsigned long long* keys_inout, int n) {
   unsigned long long* d = nullptr;
   if (cudaMalloc(&d, sizeof(unsigned long long) * (n + 2)) != cudaSuccess) return FT_ERR_CUDA;
   cudaMemcpy(d, keys_inout, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice);
-  const size_t smem = (size_t)n * 24;
+  const size_t smem = (size_t)n * 24 + 6 * (n / 16 + 2) * 4;
   cudaFuncSetAttribute(k_debug_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_debug_sort<<<1, OCT_THREADS, smem>>>(d, n);
   cudaError_t e = cudaMemcpy(keys_inout, d, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);

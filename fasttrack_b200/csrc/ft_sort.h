@@ -245,6 +245,50 @@ __device__ __forceinline__ void warp_introsort_loop(elem_t* base, int n, int* po
   }
 }
 
+// Block-cooperative introsort loop: the two halves a partition leaves are disjoint, so all pending ranges of one
+// recursion level are processed concurrently, one warp per range (same element movement as the sequential loop,
+// which only fixes the order of operations inside a range). The critical path is the recursion depth instead of
+// the number of ranges. `queue` needs 6*(n/16+2) ints; posA/posB n ints each (a range uses its own slice).
+// Call with every thread of the block (contains __syncthreads).
+__device__ __forceinline__ void cta_introsort_loop(elem_t* base, int n, int* posA, int* posB, int* queue) {
+  if (n <= 16) return;                       // uniform over the block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
+  const int Q = n / 16 + 2;
+  int* qf[2] = {queue, queue + 3 * Q};
+  __shared__ int sCnt[2];
+  if (tid == 0) { qf[0][0] = 0; qf[0][Q] = n; qf[0][2 * Q] = 2 * floor_log2(n); sCnt[0] = 1; sCnt[1] = 0; }
+  __syncthreads();
+  int cur = 0;
+  for (;;) {
+    const int cnt = sCnt[cur];
+    if (cnt == 0) break;
+    int* qc = qf[cur];
+    int* qn = qf[cur ^ 1];
+    for (int r = warp; r < cnt; r += nWarps) {
+      const int first = qc[r], last = qc[Q + r];
+      int depth = qc[2 * Q + r];
+      if (depth == 0) {
+        if (lane == 0) heap_sort(base + first, last - first);
+        __syncwarp();
+        continue;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      if (lane == 0) move_median_to_first(&base[first], &base[first + 1], &base[mid], &base[last - 1]);
+      __syncwarp();
+      const int cut = warp_partition(base, first, last, posA + first, posB + first, lane);
+      if (lane == 0) {
+        if (last - cut > 16) { const int k = atomicAdd(&sCnt[cur ^ 1], 1); qn[k] = cut; qn[Q + k] = last; qn[2 * Q + k] = depth; }
+        if (cut - first > 16) { const int k = atomicAdd(&sCnt[cur ^ 1], 1); qn[k] = first; qn[Q + k] = cut; qn[2 * Q + k] = depth; }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) sCnt[cur] = 0;
+    cur ^= 1;
+    __syncthreads();
+  }
+}
+
 // out[rank] = in[i] with rank = #(smaller keys) + #(equal keys before i): the stable sort an insertion sort yields.
 // Call with `nthreads` cooperating threads (tid in [0, nthreads)); caller synchronises before and after.
 __device__ __forceinline__ void stable_rank(const elem_t* in, elem_t* out, int n, int tid, int nthreads) {
