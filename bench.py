@@ -353,8 +353,12 @@ def main():
     }
     top = max((k_ for k_ in stage_ms if k_ in alg_bytes), key=lambda k_: stage_ms[k_])
     ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this workload
+        traffic = json.load(open(tp))["dram_bytes_per_launch"].get(top)
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                 "algorithmic_bytes_per_launch": alg_bytes[top], "launch_ms": stage_ms[top]}
     frame_bytes = sum(alg_bytes.values())
 
