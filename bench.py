@@ -253,11 +253,13 @@ def main():
                                       out_desc[1].data_ptr(), counts4.data_ptr(), out_ur.data_ptr(), out_dp.data_ptr(),
                                       None, None, None))
         nl, nr = int(counts4[0]), int(counts4[2])
-        holder[:nl] = -1; hobs[:nl] = 0
-        m = hmaps[k]
-        ctx.search_local_points_raw(M_POINTS, m["pos"].data_ptr(), m["normal"].data_ptr(), m["minmax"].data_ptr(),
-                                    m["desc"].data_ptr(), m["flags"].data_ptr(), TH, holder.data_ptr(), hobs.data_ptr(),
-                                    best.data_ptr())
+        # marshal the local map into the context's pinned staging (what the reference's CudaMapPoint loop does), then
+        # one H2D + kernels + one D2H
+        m = maps[k]
+        for key in ("pos", "normal", "minmax", "desc", "flags"):
+            np.copyto(stg[key], m[key])
+        stg["holder"].fill(-1); stg["holder_obs"].fill(0)
+        nm, h_out, ho_out, best_out = ctx.search_staged(M_POINTS, nl, TH)
         return nl, nr
 
     # resident leg: upload one snapshot per frame index lazily is not "resident"; keep ONE pool resident and
@@ -267,6 +269,8 @@ def main():
         m = maps[k]
         ctx.upload_map_points(m["pos"], m["normal"], m["minmax"], m["desc"], m["flags"])
         ctx.upload_holders(None, None)
+
+    stg = ctx.map_point_staging(M_POINTS, cap_dev)   # views over the context's pinned staging (fixed for a fixed M)
 
     def barrier():
         torch.cuda.synchronize()
@@ -306,8 +310,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + nl * 5
-    d2h = 2 * cap_dev * (24 + 32) + cap_dev * 8 + nl * 5 + M_POINTS * 8 + 13 * 4
+    h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + 2 * cap_dev * 5
+    d2h = 64 + 2 * cap_dev * (24 + 32) + cap_dev * 8 + 64 + 2 * cap_dev * 5 + M_POINTS * 8
 
     # ---- per-kernel pass: CUDA events around every kernel (direct launches), same inputs ----
     ctx.set_stage_timing(True)

@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -95,6 +95,8 @@ def load_library():
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
     L.ft_max_keypoints.argtypes = [vp]
+    L.ft_map_point_staging.argtypes = [vp, C.c_int] + [C.POINTER(vp)] * 7
+    L.ft_search_staged.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.ft_frame_enqueue_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_frame_construct.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
@@ -281,6 +283,28 @@ class Context:
         nm = C.c_int()
         self._ck(self.L.ft_search_download(self.h, _ptr(holder), _ptr(hobs), _ptr(best), C.byref(nm)))
         return nm.value, holder[:N], hobs[:N], best[:M]
+
+    def map_point_staging(self, M, N):
+        """numpy views over the context's pinned staging buffers for M map points and N frame keypoints"""
+        p = [C.c_void_p() for _ in range(7)]
+        self._ck(self.L.ft_map_point_staging(self.h, M, *[C.byref(x) for x in p]))
+        def view(ptr, ctype, count, dtype, shape):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).view(dtype).reshape(shape)
+        return dict(pos=view(p[0], C.c_float, 3 * M, np.float32, (M, 3)), normal=view(p[1], C.c_float, 3 * M, np.float32, (M, 3)),
+                    minmax=view(p[2], C.c_float, 2 * M, np.float32, (M, 2)), desc=view(p[3], C.c_uint8, 32 * M, np.uint8, (M, 32)),
+                    flags=view(p[4], C.c_int, M, np.int32, (M,)), holder=view(p[5], C.c_int, N, np.int32, (N,)),
+                    holder_obs=view(p[6], C.c_uint8, N, np.uint8, (N,)))
+
+    def search_staged(self, M, N, th, b_far=False, th_far=50.0, nnratio=0.8):
+        """search over the snapshot written into map_point_staging(); returns views into pinned result memory"""
+        ho, hb, bi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nm = C.c_int()
+        self._ck(self.L.ft_search_staged(self.h, M, th, int(b_far), th_far, nnratio, C.byref(ho), C.byref(hb), C.byref(bi),
+                                         C.byref(nm)))
+        holder = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_int)), shape=(max(N, 1),))[:N]
+        hobs = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_uint8)), shape=(max(N, 1),))[:N]
+        best = np.ctypeslib.as_array(C.cast(bi, C.POINTER(C.c_int)), shape=(max(2 * M, 1),))[:2 * M].reshape(M, 2)
+        return nm.value, holder, hobs, best
 
     def set_stage_timing(self, enable):
         self._ck(self.L.ft_set_stage_timing(self.h, int(enable)))

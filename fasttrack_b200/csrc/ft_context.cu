@@ -46,6 +46,16 @@ struct ft_context {
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evPyr = nullptr, evJoin3 = nullptr;
   uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
   int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
+  // frame result slab: header | kpsL | kpsR | descL | descR | uRight | depth | l2r | r2l | p3d, one D2H brings it back
+  uint8_t* dFrame = nullptr; uint8_t* hFrame = nullptr;
+  size_t frameBytesPinhole = 0, frameBytesAll = 0;
+  size_t offKps[2] = {0, 0}, offDesc[2] = {0, 0}, offUR = 0, offDepth = 0, offL2R = 0, offR2L = 0, offP3D = 0;
+  // map-point staging: holderInit | holderObsInit | pos | normal | minmax | desc | flags (tight for the call's M), one H2D
+  uint8_t* dMp = nullptr; uint8_t* hMp = nullptr;
+  size_t mpHolderBytes = 0;
+  // search result slab: header(cursor[8], status) | holder | holderObs | sel, one D2H
+  uint8_t* dOut = nullptr; uint8_t* hOut = nullptr;
+  size_t offOutHolder = 0, offOutObs = 0, offOutSel = 0;
   cudaGraphExec_t gExtract = nullptr, gStereo = nullptr, gFrame = nullptr;
   int useGraph = 1;
   bool extracted = false, stereoDone = false, countsValid = false;
@@ -138,7 +148,8 @@ static ft_status build_params(ft_context* c) {
     FtLevel& L = P.lv[l];
     L.w = cv_round_f((float)cfg.width * c->invScale[l]);     // (:1500)
     L.h = cv_round_f((float)cfg.height * c->invScale[l]);
-    L.pitch = align_up(L.w, 64);
+    // level 0 is only ever read: a tight pitch lets the upload be one contiguous DMA straight into the slab
+    L.pitch = (l == 0 && L.w % 4 == 0) ? L.w : align_up(L.w, 64);
     L.offset = off;
     off += align_up(L.pitch * L.h, 256);
     L.maxBorderX = L.w - FT_EDGE_THRESHOLD + 3;
@@ -276,6 +287,36 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
       return fail(FT_ERR_CUDA);                                                                    \
     }                                                                                              \
   } while (0)
+  {
+    // frame result slab
+    const size_t K = (size_t)P.maxKp;
+    size_t o = 64;
+    c->offKps[0] = o; o += K * sizeof(ft_keypoint);
+    c->offKps[1] = o; o += K * sizeof(ft_keypoint);
+    c->offDesc[0] = o; o += K * 32;
+    c->offDesc[1] = o; o += K * 32;
+    c->offUR = o; o += K * 4;
+    c->offDepth = o; o += K * 4;
+    c->frameBytesPinhole = o;
+    c->offL2R = o; o += K * 4;
+    c->offR2L = o; o += K * 4;
+    c->offP3D = o; o += K * 12;
+    c->frameBytesAll = o;
+    CKF(dalloc(c, &c->dFrame, o));
+    CKF(cudaMallocHost((void**)&c->hFrame, o));
+    memset(c->hFrame, 0, o);
+    for (int e = 0; e < 2; e++) {
+      c->B.eye[e].counts = reinterpret_cast<int*>(c->dFrame) + 2 * e;
+      c->B.eye[e].kps = reinterpret_cast<ft_keypoint*>(c->dFrame + c->offKps[e]);
+      c->B.eye[e].desc = c->dFrame + c->offDesc[e];
+    }
+    c->B.status = reinterpret_cast<int*>(c->dFrame) + 4;
+    c->S.uRight = reinterpret_cast<float*>(c->dFrame + c->offUR);
+    c->S.depth = reinterpret_cast<float*>(c->dFrame + c->offDepth);
+    c->S.l2r = reinterpret_cast<int*>(c->dFrame + c->offL2R);
+    c->S.r2l = reinterpret_cast<int*>(c->dFrame + c->offR2L);
+    c->S.p3d = reinterpret_cast<float*>(c->dFrame + c->offP3D);
+  }
   for (int e = 0; e < 2; e++) {
     FtEye& E = c->B.eye[e];
     CKF(dalloc(c, &E.pyr, (size_t)c->pyrBytes));
@@ -287,22 +328,13 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
     CKF(dalloc(c, &E.lvlCandCount, (size_t)FT_MAX_LEVELS));
     CKF(dalloc(c, &E.lvlKp, (size_t)lvlKpTotal));
     CKF(dalloc(c, &E.lvlKpCount, (size_t)FT_MAX_LEVELS));
-    CKF(dalloc(c, &E.kps, (size_t)P.maxKp));
-    CKF(dalloc(c, &E.desc, (size_t)P.maxKp * 32));
-    CKF(dalloc(c, &E.counts, (size_t)4));
     CKF(dalloc(c, &E.octClock, (size_t)2 * FT_MAX_LEVELS * 64));
     CKF(cudaMallocHost((void**)&c->hIn[e], (size_t)cfg->width * cfg->height));
   }
-  CKF(dalloc(c, &c->B.status, (size_t)4));
   if (build_tables(c, cellKpTotal, candTotal, lvlKpTotal) != FT_OK) return fail(FT_ERR_CUDA);
   // stereo
-  CKF(dalloc(c, &c->S.uRight, (size_t)P.maxKp));
-  CKF(dalloc(c, &c->S.depth, (size_t)P.maxKp));
   CKF(dalloc(c, &c->S.bestIdxR, (size_t)P.maxKp));
   CKF(dalloc(c, &c->S.sad, (size_t)P.maxKp));
-  CKF(dalloc(c, &c->S.l2r, (size_t)P.maxKp));
-  CKF(dalloc(c, &c->S.r2l, (size_t)P.maxKp));
-  CKF(dalloc(c, &c->S.p3d, (size_t)P.maxKp * 3));
   CKF(dalloc(c, &c->S.code, (size_t)P.maxKp));
   CKF(dalloc(c, &c->S.stats, (size_t)8));
   c->B.stereoStats = c->S.stats;
@@ -314,27 +346,36 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   const int MM = cfg->max_map_points > 0 ? cfg->max_map_points : 25000;
   c->cfg.max_map_points = MM;
   FtSbpBuffers& Q = c->Q;
-  CKF(dalloc(c, &Q.pos, (size_t)MM * 3));
-  CKF(dalloc(c, &Q.normal, (size_t)MM * 3));
-  CKF(dalloc(c, &Q.minmax, (size_t)MM * 2));
-  CKF(dalloc(c, &Q.desc, (size_t)MM * 32));
-  CKF(dalloc(c, &Q.flags, (size_t)MM));
+  {
+    const size_t S2 = (size_t)2 * P.maxKp;
+    c->mpHolderBytes = S2 * 4 + ((S2 + 15) / 16) * 16;
+    const size_t mpBytes = c->mpHolderBytes + (size_t)MM * 68;
+    CKF(dalloc(c, &c->dMp, mpBytes));
+    CKF(cudaMallocHost((void**)&c->hMp, mpBytes));
+    memset(c->hMp, 0, mpBytes);
+    Q.holderInit = reinterpret_cast<int*>(c->dMp);
+    Q.holderObsInit = c->dMp + S2 * 4;
+    c->holderInit = Q.holderInit; c->holderObsInit = Q.holderObsInit;
+    c->offOutHolder = 64; c->offOutObs = 64 + S2 * 4; c->offOutSel = c->offOutObs + ((S2 + 15) / 16) * 16;
+    const size_t outBytes = c->offOutSel + (size_t)MM * 8;
+    CKF(dalloc(c, &c->dOut, outBytes));
+    CKF(cudaMallocHost((void**)&c->hOut, outBytes));
+    memset(c->hOut, 0, outBytes);
+    Q.cursor = reinterpret_cast<int*>(c->dOut);
+    Q.holder = reinterpret_cast<int*>(c->dOut + c->offOutHolder);
+    Q.holderObs = c->dOut + c->offOutObs;
+    Q.sel = reinterpret_cast<int*>(c->dOut + c->offOutSel);
+    Q.pos = Q.normal = Q.minmax = nullptr; Q.desc = nullptr; Q.flags = nullptr;   // set per snapshot (tight layout for its M)
+  }
   CKF(dalloc(c, &Q.trI, (size_t)MM * 4));
   CKF(dalloc(c, &Q.trF, (size_t)MM * 9));
   CKF(dalloc(c, &Q.listOff, (size_t)MM * 2));
   CKF(dalloc(c, &Q.listLen, (size_t)MM * 2));
   Q.poolCap = MM * 96;
   CKF(dalloc(c, &Q.pool, (size_t)Q.poolCap));
-  CKF(dalloc(c, &Q.cursor, (size_t)8));
-  CKF(dalloc(c, &Q.sel, (size_t)MM * 2));
   CKF(dalloc(c, &Q.active, (size_t)MM));
-  CKF(dalloc(c, &Q.holder, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.holderObs, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &Q.minKey, (size_t)3 * 2 * P.maxKp));   // three stamp buffers rotated by k_resolve
   CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.holderInit, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.holderObsInit, (size_t)2 * P.maxKp));
-  c->holderInit = Q.holderInit; c->holderObsInit = Q.holderObsInit;
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -362,6 +403,9 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
   if (c->hCounts) cudaFreeHost(c->hCounts);
+  if (c->hFrame) cudaFreeHost(c->hFrame);
+  if (c->hMp) cudaFreeHost(c->hMp);
+  if (c->hOut) cudaFreeHost(c->hOut);
   for (int i = 0; i < FT_STAGE_COUNT; i++) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -469,7 +513,9 @@ static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, co
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     uint8_t* dst = c->B.eye[e].pyr + c->P.lv[0].offset;   // straight into level 0 of the pyramid slab
-    if (pinned) {
+    if (pinned && step[e] == w && c->P.lv[0].pitch == w) {
+      CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+    } else if (pinned) {
       CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
     } else {
       // pageable memory: stage through the context's pinned buffer so the copy stays asynchronous
@@ -544,9 +590,7 @@ static ft_status check_device_status(ft_context* c, int status) {
 
 static ft_status fetch_counts(ft_context* c) {
   if (c->countsValid) return FT_OK;
-  CK(cudaMemcpyAsync(c->hCounts, c->B.eye[0].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->hCounts + 2, c->B.eye[1].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->hCounts, c->dFrame, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // counts + status header
   CK(cudaStreamSynchronize(c->stream));
   c->countsValid = true;
   return check_device_status(c, c->hCounts[4]);
@@ -615,8 +659,13 @@ extern "C" ft_status ft_frame_enqueue_device(ft_context* c, const uint8_t* dL, i
   if (!c || !dL || !dR) { set_err("ft_frame_enqueue_device: null argument"); return FT_ERR_INVALID; }
   const int w = c->cfg.width, h = c->cfg.height;
   CK(cudaSetDevice(c->cfg.device_id));
-  CK(cudaMemcpy2DAsync(c->B.eye[0].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
-  CK(cudaMemcpy2DAsync(c->B.eye[1].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  const uint8_t* src[2] = {dL, dR};
+  const int step[2] = {stepL, stepR};
+  for (int e = 0; e < 2; e++) {
+    uint8_t* dst = c->B.eye[e].pyr + c->P.lv[0].offset;
+    if (step[e] == w && c->P.lv[0].pitch == w) CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
+    else CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyDeviceToDevice, c->stream));
+  }
   return run_frame(c);
 }
 
@@ -635,23 +684,24 @@ extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int 
   st = run_frame(c);
   if (st != FT_OK) return st;
   cudaStream_t s = c->stream;
-  const int cap = c->P.maxKp;
-  CK(cudaMemcpyAsync(c->hCounts, c->B.eye[0].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->hCounts + 2, c->B.eye[1].counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
-  if (kpsL) CK(cudaMemcpyAsync(kpsL, c->B.eye[0].kps, sizeof(ft_keypoint) * cap, cudaMemcpyDeviceToHost, s));
-  if (descL) CK(cudaMemcpyAsync(descL, c->B.eye[0].desc, (size_t)32 * cap, cudaMemcpyDeviceToHost, s));
-  if (kpsR) CK(cudaMemcpyAsync(kpsR, c->B.eye[1].kps, sizeof(ft_keypoint) * cap, cudaMemcpyDeviceToHost, s));
-  if (descR) CK(cudaMemcpyAsync(descR, c->B.eye[1].desc, (size_t)32 * cap, cudaMemcpyDeviceToHost, s));
-  if (u_right) CK(cudaMemcpyAsync(u_right, c->S.uRight, sizeof(float) * cap, cudaMemcpyDeviceToHost, s));
-  if (depth) CK(cudaMemcpyAsync(depth, c->S.depth, sizeof(float) * cap, cudaMemcpyDeviceToHost, s));
-  if (c->fisheye) {
-    if (l2r) CK(cudaMemcpyAsync(l2r, c->S.l2r, sizeof(int) * cap, cudaMemcpyDeviceToHost, s));
-    if (r2l) CK(cudaMemcpyAsync(r2l, c->S.r2l, sizeof(int) * cap, cudaMemcpyDeviceToHost, s));
-    if (p3d) CK(cudaMemcpyAsync(p3d, c->S.p3d, sizeof(float) * 3 * cap, cudaMemcpyDeviceToHost, s));
-  }
+  // one D2H of the whole result slab (header, both eyes' keypoints + descriptors, stereo outputs), then host scatter
+  const size_t bytes = c->fisheye ? c->frameBytesAll : c->frameBytesPinhole;
+  CK(cudaMemcpyAsync(c->hFrame, c->dFrame, bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  memcpy(c->hCounts, c->hFrame, 8 * sizeof(int));
   c->countsValid = true;
+  const int nl = c->hCounts[0], nr = c->hCounts[2];
+  if (kpsL) memcpy(kpsL, c->hFrame + c->offKps[0], sizeof(ft_keypoint) * nl);
+  if (kpsR) memcpy(kpsR, c->hFrame + c->offKps[1], sizeof(ft_keypoint) * nr);
+  if (descL) memcpy(descL, c->hFrame + c->offDesc[0], (size_t)32 * nl);
+  if (descR) memcpy(descR, c->hFrame + c->offDesc[1], (size_t)32 * nr);
+  if (u_right) memcpy(u_right, c->hFrame + c->offUR, sizeof(float) * nl);
+  if (depth) memcpy(depth, c->hFrame + c->offDepth, sizeof(float) * nl);
+  if (c->fisheye) {
+    if (l2r) memcpy(l2r, c->hFrame + c->offL2R, sizeof(int) * nl);
+    if (r2l) memcpy(r2l, c->hFrame + c->offR2L, sizeof(int) * nr);
+    if (p3d) memcpy(p3d, c->hFrame + c->offP3D, sizeof(float) * 3 * nl);
+  }
   for (int i = 0; i < 4; i++) counts4[i] = c->hCounts[i];
   return check_device_status(c, c->hCounts[4]);
 }
@@ -667,23 +717,58 @@ extern "C" ft_status ft_set_pose(ft_context* c, const float* Rcw, const float* t
   return FT_OK;
 }
 
+// Tight layout of one map-point snapshot behind the fixed holder region of the staging buffers.
+static void mp_layout(ft_context* c, int M, uint8_t* base, float** pos, float** normal, float** minmax, uint8_t** desc,
+                      int** flags) {
+  uint8_t* p = base + c->mpHolderBytes;
+  *pos = reinterpret_cast<float*>(p);
+  *normal = reinterpret_cast<float*>(p + (size_t)12 * M);
+  *minmax = reinterpret_cast<float*>(p + (size_t)24 * M);
+  *desc = p + (size_t)32 * M;
+  *flags = reinterpret_cast<int*>(p + (size_t)64 * M);
+}
+static void mp_bind_device(ft_context* c, int M) {
+  FtSbpBuffers& Q = c->Q;
+  mp_layout(c, M, c->dMp, &Q.pos, &Q.normal, &Q.minmax, &Q.desc, &Q.flags);
+  c->residentM = M;
+}
+
+extern "C" ft_status ft_map_point_staging(ft_context* c, int M, float** pos, float** normal, float** minmax,
+                                          uint8_t** desc, int** flags, int** holder, uint8_t** holder_obs) {
+  if (!c || M < 0) { set_err("ft_map_point_staging: bad argument"); return FT_ERR_INVALID; }
+  if (M > c->cfg.max_map_points) {
+    set_err("more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)");
+    return FT_ERR_CAPACITY;
+  }
+  float *p, *n, *mm; uint8_t* d; int* f;
+  mp_layout(c, M, c->hMp, &p, &n, &mm, &d, &f);
+  if (pos) *pos = p;
+  if (normal) *normal = n;
+  if (minmax) *minmax = mm;
+  if (desc) *desc = d;
+  if (flags) *flags = f;
+  if (holder) *holder = reinterpret_cast<int*>(c->hMp);
+  if (holder_obs) *holder_obs = c->hMp + (size_t)2 * c->P.maxKp * 4;
+  return FT_OK;
+}
+
 extern "C" ft_status ft_upload_map_points(ft_context* c, int M, const float* pos, const float* normal,
                                           const float* minmax, const uint8_t* desc, const int* flags) {
   if (!c || M < 0 || (M > 0 && (!pos || !normal || !minmax || !desc || !flags))) { set_err("ft_upload_map_points: null argument"); return FT_ERR_INVALID; }
-  if (M > c->cfg.max_map_points) {
-    set_err("ft_upload_map_points: more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)");
-    return FT_ERR_CAPACITY;
-  }
+  float *p, *n, *mm; uint8_t* d; int* f;
+  ft_status st = ft_map_point_staging(c, M, &p, &n, &mm, &d, &f, nullptr, nullptr);
+  if (st != FT_OK) return st;
   CK(cudaSetDevice(c->cfg.device_id));
-  FtSbpBuffers& Q = c->Q;
-  cudaStream_t s = c->stream;
-  c->residentM = M;
-  if (M == 0) return FT_OK;
-  CK(cudaMemcpyAsync(Q.pos, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.normal, normal, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.minmax, minmax, sizeof(float) * 2 * M, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.desc, desc, (size_t)32 * M, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(Q.flags, flags, sizeof(int) * M, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(c->stream));   // the staging buffer may still be in flight
+  if (M) {
+    if (pos != p) memcpy(p, pos, sizeof(float) * 3 * M);
+    if (normal != n) memcpy(n, normal, sizeof(float) * 3 * M);
+    if (minmax != mm) memcpy(mm, minmax, sizeof(float) * 2 * M);
+    if (desc != d) memcpy(d, desc, (size_t)32 * M);
+    if (flags != f) memcpy(f, flags, sizeof(int) * M);
+    CK(cudaMemcpyAsync(c->dMp + c->mpHolderBytes, c->hMp + c->mpHolderBytes, (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
+  }
+  mp_bind_device(c, M);
   return FT_OK;
 }
 
@@ -714,7 +799,7 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   if (M == 0) {   // nothing to project: the holders come back unchanged
     CK(cudaMemcpyAsync(Q.holder, c->holderInit, sizeof(int) * 2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(Q.holderObs, c->holderObsInit, (size_t)2 * c->P.maxKp, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemsetAsync(Q.cursor, 0, 8 * sizeof(int), s));
+    CK(cudaMemsetAsync(Q.cursor, 0, 16 * sizeof(int), s));
     return FT_OK;
   }
   FtFrustumArgs fa;
@@ -734,44 +819,84 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   return FT_OK;
 }
 
+// one D2H of the search result slab (cursors + status, holders, per-point selections), then host scatter
+static ft_status search_fetch(ft_context* c, int N, int* holder, uint8_t* holderObs, int* best_idx, int* nmatches) {
+  cudaStream_t s = c->stream;
+  const size_t bytes = c->offOutSel + (best_idx ? (size_t)8 * c->lastM : 0);
+  CK(cudaMemcpyAsync(c->hOut, c->dOut, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int* hdr = reinterpret_cast<const int*>(c->hOut);
+  memcpy(c->hCounts + 8, hdr, 8 * sizeof(int));
+  if (holder && N) memcpy(holder, c->hOut + c->offOutHolder, sizeof(int) * N);
+  if (holderObs && N) memcpy(holderObs, c->hOut + c->offOutObs, (size_t)N);
+  if (best_idx && c->lastM) memcpy(best_idx, c->hOut + c->offOutSel, sizeof(int) * 2 * c->lastM);
+  if (nmatches) *nmatches = hdr[1];
+  return check_device_status(c, hdr[8]);
+}
+
 extern "C" ft_status ft_search_download(ft_context* c, int* holder, uint8_t* holderObs, int* best_idx, int* nmatches) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
   ft_status st = fetch_counts(c);
   if (st != FT_OK) return st;
   const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
-  FtSbpBuffers& Q = c->Q;
-  cudaStream_t s = c->stream;
-  if (holder && N) CK(cudaMemcpyAsync(holder, Q.holder, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
-  if (holderObs && N) CK(cudaMemcpyAsync(holderObs, Q.holderObs, (size_t)N, cudaMemcpyDeviceToHost, s));
-  if (best_idx && c->lastM) CK(cudaMemcpyAsync(best_idx, Q.sel, sizeof(int) * 2 * c->lastM, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->hCounts + 8, Q.cursor, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->hCounts + 4, c->B.status, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  if (nmatches) *nmatches = c->hCounts[9];
-  return check_device_status(c, c->hCounts[4]);
+  return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
+}
+
+// Search over a snapshot the caller wrote into the pinned staging buffers returned by ft_map_point_staging:
+// one H2D (holders + snapshot), two kernels, one D2H.
+extern "C" ft_status ft_search_staged(ft_context* c, int M, float th, int bFar, float thFar, float nnratio,
+                                      const int** holder_out, const uint8_t** holder_obs_out, const int** best_idx_out,
+                                      int* nmatches) {
+  if (!c || M < 0 || M > c->cfg.max_map_points) { set_err("ft_search_staged: bad argument"); return FT_ERR_INVALID; }
+  if (!c->extracted || !c->stereoDone) { set_err("ft_search_staged: no stereo-matched frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  if (nmatches) *nmatches = 0;
+  CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
+  mp_bind_device(c, M);
+  ft_status st = ft_search_resident(c, th, bFar, thFar, nnratio);
+  if (st != FT_OK) return st;
+  {
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->hOut, c->dOut, c->offOutSel + (size_t)8 * M, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int* hdr = reinterpret_cast<const int*>(c->hOut);
+    memcpy(c->hCounts + 8, hdr, 8 * sizeof(int));
+    if (holder_out) *holder_out = reinterpret_cast<const int*>(c->hOut + c->offOutHolder);
+    if (holder_obs_out) *holder_obs_out = c->hOut + c->offOutObs;
+    if (best_idx_out) *best_idx_out = reinterpret_cast<const int*>(c->hOut + c->offOutSel);
+    if (nmatches) *nmatches = hdr[1];
+    return check_device_status(c, hdr[8]);
+  }
 }
 
 extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* pos, const float* normal,
                                             const float* minmax, const uint8_t* desc, const int* flags, float th,
                                             int bFar, float thFar, float nnratio, int* holder, uint8_t* holderObs,
                                             int* best_idx, int* nmatches) {
-  if (!c || !holder || !holderObs) { set_err("ft_search_local_points: null argument"); return FT_ERR_INVALID; }
+  if (!c || !holder || !holderObs || M < 0 || (M > 0 && (!pos || !normal || !minmax || !desc || !flags))) {
+    set_err("ft_search_local_points: null argument"); return FT_ERR_INVALID;
+  }
   if (!c->extracted) { set_err("ft_search_local_points: no extracted frame"); return FT_ERR_STATE; }
   if (!c->stereoDone) { set_err("ft_search_local_points: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
-  ft_status st = fetch_counts(c);
+  ft_status st = fetch_counts(c);   // synchronises: the staging buffers are free afterwards
   if (st != FT_OK) return st;
   const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
   if (nmatches) *nmatches = 0;
-  st = ft_upload_map_points(c, M, pos, normal, minmax, desc, flags);
+  float *p, *n, *mm; uint8_t* d; int *f, *h; uint8_t* ho;
+  st = ft_map_point_staging(c, M, &p, &n, &mm, &d, &f, &h, &ho);
   if (st != FT_OK) return st;
   if (M == 0 || N == 0) { c->lastM = 0; return FT_OK; }
-  st = ft_upload_holders(c, N, holder, holderObs);
-  if (st != FT_OK) return st;
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(p, pos, sizeof(float) * 3 * M); memcpy(n, normal, sizeof(float) * 3 * M); memcpy(mm, minmax, sizeof(float) * 2 * M);
+  memcpy(d, desc, (size_t)32 * M); memcpy(f, flags, sizeof(int) * M);
+  memcpy(h, holder, sizeof(int) * N); memcpy(ho, holderObs, (size_t)N);
+  CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
+  mp_bind_device(c, M);
   st = ft_search_resident(c, th, bFar, thFar, nnratio);
   if (st != FT_OK) return st;
-  return ft_search_download(c, holder, holderObs, best_idx, nmatches);
+  return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
 }
 
 extern "C" ft_status ft_set_stage_timing(ft_context* c, int enable) {

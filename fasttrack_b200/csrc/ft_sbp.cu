@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     const int k = __ldcg(&s.lastKey[i]);
     if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
   }
-  if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; }
+  if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status; }
 }
 
 // In-order execution by one thread (fisheye rigs with non-blocking map points only).
@@ -528,7 +528,7 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
       }
     }
   }
-  s.cursor[1] = nm; s.cursor[2] = 0; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0;
+  s.cursor[1] = nm; s.cursor[2] = 0; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status;
 }
 
 // ---- host launchers -----------------------------------------------------------------------

@@ -153,6 +153,18 @@ ft_status ft_upload_holders(ft_context* ctx, int N, const int* holder, const uin
 ft_status ft_search_resident(ft_context* ctx, float th, int b_far_points, float th_far_points, float nnratio);
 ft_status ft_search_download(ft_context* ctx, int* holder, uint8_t* holder_obs, int* best_idx, int* nmatches);
 
+/* Zero-copy variant for integrations that marshal MapPoints themselves (the reference's CudaMapPoint loop,
+ * src/Kernels/CudaWrappers/CudaMapPoint.cc:15-34): ft_map_point_staging returns HOST pointers into the context's
+ * pinned staging buffer, laid out for M map points (pos[M][3], normal[M][3], minmax[M][2], desc[M][32], flags[M],
+ * holder[N], holder_obs[N]); the caller fills them and calls ft_search_staged, which issues ONE H2D, the kernels and
+ * ONE D2H. The returned result pointers point into pinned host memory owned by the context and stay valid until
+ * the next search. */
+ft_status ft_map_point_staging(ft_context* ctx, int M, float** pos, float** normal, float** minmax, uint8_t** desc,
+                               int** flags, int** holder, uint8_t** holder_obs);
+ft_status ft_search_staged(ft_context* ctx, int M, float th, int b_far_points, float th_far_points, float nnratio,
+                           const int** holder_out, const uint8_t** holder_obs_out, const int** best_idx_out,
+                           int* nmatches);
+
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
 

@@ -288,3 +288,21 @@ def test_resident_search_matches_host_call(euroc):
         ctx.search_resident(3.0)
         n2, h2, o2, b2 = ctx.search_download(M)
         assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(o1, o2) and np.array_equal(b1, b2)
+
+
+def test_staged_search_matches_host_call(euroc):
+    """ft_map_point_staging + ft_search_staged (one H2D, one D2H) == ft_search_local_points"""
+    ctx = euroc["ctx"]
+    _, kL, dL = euroc["oL"]
+    M = 5000
+    mp = synth.mappoints(kL, dL, euroc["exL"].scale, M, seed=91)
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n1, h1, o1, b1 = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 2.0,
+                                             mp["holder"], mp["holder_obs"])
+    N = len(kL)
+    stg = ctx.map_point_staging(M, N)
+    for k in ("pos", "normal", "minmax", "desc", "flags"):
+        np.copyto(stg[k], mp[k])
+    np.copyto(stg["holder"], mp["holder"]); np.copyto(stg["holder_obs"], mp["holder_obs"])
+    n2, h2, o2, b2 = ctx.search_staged(M, N, 2.0)
+    assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(o1, o2) and np.array_equal(b1, b2)
