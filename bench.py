@@ -355,7 +355,8 @@ def main():
         "gather": 68 * M_POINTS + 52 * st["sbp_candidates"],
         "resolve": 4 * st["sbp_candidates"] + 8 * M_POINTS,
     }
-    top = max((k_ for k_ in stage_ms if k_ in alg_bytes), key=lambda k_: stage_ms[k_])
+    # dominant kernel = the single launch with the largest CUDA-event time ("resize" is a chain of 7 launches, reported in stages_ms)
+    top = max((k_ for k_ in stage_ms if k_ in alg_bytes and k_ != "resize"), key=lambda k_: stage_ms[k_])
     ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
