@@ -43,6 +43,8 @@ struct ft_context {
   std::vector<int> quota;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+  cudaStream_t lvStream[FT_MAX_LEVELS] = {};   // one branch per pyramid level in the captured graph
+  cudaEvent_t lvReady[FT_MAX_LEVELS] = {}, lvDone[FT_MAX_LEVELS] = {};
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evPyr = nullptr, evJoin3 = nullptr;
   uint8_t* hIn[2] = {nullptr, nullptr};     // pinned host staging
   int* hCounts = nullptr;                   // pinned: nL, monoL, nR, monoR, status, sbp cursor[4]
@@ -381,6 +383,11 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  for (int l = 0; l < P.nlevels; l++) {
+    CKF(cudaStreamCreateWithFlags(&c->lvStream[l], cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&c->lvReady[l], cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&c->lvDone[l], cudaEventDisableTiming));
+  }
   CKF(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evFork2, cudaEventDisableTiming));
@@ -416,6 +423,11 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream3) cudaStreamDestroy(c->stream3);
+  for (int l = 0; l < FT_MAX_LEVELS; l++) {
+    if (c->lvStream[l]) cudaStreamDestroy(c->lvStream[l]);
+    if (c->lvReady[l]) cudaEventDestroy(c->lvReady[l]);
+    if (c->lvDone[l]) cudaEventDestroy(c->lvDone[l]);
+  }
   delete c;
   return FT_OK;
 }
@@ -436,16 +448,20 @@ extern "C" ft_status ft_get_scale_tables(ft_context* c, float* scale, float* inv
 // The per-frame extraction chain. Enqueued on c->stream with the blur forked onto c->stream2;
 // identical whether it is being captured into a graph or launched directly.
 static int enqueue_extract(ft_context* c) {
-  // Launch topology (captured as-is into the CUDA graph): level 0 needs no resize, and its octree is the longest
-  // single dependency of the frame, so it gets its own branch that starts right after the input copy.
-  // The input images have already been copied straight into the level-0 slabs of the two pyramids.
-  //   s : resize 1..n-1 -> FAST 1..n-1 -> octree 1..n-1 ----+
-  //   s3: FAST 0 -> octree 0 --------------------------------+-> orient+descriptors
-  //   s2: blur 0, (after resizes) blur 1..n-1 ---------------+
+  // Launch topology. The input images have already been copied straight into the level-0 slabs.
+  // Graph mode (the product path): every pyramid level is its own branch, started the moment the level exists,
+  //   s    : resize 1 -> resize 2 -> ... -> resize n-1                      (the only inherent chain)
+  //   lv[l]: (after resize l; l = 0 immediately) FAST l -> octree l          (the octrees are latency-bound and
+  //                                                                           independent: they overlap on different SMs)
+  //   s2   : blur 0, (after the last resize) blur 1..n-1
+  //   join -> orientation + descriptors
+  // Direct-launch mode (per-kernel CUDA-event timing) groups levels 1..n-1 into one FAST and one octree launch so
+  // that each stage is a single timed interval.
   const FtParams& P = c->P;
   const int nl = P.nlevels;
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
+  const bool perLevel = !c->timing;
   cudaEventRecord(c->evFork, s);
   cudaStreamWaitEvent(s3, c->evFork, 0);
   cudaStreamWaitEvent(s2, c->evFork, 0);
@@ -454,12 +470,27 @@ static int enqueue_extract(ft_context* c) {
   cudaEventRecord(c->evJoin3, s3);
   { StageScope t(c, FT_STAGE_BLUR_L0, s2); ft_launch_blur(P, c->B, 0, 1, s2); n++; }
   if (nl > 1) {
-    { StageScope t(c, FT_STAGE_RESIZE, s); for (int l = 1; l < nl; l++) { ft_launch_resize(P, c->B, l, s); n++; } }
-    cudaEventRecord(c->evPyr, s);
-    cudaStreamWaitEvent(s2, c->evPyr, 0);
-    { StageScope t(c, FT_STAGE_BLUR, s2); ft_launch_blur(P, c->B, 1, nl, s2); n++; }
-    { StageScope t(c, FT_STAGE_FAST, s); ft_launch_fast(P, c->B, 1, nl, s); n++; }
-    { StageScope t(c, FT_STAGE_OCTREE, s); ft_launch_octree(P, c->B, 1, nl, s); n++; }
+    if (perLevel) {
+      for (int l = 1; l < nl; l++) {
+        ft_launch_resize(P, c->B, l, s); n++;
+        cudaEventRecord(c->lvReady[l], s);
+        cudaStreamWaitEvent(c->lvStream[l], c->lvReady[l], 0);
+        ft_launch_fast(P, c->B, l, l + 1, c->lvStream[l]); n++;
+        ft_launch_octree(P, c->B, l, l + 1, c->lvStream[l]); n++;
+        cudaEventRecord(c->lvDone[l], c->lvStream[l]);
+      }
+      cudaEventRecord(c->evPyr, s);
+      cudaStreamWaitEvent(s2, c->evPyr, 0);
+      ft_launch_blur(P, c->B, 1, nl, s2); n++;
+      for (int l = 1; l < nl; l++) cudaStreamWaitEvent(s, c->lvDone[l], 0);
+    } else {
+      { StageScope t(c, FT_STAGE_RESIZE, s); for (int l = 1; l < nl; l++) { ft_launch_resize(P, c->B, l, s); n++; } }
+      cudaEventRecord(c->evPyr, s);
+      cudaStreamWaitEvent(s2, c->evPyr, 0);
+      { StageScope t(c, FT_STAGE_BLUR, s2); ft_launch_blur(P, c->B, 1, nl, s2); n++; }
+      { StageScope t(c, FT_STAGE_FAST, s); ft_launch_fast(P, c->B, 1, nl, s); n++; }
+      { StageScope t(c, FT_STAGE_OCTREE, s); ft_launch_octree(P, c->B, 1, nl, s); n++; }
+    }
   }
   cudaEventRecord(c->evJoin, s2);
   cudaStreamWaitEvent(s, c->evJoin, 0);
