@@ -142,7 +142,9 @@ __device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const 
   if (viewCos < a.viewCosLimit) return false;
   // MapPoint::PredictScale (MapPoint.cc:531-546): ceil(log(maxDistRaw/dist)/logScale), float log via double
   const float ratio = __fdiv_rn(maxDistRaw, dist);
-  const float q = __fdiv_rn((float)log((double)ratio), a.logScale);
+  // float log first; the double evaluation (which defines the result) only when ceil() could go either way
+  float q = __fdiv_rn(logf(ratio), a.logScale);
+  if (fabsf(q - rintf(q)) < 1e-3f || !(fabsf(q) < 1e6f)) q = __fdiv_rn((float)log((double)ratio), a.logScale);
   int nScale = (int)ceilf(q);
   if (nScale < 0) nScale = 0;
   else if (nScale >= a.nlevels) nScale = a.nlevels - 1;
@@ -158,152 +160,189 @@ __device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const 
 // once: passing keypoints are collected in traversal order into a small per-warp shared-memory buffer
 // (GA_BUF entries; longer lists take a second walk straight into the pool), and the lanes finally split the
 // candidates evenly for the Hamming distances.
-#define GA_WARPS 8
+#define GA_WARPS 16
 #define GA_BUF 96
 __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                           const __grid_constant__ FtGridBuffers g,
                                                           const __grid_constant__ FtStereoBuffers st,
                                                           const __grid_constant__ FtSbpBuffers s,
                                                           const __grid_constant__ FtFrustumArgs fa,
-                                                          const __grid_constant__ FtGatherArgs a, int M) {
+                                                          const __grid_constant__ FtGatherArgs a, int M, int stage) {
+  extern __shared__ __align__(16) uint8_t gaSmem[];
   __shared__ unsigned short sBuf[GA_WARPS][GA_BUF];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mp = blockIdx.x * GA_WARPS + warp;
+  __shared__ int sCol[GA_WARPS][FT_GRID_COLS], sPre[GA_WARPS][FT_GRID_COLS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nEyes = a.fisheye ? 2 : 1;
+  // The frame-side search structure (grid CSR + 16-byte keypoint records + uRight) is ~40 KB: every CTA stages it
+  // in shared memory once, so the window walks below never leave the SM. (stage == 0: structure too large for
+  // shared memory, e.g. 10k features; the same code then reads it from L2.)
+  const float4* recP[2] = {g.rec, g.rec + p.maxKp};
+  const int* cellStartP[2] = {g.cellStart, g.cellStart + (GRID_CELLS + 1)};
+  const int* cellIdxP[2] = {g.cellIdx, g.cellIdx + p.maxKp};
+  const float* uRightP = st.uRight;
+  if (stage) {
+    uint8_t* q = gaSmem;
+    for (int e = 0; e < nEyes; e++) {
+      const int n = b.eye[e].counts[0];
+      float4* r = reinterpret_cast<float4*>(q); q += sizeof(float4) * p.maxKp;
+      int* cs = reinterpret_cast<int*>(q); q += sizeof(int) * (GRID_CELLS + 4);
+      int* ci = reinterpret_cast<int*>(q); q += sizeof(int) * p.maxKp;
+      for (int i = tid; i < n; i += GA_WARPS * 32) { r[i] = recP[e][i]; ci[i] = cellIdxP[e][i]; }
+      for (int i = tid; i <= GRID_CELLS; i += GA_WARPS * 32) cs[i] = cellStartP[e][i];
+      recP[e] = r; cellStartP[e] = cs; cellIdxP[e] = ci;
+    }
+    if (!a.fisheye) {
+      float* u = reinterpret_cast<float*>(q);
+      const int n = b.eye[0].counts[0];
+      for (int i = tid; i < n; i += GA_WARPS * 32) u[i] = st.uRight[i];
+      uRightP = u;
+    }
+    __syncthreads();
+  }
   // cursors [0] pool, [3] non-blocking count, [4] active count are accumulated here; they are zero on entry
   // (cleared at allocation and by the resolve kernel of the previous search)
-  if (mp >= M) return;
-  const int flags = s.flags[mp];
-  int inView = 0, inViewR = 0, level = -1, levelR = -1;
-  float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (!(flags & 1)) {
-    const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
-    const float Pn[3] = {s.normal[3 * mp], s.normal[3 * mp + 1], s.normal[3 * mp + 2]};
-    const float mn = s.minmax[2 * mp], mx = s.minmax[2 * mp + 1];
-    if (!fa.fisheye) {
-      float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
-      const bool ok = ft_frustum_checks(fa, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
-      f[0] = u; f[1] = v;
-      if (ok) { inView = 1; f[2] = xr; f[3] = d; f[4] = vc; level = lv; }
-    } else {
-      float u = 0, v = 0, xr = 0, d = 0, vc = 0; int lv = -1;
-      if (ft_frustum_checks(fa, P, Pn, mn, mx, false, false, u, v, xr, d, vc, lv)) {
-        inView = 1; f[0] = u; f[1] = v; f[3] = d; f[4] = vc; level = lv;
-      }
-      if (ft_frustum_checks(fa, P, Pn, mn, mx, true, false, u, v, xr, d, vc, lv)) {
-        inViewR = 1; f[5] = u; f[6] = v; f[7] = d; f[8] = vc; levelR = lv;
+  for (int mp = blockIdx.x * GA_WARPS + warp; mp < M; mp += gridDim.x * GA_WARPS) {
+    const int flags = s.flags[mp];
+    int inView = 0, inViewR = 0, level = -1, levelR = -1;
+    float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!(flags & 1)) {
+      const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
+      const float Pn[3] = {s.normal[3 * mp], s.normal[3 * mp + 1], s.normal[3 * mp + 2]};
+      const float mn = s.minmax[2 * mp], mx = s.minmax[2 * mp + 1];
+      if (!fa.fisheye) {
+        float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
+        const bool ok = ft_frustum_checks(fa, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
+        f[0] = u; f[1] = v;
+        if (ok) { inView = 1; f[2] = xr; f[3] = d; f[4] = vc; level = lv; }
+      } else {
+        float u = 0, v = 0, xr = 0, d = 0, vc = 0; int lv = -1;
+        if (ft_frustum_checks(fa, P, Pn, mn, mx, false, false, u, v, xr, d, vc, lv)) {
+          inView = 1; f[0] = u; f[1] = v; f[3] = d; f[4] = vc; level = lv;
+        }
+        if (ft_frustum_checks(fa, P, Pn, mn, mx, true, false, u, v, xr, d, vc, lv)) {
+          inViewR = 1; f[5] = u; f[6] = v; f[7] = d; f[8] = vc; levelR = lv;
+        }
       }
     }
-  }
-  if (lane < 9) s.trF[9 * mp + lane] = f[lane];
-  if (lane == 0) {
-    *reinterpret_cast<int4*>(s.trI + 4 * mp) = make_int4(inView, inViewR, level, levelR);
-    *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(-1, -1);
-  }
-  bool searched = (inView || inViewR) && !(flags & 1);
-  if (a.bFar && f[3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
-  if (lane == 0 && searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
-  int2 lens = make_int2(0, 0), offs = make_int2(0, 0);
-  if (searched) {
-    const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
-    const uint4 md0 = md[0], md1 = md[1];
-    const int nBranches = a.fisheye ? 2 : 1;
-    for (int br = 0; br < nBranches; br++) {
-      const bool active = (br == 0 ? inView : inViewR) && (br == 0 || levelR != -1);
-      if (!active) continue;
-      const int lvl = br == 0 ? level : levelR;
-      const float x = br == 0 ? f[0] : f[5];
-      const float y = br == 0 ? f[1] : f[6];
-      const float viewCos = br == 0 ? f[4] : f[8];
-      float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos (ORBmatcher.cc:314-320)
-      if (br == 0 && a.bFactor) r = __fmul_rn(r, a.th);
-      const float rr = __fmul_rn(r, p.scale[lvl]);
-      const int minLevel = lvl - 1, maxLevel = lvl;
-      // GetFeaturesInArea cell window (Frame.cc:689-707)
-      const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
-      const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
-      const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
-      const int cy1 = min(FT_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
-      if (!(cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0)) continue;
-      const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
-      const int* cellStart = g.cellStart + br * (GRID_CELLS + 1);
-      const int* cellIdx = g.cellIdx + br * p.maxKp;
-      const FtEye& E = b.eye[br];
-      const float projXR = f[2];
-      const float4* rec = g.rec + br * p.maxKp;
-      auto passes = [&](int idx) -> bool {
-        const float4 kp = __ldg(rec + idx);
-        const int oct = __float_as_int(kp.z);
-        if (oct < minLevel) return false;
-        if (maxLevel >= 0 && oct > maxLevel) return false;
-        const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
-        if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
-        if (!a.fisheye) {
-          const float ur = st.uRight[idx];
-          if (ur > 0) {
-            const float er = fabsf(__fsub_rn(projXR, ur));
-            if (er > rr) return false;                       // stereo consistency (ORBmatcher.cc:105-110)
+    if (lane < 9) s.trF[9 * mp + lane] = f[lane];
+    if (lane == 0) {
+      *reinterpret_cast<int4*>(s.trI + 4 * mp) = make_int4(inView, inViewR, level, levelR);
+      *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(-1, -1);
+    }
+    bool searched = (inView || inViewR) && !(flags & 1);
+    if (a.bFar && f[3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
+    if (lane == 0 && searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
+    int2 lens = make_int2(0, 0), offs = make_int2(0, 0);
+    if (searched) {
+      const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
+      const uint4 md0 = md[0], md1 = md[1];
+      for (int br = 0; br < nEyes; br++) {
+        const bool active = (br == 0 ? inView : inViewR) && (br == 0 || levelR != -1);
+        if (!active) continue;
+        const int lvl = br == 0 ? level : levelR;
+        const float x = br == 0 ? f[0] : f[5];
+        const float y = br == 0 ? f[1] : f[6];
+        const float viewCos = br == 0 ? f[4] : f[8];
+        float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos (ORBmatcher.cc:314-320)
+        if (br == 0 && a.bFactor) r = __fmul_rn(r, a.th);
+        const float rr = __fmul_rn(r, p.scale[lvl]);
+        const int minLevel = lvl - 1, maxLevel = lvl;
+        // GetFeaturesInArea cell window (Frame.cc:689-707)
+        const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
+        const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
+        const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
+        const int cy1 = min(FT_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
+        if (!(cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0)) continue;
+        const int* cellStart = cellStartP[br];
+        const int* cellIdx = cellIdxP[br];
+        const float4* rec = recP[br];
+        const FtEye& E = b.eye[br];
+        const float projXR = f[2];
+        auto passes = [&](int idx) -> bool {
+          const float4 kp = rec[idx];
+          const int oct = __float_as_int(kp.z);
+          if (oct < minLevel) return false;
+          if (maxLevel >= 0 && oct > maxLevel) return false;
+          const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+          if (!(fabsf(dx) < rr && fabsf(dy) < rr)) return false;
+          if (!a.fisheye) {
+            const float ur = uRightP[idx];
+            if (ur > 0) {
+              const float er = fabsf(__fsub_rn(projXR, ur));
+              if (er > rr) return false;                       // stereo consistency (ORBmatcher.cc:105-110)
+            }
           }
-        }
-        return true;
-      };
-      // walk the window in traversal order (ix outer, iy inner, cell insertion order); dst == nullptr: into sBuf
-      auto walk = [&](uint32_t* dst) -> int {
-        int run = 0;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-          const int c = c0 + lane;
-          int mine = 0, k0 = 0, k1 = 0;
-          if (c < nc) {
-            const int cell = (cx0 + c / ny) * FT_GRID_ROWS + (cy0 + c % ny);
-            k0 = cellStart[cell]; k1 = cellStart[cell + 1];
-            for (int k = k0; k < k1; k++) mine += passes(cellIdx[k]);
-          }
-          int incl = mine;
+          return true;
+        };
+        // Cells of one grid column are consecutive in the CSR (cell = ix*48 + iy), so the window is ncol contiguous
+        // index ranges that, concatenated in ix order, are exactly the traversal order (ix outer, iy inner, insertion
+        // order). Lanes first fetch the per-column ranges, then split the flattened element list evenly.
+        const int ncol = cx1 - cx0 + 1;
+        int T = 0;
+        for (int j0 = 0; j0 < ncol; j0 += 32) {
+          const int j = j0 + lane;
+          int cs = 0, ce = 0;
+          if (j < ncol) { const int cb = (cx0 + j) * FT_GRID_ROWS; cs = cellStart[cb + cy0]; ce = cellStart[cb + cy1 + 1]; }
+          const int len = ce - cs;
+          int incl = len;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += t;
           }
-          int w = run + incl - mine;
-          if (mine) {
-            for (int k = k0; k < k1; k++) {
-              const int idx = cellIdx[k];
-              if (passes(idx)) {
-                if (dst) dst[w] = (uint32_t)idx;
-                else if (w < GA_BUF) sBuf[warp][w] = (unsigned short)idx;
-                w++;
-              }
-            }
-          }
-          run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (j < ncol) { sCol[warp][j] = cs; sPre[warp][j] = T + incl - len; }
+          T += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        return run;
-      };
-      const int total = walk(nullptr);
-      if (total == 0) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s.cursor[0], total);
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (base + total > s.poolCap) {
-        if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
-        continue;
+        __syncwarp();
+        auto walk = [&](uint32_t* dst) -> int {
+          int run = 0;
+          for (int e0 = 0; e0 < T; e0 += 32) {
+            const int e = e0 + lane;
+            bool ok = false;
+            int idx = 0;
+            if (e < T) {
+              int lo = 0, hi = ncol;                 // last column whose first element is <= e
+              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sPre[warp][mid] <= e) lo = mid; else hi = mid; }
+              idx = cellIdx[sCol[warp][lo] + (e - sPre[warp][lo])];
+              ok = passes(idx);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) {
+              const int w = run + __popc(m & ((1u << lane) - 1u));
+              if (dst) dst[w] = (uint32_t)idx;
+              else if (w < GA_BUF) sBuf[warp][w] = (unsigned short)idx;
+            }
+            run += __popc(m);
+          }
+          return run;
+        };
+        const int total = walk(nullptr);
+        if (total == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s.cursor[0], total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base + total > s.poolCap) {
+          if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
+          continue;
+        }
+        if (total > GA_BUF) walk(s.pool + base);
+        __syncwarp();
+        // Hamming distance + octave per candidate
+        for (int k = lane; k < total; k += 32) {
+          const int idx = total > GA_BUF ? (int)s.pool[base + k] : (int)sBuf[warp][k];
+          const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
+          const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
+          s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)__float_as_int(rec[idx].z) << 25);
+        }
+        __syncwarp();
+        if (br == 0) { lens.x = total; offs.x = base; } else { lens.y = total; offs.y = base; }
       }
-      if (total > GA_BUF) walk(s.pool + base);
-      __syncwarp();
-      // Hamming distance + octave per candidate
-      for (int k = lane; k < total; k += 32) {
-        const int idx = total > GA_BUF ? (int)s.pool[base + k] : (int)sBuf[warp][k];
-        const uint4* dd = reinterpret_cast<const uint4*>(E.desc + (size_t)idx * 32);
-        const int dist = ft_hamming256(md0, md1, dd[0], dd[1]);
-        s.pool[base + k] = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)__float_as_int(__ldg(rec + idx).z) << 25);
-      }
-      __syncwarp();
-      if (br == 0) { lens.x = total; offs.x = base; } else { lens.y = total; offs.y = base; }
     }
-  }
-  if (lane == 0) {
-    *reinterpret_cast<int2*>(s.listOff + 2 * mp) = offs;
-    *reinterpret_cast<int2*>(s.listLen + 2 * mp) = lens;
-    if (lens.x | lens.y) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
+    if (lane == 0) {
+      *reinterpret_cast<int2*>(s.listOff + 2 * mp) = offs;
+      *reinterpret_cast<int2*>(s.listLen + 2 * mp) = lens;
+      if (lens.x | lens.y) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
+    }
   }
 }
 
@@ -533,9 +572,18 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
 
 // ---- host launchers -----------------------------------------------------------------------
 static int g_resolveCluster = 8;
+static size_t ft_gather_smem(const FtParams& p, int fisheye) {
+  const size_t perEye = sizeof(float4) * p.maxKp + sizeof(int) * (GRID_CELLS + 4) + sizeof(int) * p.maxKp;
+  return (fisheye ? 2 : 1) * perEye + (fisheye ? 0 : sizeof(float) * p.maxKp) + 16;
+}
 static size_t ft_resolve_smem(int slotCap) { return (size_t)slotCap * 4 + (size_t)((slotCap + 3) / 4) * 4 + 2 * RS_LCAP * RS_THREADS * 4 + 16; }
 cudaError_t ft_launch_sbp_setup(const FtParams& p) {
   cudaError_t e = cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_resolve_smem(2 * p.maxKp));
+  if (e != cudaSuccess) return e;
+  {
+    const size_t g1 = ft_gather_smem(p, 1);
+    e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(g1 <= 200 * 1024 ? g1 : ft_gather_smem(p, 0) <= 200 * 1024 ? ft_gather_smem(p, 0) : 0));
+  }
   if (e != cudaSuccess) return e;
   // 16-CTA clusters are a non-portable size: opt in, and fall back to the portable 8 when the device cannot place one
   g_resolveCluster = 8;
@@ -558,7 +606,10 @@ void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& 
 }
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st) {
-  k_gather<<<(M + GA_WARPS - 1) / GA_WARPS, GA_WARPS * 32, 0, st>>>(p, b, g, stb, s, fa, ga, M);
+  const size_t smem = ft_gather_smem(p, ga.fisheye);
+  const int stage = smem <= 200 * 1024;
+  const int ctas = min((M + GA_WARPS - 1) / GA_WARPS, 2 * 148);   // two resident CTAs per SM, grid-stride over map points
+  k_gather<<<ctas, GA_WARPS * 32, stage ? smem : 0, st>>>(p, b, g, stb, s, fa, ga, M, stage);
 }
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st) {
