@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -95,6 +95,7 @@ def load_library():
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
     L.ft_max_keypoints.argtypes = [vp]
+    L.ft_search_last_frame.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp, ip]
     L.ft_map_point_staging.argtypes = [vp, C.c_int] + [C.POINTER(vp)] * 7
     L.ft_search_staged.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.ft_frame_enqueue_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
@@ -305,6 +306,22 @@ class Context:
         hobs = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_uint8)), shape=(max(N, 1),))[:N]
         best = np.ctypeslib.as_array(C.cast(bi, C.POINTER(C.c_int)), shape=(max(2 * M, 1),))[:2 * M].reshape(M, 2)
         return nm.value, holder, hobs, best
+
+    def search_last_frame(self, pos, desc, octave, angle, flags, Rlw, tlw, th, holder, holder_obs, b_mono=False,
+                          check_ori=True):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)"""
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        pos, angle, Rlw, tlw = f(pos), f(angle), f(Rlw).reshape(-1), f(tlw)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        octave = np.ascontiguousarray(octave, np.int32); flags = np.ascontiguousarray(flags, np.int32)
+        holder = np.ascontiguousarray(holder, np.int32).copy(); holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        n = len(pos)
+        best = np.full((max(n, 1), 2), -1, np.int32)
+        nm = C.c_int()
+        self._ck(self.L.ft_search_last_frame(self.h, n, _ptr(pos), _ptr(desc), _ptr(octave), _ptr(angle), _ptr(flags), _ptr(Rlw),
+                                             _ptr(tlw), th, int(b_mono), int(check_ori), _ptr(holder), _ptr(holder_obs),
+                                             _ptr(best), C.byref(nm)))
+        return nm.value, holder, holder_obs, best[:n]
 
     def set_stage_timing(self, enable):
         self._ck(self.L.ft_set_stage_timing(self.h, int(enable)))

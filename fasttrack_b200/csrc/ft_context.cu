@@ -378,6 +378,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &Q.active, (size_t)MM));
   CKF(dalloc(c, &Q.minKey, (size_t)3 * 2 * P.maxKp));   // three stamp buffers rotated by k_resolve
   CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &Q.rotHist, (size_t)32));
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -817,7 +818,13 @@ extern "C" ft_status ft_upload_holders(ft_context* c, int N, const int* holder, 
   return FT_OK;
 }
 
+static ft_status search_run(ft_context* c, float th, int bFar, float thFar, float nnratio, int mode, int direction, int checkOri);
+
 extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float thFar, float nnratio) {
+  return search_run(c, th, bFar, thFar, nnratio, 0, 0, 0);
+}
+
+static ft_status search_run(ft_context* c, float th, int bFar, float thFar, float nnratio, int mode, int direction, int checkOri) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   if (!c->extracted) { set_err("ft_search_resident: no extracted frame"); return FT_ERR_STATE; }
   if (!c->stereoDone) { set_err("ft_search_resident: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
@@ -841,8 +848,10 @@ extern "C" ft_status ft_search_resident(ft_context* c, float th, int bFar, float
   FtGatherArgs ga;
   ga.minX = c->minX; ga.minY = c->minY; ga.gridWInv = c->gridWInv; ga.gridHInv = c->gridHInv;
   ga.th = th; ga.bFactor = (th != 1.0f); ga.bFar = bFar; ga.thFar = thFar; ga.fisheye = c->fisheye;
+  ga.mode = mode; ga.direction = direction;
   FtResolveArgs ra;
   ra.M = M; ra.nLeft = 0; ra.nSlots = 2 * c->P.maxKp; ra.fisheye = c->fisheye; ra.nnratio = nnratio;   // nSlots: smem sizing bound
+  ra.mode = mode; ra.checkOri = checkOri;
   { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s); }
   { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
   c->nLaunchSearch = 2 + (c->fisheye ? 1 : 0);
@@ -926,6 +935,44 @@ extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* p
   CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
   mp_bind_device(c, M);
   st = ft_search_resident(c, th, bFar, thFar, nnratio);
+  if (st != FT_OK) return st;
+  return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (reference src/ORBmatcher.cc:1775-2085), the
+// frame-to-last-frame search of Tracking::TrackWithMotionModel (src/Tracking.cc:2911-2990). One entry per last-frame
+// keypoint that holds a map point: world position + descriptor of the map point, octave + angle of that keypoint.
+extern "C" ft_status ft_search_last_frame(ft_context* c, int n, const float* pos, const uint8_t* desc, const int* octave,
+                                          const float* angle, const int* flags, const float* Rlw, const float* tlw,
+                                          float th, int bMono, int checkOrientation, int* holder, uint8_t* holderObs,
+                                          int* best_idx, int* nmatches) {
+  if (!c || n < 0 || !holder || !holderObs || (n > 0 && (!pos || !desc || !octave || !angle || !flags)) || !Rlw || !tlw) {
+    set_err("ft_search_last_frame: null argument"); return FT_ERR_INVALID;
+  }
+  if (!c->extracted || !c->stereoDone) { set_err("ft_search_last_frame: no stereo-matched frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
+  if (nmatches) *nmatches = 0;
+  for (int i = 0; i < n; i++)
+    if (octave[i] < 0 || octave[i] >= c->P.nlevels) { set_err("ft_search_last_frame: octave out of range"); return FT_ERR_INVALID; }
+  float *p, *nn, *mm; uint8_t* d; int *f, *h; uint8_t* ho;
+  st = ft_map_point_staging(c, n, &p, &nn, &mm, &d, &f, &h, &ho);
+  if (st != FT_OK) return st;
+  if (n == 0 || N == 0) { c->lastM = 0; return FT_OK; }
+  // bForward / bBackward (ORBmatcher.cc:1789-1794): tlc = Tlw * twc, twc = camera centre of the current frame
+  float tlcz = Rlw[6] * c->pose.Ow[0] + Rlw[7] * c->pose.Ow[1] + Rlw[8] * c->pose.Ow[2] + tlw[2];
+  const int direction = bMono ? 0 : (tlcz > c->mb ? 1 : (-tlcz > c->mb ? -1 : 0));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(p, pos, sizeof(float) * 3 * n);
+  memset(nn, 0, sizeof(float) * 3 * n);
+  for (int i = 0; i < n; i++) { mm[2 * i] = angle[i]; mm[2 * i + 1] = (float)octave[i]; }
+  memcpy(d, desc, (size_t)32 * n); memcpy(f, flags, sizeof(int) * n);
+  memcpy(h, holder, sizeof(int) * N); memcpy(ho, holderObs, (size_t)N);
+  CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)68 * n, cudaMemcpyHostToDevice, c->stream));
+  mp_bind_device(c, n);
+  st = search_run(c, th, 0, 0.f, 1.0f, 1, direction, checkOrientation ? 1 : 0);
   if (st != FT_OK) return st;
   return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
 }

@@ -152,6 +152,7 @@ struct FtSbpBuffers {
   uint8_t* holderObs;      // [2*maxKp]
   int* minKey;             // [2*maxKp]
   int* lastKey;            // [2*maxKp]
+  int* rotHist;            // [32] rotation histogram of the last-frame search
 };
 
 // ---- projection-search kernel arguments ----
@@ -168,10 +169,14 @@ struct FtGatherArgs {
   float minX, minY, gridWInv, gridHInv;
   float th; int bFactor; int bFar; float thFar;
   int fisheye;
+  int mode;        // 0: local map points (Tracking::SearchLocalPoints), 1: last frame's points (TrackWithMotionModel)
+  int direction;   // mode 1: +1 bForward, -1 bBackward, 0 neither (ORBmatcher.cc:1793-1794)
 };
 
 struct FtResolveArgs {
   int M, nLeft, nSlots, fisheye;
   float nnratio;
+  int mode;        // 1: best match only, no ratio test (ORBmatcher.cc:1847-1880)
+  int checkOri;    // mode 1: rotation-histogram consistency (ORBmatcher.cc:1884-1900, 2057-2079)
 };
 

@@ -205,7 +205,37 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
     const int flags = s.flags[mp];
     int inView = 0, inViewR = 0, level = -1, levelR = -1;
     float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (!(flags & 1)) {
+    float f2fRadius = 0.f;
+    if (a.mode == 1) {
+      // frame-to-last-frame search (ORBmatcher.cc:1797-1822): plain projection of the last frame's map point, window
+      // th * scale[octave of the last-frame keypoint]; minmax[] carries {angle, octave} of that keypoint
+      if (!(flags & 1)) {
+        const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
+        float Pc[3];
+        ft_mat3_vec(fa.pose.Rcw, P, Pc);
+        for (int i = 0; i < 3; i++) Pc[i] = __fadd_rn(Pc[i], fa.pose.tcw[i]);
+        const float invzc = (float)(1.0 / (double)Pc[2]);
+        if (!(invzc < 0)) {
+          float uv[2];
+          ft_cam_project(fa.cam1, Pc, uv);
+          if (!(uv[0] < fa.minX || uv[0] > fa.maxX) && !(uv[1] < fa.minY || uv[1] > fa.maxY)) {
+            const int oct = (int)s.minmax[2 * mp + 1];
+            inView = 1; level = oct;
+            f[0] = uv[0]; f[1] = uv[1];
+            f[2] = __fsub_rn(uv[0], __fmul_rn(fa.mbf, invzc));   // ur = uv(0) - mbf*invzc (:1857)
+            f2fRadius = __fmul_rn(a.th, p.scale[oct]);
+            if (fa.fisheye) {
+              // right image: Trl * x3Dc projected with the LEFT camera model, as the reference does (:1919-1921)
+              float Pr[3], uvr[2];
+              ft_mat3_vec(fa.pose.Rrl, Pc, Pr);
+              for (int i = 0; i < 3; i++) Pr[i] = __fadd_rn(Pr[i], fa.pose.trl[i]);
+              ft_cam_project(fa.cam1, Pr, uvr);
+              inViewR = 1; levelR = oct; f[5] = uvr[0]; f[6] = uvr[1];
+            }
+          }
+        }
+      }
+    } else if (!(flags & 1)) {
       const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
       const float Pn[3] = {s.normal[3 * mp], s.normal[3 * mp + 1], s.normal[3 * mp + 2]};
       const float mn = s.minmax[2 * mp], mx = s.minmax[2 * mp + 1];
@@ -245,8 +275,14 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         const float viewCos = br == 0 ? f[4] : f[8];
         float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos (ORBmatcher.cc:314-320)
         if (br == 0 && a.bFactor) r = __fmul_rn(r, a.th);
-        const float rr = __fmul_rn(r, p.scale[lvl]);
-        const int minLevel = lvl - 1, maxLevel = lvl;
+        float rr = __fmul_rn(r, p.scale[lvl]);
+        int minLevel = lvl - 1, maxLevel = lvl;
+        if (a.mode == 1) {   // (:1826-1834)
+          rr = f2fRadius;
+          if (a.direction > 0) { minLevel = lvl; maxLevel = -1; }
+          else if (a.direction < 0) { minLevel = 0; maxLevel = lvl; }
+          else { minLevel = lvl - 1; maxLevel = lvl + 1; }
+        }
         // GetFeaturesInArea cell window (Frame.cc:689-707)
         const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
         const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
@@ -351,7 +387,8 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
 // best / second-best scan of one candidate list (ORBmatcher.cc:88-141). Returns the accepted keypoint or -1;
 // *cont is set when the reference executes `continue` (ratio test failed on same-level neighbours).
 template <typename BlockedFn>
-__device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float nnratio, BlockedFn blocked, bool* cont) {
+__device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float nnratio, BlockedFn blocked, bool* cont,
+                                            bool bestOnly = false) {
   int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
   for (int k = 0; k < len; k++) {
     const uint32_t e = __ldg(list + k);
@@ -363,7 +400,7 @@ __device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float
   }
   *cont = false;
   if (bestDist <= 100) {   // TH_HIGH
-    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
+    if (!bestOnly && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
     return bestIdx;
   }
   return -1;
@@ -385,7 +422,7 @@ namespace cg = cooperative_groups;
 // per thread) and the rest in global memory
 template <typename BlockedFn>
 __device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32_t* gList, int len, float nnratio,
-                                              BlockedFn blocked, bool* cont) {
+                                              BlockedFn blocked, bool* cont, bool bestOnly = false) {
   int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
   for (int k = 0; k < len; k++) {
     const uint32_t e = k < RS_LCAP ? sEnt[k * RS_THREADS] : __ldg(gList + k);
@@ -397,7 +434,7 @@ __device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32
   }
   *cont = false;
   if (bestDist <= 100) {
-    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
+    if (!bestOnly && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) { *cont = true; return -1; }
     return bestIdx;
   }
   return -1;
@@ -416,7 +453,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
   const int nS = a.nSlots;
   const int nA = s.cursor[4];
-  const bool seqMode = a.fisheye && s.cursor[3] > 0;   // k_resolve_seq resolves this frame (uniform over the cluster)
+  // k_resolve_seq resolves fisheye local-map searches with non-blocking map points (uniform over the cluster); the
+  // last-frame search has no mirrored writes, so the stamp rule is exact for it in every case
+  const bool seqMode = a.fisheye && a.mode == 0 && s.cursor[3] > 0;
+  const bool bestOnly = a.mode == 1;
   const int stride = a0.nSlots;               // a0.nSlots = capacity bound (2*maxKp): distance between stamp buffers
   // shared memory: mkS[cap] int (this round's stamps), pre[cap] u8, entL / entR [RS_LCAP][RS_THREADS] u32
   int* mkS = sMem;
@@ -433,6 +473,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   }
   if (gtid < 3) s.cursor[5 + gtid] = 0;
   if (gtid == 3) s.cursor[1] = 0;
+  if (gtid >= 32 && gtid < 64) s.rotHist[gtid - 32] = 0;
   // this thread's first map point: list heads cached in shared memory, decision kept in registers
   int myMp = -1, myFlags = 0;
   int2 myOff = make_int2(0, 0), myLen = make_int2(0, 0);
@@ -472,16 +513,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
       const int t = 2 * mp;
       if (len.x > 0) {
         auto blk = [&](int idx) { return pre[idx] || mkS[idx] < t; };
-        newL = mine ? ft_scan_cached(entL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont)
-                    : ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont);
+        newL = mine ? ft_scan_cached(entL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly)
+                    : ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly);
       }
       if (len.y > 0 && !cont) {
         // own left writes (stamp 2mp) are handled explicitly, older stamps through the table
-        const int ownMirror = (blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
+        const int ownMirror = (a.mode == 0 && blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
         bool contR = false;
         auto blk = [&](int idx) { const int slot = idx + a.nLeft; return pre[slot] || mkS[slot] < t || idx == ownMirror; };
-        newR = mine ? ft_scan_cached(entR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR)
-                    : ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR);
+        newR = mine ? ft_scan_cached(entR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly)
+                    : ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly);
       }
       if (mine) {
         if (newL != selL || newR != selR) { changed = 1; selL = newL; selR = newR; }
@@ -490,13 +531,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
         if (newL != old.x || newR != old.y) { changed = 1; *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(newL, newR); }
       }
       if (blocking) {   // stamps the next round reads (writes of map points without observations never block)
+        const bool mirror = a.fisheye && a.mode == 0;   // mirrored assignments exist only in the local-map search
         if (newL >= 0) {
           atomicMin(&mkNext[newL], 2 * mp);
-          if (a.fisheye && st.l2r[newL] != -1) atomicMin(&mkNext[st.l2r[newL] + a.nLeft], 2 * mp);
+          if (mirror && st.l2r[newL] != -1) atomicMin(&mkNext[st.l2r[newL] + a.nLeft], 2 * mp);
         }
         if (newR >= 0) {
           atomicMin(&mkNext[newR + a.nLeft], 2 * mp + 1);
-          if (st.r2l[newR] != -1) atomicMin(&mkNext[st.r2l[newR]], 2 * mp + 1);
+          if (mirror && st.r2l[newR] != -1) atomicMin(&mkNext[st.r2l[newR]], 2 * mp + 1);
         }
       }
     }
@@ -508,6 +550,17 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if (rounds > a.M + 2) { if (gtid == 0) atomicOr(b.status, FT_ST_RESOLVE_NOCONV); break; }
   }
   // final holders: the write with the highest stamp wins each slot; count matches (ORBmatcher.cc:142-155,207-222)
+  const bool mirror = a.fisheye && a.mode == 0;
+  const bool rotCheck = a.mode == 1 && a.checkOri;
+  auto rotBin = [&](int mp, int idx, bool right) -> int {   // (ORBmatcher.cc:1890-1899): factor = 1/HISTO_LENGTH
+    const float angLF = s.minmax[2 * mp];
+    const float angCF = right ? b.eye[1].kps[idx].angle : b.eye[0].kps[idx].angle;
+    float rot = __fsub_rn(angLF, angCF);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+    if (bin == 30) bin = 0;
+    return bin;
+  };
   int nm = 0;
   for (int k = gtid; k < nA; k += nThreads) {
     const bool mine = (k == gtid);
@@ -516,11 +569,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if (mine) *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(sl, sr);
     if (sl >= 0) {
       atomicMax(&s.lastKey[sl], 2 * mp); nm++;
-      if (a.fisheye && st.l2r[sl] != -1) { atomicMax(&s.lastKey[st.l2r[sl] + a.nLeft], 2 * mp); nm++; }
+      if (mirror && st.l2r[sl] != -1) { atomicMax(&s.lastKey[st.l2r[sl] + a.nLeft], 2 * mp); nm++; }
+      if (rotCheck) atomicAdd(&s.rotHist[rotBin(mp, sl, false)], 1);
     }
     if (sr >= 0) {
       atomicMax(&s.lastKey[sr + a.nLeft], 2 * mp + 1); nm++;
-      if (st.r2l[sr] != -1) { atomicMax(&s.lastKey[st.r2l[sr]], 2 * mp + 1); nm++; }
+      if (mirror && st.r2l[sr] != -1) { atomicMax(&s.lastKey[st.r2l[sr]], 2 * mp + 1); nm++; }
+      if (rotCheck) atomicAdd(&s.rotHist[rotBin(mp, sr, true)], 1);
     }
   }
   if (nm) atomicAdd(&s.cursor[1], nm);
@@ -528,6 +583,35 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   for (int i = gtid; i < nS; i += nThreads) {
     const int k = __ldcg(&s.lastKey[i]);
     if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
+  }
+  if (rotCheck) {
+    // ComputeThreeMaxima (ORBmatcher.cc:2210-2254) on the bin counts, then every match outside the three strongest
+    // bins is withdrawn (:2057-2079)
+    cluster.sync();
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < 30; i++) {
+      const int c = __ldcg(&s.rotHist[i]);
+      if (c > max1) { max3 = max2; max2 = max1; max1 = c; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (c > max2) { max3 = max2; max2 = c; ind3 = ind2; ind2 = i; }
+      else if (c > max3) { max3 = c; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+    int removed = 0;
+    for (int k = gtid; k < nA; k += nThreads) {
+      const int mp = __ldg(&s.active[k]);
+      const int sl = __ldcg(&s.sel[2 * mp]), sr = __ldcg(&s.sel[2 * mp + 1]);
+      if (sl >= 0) {
+        const int bn = rotBin(mp, sl, false);
+        if (bn != ind1 && bn != ind2 && bn != ind3) { s.holder[sl] = -1; s.holderObs[sl] = 0; removed++; }
+      }
+      if (sr >= 0) {
+        const int bn = rotBin(mp, sr, true);
+        if (bn != ind1 && bn != ind2 && bn != ind3) { s.holder[sr + a.nLeft] = -1; s.holderObs[sr + a.nLeft] = 0; removed++; }
+      }
+    }
+    if (removed) atomicSub(&s.cursor[1], removed);
+    cluster.sync();
   }
   if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status; }
 }
@@ -539,7 +623,7 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
-  if (!(a.fisheye && s.cursor[3] > 0)) return;   // the fix-point kernel handles this frame
+  if (!(a.fisheye && a.mode == 0 && s.cursor[3] > 0)) return;   // the fix-point kernel handles this frame
   int nm = 0;
   for (int mp = 0; mp < a.M; mp++) {
     const int lenL = s.listLen[2 * mp], lenR = s.listLen[2 * mp + 1];

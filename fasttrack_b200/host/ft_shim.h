@@ -195,7 +195,12 @@ class Frame {
     ft_check(ft_stereo_match_fisheye(fe_->get()));
     fetchStereo(true);
   }
-  void SetPose(const float Rcw[9], const float tcw[3]) { ft_check(ft_set_pose(fe_->get(), Rcw, tcw, nullptr, nullptr)); }
+  void SetPose(const float Rcw[9], const float tcw[3]) {
+    memcpy(mRcw, Rcw, sizeof(mRcw)); memcpy(mtcw, tcw, sizeof(mtcw));
+    ft_check(ft_set_pose(fe_->get(), Rcw, tcw, nullptr, nullptr));
+  }
+  float mRcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, mtcw[3] = {0, 0, 0};   // Tcw (Frame::SetPose)
+  std::vector<bool> mvbOutlier;
 
   unsigned long mnId;
   int N = 0, Nleft = -1, Nright = -1;
@@ -222,6 +227,7 @@ class Frame {
                                  nullptr, nullptr, nullptr));
     }
     mvpMapPoints.assign(N, nullptr);
+    mvbOutlier.assign(N, false);
   }
   std::shared_ptr<FrontEndContext> fe_;
 };
@@ -275,6 +281,42 @@ class ORBmatcher {
         p->mTrackProjXR_r = f[5]; p->mTrackProjYR = f[6]; p->mTrackDepthR = f[7]; p->mTrackViewCosR = f[8];
       }
     }
+    return nmatches;
+  }
+
+  // Frame-to-last-frame search of Tracking::TrackWithMotionModel (reference src/ORBmatcher.cc:1775-2085).
+  // LastFrame needs mvKeys / mvKeysRight (octave, angle), mvpMapPoints, mvbOutlier and its pose; CurrentFrame must be
+  // the frame the context extracted last, with SetPose() already called (mVelocity * mLastFrame.GetPose()).
+  int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    const int nLast = LastFrame.N, N = CurrentFrame.N;
+    std::vector<float> pos((size_t)nLast * 3, 0.f), angle(nLast, 0.f);
+    std::vector<unsigned char> desc((size_t)nLast * 32, 0);
+    std::vector<int> octave(nLast, 0), flags(nLast, 1);
+    std::vector<MapPoint*> src(nLast, nullptr);
+    for (int i = 0; i < nLast; i++) {
+      MapPoint* p = LastFrame.mvpMapPoints[i];
+      const ftcv::KeyPoint& kp = (LastFrame.Nleft == -1 || i < LastFrame.Nleft) ? LastFrame.mvKeys[i]
+                                                                                : LastFrame.mvKeysRight[i - LastFrame.Nleft];
+      octave[i] = kp.octave; angle[i] = kp.angle;
+      if (!p || LastFrame.mvbOutlier[i]) continue;
+      src[i] = p;
+      memcpy(&pos[3 * (size_t)i], p->mWorldPos, 12); memcpy(&desc[32 * (size_t)i], p->mDescriptor, 32);
+      flags[i] = p->Observations() > 0 ? 2 : 0;
+    }
+    std::vector<int> holder(N, -1);
+    std::vector<unsigned char> hobs(N, 0);
+    std::vector<MapPoint*> foreign(N, nullptr);
+    for (int i = 0; i < N; i++) {
+      MapPoint* q = CurrentFrame.mvpMapPoints[i];
+      if (!q) continue;
+      foreign[i] = q; holder[i] = -2; hobs[i] = q->Observations() > 0;
+    }
+    int nmatches = 0;
+    ft_check(ft_search_last_frame(CurrentFrame.context()->get(), nLast, pos.data(), desc.data(), octave.data(), angle.data(),
+                                  flags.data(), LastFrame.mRcw, LastFrame.mtcw, th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0,
+                                  holder.data(), hobs.data(), nullptr, &nmatches));
+    for (int i = 0; i < N; i++)
+      CurrentFrame.mvpMapPoints[i] = holder[i] >= 0 ? src[holder[i]] : (holder[i] == -2 ? foreign[i] : nullptr);
     return nmatches;
   }
 

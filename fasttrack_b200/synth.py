@@ -226,3 +226,38 @@ def mappoints(keys, desc, scale_factors, M, seed=4, width=752, height=480, fx=45
     holder[cl] = -2
     holder_obs[cl] = (rng.random(int(cl.sum())) < 0.9).astype(np.uint8)
     return dict(pos=pos, normal=normal, minmax=minmax, desc=d, flags=flags, holder=holder, holder_obs=holder_obs)
+
+
+def last_frame_points(keys, desc, n, seed, Rcw, tcw, fx, fy, cx, cy, nlevels=8, kb8=None):
+    """Synthetic input of the frame-to-last-frame search (TrackWithMotionModel): n last-frame keypoints holding map
+    points that re-project (under the CURRENT pose Rcw, tcw) close to current keypoints.
+
+    returns dict(pos[n,3], desc[n,32], octave[n], angle[n], flags[n])"""
+    rng = np.random.default_rng(seed)
+    N = len(keys)
+    k = rng.integers(0, N, n)
+    z = rng.uniform(1.0, 20.0, n)
+    jit = rng.uniform(-2.0, 2.0, (n, 2)) * (1.0 + keys[k, 5:6] * 0.3)
+    u = keys[k, 0] + jit[:, 0]; v = keys[k, 1] + jit[:, 1]
+    if kb8 is None:
+        Pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    else:
+        ray = kb8_unproject(np.asarray(kb8, np.float64), u.astype(np.float64), v.astype(np.float64))
+        Pc = ray * z[:, None]
+    Rwc = np.asarray(Rcw, np.float64).T
+    P = (Pc - np.asarray(tcw, np.float64)) @ Rwc.T
+    bits = np.unpackbits(desc[k], axis=1)
+    nflip = rng.integers(0, 41, n)
+    flip = rng.random((n, 256)).argsort(axis=1) < nflip[:, None]
+    d = np.packbits(bits ^ flip.astype(np.uint8), axis=1)
+    rnd = rng.random(n) < 0.15
+    d[rnd] = rng.integers(0, 256, (int(rnd.sum()), 32), dtype=np.uint8)
+    octave = np.clip(keys[k, 5].astype(np.int32) + rng.choice([0, 0, 0, 1, -1], n), 0, nlevels - 1).astype(np.int32)
+    angle = (keys[k, 3] + rng.normal(0, 3.0, n)).astype(np.float32)
+    wild = rng.random(n) < 0.2
+    angle[wild] = rng.uniform(0, 360, int(wild.sum()))
+    angle = np.mod(angle, 360.0).astype(np.float32)
+    flags = np.full(n, 2, np.int32)
+    flags[rng.random(n) < 0.05] = 0
+    flags[rng.random(n) < 0.05] |= 1
+    return dict(pos=np.ascontiguousarray(P, np.float32), desc=np.ascontiguousarray(d), octave=octave, angle=angle, flags=flags)

@@ -165,6 +165,19 @@ ft_status ft_search_staged(ft_context* ctx, int M, float th, int b_far_points, f
                            const int** holder_out, const uint8_t** holder_obs_out, const int** best_idx_out,
                            int* nmatches);
 
+/* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) -- the frame-to-last-frame search of
+ * Tracking::TrackWithMotionModel (reference src/ORBmatcher.cc:1775-2085, src/Tracking.cc:2911-2990), incl. the
+ * rotation-histogram consistency check (ComputeThreeMaxima, :2210-2254) when check_orientation != 0.
+ * One entry per last-frame keypoint that holds a map point: pos[n][3] = GetWorldPos(), desc[n][32] = GetDescriptor(),
+ * octave[n] / angle[n] of that last-frame keypoint, flags[n]: bit0 = skip (no map point / mvbOutlier), bit1 =
+ * Observations() > 0. Rlw/tlw = LastFrame pose (row-major 3x3, 3); the current pose comes from ft_set_pose.
+ * holder / holder_obs / best_idx / nmatches as in ft_search_local_points (the caller clears F.mvpMapPoints first, as
+ * TrackWithMotionModel does). */
+ft_status ft_search_last_frame(ft_context* ctx, int n, const float* pos, const uint8_t* desc, const int* octave,
+                               const float* angle, const int* flags, const float* Rlw, const float* tlw, float th,
+                               int b_mono, int check_orientation, int* holder, uint8_t* holder_obs, int* best_idx,
+                               int* nmatches);
+
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
 

@@ -95,6 +95,8 @@ def lib():
     L.fto_search_local_points.restype = C.c_int
     L.fto_search_local_points.argtypes = [C.c_void_p, C.c_int, f32p, f32p, f32p, u8p, i32p, C.c_float, C.c_int,
                                           C.c_float, C.c_float, i32p, u8p, C.c_void_p, C.c_void_p]
+    L.fto_search_last_frame.restype = C.c_int
+    L.fto_search_last_frame.argtypes = [C.c_void_p, C.c_int, f32p, u8p, i32p, f32p, i32p, C.c_float, C.c_int, C.c_int, i32p, u8p, i32p]
     L.fto_time_stereo_frame.restype = C.c_double
     L.fto_time_stereo_frame.argtypes = [C.c_void_p, C.c_void_p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -307,6 +309,21 @@ class Frame:
         n = self.L.fto_search_local_points(self.h, M, pos, normal, minmax, desc, flags, th, int(b_far), th_far, nnratio,
                                            holder, holder_obs, ti.ctypes.data, tf.ctypes.data)
         return n, holder, holder_obs, ti, tf
+
+
+def _frame_search_last_frame(self, pos, desc, octave, angle, flags, th, direction, holder, holder_obs, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on this (current) frame"""
+    pos = np.ascontiguousarray(pos, np.float32); desc = np.ascontiguousarray(desc, np.uint8)
+    octave = np.ascontiguousarray(octave, np.int32); angle = np.ascontiguousarray(angle, np.float32)
+    flags = np.ascontiguousarray(flags, np.int32)
+    holder = np.ascontiguousarray(holder, np.int32).copy(); holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+    bl = np.zeros(max(len(pos), 1), np.int32)
+    n = self.L.fto_search_last_frame(self.h, len(pos), pos, desc, octave, angle, flags, th, direction, int(check_ori), holder,
+                                     holder_obs, bl)
+    return n, holder, holder_obs, bl[: len(pos)]
+
+
+Frame.search_last_frame = _frame_search_last_frame
 
 
 def time_stereo_frame(exL, exR, imgL, imgR, mbf, mb, two_threads=True):

@@ -1017,4 +1017,119 @@ int search_by_projection(FrameModel& F, const std::vector<MapPointIn>& mps, cons
   return nmatches;
 }
 
+
+// ---------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1775-2085),
+// ORBmatcher::ComputeThreeMaxima (:2210-2254). Used by Tracking::TrackWithMotionModel (Tracking.cc:2911-2990).
+// ---------------------------------------------------------------------------
+static void compute_three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int search_by_projection_last_frame(FrameModel& F, const std::vector<LastFramePoint>& pts, float th, int direction,
+                                    bool checkOrientation, float mb, std::vector<int>& holder,
+                                    std::vector<uint8_t>& holderObs, std::vector<int>& borderline) {
+  (void)mb;
+  const int HISTO_LENGTH = 30, TH_HIGH = 100;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  const bool bForward = direction > 0, bBackward = direction < 0;
+  std::vector<int> vIdx;
+  borderline.assign(pts.size(), 0);
+  auto blocked = [&](int slot) { return holder[slot] != -1 && holderObs[slot]; };
+  for (size_t i = 0; i < pts.size(); i++) {
+    const LastFramePoint& lp = pts[i];
+    if (lp.flags & 1) continue;
+    float x3Dc[3];
+    mat3_mul_vec(F.Rcw, lp.pos, x3Dc);
+    for (int k = 0; k < 3; k++) x3Dc[k] += F.tcw[k];
+    const float invzc = (float)(1.0 / x3Dc[2]);
+    if (std::fabs((double)x3Dc[2]) < 1e-6) borderline[i] = 1;
+    if (invzc < 0) continue;
+    float uv[2];
+    cam_project(F.cam1, x3Dc, uv);
+    if (near_rel(uv[0], F.minX, 1e-5) || near_rel(uv[0], F.maxX, 1e-5) || near_rel(uv[1], F.minY, 1e-5) ||
+        near_rel(uv[1], F.maxY, 1e-5)) borderline[i] = 1;
+    if (uv[0] < F.minX || uv[0] > F.maxX) continue;
+    if (uv[1] < F.minY || uv[1] > F.maxY) continue;
+    const int nLastOctave = lp.octave;
+    const float radius = th * F.scale[nLastOctave];
+    if (bForward) F.featuresInArea(uv[0], uv[1], radius, nLastOctave, -1, false, vIdx);
+    else if (bBackward) F.featuresInArea(uv[0], uv[1], radius, 0, nLastOctave, false, vIdx);
+    else F.featuresInArea(uv[0], uv[1], radius, nLastOctave - 1, nLastOctave + 1, false, vIdx);
+    if (vIdx.empty()) continue;
+    const uint8_t obs = (uint8_t)((lp.flags >> 1) & 1);
+    {
+      int bestDist = 256, bestIdx2 = -1;
+      for (int i2 : vIdx) {
+        if (blocked(i2)) continue;
+        if (F.Nleft == -1 && F.uRight[i2] > 0) {
+          const float ur = uv[0] - F.mbf * invzc;
+          const float er = std::fabs(ur - F.uRight[i2]);
+          if (er > radius) continue;
+        }
+        const int dist = descriptor_distance(lp.desc, &F.desc[(size_t)i2 * 32]);
+        if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+      }
+      if (bestDist <= TH_HIGH) {
+        holder[bestIdx2] = (int)i; holderObs[bestIdx2] = obs;
+        nmatches++;
+        if (checkOrientation) {
+          float rot = lp.angle - F.keys[bestIdx2].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back(bestIdx2);
+        }
+      }
+    }
+    if (F.Nleft != -1) {
+      float x3Dr[3];
+      mat3_mul_vec(F.Rrl, x3Dc, x3Dr);
+      for (int k = 0; k < 3; k++) x3Dr[k] += F.trl[k];
+      float uvr[2];
+      cam_project(F.cam1, x3Dr, uvr);   // the reference projects with mpCamera (the LEFT model) here (:1921)
+      if (bForward) F.featuresInArea(uvr[0], uvr[1], radius, nLastOctave, -1, true, vIdx);
+      else if (bBackward) F.featuresInArea(uvr[0], uvr[1], radius, 0, nLastOctave, true, vIdx);
+      else F.featuresInArea(uvr[0], uvr[1], radius, nLastOctave - 1, nLastOctave + 1, true, vIdx);
+      int bestDist = 256, bestIdx2 = -1;
+      for (int i2 : vIdx) {
+        if (blocked(i2 + F.Nleft)) continue;
+        const int dist = descriptor_distance(lp.desc, &F.desc[(size_t)(i2 + F.Nleft) * 32]);
+        if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+      }
+      if (bestDist <= TH_HIGH) {
+        holder[bestIdx2 + F.Nleft] = (int)i; holderObs[bestIdx2 + F.Nleft] = obs;
+        nmatches++;
+        if (checkOrientation) {
+          float rot = lp.angle - F.keys[bestIdx2 + F.Nleft].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back(bestIdx2 + F.Nleft);
+        }
+      }
+    }
+  }
+  if (checkOrientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i != ind1 && i != ind2 && i != ind3) {
+        for (int slot : rotHist[i]) { holder[slot] = -1; holderObs[slot] = 0; nmatches--; }
+      }
+    }
+  }
+  return nmatches;
+}
+
 }  // namespace fto

@@ -146,4 +146,18 @@ int search_by_projection(FrameModel& F, const std::vector<MapPointIn>& mps, cons
                          float th, bool bFar, float thFar, float nnratio,
                          std::vector<int>& holder, std::vector<uint8_t>& holderObs);
 
+
+// ---- frame-to-last-frame SearchByProjection (ORBmatcher.cc:1775-2085) + ComputeThreeMaxima (:2210-2254) ----
+struct LastFramePoint {      // one keypoint of the last frame that holds a (non-outlier) MapPoint
+  float pos[3];              // pMP->GetWorldPos()
+  uint8_t desc[32];          // pMP->GetDescriptor()
+  int octave;                // last-frame keypoint octave
+  float angle;               // last-frame keypoint angle (degrees)
+  int flags;                 // bit0 skip (no MapPoint / outlier), bit1 Observations()>0
+};
+// direction: +1 bForward, -1 bBackward, 0 neither. holder/holderObs as in search_by_projection. Returns nmatches.
+int search_by_projection_last_frame(FrameModel& F, const std::vector<LastFramePoint>& pts, float th, int direction,
+                                    bool checkOrientation, float mb, std::vector<int>& holder,
+                                    std::vector<uint8_t>& holderObs, std::vector<int>& borderline);
+
 }  // namespace fto

@@ -265,6 +265,25 @@ int fto_search_local_points(void* F_, int M, const float* pos, const float* norm
   return n;
 }
 
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono): the caller passes the last frame's map points
+// as SoA arrays (one entry per last-frame keypoint that holds a map point)
+int fto_search_last_frame(void* F_, int n, const float* pos, const uint8_t* desc, const int* octave, const float* angle,
+                          const int* flags, float th, int direction, int checkOri, int* holder, uint8_t* holderObs,
+                          int* borderline) {
+  FrameModel* F = (FrameModel*)F_;
+  std::vector<LastFramePoint> pts(n);
+  for (int i = 0; i < n; i++) {
+    memcpy(pts[i].pos, pos + 3 * (size_t)i, 12); memcpy(pts[i].desc, desc + 32 * (size_t)i, 32);
+    pts[i].octave = octave[i]; pts[i].angle = angle[i]; pts[i].flags = flags[i];
+  }
+  std::vector<int> h(holder, holder + F->N), bl;
+  std::vector<uint8_t> ho(holderObs, holderObs + F->N);
+  const int nm = search_by_projection_last_frame(*F, pts, th, direction, checkOri != 0, 0.f, h, ho, bl);
+  memcpy(holder, h.data(), sizeof(int) * F->N); memcpy(holderObs, ho.data(), F->N);
+  if (borderline) memcpy(borderline, bl.data(), sizeof(int) * n);
+  return nm;
+}
+
 // ---- timing helper for bench.py's cpu_baseline / --impl reference legs ----
 // One stereo frame as the reference threads it: L/R extraction on two std::threads
 // (Frame.cc:127-130), then stereo matching on the caller's thread. Returns milliseconds.
