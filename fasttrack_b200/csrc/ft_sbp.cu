@@ -17,6 +17,8 @@
 // decision only depends on decisions with smaller stamps, so iterating the two steps reaches the unique
 // sequential result; each round finalises at least the next undecided map point and in practice the depth
 // of the longest chain of displaced matches (reported as `rounds`).
+#include <cstdlib>
+
 #include "ft_device.cuh"
 #include "ft_camera.cuh"
 
@@ -448,6 +450,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   const int tid = threadIdx.x;
   const int nThreads = gridDim.x * RS_THREADS;
   const int gtid = blockIdx.x * RS_THREADS + tid;
+  // map points are dealt round-robin over the CTAs of the cluster so that every SM gets an equal share of the
+  // candidate-list scans (the active list is usually shorter than the cluster's thread count)
+  const int vid = tid * gridDim.x + blockIdx.x;
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
@@ -478,8 +483,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   int myMp = -1, myFlags = 0;
   int2 myOff = make_int2(0, 0), myLen = make_int2(0, 0);
   int selL = -1, selR = -1;
-  if (gtid < nA) {
-    myMp = __ldg(&s.active[gtid]);
+  if (vid < nA) {
+    myMp = __ldg(&s.active[vid]);
     myFlags = __ldg(&s.flags[myMp]);
     myOff = __ldg(reinterpret_cast<const int2*>(s.listOff) + myMp);
     myLen = __ldg(reinterpret_cast<const int2*>(s.listLen) + myMp);
@@ -502,8 +507,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     for (int i = gtid; i < nS; i += nThreads) mkClear[i] = 0x7FFFFFFF;
     if (gtid == 0) s.cursor[5 + ((rounds + 2) % 3)] = 0;
     int changed = 0;
-    for (int k = gtid; k < nA; k += nThreads) {
-      const bool mine = (k == gtid);
+    for (int k = vid; k < nA; k += nThreads) {
+      const bool mine = (k == vid);
       const int mp = mine ? myMp : __ldg(&s.active[k]);
       const int2 off = mine ? myOff : __ldg(reinterpret_cast<const int2*>(s.listOff) + mp);
       const int2 len = mine ? myLen : __ldg(reinterpret_cast<const int2*>(s.listLen) + mp);
@@ -562,8 +567,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     return bin;
   };
   int nm = 0;
-  for (int k = gtid; k < nA; k += nThreads) {
-    const bool mine = (k == gtid);
+  for (int k = vid; k < nA; k += nThreads) {
+    const bool mine = (k == vid);
     const int mp = mine ? myMp : __ldg(&s.active[k]);
     const int sl = mine ? selL : __ldcg(&s.sel[2 * mp]), sr = mine ? selR : __ldcg(&s.sel[2 * mp + 1]);
     if (mine) *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(sl, sr);
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
     int removed = 0;
-    for (int k = gtid; k < nA; k += nThreads) {
+    for (int k = vid; k < nA; k += nThreads) {
       const int mp = __ldg(&s.active[k]);
       const int sl = __ldcg(&s.sel[2 * mp]), sr = __ldcg(&s.sel[2 * mp + 1]);
       if (sl >= 0) {
@@ -681,6 +686,7 @@ cudaError_t ft_launch_sbp_setup(const FtParams& p) {
     int nClusters = 0;
     if (cudaOccupancyMaxActiveClusters(&nClusters, k_resolve, &cfg) == cudaSuccess && nClusters >= 1) g_resolveCluster = 16;
   }
+  if (const char* e = getenv("FT_RESOLVE_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) g_resolveCluster = v; }
   cudaGetLastError();
   return cudaSuccess;
 }
