@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -95,6 +95,7 @@ def load_library():
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
     L.ft_max_keypoints.argtypes = [vp]
+    L.ft_set_rectification.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.ft_search_last_frame.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp, ip]
     L.ft_map_point_staging.argtypes = [vp, C.c_int] + [C.POINTER(vp)] * 7
     L.ft_search_staged.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
@@ -165,10 +166,17 @@ class Context:
         self._ck(self.L.ft_get_scale_tables(self.h, *[_ptr(x) for x in a], _ptr(q)))
         return dict(scale=a[0], inv_scale=a[1], sigma2=a[2], inv_sigma2=a[3], features_per_level=q)
 
+    def set_rectification(self, raw_w, raw_h, m1l, m2l, m1r, m2r):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        maps = [f(m1l), f(m2l), f(m1r), f(m2r)]
+        self._ck(self.L.ft_set_rectification(self.h, raw_w, raw_h, *[_ptr(m) for m in maps]))
+        self._raw = (raw_h, raw_w) if maps[0] is not None else None
+
     # ---- per-frame operators ----
     def extract_stereo(self, imgL, imgR):
         assert imgL.dtype == np.uint8 and imgR.dtype == np.uint8 and imgL.strides[1] == 1 and imgR.strides[1] == 1
-        assert imgL.shape == (self.height, self.width) and imgR.shape == (self.height, self.width)
+        shape = getattr(self, "_raw", None) or (self.height, self.width)
+        assert imgL.shape == shape and imgR.shape == shape
         self._ck(self.L.ft_extract_stereo(self.h, imgL.ctypes.data, imgL.strides[0], imgR.ctypes.data, imgR.strides[0]))
 
     def extract_stereo_ptr(self, ptrL, stepL, ptrR, stepR, device=False):

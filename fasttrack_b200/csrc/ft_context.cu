@@ -64,6 +64,10 @@ struct ft_context {
   int lastM = 0;
   int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
   long long pyrBytes = 0;
+  // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
+  int rectify = 0, rawW = 0, rawH = 0;
+  uint8_t* dRaw[2] = {nullptr, nullptr};
+  int2* dRemapTab = nullptr;
   // resident map-point snapshot + initial holders for ft_search_resident
   int residentM = 0;
   int* holderInit = nullptr;
@@ -463,6 +467,7 @@ static int enqueue_extract(ft_context* c) {
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
   const bool perLevel = !c->timing;
+  if (c->rectify) { ft_launch_remap(P, c->B, c->dRaw[0], c->dRaw[1], c->dRemapTab, c->rawW, c->rawH, s); n++; }
   cudaEventRecord(c->evFork, s);
   cudaStreamWaitEvent(s3, c->evFork, 0);
   cudaStreamWaitEvent(s2, c->evFork, 0);
@@ -535,7 +540,9 @@ static ft_status run_extract(ft_context* c) {
 
 static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
   if (!c || !imgL || !imgR) { set_err("null image (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
-  const int w = c->cfg.width, h = c->cfg.height;
+  // with rectification the raw image goes to a staging buffer (k_remap writes level 0); otherwise straight into level 0
+  const int w = c->rectify ? c->rawW : c->cfg.width, h = c->rectify ? c->rawH : c->cfg.height;
+  const int dpitch = c->rectify ? w : c->P.lv[0].pitch;
   if (stepL < w || stepR < w) { set_err("image step smaller than width"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
   const uint8_t* src[2] = {imgL, imgR};
@@ -544,16 +551,16 @@ static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, co
     cudaPointerAttributes at;
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    uint8_t* dst = c->B.eye[e].pyr + c->P.lv[0].offset;   // straight into level 0 of the pyramid slab
-    if (pinned && step[e] == w && c->P.lv[0].pitch == w) {
+    uint8_t* dst = c->rectify ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
+    if (pinned && step[e] == w && dpitch == w) {
       CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
     } else if (pinned) {
-      CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(dst, dpitch, src[e], step[e], w, h, cudaMemcpyHostToDevice, c->stream));
     } else {
       // pageable memory: stage through the context's pinned buffer so the copy stays asynchronous
       CK(cudaStreamSynchronize(c->stream));   // previous frame may still be reading the staging buffer
       for (int y = 0; y < h; y++) memcpy(c->hIn[e] + (size_t)y * w, src[e] + (size_t)y * step[e], w);
-      CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, c->hIn[e], w, w, h, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(dst, dpitch, c->hIn[e], w, w, h, cudaMemcpyHostToDevice, c->stream));
     }
   }
   return FT_OK;
@@ -565,12 +572,24 @@ extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int s
   return run_extract(c);
 }
 
+static ft_status copy_device_images(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
+  const int w = c->rectify ? c->rawW : c->cfg.width, h = c->rectify ? c->rawH : c->cfg.height;
+  const int dpitch = c->rectify ? w : c->P.lv[0].pitch;
+  const uint8_t* src[2] = {dL, dR};
+  const int step[2] = {stepL, stepR};
+  for (int e = 0; e < 2; e++) {
+    uint8_t* dst = c->rectify ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
+    if (step[e] == w && dpitch == w) CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
+    else CK(cudaMemcpy2DAsync(dst, dpitch, src[e], step[e], w, h, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return FT_OK;
+}
+
 extern "C" ft_status ft_extract_stereo_device(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
   if (!c || !dL || !dR) { set_err("ft_extract_stereo_device: null argument"); return FT_ERR_INVALID; }
-  const int w = c->cfg.width, h = c->cfg.height;
   CK(cudaSetDevice(c->cfg.device_id));
-  CK(cudaMemcpy2DAsync(c->B.eye[0].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dL, stepL, w, h, cudaMemcpyDeviceToDevice, c->stream));
-  CK(cudaMemcpy2DAsync(c->B.eye[1].pyr + c->P.lv[0].offset, c->P.lv[0].pitch, dR, stepR, w, h, cudaMemcpyDeviceToDevice, c->stream));
+  ft_status st = copy_device_images(c, dL, stepL, dR, stepR);
+  if (st != FT_OK) return st;
   return run_extract(c);
 }
 
@@ -689,16 +708,47 @@ static ft_status run_frame(ft_context* c) {
 // Device-resident inputs: copy into the level-0 slabs, then extract + stereo-match as one graph; asynchronous.
 extern "C" ft_status ft_frame_enqueue_device(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
   if (!c || !dL || !dR) { set_err("ft_frame_enqueue_device: null argument"); return FT_ERR_INVALID; }
-  const int w = c->cfg.width, h = c->cfg.height;
   CK(cudaSetDevice(c->cfg.device_id));
-  const uint8_t* src[2] = {dL, dR};
-  const int step[2] = {stepL, stepR};
-  for (int e = 0; e < 2; e++) {
-    uint8_t* dst = c->B.eye[e].pyr + c->P.lv[0].offset;
-    if (step[e] == w && c->P.lv[0].pitch == w) CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
-    else CK(cudaMemcpy2DAsync(dst, c->P.lv[0].pitch, src[e], step[e], w, h, cudaMemcpyDeviceToDevice, c->stream));
-  }
+  ft_status st = copy_device_images(c, dL, stepL, dR, stepR);
+  if (st != FT_OK) return st;
   return run_frame(c);
+}
+
+// Stereo rectification in front of the extractor (reference System::TrackStereo, src/System.cc:273-281:
+// cv::remap(im, M1, M2, INTER_LINEAR) with the CV_32F maps of Settings.cc:506-509). Maps are width x height floats
+// (x map, y map) per eye; raw images are raw_width x raw_height. Passing NULL maps switches rectification off.
+extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_height, const float* M1l, const float* M2l,
+                                          const float* M1r, const float* M2r) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  // the launch graphs bake the topology in: drop them so that the next frame re-captures
+  if (c->gExtract) { cudaGraphExecDestroy(c->gExtract); c->gExtract = nullptr; }
+  if (c->gFrame) { cudaGraphExecDestroy(c->gFrame); c->gFrame = nullptr; }
+  if (!M1l || !M2l || !M1r || !M2r) { c->rectify = 0; return FT_OK; }
+  if (raw_width < 8 || raw_height < 8 || raw_width > 8192 || raw_height > 8192) { set_err("ft_set_rectification: bad raw size"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  std::vector<int2> tab((size_t)2 * w * h);
+  const float* mx[2] = {M1l, M1r};
+  const float* my[2] = {M2l, M2r};
+  for (int e = 0; e < 2; e++)
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+      // OpenCV remap, CV_32FC1 pair -> fixed point: sx = cvRound(x * INTER_TAB_SIZE), integer part saturated to short
+      const int sx = cv_round_f(mx[e][i] * 32.f), sy = cv_round_f(my[e][i] * 32.f);
+      const int ix = std::min(std::max(sx >> 5, -32768), 32767), iy = std::min(std::max(sy >> 5, -32768), 32767);
+      tab[(size_t)e * w * h + i] = make_int2((ix & 0xFFFF) | (iy << 16), (sx & 31) | ((sy & 31) << 8));
+    }
+  if (!c->dRemapTab) CK(dalloc(c, &c->dRemapTab, tab.size()));
+  CK(cudaMemcpy(c->dRemapTab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  if (c->rawW * c->rawH < raw_width * raw_height || !c->dRaw[0]) {
+    for (int e = 0; e < 2; e++) {
+      CK(dalloc(c, &c->dRaw[e], (size_t)raw_width * raw_height));
+      if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
+      CK(cudaMallocHost((void**)&c->hIn[e], std::max((size_t)raw_width * raw_height, (size_t)w * h)));
+    }
+  }
+  c->rawW = raw_width; c->rawH = raw_height; c->rectify = 1;
+  return FT_OK;
 }
 
 extern "C" int ft_max_keypoints(ft_context* c) { return c ? c->P.maxKp : 0; }

@@ -54,6 +54,29 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams
 }
 
 // ------------------------------------------------------------------------------------
+// Stereo rectification ("next" row 2, reference System::TrackStereo, src/System.cc:273-281):
+// cv::remap(raw, M1, M2, INTER_LINEAR) straight into level 0 of the pyramid. The float maps are converted once on
+// the host to OpenCV's fixed-point form (integer source pixel + 5-bit fractions); the 2x2 weights are
+// (32-fy)(32-fx)*32 ... scaled by 2^15 with BilinearTab_i's single saturated entry {32767,0,0,1} at fx = fy = 0.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_remap(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                               const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW, int rawH) {
+  const FtLevel& L = p.lv[0];
+  const int eye = blockIdx.z;
+  const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
+  if (x >= L.w || y >= L.h) return;
+  const uint8_t* src = eye ? rawR : rawL;
+  const int2 t = tab[(size_t)eye * L.w * L.h + (size_t)y * L.w + x];
+  const int ix = (short)(t.x & 0xFFFF), iy = (short)(t.x >> 16);
+  const int fx = t.y & 0xFF, fy = (t.y >> 8) & 0xFF;
+  int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+  if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+  auto px = [&](int yy, int xx) -> int { return (xx >= 0 && xx < rawW && yy >= 0 && yy < rawH) ? (int)src[(size_t)yy * rawW + xx] : 0; };
+  const int v = w00 * px(iy, ix) + w01 * px(iy, ix + 1) + w10 * px(iy + 1, ix) + w11 * px(iy + 1, ix + 1);
+  b.eye[eye].pyr[L.offset + (size_t)y * L.pitch + x] = (uint8_t)min(max((v + (1 << 14)) >> 15, 0), 255);
+}
+
+// ------------------------------------------------------------------------------------
 // Gaussian blur, all levels of both eyes in one launch. Tile = 64 x 32 outputs per CTA.
 // ------------------------------------------------------------------------------------
 #define BLUR_TW 64
@@ -950,6 +973,11 @@ cudaError_t ft_launch_extract_setup(const FtParams& p) {
   return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_fast_smem_bytes(p));
 }
 
+void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,
+                     int rawH, cudaStream_t st) {
+  dim3 blk(64, 4), grd((p.lv[0].w + 63) / 64, (p.lv[0].h + 3) / 4, 2);
+  k_remap<<<grd, blk, 0, st>>>(p, b, rawL, rawR, tab, rawW, rawH);
+}
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
   dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, 2);
   k_resize<<<grd, blk, 0, st>>>(p, b, level);

@@ -110,6 +110,13 @@ ft_status ft_frame_counts(ft_context* ctx, int* n_left, int* n_right, int* mono_
 ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps, uint8_t* desc, int* n, int* mono_index,
                             float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
 
+/* Stereo rectification in front of the extractor: cv::remap(im, M1, M2, INTER_LINEAR) of System::TrackStereo
+ * (reference src/System.cc:273-281) fused into the level-0 load. M1x/M2x: the CV_32F x / y maps of
+ * cv::initUndistortRectifyMap (src/Settings.cc:506-509), width*height floats each (the context's camera size); raw
+ * images handed to ft_extract_stereo / ft_frame_construct are then raw_width x raw_height. NULL maps switch it off. */
+ft_status ft_set_rectification(ft_context* ctx, int raw_width, int raw_height, const float* M1l, const float* M2l,
+                               const float* M1r, const float* M2r);
+
 /* Capacity (entries) of the per-eye keypoint arrays: nfeatures + a few per level (the octree may exceed a level
  * quota by up to 3, reference sizes its buffers nfeatures+20, include/Kernels/CudaUtils.h:16). */
 int ft_max_keypoints(ft_context* ctx);

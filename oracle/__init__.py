@@ -69,6 +69,7 @@ def lib():
     L.fto_desc_borderline.argtypes = [C.c_void_p]
     L.fto_resize.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
     L.fto_blur.argtypes = [u8p, C.c_int, C.c_int, u8p]
+    L.fto_remap.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, u8p]
     L.fto_fast.restype = C.c_int
     L.fto_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
     L.fto_fast_atan2.restype = C.c_float
@@ -183,6 +184,16 @@ def blur(src):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.zeros_like(src)
     lib().fto_blur(src, src.shape[1], src.shape[0], dst)
+    return dst
+
+
+def remap(src, mapx, mapy):
+    """cv::remap(src, map1=mapx, map2=mapy, INTER_LINEAR) with the default constant-0 border"""
+    src = np.ascontiguousarray(src, np.uint8)
+    mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().fto_remap(src, src.shape[1], src.shape[0], mapx, mapy, dw, dh, dst)
     return dst
 
 

@@ -199,6 +199,29 @@ float fast_atan2(float y, float x) {
   return a;
 }
 
+// ---------------------------------------------------------------------------
+// cv::remap, 8UC1, CV_32FC1 map pair, INTER_LINEAR, BORDER_CONSTANT(0) -- OpenCV imgproc imgwarp.cpp fixed-point
+// path: coordinates rounded to 1/32 px (INTER_BITS = 5), 2x2 weights from BilinearTab_i scaled by 2^15 with the
+// table's sum correction (only the entry fx = fy = 0 saturates: {32767, 0, 0, 1}), result (sum + 2^14) >> 15.
+// Call site: System::TrackStereo (System.cc:279-280), "next" row 2 of SURVEY.md 8f.
+// ---------------------------------------------------------------------------
+void remap_linear_u8(const Img& src, const float* mapx, const float* mapy, int dw, int dh, Img& dst) {
+  dst.w = dw; dst.h = dh; dst.d.assign((size_t)dw * dh, 0);
+  const int sw = src.w, sh = src.h;
+  auto px = [&](int y, int x) -> int { return (x >= 0 && x < sw && y >= 0 && y < sh) ? src.d[(size_t)y * sw + x] : 0; };
+  for (int y = 0; y < dh; y++)
+    for (int x = 0; x < dw; x++) {
+      int sx = cv_round(mapx[(size_t)y * dw + x] * 32.f), sy = cv_round(mapy[(size_t)y * dw + x] * 32.f);
+      const int fx = sx & 31, fy = sy & 31;
+      int ix = sx >> 5, iy = sy >> 5;
+      ix = std::min(std::max(ix, -32768), 32767); iy = std::min(std::max(iy, -32768), 32767);   // saturate_cast<short>
+      int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+      if (fx == 0 && fy == 0) { w00 = 32767; w11 = 1; }
+      const int v = w00 * px(iy, ix) + w01 * px(iy, ix + 1) + w10 * px(iy + 1, ix) + w11 * px(iy + 1, ix + 1);
+      dst.d[(size_t)y * dw + x] = (uint8_t)std::min(std::max((v + (1 << 14)) >> 15, 0), 255);
+    }
+}
+
 // ORBmatcher::DescriptorDistance (ORBmatcher.cc:2256-2273): popcount of 256-bit XOR.
 int descriptor_distance(const uint8_t* a, const uint8_t* b) {
   int dist = 0;

@@ -43,6 +43,8 @@ void fast_detect(const uint8_t* roi, int stride, int w, int h, int th, std::vect
 float fast_atan2(float y, float x);                                 // cv::fastAtan2
 void knn2_hamming(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx2, int* dist2);  // BFMatcher knnMatch k=2
 int descriptor_distance(const uint8_t* a, const uint8_t* b);        // ORBmatcher.cc:2256-2273
+// cv::remap(src, dst, map1 (CV_32FC1 x), map2 (CV_32FC1 y), INTER_LINEAR, BORDER_CONSTANT 0) on 8UC1 (System.cc:279-280)
+void remap_linear_u8(const Img& src, const float* mapx, const float* mapy, int dw, int dh, Img& dst);
 
 // ---- ORBextractor (ORBextractor.cc CPU branches) ----
 class Extractor {

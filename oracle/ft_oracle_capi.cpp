@@ -97,6 +97,12 @@ void fto_blur(const uint8_t* src, int w, int h, uint8_t* dst) {
   gaussian_blur_7x7_s2(s, d);
   memcpy(dst, d.d.data(), d.d.size());
 }
+void fto_remap(const uint8_t* src, int sw, int sh, const float* mapx, const float* mapy, int dw, int dh, uint8_t* dst) {
+  Img s, d;
+  s.w = sw; s.h = sh; s.d.assign(src, src + (size_t)sw * sh);
+  remap_linear_u8(s, mapx, mapy, dw, dh, d);
+  memcpy(dst, d.d.data(), d.d.size());
+}
 int fto_fast(const uint8_t* img, int stride, int w, int h, int th, int cap, float* xyr) {
   std::vector<Candidate> c;
   fast_detect(img, stride, w, h, th, c);

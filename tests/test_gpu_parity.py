@@ -306,3 +306,33 @@ def test_staged_search_matches_host_call(euroc):
     np.copyto(stg["holder"], mp["holder"]); np.copyto(stg["holder_obs"], mp["holder_obs"])
     n2, h2, o2, b2 = ctx.search_staged(M, N, 2.0)
     assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(o1, o2) and np.array_equal(b1, b2)
+
+
+def test_rectification_fused_into_level0(euroc_pair):
+    """'next' row 2: cv::remap of System::TrackStereo in front of the extractor (raw 800x500 -> rectified 752x480)"""
+    rawL = synth.texture(500, 800, 41); rawR = np.roll(rawL, -9, axis=1)
+    yy, xx = np.mgrid[0:480, 0:752].astype(np.float32)
+    def maps(cx, cy, k1, dx, dy):
+        xn, yn = (xx - cx) / 458.6, (yy - cy) / 457.3
+        r2 = xn * xn + yn * yn
+        f = 1 + k1 * r2 + 0.074 * r2 * r2
+        return (xn * f * 470.0 + cx + 24 + dx).astype(np.float32), (yn * f * 470.0 + cy + 10 + dy).astype(np.float32)
+    m1l, m2l = maps(367.2, 248.4, -0.283, 1.3, -0.7)
+    m1r, m2r = maps(379.9, 255.2, -0.284, -2.1, 0.4)
+    ctx, mbf, mb = _ctx(E)
+    ctx.set_rectification(800, 500, m1l, m2l, m1r, m2r)
+    ctx.extract_stereo(rawL, rawR); ctx.stereo_match()
+    rectL, rectR = oracle.remap(rawL, m1l, m2l), oracle.remap(rawR, m1r, m2r)
+    assert np.array_equal(ctx.level_image(0, 0), rectL) and np.array_equal(ctx.level_image(1, 0), rectR)
+    exL, exR, oL, oR = _oracle_pair(rectL, rectR, 1200, 8)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    assert np.array_equal(gl["u_right"], st["uRight"])
+    # switching it off again restores the plain path
+    ctx.set_rectification(0, 0, None, None, None, None)
+    L, R = euroc_pair
+    ctx.extract_stereo(L, R)
+    assert np.array_equal(ctx.level_image(0, 0), L)
+    ctx.close()

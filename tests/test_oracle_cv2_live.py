@@ -70,3 +70,16 @@ def test_fast_random_rois():
         k = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=True).detect(np.ascontiguousarray(roi))
         ref = np.array([[p.pt[0], p.pt[1], p.response] for p in k], np.float32).reshape(-1, 3)
         assert np.array_equal(oracle.fast(roi, th), ref)
+
+
+def test_remap_live():
+    rng = np.random.default_rng(5)
+    img = synth.texture(480, 752, 3)
+    yy, xx = np.mgrid[0:480, 0:752].astype(np.float32)
+    xn, yn = (xx - 367.2) / 458.6, (yy - 248.4) / 457.3
+    r2 = xn * xn + yn * yn
+    f = 1 - 0.283 * r2 + 0.074 * r2 * r2
+    mx = (xn * f * 458.6 + 367.2 + 1.3).astype(np.float32); my = (yn * f * 457.3 + 248.4 - 0.7).astype(np.float32)
+    assert np.array_equal(oracle.remap(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+    mx2 = rng.uniform(-8, 760, (100, 120)).astype(np.float32); my2 = rng.uniform(-8, 488, (100, 120)).astype(np.float32)
+    assert np.array_equal(oracle.remap(img, mx2, my2), cv2.remap(img, mx2, my2, cv2.INTER_LINEAR))

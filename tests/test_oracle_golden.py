@@ -52,3 +52,10 @@ def test_knn_matches_cv2(cv2_golden):
 def test_cv_round_half_even():
     for v, r in [(0.5, 0), (1.5, 2), (2.5, 2), (-0.5, 0), (-1.5, -2), (-2.5, -2), (3.4999, 3), (3.5001, 4)]:
         assert oracle.cv_round(v) == r
+
+
+def test_remap_matches_cv2():
+    """cv::remap INTER_LINEAR, CV_32F maps, constant-0 border (System.cc:279-280), incl. out-of-range and integer coordinates"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_remap.npz"))
+    assert np.array_equal(oracle.remap(g["img"], g["mx"], g["my"]), g["ref"])
