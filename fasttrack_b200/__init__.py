@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -95,6 +95,7 @@ def load_library():
     L.ft_debug_level_counts.argtypes = [vp, C.c_int, vp, vp]
     L.ft_debug_sort.argtypes = [vp, C.c_int]
     L.ft_max_keypoints.argtypes = [vp]
+    L.ft_bind_map_points_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     L.ft_set_rectification.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.ft_search_last_frame.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp, ip]
     L.ft_map_point_staging.argtypes = [vp, C.c_int] + [C.POINTER(vp)] * 7
@@ -273,6 +274,10 @@ class Context:
         self._mp_keep = (f(pos), f(normal), f(minmax), np.ascontiguousarray(desc, np.uint8),
                          np.ascontiguousarray(flags, np.int32))
         self._ck(self.L.ft_upload_map_points(self.h, len(self._mp_keep[0]), *[_ptr(a) for a in self._mp_keep]))
+
+    def bind_map_points_device(self, M, d_pos, d_normal, d_minmax, d_desc, d_flags):
+        """device pointers (ints) of a snapshot that already lives in HBM; used in place"""
+        self._ck(self.L.ft_bind_map_points_device(self.h, M, d_pos, d_normal, d_minmax, d_desc, d_flags))
 
     def upload_holders(self, holder=None, holder_obs=None):
         if holder is None:

@@ -854,6 +854,20 @@ extern "C" ft_status ft_upload_map_points(ft_context* c, int M, const float* pos
   return FT_OK;
 }
 
+// Bind a map-point snapshot that already lives in device memory (e.g. a persistent device-side map store kept up to
+// date by the mapping thread): no copy, the search kernels read the caller's arrays directly.
+extern "C" ft_status ft_bind_map_points_device(ft_context* c, int M, const float* d_pos, const float* d_normal,
+                                               const float* d_minmax, const uint8_t* d_desc, const int* d_flags) {
+  if (!c || M < 0 || (M > 0 && (!d_pos || !d_normal || !d_minmax || !d_desc || !d_flags))) { set_err("ft_bind_map_points_device: null argument"); return FT_ERR_INVALID; }
+  if (M > c->cfg.max_map_points) { set_err("more map points than ft_config.max_map_points"); return FT_ERR_CAPACITY; }
+  if ((reinterpret_cast<uintptr_t>(d_desc) & 15) != 0) { set_err("ft_bind_map_points_device: descriptors must be 16-byte aligned"); return FT_ERR_INVALID; }
+  FtSbpBuffers& Q = c->Q;
+  Q.pos = const_cast<float*>(d_pos); Q.normal = const_cast<float*>(d_normal); Q.minmax = const_cast<float*>(d_minmax);
+  Q.desc = const_cast<uint8_t*>(d_desc); Q.flags = const_cast<int*>(d_flags);
+  c->residentM = M;
+  return FT_OK;
+}
+
 extern "C" ft_status ft_upload_holders(ft_context* c, int N, const int* holder, const uint8_t* holderObs) {
   if (!c || N < 0 || N > 2 * c->P.maxKp) { set_err("ft_upload_holders: bad argument"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));

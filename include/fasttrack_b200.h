@@ -157,6 +157,9 @@ ft_status ft_search_local_points(ft_context* ctx, int M, const float* pos, const
 ft_status ft_upload_map_points(ft_context* ctx, int M, const float* pos, const float* normal, const float* minmax,
                                const uint8_t* desc, const int* flags);
 ft_status ft_upload_holders(ft_context* ctx, int N, const int* holder, const uint8_t* holder_obs);
+/* like ft_upload_map_points, but the SoA arrays already live in DEVICE memory and are used in place (no copy) */
+ft_status ft_bind_map_points_device(ft_context* ctx, int M, const float* d_pos, const float* d_normal,
+                                    const float* d_minmax, const uint8_t* d_desc, const int* d_flags);
 ft_status ft_search_resident(ft_context* ctx, float th, int b_far_points, float th_far_points, float nnratio);
 ft_status ft_search_download(ft_context* ctx, int* holder, uint8_t* holder_obs, int* best_idx, int* nmatches);
 

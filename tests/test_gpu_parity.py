@@ -336,3 +336,48 @@ def test_rectification_fused_into_level0(euroc_pair):
     ctx.extract_stereo(L, R)
     assert np.array_equal(ctx.level_image(0, 0), L)
     ctx.close()
+
+
+def test_two_contexts_pipelined_match_sequential(euroc_pair):
+    """bench.py's throughput leg alternates the frames of one sequence between two contexts (2-deep pipeline):
+    every frame's results must equal the one-context, one-frame-at-a-time results"""
+    import torch
+    L, R = euroc_pair
+    sc = synth.StereoScene(seed=9)
+    frames = [(L, R)] + [sc.pair(pan=(3 * t, t), noise_seed=t) for t in range(1, 6)]
+    ctxs = [_ctx(E)[0] for _ in range(2)]
+    ref = _ctx(E)[0]
+    streams = [torch.cuda.ExternalStream(c.stream()) for c in ctxs]
+    dimgs = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in frames]
+    exp, maps = [], []
+    for (a, b) in frames:
+        l, r = ref.frame_construct(a, b)
+        mp = synth.mappoints(ft.keypoints_as_array(l["kps"]), l["desc"], ref.scale_tables()["scale"], 3000, seed=len(exp))
+        mp["flags"] |= 2
+        ref.set_pose(np.eye(3), np.zeros(3))
+        n, h, ho, _ = ref.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0,
+                                              np.full(l["n"], -1, np.int32), np.zeros(l["n"], np.uint8))
+        exp.append((l, n, h)); maps.append({k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in mp.items() if k in ("pos", "normal", "minmax", "desc", "flags")})
+    for c in ctxs:
+        c.set_pose(np.eye(3), np.zeros(3)); c.upload_holders(None, None)
+    done = [torch.cuda.Event() for _ in frames]
+    got = []
+    for i, (da, db) in enumerate(dimgs):
+        c, s = ctxs[i & 1], streams[i & 1]
+        c.frame_enqueue_device(da.data_ptr(), E["width"], db.data_ptr(), E["width"])
+        if i > 0:
+            s.wait_event(done[i - 1])
+        m = maps[i]
+        c.bind_map_points_device(3000, m["pos"].data_ptr(), m["normal"].data_ptr(), m["minmax"].data_ptr(), m["desc"].data_ptr(),
+                                 m["flags"].data_ptr())
+        c.search_resident(3.0)
+        done[i].record(s)
+        if i >= 1:      # results of frame i-1 are read back while frame i is in flight on the other context
+            p = ctxs[(i - 1) & 1]
+            got.append((p.download(0, stereo=True), p.search_download(3000)))
+    got.append((ctxs[(len(frames) - 1) & 1].download(0, stereo=True), ctxs[(len(frames) - 1) & 1].search_download(3000)))
+    for (l, n, h), (gl, (gn, gh, _, _)) in zip(exp, got):
+        assert np.array_equal(gl["kps"], l["kps"]) and np.array_equal(gl["desc"], l["desc"]) and np.array_equal(gl["u_right"], l["u_right"])
+        assert gn == n and np.array_equal(gh, h)
+    for c in ctxs + [ref]:
+        c.close()
