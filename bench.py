@@ -41,11 +41,34 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampler running during the timed region (profiling recipe's clocks line)."""
+    """SM clock + throttle-reason sampler running during the timed regions (profiling recipe's clocks line): NVML
+    polled every 20 ms from a thread; falls back to an `nvidia-smi -lms 100` child when NVML is unusable."""
 
-    def __init__(self, gpu_index):
-        self.rows = []
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index, uuid=None):
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.stop_flag = threading.Event()
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if not str(uuid).startswith("GPU-") else str(uuid))
+                except Exception:
+                    h = None
+            self.h = h or pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -53,34 +76,53 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.BITS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                self.sm.append(float(r[1])); self.mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.th.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def make_frames(seed, n):
@@ -181,11 +223,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
+    ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight in the throughput leg (contexts/streams)")
     args = ap.parse_args()
     rank, local, world = replicas.env_rank()
     if args.impl == "reference":
@@ -207,7 +250,8 @@ def main():
         return ft.Context(E["width"], E["height"], nfeatures=E["nfeatures"], nlevels=E["nlevels"], scale_factor=E["scale"],
                           cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), max_map_points=25000, device_id=local)
     # two contexts = a 2-deep software pipeline over ONE sequence: frame t+1 is extracted while frame t is searched
-    ctxs = [make_ctx(), make_ctx()]
+    D = max(1, args.pipeline_depth)
+    ctxs = [make_ctx() for _ in range(max(D, 2))]
     ctx = ctxs[0]
     streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
     stream = streams[0]
@@ -276,7 +320,22 @@ def main():
         nm, h_out, ho_out, best_out = ctx.search_staged(M_POINTS, nl, TH)
         return nl, nr
 
-    stg = ctx.map_point_staging(M_POINTS, cap_dev)   # views over the context's pinned staging (fixed for a fixed M)
+    stgs = [c_.map_point_staging(M_POINTS, cap_dev) for c_ in ctxs[:2]]   # views over each context's pinned staging
+    stg = stgs[0]
+
+    def e2e_submit(c_, k):
+        c_._ck(L_.ft_frame_submit(c_.h, hL[k].data_ptr(), E["width"], hR[k].data_ptr(), E["width"]))
+
+    def e2e_collect_and_search(c_, sg, k):
+        c_._ck(L_.ft_frame_collect(c_.h, out_kps[0].data_ptr(), out_desc[0].data_ptr(), out_kps[1].data_ptr(),
+                                   out_desc[1].data_ptr(), counts4.data_ptr(), out_ur.data_ptr(), out_dp.data_ptr(),
+                                   None, None, None))
+        nl = int(counts4[0])
+        m = maps[k]
+        for key in ("pos", "normal", "minmax", "desc", "flags"):
+            np.copyto(sg[key], m[key])
+        sg["holder"].fill(-1); sg["holder_obs"].fill(0)
+        return c_.search_staged(M_POINTS, nl, TH)
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,7 +350,7 @@ def main():
     for i in range(3):
         step_e2e(i)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None))
     # ---- timed region 1a: per-frame LATENCY, one frame at a time, CUDA events per step, L2 flushed between steps ----
     n_lat = min(args.steps, 100)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_lat)]
@@ -313,9 +372,10 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     ev_start.record(streams[0])
-    streams[1].wait_event(ev_start)
+    for s_ in streams[1:]:
+        s_.wait_event(ev_start)
     for i in range(args.steps):
-        c_, s_ = ctxs[i & 1], streams[i & 1]
+        c_, s_ = ctxs[i % D], streams[i % D]
         k = i % N_FRAMES
         c_.frame_enqueue_device(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"])
         if i > 0:
@@ -323,7 +383,9 @@ def main():
         bind_map(c_, k)
         c_.search_resident(TH)
         done[i].record(s_)
-    streams[0].wait_event(done[args.steps - 1]); streams[0].wait_event(done[args.steps - 2])
+    for j in range(1, min(D, args.steps) + 1):
+        streams[0].wait_event(done[args.steps - j])
+    host_submit_s = time.perf_counter() - wall0
     ev_end.record(streams[0])
     barrier()
     wall1 = time.perf_counter()
@@ -331,11 +393,23 @@ def main():
     ext_l, st_l, se_l = ctx.launch_counts()
     launches_per_step = ext_l + st_l + se_l
 
-    # ---- timed region 2: end to end through the C ABI with host buffers ----
+    # ---- timed region 2: end to end through the C ABI with host buffers, one frame at a time (ft_frame_construct +
+    # marshal + ft_search_staged; every step: H2D of both images and the map snapshot, D2H of every host vector) ----
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         nl, nr = step_e2e(i)
+    barrier()
+    e2e_serial_s = time.perf_counter() - t0
+    # ---- timed region 2b: the same calls split as ft_frame_submit / ft_frame_collect over two contexts: the upload,
+    # extraction and stereo of frame t+1 run while the host marshals and searches frame t. Same bytes per step. ----
+    barrier()
+    t0 = time.perf_counter()
+    e2e_submit(ctxs[0], 0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            e2e_submit(ctxs[(i + 1) & 1], (i + 1) % N_FRAMES)
+        e2e_collect_and_search(ctxs[i & 1], stgs[i & 1], i % N_FRAMES)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -354,7 +428,7 @@ def main():
     st = ctx.stats()
 
     # ---- reductions over ranks (max time) ----
-    dev_ms_total, e2e_s, wall_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0], device="cuda")
+    dev_ms_total, e2e_s, wall_s, e2e_serial_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0, e2e_serial_s], device="cuda")
     ms_per_step = dev_ms_total / args.steps
     value = replicas.aggregate_throughput(world, args.steps, dev_ms_total / 1e3)
     e2e_value = replicas.aggregate_throughput(world, args.steps, e2e_s)
@@ -403,10 +477,15 @@ def main():
             "config": {"workload": WORKLOAD, "frames_cycled": N_FRAMES,
                        "l2": "throughput leg: %d distinct frames cycled, inputs %.0f MB > 126 MB L2; latency leg: L2 flushed "
                              "between steps (256 MiB write)" % (N_FRAMES, N_FRAMES * (2 * E["width"] * E["height"] + 68 * M_POINTS) / 1e6),
-                       "pipeline": "2 frames in flight over one sequence (extract t+1 || search t); searches stay ordered",
+                       "pipeline": "%d frames in flight over one sequence (extract t+1.. || search t); searches stay ordered" % D,
+                       "pipeline_depth": D,
                        "sequences": world, "parallelism": "independent sequence per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3 / args.steps},
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_in_flight": 2,
+                    "serial_ms_per_step": e2e_serial_s * 1e3 / args.steps,
+                    "serial_value": replicas.aggregate_throughput(world, args.steps, e2e_serial_s),
+                    "note": "value: ft_frame_submit(t+1) overlaps marshal + ft_search_staged(t) on two contexts, host "
+                            "wall clock; serial_*: ft_frame_construct then ft_search_staged, one frame at a time"},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": launches_per_step,
             "clocks": clocks,
@@ -416,7 +495,7 @@ def main():
             "frame_hbm_roofline_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
             "frame_hbm_roofline_frac_latency": frame_bytes / (lat_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
             "counts": st,
-            "wall_s_resident_loop": wall_s,
+            "wall_s_resident_loop": wall_s, "host_submit_s_resident_loop": host_submit_s,
             "latency": {"ms_per_frame_mean": float(step_ms.mean()), "p50": float(np.percentile(step_ms, 50)),
                         "p95": float(np.percentile(step_ms, 95)), "frames": int(n_lat),
                         "note": "one frame at a time on one context, CUDA events per frame, L2 flushed between frames"}}

@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -102,6 +102,8 @@ def load_library():
     L.ft_search_staged.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.ft_frame_enqueue_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_frame_construct.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ft_frame_submit.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.ft_frame_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
             getattr(L, name).restype = C.c_int
@@ -221,6 +223,17 @@ class Context:
 
     def frame_construct(self, imgL, imgR):
         """Frame constructor in one call: returns (left dict, right dict) like download()"""
+        self.frame_submit(imgL, imgR)
+        return self.frame_collect()
+
+    def frame_submit(self, imgL, imgR):
+        """asynchronous half of frame_construct: upload + extract + stereo + result download enqueued; the images are
+        kept alive until frame_collect()"""
+        self._keep_frame = (imgL, imgR)
+        self._ck(self.L.ft_frame_submit(self.h, imgL.ctypes.data, imgL.strides[0], imgR.ctypes.data, imgR.strides[0]))
+
+    def frame_collect(self):
+        """waits for the submitted frame; returns (left dict, right dict) like download()"""
         cap = self.cap
         kL = np.zeros(cap, KEYPOINT_DTYPE); kR = np.zeros(cap, KEYPOINT_DTYPE)
         dL = np.zeros((cap, 32), np.uint8); dR = np.zeros((cap, 32), np.uint8)
@@ -229,9 +242,9 @@ class Context:
         l2r = r2l = p3d = None
         if self.fisheye:
             l2r = np.zeros(cap, np.int32); r2l = np.zeros(cap, np.int32); p3d = np.zeros((cap, 3), np.float32)
-        self._ck(self.L.ft_frame_construct(self.h, imgL.ctypes.data, imgL.strides[0], imgR.ctypes.data, imgR.strides[0],
-                                           _ptr(kL), _ptr(dL), _ptr(kR), _ptr(dR), _ptr(cnt), _ptr(ur), _ptr(dp),
-                                           _ptr(l2r), _ptr(r2l), _ptr(p3d)))
+        self._ck(self.L.ft_frame_collect(self.h, _ptr(kL), _ptr(dL), _ptr(kR), _ptr(dR), _ptr(cnt), _ptr(ur), _ptr(dp),
+                                         _ptr(l2r), _ptr(r2l), _ptr(p3d)))
+        self._keep_frame = None
         nl, ml, nr, mr = [int(x) for x in cnt]
         left = dict(kps=kL[:nl].copy(), desc=dL[:nl].copy(), n=nl, mono_index=ml, u_right=ur[:nl].copy(), depth=dp[:nl].copy())
         right = dict(kps=kR[:nr].copy(), desc=dR[:nr].copy(), n=nr, mono_index=mr)

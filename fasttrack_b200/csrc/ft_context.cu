@@ -60,7 +60,7 @@ struct ft_context {
   size_t offOutHolder = 0, offOutObs = 0, offOutSel = 0;
   cudaGraphExec_t gExtract = nullptr, gStereo = nullptr, gFrame = nullptr;
   int useGraph = 1;
-  bool extracted = false, stereoDone = false, countsValid = false;
+  bool extracted = false, stereoDone = false, countsValid = false, framePending = false;
   int lastM = 0;
   int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
   long long pyrBytes = 0;
@@ -756,20 +756,30 @@ extern "C" int ft_max_keypoints(ft_context* c) { return c ? c->P.maxKp : 0; }
 // Frame constructor in one call (reference src/Frame.cc:102-223 for pinhole rigs, :1115-1229 for fisheye):
 // upload both images, extract, stereo-match, and bring every host vector the constructor fills back with a
 // single synchronisation. Output arrays must hold ft_max_keypoints() entries.
-extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR,
-                                        ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR,
-                                        int* counts4 /* nL, monoL, nR, monoR */, float* u_right, float* depth,
-                                        int* l2r, int* r2l, float* p3d) {
-  if (!c || !counts4) { set_err("ft_frame_construct: null argument"); return FT_ERR_INVALID; }
+// Asynchronous half of the Frame constructor: upload + extract + stereo + the D2H of the result slab are enqueued and
+// the call returns; ft_frame_collect waits and scatters. With two contexts a caller overlaps the extraction of frame
+// t+1 with the tracking of frame t (extraction does not depend on the SLAM state).
+extern "C" ft_status ft_frame_submit(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
+  if (!c) { set_err("ft_frame_submit: null context"); return FT_ERR_INVALID; }
   ft_status st = upload_images(c, imgL, stepL, imgR, stepR);
   if (st != FT_OK) return st;
   st = run_frame(c);
   if (st != FT_OK) return st;
-  cudaStream_t s = c->stream;
-  // one D2H of the whole result slab (header, both eyes' keypoints + descriptors, stereo outputs), then host scatter
+  // one D2H of the whole result slab (header, both eyes' keypoints + descriptors, stereo outputs)
   const size_t bytes = c->fisheye ? c->frameBytesAll : c->frameBytesPinhole;
-  CK(cudaMemcpyAsync(c->hFrame, c->dFrame, bytes, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpyAsync(c->hFrame, c->dFrame, bytes, cudaMemcpyDeviceToHost, c->stream));
+  c->framePending = true;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_frame_collect(ft_context* c, ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR,
+                                      int* counts4 /* nL, monoL, nR, monoR */, float* u_right, float* depth,
+                                      int* l2r, int* r2l, float* p3d) {
+  if (!c || !counts4) { set_err("ft_frame_collect: null argument"); return FT_ERR_INVALID; }
+  if (!c->framePending) { set_err("ft_frame_collect: no submitted frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  c->framePending = false;
   memcpy(c->hCounts, c->hFrame, 8 * sizeof(int));
   c->countsValid = true;
   const int nl = c->hCounts[0], nr = c->hCounts[2];
@@ -786,6 +796,16 @@ extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int 
   }
   for (int i = 0; i < 4; i++) counts4[i] = c->hCounts[i];
   return check_device_status(c, c->hCounts[4]);
+}
+
+extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR,
+                                        ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR,
+                                        int* counts4 /* nL, monoL, nR, monoR */, float* u_right, float* depth,
+                                        int* l2r, int* r2l, float* p3d) {
+  if (!c || !counts4) { set_err("ft_frame_construct: null argument"); return FT_ERR_INVALID; }
+  ft_status st = ft_frame_submit(c, imgL, stepL, imgR, stepR);
+  if (st != FT_OK) return st;
+  return ft_frame_collect(c, kpsL, descL, kpsR, descR, counts4, u_right, depth, l2r, r2l, p3d);
 }
 
 extern "C" ft_status ft_set_pose(ft_context* c, const float* Rcw, const float* tcw, const float* Rwc, const float* Ow) {

@@ -129,6 +129,16 @@ ft_status ft_frame_construct(ft_context* ctx, const uint8_t* imgL, int stepL, co
                              ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR, int* counts4,
                              float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
 
+/* ft_frame_construct in two halves, so that a caller keeps two frames in flight on two contexts: ORB extraction and
+ * stereo matching of frame t+1 do not depend on the SLAM state and overlap the tracking of frame t (the reference
+ * runs them strictly in sequence inside the Frame constructor, src/Frame.cc:102-223). ft_frame_submit enqueues
+ * upload + extract + stereo + the download of the result slab and returns at once; the images must stay valid until
+ * ft_frame_collect, which waits for the frame and fills the host vectors exactly as ft_frame_construct does.
+ * FT_ERR_STATE when no frame is pending. */
+ft_status ft_frame_submit(ft_context* ctx, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR);
+ft_status ft_frame_collect(ft_context* ctx, ft_keypoint* kpsL, uint8_t* descL, ft_keypoint* kpsR, uint8_t* descR,
+                           int* counts4, float* u_right, float* depth, int* l2r, int* r2l, float* p3d);
+
 /* ft_frame_construct without the downloads, for images already in device memory; asynchronous. */
 ft_status ft_frame_enqueue_device(ft_context* ctx, const uint8_t* d_imgL, int stepL, const uint8_t* d_imgR, int stepR);
 

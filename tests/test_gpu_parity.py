@@ -381,3 +381,27 @@ def test_two_contexts_pipelined_match_sequential(euroc_pair):
         assert gn == n and np.array_equal(gh, h)
     for c in ctxs + [ref]:
         c.close()
+
+
+def test_frame_submit_collect_two_contexts(euroc_pair):
+    """ft_frame_submit / ft_frame_collect on two contexts (frame t+1 in flight while frame t is collected) return what
+    ft_frame_construct returns; collect without a pending frame is FT_ERR_STATE"""
+    L, R = euroc_pair
+    sc = synth.StereoScene(seed=11)
+    frames = [(L, R)] + [sc.pair(pan=(2 * t, -t), noise_seed=20 + t) for t in range(1, 5)]
+    ref = _ctx(E)[0]
+    exp = [ref.frame_construct(a, b) for a, b in frames]
+    ctxs = [_ctx(E)[0] for _ in range(2)]
+    with pytest.raises(RuntimeError):
+        ctxs[0].frame_collect()
+    ctxs[0].frame_submit(*frames[0])
+    for i in range(len(frames)):
+        if i + 1 < len(frames):
+            ctxs[(i + 1) & 1].frame_submit(*frames[i + 1])
+        l, r = ctxs[i & 1].frame_collect()
+        el, er = exp[i]
+        for k in ("kps", "desc", "u_right", "depth"):
+            assert np.array_equal(l[k], el[k]), (i, k)
+        assert np.array_equal(r["kps"], er["kps"]) and np.array_equal(r["desc"], er["desc"])
+    for c in ctxs + [ref]:
+        c.close()
