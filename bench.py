@@ -28,6 +28,7 @@ E = synth.EUROC
 N_FRAMES = 104           # distinct pre-generated frames per rank, cycled: 104 x (2 images + map snapshot) = 132 MB > L2 (126 MB)
 M_POINTS = 8000          # local map size per frame
 TH = 3.0
+STORE_UPSERTS = 400     # rows the mapping side changes per frame in the map-store e2e leg
 WORKLOAD = ("euroc_752x480_stereo_sequence: extract(L,R; 1200 features, 8 levels, x1.2) + ComputeStereoMatches + "
             "SearchLocalPoints(M=%d, th=%g)" % (M_POINTS, TH))
 METRIC = "frames/sec (ORB extract L+R + stereo match + projection search)"
@@ -228,6 +229,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight in the end-to-end legs (<= pipeline depth)")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight in the throughput leg (contexts/streams)")
     args = ap.parse_args()
     rank, local, world = replicas.env_rank()
@@ -251,6 +253,7 @@ def main():
                           cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), max_map_points=25000, device_id=local)
     # two contexts = a 2-deep software pipeline over ONE sequence: frame t+1 is extracted while frame t is searched
     D = max(1, args.pipeline_depth)
+    DE = max(2, min(args.e2e_depth, max(D, 2)))   # frames in flight in the end-to-end legs
     ctxs = [make_ctx() for _ in range(max(D, 2))]
     ctx = ctxs[0]
     streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
@@ -320,7 +323,7 @@ def main():
         nm, h_out, ho_out, best_out = ctx.search_staged(M_POINTS, nl, TH)
         return nl, nr
 
-    stgs = [c_.map_point_staging(M_POINTS, cap_dev) for c_ in ctxs[:2]]   # views over each context's pinned staging
+    stgs = [c_.map_point_staging(M_POINTS, cap_dev) for c_ in ctxs]   # views over each context's pinned staging
     stg = stgs[0]
 
     def e2e_submit(c_, k):
@@ -405,13 +408,60 @@ def main():
     # extraction and stereo of frame t+1 run while the host marshals and searches frame t. Same bytes per step. ----
     barrier()
     t0 = time.perf_counter()
-    e2e_submit(ctxs[0], 0)
+    for j in range(min(DE - 1, args.steps)):
+        e2e_submit(ctxs[j % DE], j % N_FRAMES)
     for i in range(args.steps):
-        if i + 1 < args.steps:
-            e2e_submit(ctxs[(i + 1) & 1], (i + 1) % N_FRAMES)
-        e2e_collect_and_search(ctxs[i & 1], stgs[i & 1], i % N_FRAMES)
+        j = i + DE - 1
+        if j < args.steps:
+            e2e_submit(ctxs[j % DE], j % N_FRAMES)
+        e2e_collect_and_search(ctxs[i % DE], stgs[i % DE], i % N_FRAMES)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # ---- timed region 2c: as 2b, with the local map named as rows of the persistent device-side map store
+    # (SURVEY.md 8f row 3): per step the host upserts STORE_UPSERTS changed rows and sends 8 bytes per map point
+    # (row, flags) instead of the 68-byte snapshot. The store is loaded before the timed region (it persists).
+    ctxs[0].map_store_create(N_FRAMES * M_POINTS)
+    for c_ in ctxs[1:]:
+        c_.map_store_attach(ctxs[0])
+    for k in range(N_FRAMES):
+        m = maps[k]
+        ctxs[0].map_store_update(np.arange(k * M_POINTS, (k + 1) * M_POINTS, dtype=np.int32), m["pos"], m["normal"], m["minmax"], m["desc"])
+    rows = [np.arange(k * M_POINTS, (k + 1) * M_POINTS, dtype=np.int32) for k in range(N_FRAMES)]
+    h_in = np.full(cap_dev, -1, np.int32); ho_in = np.zeros(cap_dev, np.uint8)
+    h_io = np.empty(cap_dev, np.int32); ho_io = np.empty(cap_dev, np.uint8)
+    best_io = np.empty((M_POINTS, 2), np.int32); nm_io = C.c_int()
+
+    def e2e_collect_and_search_store(c_, k):
+        c_._ck(L_.ft_frame_collect(c_.h, out_kps[0].data_ptr(), out_desc[0].data_ptr(), out_kps[1].data_ptr(),
+                                   out_desc[1].data_ptr(), counts4.data_ptr(), out_ur.data_ptr(), out_dp.data_ptr(),
+                                   None, None, None))
+        m = maps[k]; r = rows[k]; u = STORE_UPSERTS
+        c_._ck(L_.ft_map_store_update(c_.h, u, r.ctypes.data, m["pos"].ctypes.data, m["normal"].ctypes.data,
+                                      m["minmax"].ctypes.data, m["desc"].ctypes.data))
+        np.copyto(h_io, h_in); np.copyto(ho_io, ho_in)
+        c_._ck(L_.ft_search_store(c_.h, M_POINTS, r.ctypes.data, m["flags"].ctypes.data, TH, 0, 50.0, 0.8, h_io.ctypes.data,
+                                  ho_io.ctypes.data, best_io.ctypes.data, C.byref(nm_io)))
+        return nm_io.value
+
+    # the store path returns what the snapshot path returns (checked on a few frames outside the timed region)
+    for k in range(3):
+        e2e_submit(ctxs[k & 1], k)
+        nm_snap = e2e_collect_and_search(ctxs[k & 1], stgs[k & 1], k)[0]
+        e2e_submit(ctxs[k & 1], k)
+        nm_store = e2e_collect_and_search_store(ctxs[k & 1], k)
+        if nm_snap != nm_store:
+            raise SystemExit("bench.py: map-store search differs from the snapshot search (%d vs %d)" % (nm_store, nm_snap))
+    barrier()
+    t0 = time.perf_counter()
+    for j in range(min(DE - 1, args.steps)):
+        e2e_submit(ctxs[j % DE], j % N_FRAMES)
+    for i in range(args.steps):
+        j = i + DE - 1
+        if j < args.steps:
+            e2e_submit(ctxs[j % DE], j % N_FRAMES)
+        e2e_collect_and_search_store(ctxs[i % DE], i % N_FRAMES)
+    barrier()
+    e2e_store_s = time.perf_counter() - t0
     clocks = sampler.stop()
     h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + 2 * cap_dev * 5
     d2h = 64 + 2 * cap_dev * (24 + 32) + cap_dev * 8 + 64 + 2 * cap_dev * 5 + M_POINTS * 8
@@ -428,7 +478,7 @@ def main():
     st = ctx.stats()
 
     # ---- reductions over ranks (max time) ----
-    dev_ms_total, e2e_s, wall_s, e2e_serial_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0, e2e_serial_s], device="cuda")
+    dev_ms_total, e2e_s, wall_s, e2e_serial_s, e2e_store_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0, e2e_serial_s, e2e_store_s], device="cuda")
     ms_per_step = dev_ms_total / args.steps
     value = replicas.aggregate_throughput(world, args.steps, dev_ms_total / 1e3)
     e2e_value = replicas.aggregate_throughput(world, args.steps, e2e_s)
@@ -481,10 +531,15 @@ def main():
                        "pipeline_depth": D,
                        "sequences": world, "parallelism": "independent sequence per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_in_flight": 2,
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_in_flight": DE,
                     "serial_ms_per_step": e2e_serial_s * 1e3 / args.steps,
                     "serial_value": replicas.aggregate_throughput(world, args.steps, e2e_serial_s),
-                    "note": "value: ft_frame_submit(t+1) overlaps marshal + ft_search_staged(t) on two contexts, host "
+                    "map_store": {"value": replicas.aggregate_throughput(world, args.steps, e2e_store_s),
+                                  "ms_per_step": e2e_store_s * 1e3 / args.steps,
+                                  "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
+                                  "upserts_per_step": STORE_UPSERTS,
+                                  "note": "local map named as rows of the persistent device-side store (8f row 3)"},
+                    "note": "value: ft_frame_submit(t+1..) overlaps marshal + ft_search_staged(t) on frames_in_flight contexts, host "
                             "wall clock; serial_*: ft_frame_construct then ft_search_staged, one frame at a time"},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": launches_per_step,

@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -103,6 +103,10 @@ def load_library():
     L.ft_frame_enqueue_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_frame_construct.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ft_frame_submit.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.ft_map_store_create.argtypes = [vp, C.c_int]
+    L.ft_map_store_attach.argtypes = [vp, vp]
+    L.ft_map_store_update.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.ft_search_store.argtypes = [vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]
     L.ft_frame_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
@@ -251,6 +255,31 @@ class Context:
         if self.fisheye:
             left.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
         return left, right
+
+    # ---- persistent map store ----
+    def map_store_create(self, capacity):
+        self._ck(self.L.ft_map_store_create(self.h, int(capacity)))
+
+    def map_store_attach(self, owner):
+        self._ck(self.L.ft_map_store_attach(self.h, owner.h))
+
+    def map_store_update(self, slots, pos, normal, minmax, desc):
+        slots = np.ascontiguousarray(slots, np.int32)
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        pos, normal, minmax = f(pos), f(normal), f(minmax)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        self._ck(self.L.ft_map_store_update(self.h, len(slots), _ptr(slots), _ptr(pos), _ptr(normal), _ptr(minmax), _ptr(desc)))
+
+    def search_store(self, slots, flags, th, holder, holder_obs, b_far=False, th_far=50.0, nnratio=0.8):
+        slots = np.ascontiguousarray(slots, np.int32); flags = np.ascontiguousarray(flags, np.int32)
+        holder = np.ascontiguousarray(holder, np.int32).copy()
+        holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        M = len(slots)
+        best = np.full((max(M, 1), 2), -1, np.int32)
+        nm = C.c_int()
+        self._ck(self.L.ft_search_store(self.h, M, _ptr(slots), _ptr(flags), th, int(b_far), th_far, nnratio,
+                                        _ptr(holder), _ptr(holder_obs), _ptr(best), C.byref(nm)))
+        return nm.value, holder, holder_obs, best[:M]
 
     def set_pose(self, Rcw, tcw, Rwc=None, Ow=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1)

@@ -27,6 +27,17 @@ static void set_err(const std::string& s) { g_err = s; }
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// Persistent device-side MapPoint store: rows of pos/normal/minmax/descriptor that outlive a
+// frame, shared by the contexts of one sequence. Updates and searches are ordered across the contexts' streams by events.
+struct ft_map_store {
+  int cap = 0, device = 0;
+  float *pos = nullptr, *normal = nullptr, *minmax = nullptr;
+  uint8_t* desc = nullptr;
+  cudaEvent_t updated = nullptr;      // recorded after every scatter; a search on any context waits for it
+  bool everUpdated = false;
+  std::vector<ft_context*> users;     // attached contexts (an update waits for the last search of each)
+};
+
 struct ft_context {
   ft_config cfg;
   FtParams P;
@@ -72,6 +83,12 @@ struct ft_context {
   int residentM = 0;
   int* holderInit = nullptr;
   uint8_t* holderObsInit = nullptr;
+  // persistent map store (optional)
+  ft_map_store* store = nullptr;
+  cudaEvent_t storeSearched = nullptr, updStaged = nullptr;
+  bool storeSearchedValid = false, updStagedValid = false;
+  uint8_t *hUpd = nullptr, *dUpd = nullptr;
+  int updCap = 0;
   // per-stage CUDA-event timing (direct-launch mode only)
   int timing = 0;
   cudaEvent_t evA[FT_STAGE_COUNT] = {}, evB[FT_STAGE_COUNT] = {};
@@ -371,7 +388,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
     Q.holder = reinterpret_cast<int*>(c->dOut + c->offOutHolder);
     Q.holderObs = c->dOut + c->offOutObs;
     Q.sel = reinterpret_cast<int*>(c->dOut + c->offOutSel);
-    Q.pos = Q.normal = Q.minmax = nullptr; Q.desc = nullptr; Q.flags = nullptr;   // set per snapshot (tight layout for its M)
+    Q.pos = Q.normal = Q.minmax = nullptr; Q.desc = nullptr; Q.flags = nullptr; Q.slot = nullptr;   // set per snapshot (tight layout for its M)
   }
   CKF(dalloc(c, &Q.trI, (size_t)MM * 4));
   CKF(dalloc(c, &Q.trF, (size_t)MM * 9));
@@ -405,6 +422,18 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   return FT_OK;
 }
 
+static void store_detach(ft_context* c) {
+  ft_map_store* st = c->store;
+  if (!st) return;
+  c->store = nullptr;
+  for (size_t i = 0; i < st->users.size(); i++)
+    if (st->users[i] == c) { st->users.erase(st->users.begin() + i); break; }
+  if (!st->users.empty()) return;
+  cudaFree(st->pos); cudaFree(st->normal); cudaFree(st->minmax); cudaFree(st->desc);
+  if (st->updated) cudaEventDestroy(st->updated);
+  delete st;
+}
+
 extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (!c) return FT_OK;
   cudaSetDevice(c->cfg.device_id);
@@ -412,6 +441,11 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->gExtract) cudaGraphExecDestroy(c->gExtract);
   if (c->gStereo) cudaGraphExecDestroy(c->gStereo);
   if (c->gFrame) cudaGraphExecDestroy(c->gFrame);
+  store_detach(c);
+  if (c->hUpd) cudaFreeHost(c->hUpd);
+  if (c->dUpd) cudaFree(c->dUpd);
+  if (c->storeSearched) cudaEventDestroy(c->storeSearched);
+  if (c->updStaged) cudaEventDestroy(c->updStaged);
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
   if (c->hCounts) cudaFreeHost(c->hCounts);
@@ -832,6 +866,7 @@ static void mp_layout(ft_context* c, int M, uint8_t* base, float** pos, float** 
 static void mp_bind_device(ft_context* c, int M) {
   FtSbpBuffers& Q = c->Q;
   mp_layout(c, M, c->dMp, &Q.pos, &Q.normal, &Q.minmax, &Q.desc, &Q.flags);
+  Q.slot = nullptr;
   c->residentM = M;
 }
 
@@ -884,6 +919,7 @@ extern "C" ft_status ft_bind_map_points_device(ft_context* c, int M, const float
   FtSbpBuffers& Q = c->Q;
   Q.pos = const_cast<float*>(d_pos); Q.normal = const_cast<float*>(d_normal); Q.minmax = const_cast<float*>(d_minmax);
   Q.desc = const_cast<uint8_t*>(d_desc); Q.flags = const_cast<int*>(d_flags);
+  Q.slot = nullptr;
   c->residentM = M;
   return FT_OK;
 }
@@ -1020,6 +1056,119 @@ extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* p
   mp_bind_device(c, M);
   st = ft_search_resident(c, th, bFar, thFar, nnratio);
   if (st != FT_OK) return st;
+  return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
+}
+
+// ---- persistent map store (replaces the per-frame CudaMapPoint marshalling of the reference,
+// src/Kernels/CudaWrappers/CudaMapPoint.cc:15-34 + src/Kernels/SearchLocalPointsKernel.cu:368-409) ----
+extern "C" ft_status ft_map_store_create(ft_context* c, int capacity) {
+  if (!c || capacity <= 0) { set_err("ft_map_store_create: bad argument"); return FT_ERR_INVALID; }
+  if (c->store) { set_err("ft_map_store_create: the context already has a map store"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_map_store* st = new ft_map_store();
+  st->cap = capacity; st->device = c->cfg.device_id;
+  cudaError_t e = cudaMalloc((void**)&st->pos, (size_t)12 * capacity);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&st->normal, (size_t)12 * capacity);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&st->minmax, (size_t)8 * capacity);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&st->desc, (size_t)32 * capacity);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->updated, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    cudaFree(st->pos); cudaFree(st->normal); cudaFree(st->minmax); cudaFree(st->desc);
+    delete st;
+    set_err(std::string("ft_map_store_create: ") + cudaGetErrorString(e));
+    return FT_ERR_CUDA;
+  }
+  cudaMemsetAsync(st->pos, 0, (size_t)12 * capacity, c->stream); cudaMemsetAsync(st->normal, 0, (size_t)12 * capacity, c->stream);
+  cudaMemsetAsync(st->minmax, 0, (size_t)8 * capacity, c->stream); cudaMemsetAsync(st->desc, 0, (size_t)32 * capacity, c->stream);
+  CK(cudaEventRecord(st->updated, c->stream));
+  st->everUpdated = true;
+  st->users.push_back(c);
+  c->store = st;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_map_store_attach(ft_context* c, ft_context* owner) {
+  if (!c || !owner || c == owner) { set_err("ft_map_store_attach: bad argument"); return FT_ERR_INVALID; }
+  if (!owner->store) { set_err("ft_map_store_attach: the other context has no map store"); return FT_ERR_STATE; }
+  if (c->store) { set_err("ft_map_store_attach: the context already has a map store"); return FT_ERR_STATE; }
+  if (owner->store->device != c->cfg.device_id) { set_err("ft_map_store_attach: contexts live on different devices"); return FT_ERR_INVALID; }
+  c->store = owner->store;
+  c->store->users.push_back(c);
+  return FT_OK;
+}
+
+extern "C" ft_status ft_map_store_update(ft_context* c, int n, const int* slots, const float* pos, const float* normal,
+                                         const float* minmax, const uint8_t* desc) {
+  if (!c || n < 0 || (n > 0 && (!slots || !pos || !normal || !minmax || !desc))) { set_err("ft_map_store_update: null argument"); return FT_ERR_INVALID; }
+  ft_map_store* st = c->store;
+  if (!st) { set_err("ft_map_store_update: no map store (ft_map_store_create / ft_map_store_attach first)"); return FT_ERR_STATE; }
+  if (n == 0) return FT_OK;
+  for (int i = 0; i < n; i++)
+    if (slots[i] < 0 || slots[i] >= st->cap) { set_err("ft_map_store_update: slot outside the store's capacity"); return FT_ERR_CAPACITY; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  if (c->updStagedValid) CK(cudaEventSynchronize(c->updStaged));   // the previous update may still be reading the staging buffer
+  if (n > c->updCap) {
+    const int cap = std::max(n, std::max(1024, 2 * c->updCap));
+    if (c->hUpd) cudaFreeHost(c->hUpd);
+    if (c->dUpd) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->dUpd); }
+    c->hUpd = nullptr; c->dUpd = nullptr; c->updCap = 0;
+    CK(cudaMallocHost((void**)&c->hUpd, (size_t)72 * cap));
+    CK(cudaMalloc((void**)&c->dUpd, (size_t)72 * cap));
+    c->updCap = cap;
+  }
+  if (!c->updStaged) CK(cudaEventCreateWithFlags(&c->updStaged, cudaEventDisableTiming));
+  uint8_t* h = c->hUpd;
+  memcpy(h, slots, (size_t)4 * n); memcpy(h + (size_t)4 * n, pos, (size_t)12 * n); memcpy(h + (size_t)16 * n, normal, (size_t)12 * n);
+  memcpy(h + (size_t)28 * n, minmax, (size_t)8 * n); memcpy(h + (size_t)36 * n, desc, (size_t)32 * n);
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(c->dUpd, h, (size_t)68 * n + (size_t)4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(c->updStaged, s));
+  c->updStagedValid = true;
+  // rows may be read by a search in flight on another context of the sequence: wait for the last search of each
+  for (ft_context* u : st->users)
+    if (u != c && u->storeSearchedValid) CK(cudaStreamWaitEvent(s, u->storeSearched, 0));
+  ft_launch_store_scatter(n, c->dUpd, st->pos, st->normal, st->minmax, st->desc, s);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(st->updated, s));
+  return FT_OK;
+}
+
+// Tracking::SearchLocalPoints against the store: the local map is a list of rows (mvpLocalMapPoints order) plus the
+// per-call flags; 8 bytes per map point cross PCIe instead of 68.
+extern "C" ft_status ft_search_store(ft_context* c, int M, const int* slots, const int* flags, float th, int bFar,
+                                     float thFar, float nnratio, int* holder, uint8_t* holderObs, int* best_idx,
+                                     int* nmatches) {
+  if (!c || !holder || !holderObs || M < 0 || (M > 0 && (!slots || !flags))) { set_err("ft_search_store: null argument"); return FT_ERR_INVALID; }
+  ft_map_store* st = c->store;
+  if (!st) { set_err("ft_search_store: no map store (ft_map_store_create / ft_map_store_attach first)"); return FT_ERR_STATE; }
+  if (M > c->cfg.max_map_points) { set_err("more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)"); return FT_ERR_CAPACITY; }
+  if (!c->extracted || !c->stereoDone) { set_err("ft_search_store: no stereo-matched frame"); return FT_ERR_STATE; }
+  for (int i = 0; i < M; i++)
+    if (slots[i] < 0 || slots[i] >= st->cap) { set_err("ft_search_store: slot outside the store's capacity"); return FT_ERR_CAPACITY; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status rs = fetch_counts(c);   // synchronises: the staging buffers are free afterwards
+  if (rs != FT_OK) return rs;
+  const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
+  if (nmatches) *nmatches = 0;
+  if (M == 0 || N == 0) { c->lastM = 0; return FT_OK; }
+  cudaStream_t s = c->stream;
+  CK(cudaStreamSynchronize(s));
+  memcpy(c->hMp, holder, sizeof(int) * N);
+  memcpy(c->hMp + (size_t)2 * c->P.maxKp * 4, holderObs, (size_t)N);
+  uint8_t* hs = c->hMp + c->mpHolderBytes;
+  memcpy(hs, slots, (size_t)4 * M); memcpy(hs + (size_t)4 * M, flags, (size_t)4 * M);
+  CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)8 * M, cudaMemcpyHostToDevice, s));
+  FtSbpBuffers& Q = c->Q;
+  Q.pos = st->pos; Q.normal = st->normal; Q.minmax = st->minmax; Q.desc = st->desc;
+  Q.slot = reinterpret_cast<const int*>(c->dMp + c->mpHolderBytes);
+  Q.flags = reinterpret_cast<int*>(c->dMp + c->mpHolderBytes + (size_t)4 * M);
+  c->residentM = M;
+  if (st->everUpdated) CK(cudaStreamWaitEvent(s, st->updated, 0));
+  rs = ft_search_resident(c, th, bFar, thFar, nnratio);
+  if (rs != FT_OK) return rs;
+  if (!c->storeSearched) CK(cudaEventCreateWithFlags(&c->storeSearched, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->storeSearched, s));
+  c->storeSearchedValid = true;
   return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
 }
 

@@ -136,6 +136,7 @@ struct FtSbpBuffers {
   float* minmax;           // [M][2] raw mfMinDistance, mfMaxDistance
   uint8_t* desc;           // [M][32]
   int* flags;              // [M] bit0 skip, bit1 Observations()>0
+  const int* slot;         // [M] row of pos/normal/minmax/desc for map point j (persistent store), nullptr = j itself
   int* trI;                // [M][4] inView, inViewR, level, levelR
   float* trF;              // [M][9] projX, projY, projXR, depth, viewCos, projXR_r, projYR_r, depthR, viewCosR
   int* listOff;            // [M][2]

@@ -16,6 +16,8 @@ void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStere
                             cudaStream_t st);
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st);
+void ft_launch_store_scatter(int n, const uint8_t* staged, float* pos, float* normal, float* minmax, uint8_t* desc,
+                             cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
                     float gridWInv, float gridHInv, cudaStream_t st);
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,

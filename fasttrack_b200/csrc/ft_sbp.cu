@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
   // (cleared at allocation and by the resolve kernel of the previous search)
   for (int mp = blockIdx.x * GA_WARPS + warp; mp < M; mp += gridDim.x * GA_WARPS) {
     const int flags = s.flags[mp];
+    const int src = s.slot ? s.slot[mp] : mp;   // persistent map store: the local map is a list of rows
     int inView = 0, inViewR = 0, level = -1, levelR = -1;
     float f[9] = {-1.f, -1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float f2fRadius = 0.f;
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         }
       }
     } else if (!(flags & 1)) {
-      const float P[3] = {s.pos[3 * mp], s.pos[3 * mp + 1], s.pos[3 * mp + 2]};
-      const float Pn[3] = {s.normal[3 * mp], s.normal[3 * mp + 1], s.normal[3 * mp + 2]};
-      const float mn = s.minmax[2 * mp], mx = s.minmax[2 * mp + 1];
+      const float P[3] = {s.pos[3 * src], s.pos[3 * src + 1], s.pos[3 * src + 2]};
+      const float Pn[3] = {s.normal[3 * src], s.normal[3 * src + 1], s.normal[3 * src + 2]};
+      const float mn = s.minmax[2 * src], mx = s.minmax[2 * src + 1];
       if (!fa.fisheye) {
         float u = -1, v = -1, xr = 0, d = 0, vc = 0; int lv = -1;
         const bool ok = ft_frustum_checks(fa, P, Pn, mn, mx, false, true, u, v, xr, d, vc, lv);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
     if (lane == 0 && searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
     int2 lens = make_int2(0, 0), offs = make_int2(0, 0);
     if (searched) {
-      const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)mp * 32);
+      const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)src * 32);
       const uint4 md0 = md[0], md1 = md[1];
       for (int br = 0; br < nEyes; br++) {
         const bool active = (br == 0 ? inView : inViewR) && (br == 0 || levelR != -1);
@@ -689,6 +690,35 @@ cudaError_t ft_launch_sbp_setup(const FtParams& p) {
   if (const char* e = getenv("FT_RESOLVE_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) g_resolveCluster = v; }
   cudaGetLastError();
   return cudaSuccess;
+}
+// Persistent map store: upsert n packed records (staging layout: slots | pos | normal | minmax | desc) into the rows
+// they name. One thread per 32-bit word of a record (16 words = 64 bytes; the slot id is the 17th word of the staging record).
+__global__ void k_store_scatter(int n, const int* __restrict__ slots, const uint32_t* __restrict__ pos,
+                                const uint32_t* __restrict__ normal, const uint32_t* __restrict__ minmax,
+                                const uint32_t* __restrict__ desc, uint32_t* dPos, uint32_t* dNormal, uint32_t* dMinmax,
+                                uint32_t* dDesc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t >> 4, w = t & 15;
+  if (r >= n) return;
+  const size_t row = (size_t)slots[r];
+  if (w < 3) dPos[row * 3 + w] = pos[(size_t)r * 3 + w];
+  else if (w < 6) dNormal[row * 3 + (w - 3)] = normal[(size_t)r * 3 + (w - 3)];
+  else if (w < 8) dMinmax[row * 2 + (w - 6)] = minmax[(size_t)r * 2 + (w - 6)];
+  else dDesc[row * 8 + (w - 8)] = desc[(size_t)r * 8 + (w - 8)];
+}
+void ft_launch_store_scatter(int n, const uint8_t* staged, float* pos, float* normal, float* minmax, uint8_t* desc,
+                             cudaStream_t st) {
+  if (n <= 0) return;
+  const int* slots = reinterpret_cast<const int*>(staged);
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(staged + (size_t)4 * n);
+  const uint32_t* nm = reinterpret_cast<const uint32_t*>(staged + (size_t)16 * n);
+  const uint32_t* mm = reinterpret_cast<const uint32_t*>(staged + (size_t)28 * n);
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(staged + (size_t)36 * n);
+  const long long threads = 16LL * n;
+  k_store_scatter<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, slots, p, nm, mm, d, reinterpret_cast<uint32_t*>(pos),
+                                                                   reinterpret_cast<uint32_t*>(normal),
+                                                                   reinterpret_cast<uint32_t*>(minmax),
+                                                                   reinterpret_cast<uint32_t*>(desc));
 }
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
                     float gridWInv, float gridHInv, cudaStream_t st) {

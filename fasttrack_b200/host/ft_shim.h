@@ -176,6 +176,10 @@ struct MapPoint {
   float mTrackProjX = -1, mTrackProjY = -1, mTrackProjXR = 0, mTrackDepth = 0, mTrackViewCos = 0;
   float mTrackProjXR_r = 0, mTrackProjYR = 0, mTrackDepthR = 0, mTrackViewCosR = 0;
   int mnTrackScaleLevel = -1, mnTrackScaleLevelR = -1;
+  // row in the persistent device-side store (MapStore below); -1 = not inserted. The setters of a full MapPoint
+  // (SetWorldPos, UpdateNormalAndDepth, ComputeDistinctiveDescriptors) set mbStoreDirty.
+  int mnStoreRow = -1;
+  bool mbStoreDirty = true;
   bool isBad() const { return mbBad; }
   int Observations() const { return nObs; }
 };
@@ -232,6 +236,51 @@ class Frame {
   std::shared_ptr<FrontEndContext> fe_;
 };
 
+// Host side of the persistent device-side MapPoint store (ft_map_store_*): a MapPoint keeps one row for its lifetime;
+// Flush() upserts the rows whose MapPoint changed since the last flush. Replaces the per-frame CudaMapPoint marshalling
+// (reference src/Kernels/CudaWrappers/CudaMapPoint.cc:15-34, src/Tracking.cc:3595-3632).
+class MapStore {
+ public:
+  MapStore(std::shared_ptr<FrontEndContext> fe, int capacity) : fe_(fe), cap_(capacity) {
+    ft_check(ft_map_store_create(fe_->get(), capacity));
+  }
+  // gives pMP a row (no-op when it has one) and queues it for the next Flush()
+  void Insert(MapPoint* pMP) {
+    if (pMP->mnStoreRow < 0) {
+      if (!free_.empty()) { pMP->mnStoreRow = free_.back(); free_.pop_back(); }
+      else if (next_ < cap_) pMP->mnStoreRow = next_++;
+      else throw FtError(FT_ERR_CAPACITY, "MapStore: no free row");
+      pMP->mbStoreDirty = true;
+    }
+    if (pMP->mbStoreDirty) pending_.push_back(pMP);
+  }
+  void Erase(MapPoint* pMP) {   // MapPoint::SetBadFlag / culling
+    if (pMP->mnStoreRow >= 0) free_.push_back(pMP->mnStoreRow);
+    pMP->mnStoreRow = -1;
+  }
+  void Flush() {
+    std::vector<int> rows; std::vector<float> pos, nrm, mm; std::vector<unsigned char> desc;
+    for (MapPoint* p : pending_) {
+      if (!p->mbStoreDirty || p->mnStoreRow < 0) continue;
+      rows.push_back(p->mnStoreRow);
+      pos.insert(pos.end(), p->mWorldPos, p->mWorldPos + 3); nrm.insert(nrm.end(), p->mNormalVector, p->mNormalVector + 3);
+      mm.push_back(p->mfMinDistance); mm.push_back(p->mfMaxDistance);
+      desc.insert(desc.end(), p->mDescriptor, p->mDescriptor + 32);
+      p->mbStoreDirty = false;
+    }
+    pending_.clear();
+    if (!rows.empty())
+      ft_check(ft_map_store_update(fe_->get(), (int)rows.size(), rows.data(), pos.data(), nrm.data(), mm.data(), desc.data()));
+  }
+  std::shared_ptr<FrontEndContext> context() const { return fe_; }
+
+ private:
+  std::shared_ptr<FrontEndContext> fe_;
+  int cap_, next_ = 0;
+  std::vector<int> free_;
+  std::vector<MapPoint*> pending_;
+};
+
 class ORBmatcher {
  public:
   static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;
@@ -281,6 +330,38 @@ class ORBmatcher {
         p->mTrackProjXR_r = f[5]; p->mTrackProjYR = f[6]; p->mTrackDepthR = f[7]; p->mTrackViewCosR = f[8];
       }
     }
+    return nmatches;
+  }
+
+  // The same search with the local map named as rows of a MapStore: map points without a row or with pending changes
+  // are inserted / flushed first, then 8 bytes per map point (row, flags) go to the device instead of 68.
+  int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, MapStore& store, const float th = 3,
+                         const bool bFarPoints = false, const float thFarPoints = 50.0f) {
+    const int M = (int)vpMapPoints.size(), N = F.N;
+    std::vector<int> rows(M), flags(M);
+    for (int i = 0; i < M; i++) {
+      MapPoint* p = vpMapPoints[i];
+      if (p->mnStoreRow < 0 || p->mbStoreDirty) store.Insert(p);
+    }
+    store.Flush();
+    for (int i = 0; i < M; i++) {
+      const MapPoint* p = vpMapPoints[i];
+      rows[i] = p->mnStoreRow;
+      flags[i] = ((p->isBad() || p->mnLastFrameSeen == F.mnId) ? 1 : 0) | (p->Observations() > 0 ? 2 : 0);
+    }
+    std::vector<int> holder(N, -1);
+    std::vector<unsigned char> hobs(N, 0);
+    std::vector<MapPoint*> foreign(N, nullptr);
+    for (int i = 0; i < N; i++) {
+      MapPoint* q = F.mvpMapPoints[i];
+      if (!q) continue;
+      foreign[i] = q; holder[i] = -2; hobs[i] = q->Observations() > 0;
+    }
+    std::vector<int> best((size_t)std::max(M, 1) * 2, -1);
+    int nmatches = 0;
+    ft_check(ft_search_store(F.context()->get(), M, rows.data(), flags.data(), th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio,
+                             holder.data(), hobs.data(), best.data(), &nmatches));
+    for (int i = 0; i < N; i++) F.mvpMapPoints[i] = holder[i] >= 0 ? vpMapPoints[holder[i]] : (holder[i] == -2 ? foreign[i] : nullptr);
     return nmatches;
   }
 

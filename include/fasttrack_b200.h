@@ -185,6 +185,29 @@ ft_status ft_search_staged(ft_context* ctx, int M, float th, int b_far_points, f
                            const int** holder_out, const uint8_t** holder_obs_out, const int** best_idx_out,
                            int* nmatches);
 
+/* ---- Persistent device-side MapPoint store ----
+ * The reference re-marshals every local MapPoint into a CudaMapPoint on every frame (an `omp parallel for` over
+ * mutex-guarded getters, src/Kernels/CudaWrappers/CudaMapPoint.cc:15-34, src/Kernels/SearchLocalPointsKernel.cu:368-409,
+ * called from Tracking::SearchLocalPoints, src/Tracking.cc:3595-3632) and uploads all of them. Here a MapPoint owns a
+ * row of the store for its lifetime; the mapping side upserts the rows it created or changed (MapPoint::SetWorldPos,
+ * UpdateNormalAndDepth, ComputeDistinctiveDescriptors: src/MapPoint.cc:83-96,383-473,475-529), and a frame's search
+ * names its local map as a list of rows (the order of mvpLocalMapPoints, which the claim resolution observes) plus
+ * the per-call flags. Results are identical to ft_search_local_points on the gathered arrays.
+ *
+ * ft_map_store_create: `capacity` rows owned by this context. ft_map_store_attach: another context of the SAME
+ * sequence and device (e.g. the second context of a two-frames-in-flight pipeline) searches the same rows; updates
+ * and searches are ordered across the contexts' streams inside the library. The store is freed with its last context.
+ * ft_map_store_update: upsert n rows (slots[i] in [0, capacity)); arrays as in ft_search_local_points.
+ * ft_search_store: as ft_search_local_points with (slots[M], flags[M]) in place of the five arrays.
+ * Errors: FT_ERR_STATE without a store / frame, FT_ERR_CAPACITY for a row outside the store or M > max_map_points. */
+ft_status ft_map_store_create(ft_context* ctx, int capacity);
+ft_status ft_map_store_attach(ft_context* ctx, ft_context* owner);
+ft_status ft_map_store_update(ft_context* ctx, int n, const int* slots, const float* pos, const float* normal,
+                              const float* minmax, const uint8_t* desc);
+ft_status ft_search_store(ft_context* ctx, int M, const int* slots, const int* flags, float th, int bFarPoints,
+                          float thFarPoints, float nnratio, int* holder, uint8_t* holder_obs, int* best_idx,
+                          int* nmatches);
+
 /* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) -- the frame-to-last-frame search of
  * Tracking::TrackWithMotionModel (reference src/ORBmatcher.cc:1775-2085, src/Tracking.cc:2911-2990), incl. the
  * rotation-histogram consistency check (ComputeThreeMaxima, :2210-2254) when check_orientation != 0.

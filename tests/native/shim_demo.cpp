@@ -61,6 +61,27 @@ int main(int argc, char** argv) {
     F.SetPose(Rcw, tcw);
     ORBmatcher matcher(0.8f);
     const int nm = matcher.SearchByProjection(F, vp, 3.0f, false, 50.0f);
+    // the same search over the persistent map store: identical assignments, also after a change + re-flush
+    std::vector<MapPoint*> snapshot = F.mvpMapPoints;
+    MapStore store(fe, 30000);
+    int storeOk = 1;
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1) {   // the mapping side moves some points: both paths must agree again
+        for (int i = 0; i < M; i += 7) { mps[i].mWorldPos[0] += 0.01f; mps[i].mbStoreDirty = true; }
+        F.mvpMapPoints.assign(F.N, nullptr);
+        matcher.SearchByProjection(F, vp, 3.0f, false, 50.0f);
+        snapshot = F.mvpMapPoints;
+      }
+      F.mvpMapPoints.assign(F.N, nullptr);
+      const int nms = matcher.SearchByProjection(F, vp, store, 3.0f, false, 50.0f);
+      if (F.mvpMapPoints != snapshot) storeOk = 0;
+      if (pass == 0 && nms != nm) storeOk = 0;
+    }
+    if (!storeOk) { fprintf(stderr, "shim_demo: MapStore search differs from the snapshot search\n"); return 3; }
+    // restore the first result for the outputs below
+    for (int i = 0; i < M; i += 7) { mps[i].mWorldPos[0] -= 0.01f; }
+    F.mvpMapPoints.assign(F.N, nullptr);
+    matcher.SearchByProjection(F, vp, 3.0f, false, 50.0f);
     // outputs
     std::vector<float> k;
     for (auto& kp : F.mvKeys) { k.push_back(kp.pt.x); k.push_back(kp.pt.y); k.push_back(kp.size); k.push_back(kp.angle); k.push_back(kp.response); k.push_back((float)kp.octave); }

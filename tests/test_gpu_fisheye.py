@@ -113,3 +113,20 @@ def test_fisheye_projection_search(tum, all_obs):
     else:
         assert abs(n_g - n_o) <= 0.02 * max(n_o, 1) + 2
     assert n_o > 20
+
+
+def test_fisheye_store_search_equals_snapshot_search(tum):
+    """persistent map store on the fisheye path, both resolve kernels"""
+    ctx = tum["ctx"]
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    M, CAP = 5000, 12000
+    ctx.map_store_create(CAP)
+    for all_obs in (True, False):
+        mp, holder, hobs = _fisheye_map(tum, M, 29, all_obs)
+        slots = np.random.default_rng(7).permutation(CAP)[:M].astype(np.int32)
+        ctx.map_store_update(slots, mp["pos"], mp["normal"], mp["minmax"], mp["desc"])
+        ref = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, holder, hobs)
+        got = ctx.search_store(slots, mp["flags"], 3.0, holder, hobs)
+        assert ref[0] == got[0] and ref[0] > 20
+        for a, b in zip(ref[1:], got[1:]):
+            assert np.array_equal(a, b)
