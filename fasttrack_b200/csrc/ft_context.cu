@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ft_internal.h"
+#include "ft_camera.cuh"
 
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
@@ -47,6 +48,7 @@ struct ft_context {
   FtSbpBuffers Q;
   FtCamera cam1, cam2;
   FtPose pose;
+  FtUndistort und = {};   // pinhole distortion (Frame::UndistortKeyPoints); off by default
   float mbf, mb;
   float minX, maxX, minY, maxY, gridWInv, gridHInv, logScale;
   int fisheye;
@@ -365,6 +367,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &c->G.cellStart, (size_t)2 * (FT_GRID_COLS * FT_GRID_ROWS + 1)));
   CKF(dalloc(c, &c->G.cellIdx, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &c->G.rec, (size_t)2 * P.maxKp));
+  CKF(dalloc(c, &c->G.kpUn, (size_t)P.maxKp));
   // projection search
   const int MM = cfg->max_map_points > 0 ? cfg->max_map_points : 25000;
   c->cfg.max_map_points = MM;
@@ -544,7 +547,7 @@ static int enqueue_stereo(ft_context* c) {
   cudaStream_t s = c->stream, s2 = c->stream2;
   cudaEventRecord(c->evFork2, s);
   cudaStreamWaitEvent(s2, c->evFork2, 0);
-  { StageScope t(c, FT_STAGE_GRID, s2); ft_launch_grid(c->P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, s2); }
+  { StageScope t(c, FT_STAGE_GRID, s2); ft_launch_grid(c->P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, c->und, s2); }
   cudaEventRecord(c->evJoin2, s2);
   if (c->fisheye) { StageScope t(c, FT_STAGE_STEREO, s); ft_launch_fisheye(c->P, c->B, c->S, c->cam1, c->cam2, c->pose, s); }
   else { StageScope t(c, FT_STAGE_STEREO, s); ft_launch_stereo_match(c->P, c->B, c->S, c->mbf, c->mb, s); }
@@ -782,6 +785,61 @@ extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_
     }
   }
   c->rawW = raw_width; c->rawH = raw_height; c->rectify = 1;
+  return FT_OK;
+}
+
+// Frame::UndistortKeyPoints + Frame::ComputeImageBounds (reference src/Frame.cc:771-835) for a pinhole camera with
+// distortion coefficients (mDistCoef = k1 k2 p1 p2 [k3]). With k1 == 0 the reference copies mvKeys (Frame.cc:773-777).
+extern "C" ft_status ft_set_distortion(ft_context* c, const float* dist_coef, int n) {
+  if (!c || n < 0 || n > 5 || (n > 0 && !dist_coef)) { set_err("ft_set_distortion: bad argument (0, 4 or 5 coefficients)"); return FT_ERR_INVALID; }
+  if (c->fisheye && n > 0 && dist_coef[0] != 0.0f) { set_err("ft_set_distortion: KannalaBrandt8 rigs keep mvKeys (Frame.cc:1157: no undistortion)"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  // the launch graphs bake the kernel arguments in: drop them so that the next frame re-captures
+  if (c->gExtract) { cudaGraphExecDestroy(c->gExtract); c->gExtract = nullptr; }
+  if (c->gStereo) { cudaGraphExecDestroy(c->gStereo); c->gStereo = nullptr; }
+  if (c->gFrame) { cudaGraphExecDestroy(c->gFrame); c->gFrame = nullptr; }
+  FtUndistort u = {};
+  u.fx = c->cam1.p[0]; u.fy = c->cam1.p[1]; u.cx = c->cam1.p[2]; u.cy = c->cam1.p[3];
+  u.ifx = 1. / u.fx; u.ify = 1. / u.fy;
+  for (int i = 0; i < n; i++) u.k[i] = (double)dist_coef[i];
+  u.on = (n > 0 && dist_coef[0] != 0.0f) ? 1 : 0;
+  c->und = u;
+  const float cols = (float)c->cfg.width, rows = (float)c->cfg.height;
+  if (u.on) {   // ComputeImageBounds: the four undistorted corners
+    float x[4], y[4];
+    const float cx[4] = {0.f, cols, 0.f, cols}, cy[4] = {0.f, 0.f, rows, rows};
+    for (int i = 0; i < 4; i++) ft_undistort_point(u, cx[i], cy[i], x[i], y[i]);
+    c->minX = std::min(x[0], x[2]); c->maxX = std::max(x[1], x[3]);
+    c->minY = std::min(y[0], y[1]); c->maxY = std::max(y[2], y[3]);
+  } else {
+    c->minX = 0.f; c->maxX = cols; c->minY = 0.f; c->maxY = rows;
+  }
+  c->gridWInv = (float)FT_GRID_COLS / (c->maxX - c->minX);
+  c->gridHInv = (float)FT_GRID_ROWS / (c->maxY - c->minY);
+  return FT_OK;
+}
+
+// mnMinX, mnMaxX, mnMinY, mnMaxY (Frame::ComputeImageBounds)
+extern "C" ft_status ft_image_bounds(ft_context* c, float* out4) {
+  if (!c || !out4) { set_err("ft_image_bounds: null argument"); return FT_ERR_INVALID; }
+  out4[0] = c->minX; out4[1] = c->maxX; out4[2] = c->minY; out4[3] = c->maxY;
+  return FT_OK;
+}
+
+// mvKeysUn[i].pt of the left eye (every other KeyPoint field equals mvKeys[i]); xy holds 2*cap floats. Needs the frame
+// grid, i.e. a frame processed by ft_stereo_match / ft_frame_construct / ft_frame_enqueue_device.
+extern "C" ft_status ft_frame_keypoints_undistorted(ft_context* c, int cap, float* xy, int* n) {
+  if (!c || !xy) { set_err("ft_frame_keypoints_undistorted: null argument"); return FT_ERR_INVALID; }
+  if (!c->extracted || !c->stereoDone) { set_err("ft_frame_keypoints_undistorted: the frame grid has not been built (stereo stage)"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int nl = c->hCounts[0];
+  if (n) *n = nl;
+  if (cap < nl) { set_err("ft_frame_keypoints_undistorted: capacity smaller than keypoint count"); return FT_ERR_INVALID; }
+  if (nl) CK(cudaMemcpyAsync(xy, c->G.kpUn, sizeof(float) * 2 * nl, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return FT_OK;
 }
 

@@ -127,6 +127,14 @@ struct FtGridBuffers {
   int* cellStart;          // [2][64*48+1] (left, right)
   int* cellIdx;            // [2][maxKp]
   float4* rec;             // [2][maxKp] per keypoint {x, y, uRight (pinhole; -1 otherwise), octave as float bits}
+  float2* kpUn;            // [maxKp] mvKeysUn coordinates of the left eye (Frame::UndistortKeyPoints)
+};
+
+// Pinhole distortion model of Frame::UndistortKeyPoints (cv::undistortPoints with K, mDistCoef, P = K)
+struct FtUndistort {
+  int on;                  // mDistCoef[0] != 0 (Frame.cc:773)
+  double fx, fy, cx, cy, ifx, ify;
+  double k[5];             // k1 k2 p1 p2 k3
 };
 
 // Map-point snapshot, frustum scratch, candidate lists and claim tables of the projection search.

@@ -19,7 +19,7 @@ void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuff
 void ft_launch_store_scatter(int n, const uint8_t* staged, float* pos, float* normal, float* minmax, uint8_t* desc,
                              cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
-                    float gridWInv, float gridHInv, cudaStream_t st);
+                    float gridWInv, float gridHInv, const FtUndistort& und, cudaStream_t st);
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st);
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,

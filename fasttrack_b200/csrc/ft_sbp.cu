@@ -27,7 +27,8 @@
 // ---- frame grid -------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                      const __grid_constant__ FtGridBuffers g, int fisheye, float minX,
-                                                     float minY, float gridWInv, float gridHInv) {
+                                                     float minY, float gridWInv, float gridHInv,
+                                                     const __grid_constant__ FtUndistort und) {
   __shared__ int sCnt[GRID_CELLS];
   __shared__ int sStart[GRID_CELLS + 1];
   __shared__ int sWarp[32];
@@ -43,9 +44,14 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
     float4* rec = g.rec + eye * p.maxKp;
     for (int i = tid; i < n; i += 1024) {
       const ft_keypoint kp = E.kps[i];
-      rec[i] = make_float4(kp.x, kp.y, __int_as_float(kp.octave), 0.f);   // 16-byte search record read by k_gather
-      const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), gridWInv));
-      const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), gridHInv));
+      float kx = kp.x, ky = kp.y;
+      if (eye == 0) {   // mvKeysUn (Frame::UndistortKeyPoints): the grid and the search use the undistorted keypoint
+        if (und.on) ft_undistort_point(und, kp.x, kp.y, kx, ky);
+        g.kpUn[i] = make_float2(kx, ky);
+      }
+      rec[i] = make_float4(kx, ky, __int_as_float(kp.octave), 0.f);   // 16-byte search record read by k_gather
+      const int px = (int)roundf(__fmul_rn(__fsub_rn(kx, minX), gridWInv));
+      const int py = (int)roundf(__fmul_rn(__fsub_rn(ky, minY), gridHInv));
       if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
       atomicAdd(&sCnt[px * FT_GRID_ROWS + py], 1);
     }
@@ -82,9 +88,9 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
     for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
-      const ft_keypoint kp = E.kps[i];
-      const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), gridWInv));
-      const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), gridHInv));
+      const float4 kr = rec[i];   // written above by this thread
+      const int px = (int)roundf(__fmul_rn(__fsub_rn(kr.x, minX), gridWInv));
+      const int py = (int)roundf(__fmul_rn(__fsub_rn(kr.y, minY), gridHInv));
       if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
       const int c = px * FT_GRID_ROWS + py;
       cellIdx[sStart[c] + atomicAdd(&sCnt[c], 1)] = i;
@@ -721,8 +727,8 @@ void ft_launch_store_scatter(int n, const uint8_t* staged, float* pos, float* no
                                                                    reinterpret_cast<uint32_t*>(desc));
 }
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,
-                    float gridWInv, float gridHInv, cudaStream_t st) {
-  k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv);
+                    float gridWInv, float gridHInv, const FtUndistort& und, cudaStream_t st) {
+  k_grid_build<<<1, 1024, 0, st>>>(p, b, g, fisheye, minX, minY, gridWInv, gridHInv, und);
 }
 void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, const FtStereoBuffers& stb,
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st) {

@@ -117,6 +117,16 @@ ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps,
 ft_status ft_set_rectification(ft_context* ctx, int raw_width, int raw_height, const float* M1l, const float* M2l,
                                const float* M1r, const float* M2r);
 
+/* Frame::UndistortKeyPoints + Frame::ComputeImageBounds (reference src/Frame.cc:771-835) for a pinhole camera with
+ * distortion: dist_coef = mDistCoef (k1 k2 p1 p2 [k3]; n = 4 or 5, n = 0 or k1 == 0 switches it off as Frame.cc:773
+ * does). cv::undistortPoints(pt, K, mDistCoef, Mat(), K) runs per left keypoint inside the frame-grid kernel; the
+ * grid (AssignFeaturesToGrid), the image bounds of isInFrustum and both projection searches then use mvKeysUn, as
+ * the reference does; ComputeStereoMatches keeps mvKeys. ft_image_bounds returns {mnMinX, mnMaxX, mnMinY, mnMaxY};
+ * ft_frame_keypoints_undistorted returns mvKeysUn[i].pt (x, y interleaved, 2*cap floats). */
+ft_status ft_set_distortion(ft_context* ctx, const float* dist_coef, int n);
+ft_status ft_image_bounds(ft_context* ctx, float* out4);
+ft_status ft_frame_keypoints_undistorted(ft_context* ctx, int cap, float* xy, int* n);
+
 /* Capacity (entries) of the per-eye keypoint arrays: nfeatures + a few per level (the octree may exceed a level
  * quota by up to 3, reference sizes its buffers nfeatures+20, include/Kernels/CudaUtils.h:16). */
 int ft_max_keypoints(ft_context* ctx);

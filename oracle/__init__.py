@@ -70,6 +70,8 @@ def lib():
     L.fto_resize.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
     L.fto_blur.argtypes = [u8p, C.c_int, C.c_int, u8p]
     L.fto_remap.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, u8p]
+    L.fto_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
+    L.fto_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_fast.restype = C.c_int
     L.fto_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
     L.fto_fast_atan2.restype = C.c_float
@@ -197,6 +199,23 @@ def remap(src, mapx, mapy):
     return dst
 
 
+def undistort_points(xy, K, dist):
+    """cv::undistortPoints(xy, K, dist, R=None, P=K) -> [n,2] float32 (Frame::UndistortKeyPoints)"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(xy)
+    lib().fto_undistort_points(xy, len(xy), K, dist, len(dist), out)
+    return out
+
+
+def image_bounds(cols, rows, K, dist):
+    """Frame::ComputeImageBounds -> (minX, maxX, minY, maxY)"""
+    K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros(4, np.float32)
+    lib().fto_image_bounds(cols, rows, K, dist, len(dist), out)
+    return out
+
+
 def fast(img, th):
     """cv::FAST(img, th, nonmax=True) on a (possibly strided) 2-D uint8 view; returns [n,3] x,y,response"""
     assert img.dtype == np.uint8 and img.strides[1] == 1
@@ -251,7 +270,7 @@ class Frame:
     """Oracle mirror of the parts of ORB_SLAM3::Frame that the projection search reads."""
 
     def __init__(self, keys, desc, scale, width, height, cam_type=0, cam1=None, cam2=None, mbf=0.0, u_right=None,
-                 n_left=-1, n_right=-1, l2r=None, r2l=None, Rcw=None, tcw=None, Rrl=None, trl=None, tlr=None):
+                 n_left=-1, n_right=-1, l2r=None, r2l=None, Rcw=None, tcw=None, Rrl=None, trl=None, tlr=None, bounds=None):
         self.L = lib()
         f = lambda a: np.ascontiguousarray(a, np.float32)
         self._keep = dict(keys=f(keys), desc=np.ascontiguousarray(desc, np.uint8), scale=f(scale))
@@ -266,6 +285,8 @@ class Frame:
         if r2l is not None:
             self._keep["r2l"] = np.ascontiguousarray(r2l, np.int32); d.r2l = self._keep["r2l"].ctypes.data
         d.minX, d.maxX, d.minY, d.maxY = 0.0, float(width), 0.0, float(height)
+        if bounds is not None:   # Frame::ComputeImageBounds with a distorted pinhole camera
+            d.minX, d.maxX, d.minY, d.maxY = [float(b) for b in bounds]
         d.nlevels = len(scale)
         d.scale = self._keep["scale"].ctypes.data
         d.logScale = float(np.log(np.float32(scale[1]))) if len(scale) > 1 else 1.0

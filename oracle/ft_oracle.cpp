@@ -1155,4 +1155,54 @@ int search_by_projection_last_frame(FrameModel& F, const std::vector<LastFramePo
   return nmatches;
 }
 
+// ---------------------------------------------------------------------------
+// cv::undistortPoints(src, dst, K, distCoef, Mat(), P=K) as Frame::UndistortKeyPoints / ComputeImageBounds call it
+// (Frame.cc:771-835; "next" row 2 of SURVEY.md 8f). OpenCV (calib3d undistort, pinned against cv2 4.13): all in
+// double; normalise with 1/fx, 1/fy; FIVE fixed-point iterations (default TermCriteria(MAX_ITER, 5, 0.01): only the
+// count is active) of x = (x0 - deltaX) * icdist with the rational radial factor and the tangential terms; bail out
+// to the plain normalised point when icdist < 0; re-project with P (xx*ww, ww = 1/1); store as float.
+// dist = k1 k2 p1 p2 [k3] (ORB-SLAM3's mDistCoef has 4 or 5 entries, Settings / Tracking::ParseCamParamFile).
+// ---------------------------------------------------------------------------
+void undistort_points(const float* xy, int n, const float K[4], const float* dist, int ndist, float* out) {
+  double k[14] = {0};
+  for (int i = 0; i < ndist && i < 14; i++) k[i] = (double)dist[i];
+  const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  for (int i = 0; i < n; i++) {
+    double x = xy[2 * i], y = xy[2 * i + 1];
+    const double u = x, v = y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) {
+        x = (u - cx) * ifx;
+        y = (v - cy) * ify;
+        break;
+      }
+      const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+    const double xx = fx * x + 0. * y + cx;
+    const double yy = 0. * x + fy * y + cy;
+    const double ww = 1. / (0. * x + 0. * y + 1.);
+    out[2 * i] = (float)(xx * ww);
+    out[2 * i + 1] = (float)(yy * ww);
+  }
+}
+
+// Frame::ComputeImageBounds (Frame.cc:806-833): {mnMinX, mnMaxX, mnMinY, mnMaxY}
+void image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float out[4]) {
+  if (ndist == 0 || dist[0] == 0.0f) { out[0] = 0.f; out[1] = (float)cols; out[2] = 0.f; out[3] = (float)rows; return; }
+  const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+  float u[8];
+  undistort_points(c, 4, K, dist, ndist, u);
+  out[0] = std::min(u[0], u[4]); out[1] = std::max(u[2], u[6]);
+  out[2] = std::min(u[1], u[3]); out[3] = std::max(u[5], u[7]);
+}
+
 }  // namespace fto

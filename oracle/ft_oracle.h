@@ -46,6 +46,10 @@ int descriptor_distance(const uint8_t* a, const uint8_t* b);        // ORBmatche
 // cv::remap(src, dst, map1 (CV_32FC1 x), map2 (CV_32FC1 y), INTER_LINEAR, BORDER_CONSTANT 0) on 8UC1 (System.cc:279-280)
 void remap_linear_u8(const Img& src, const float* mapx, const float* mapy, int dw, int dh, Img& dst);
 
+// cv::undistortPoints(src, dst, K, dist, Mat(), K) of Frame::UndistortKeyPoints (Frame.cc:771-804); K = fx fy cx cy
+void undistort_points(const float* xy, int n, const float K[4], const float* dist, int ndist, float* out);
+void image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float out[4]);  // Frame.cc:806-833
+
 // ---- ORBextractor (ORBextractor.cc CPU branches) ----
 class Extractor {
  public:

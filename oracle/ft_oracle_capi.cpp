@@ -97,6 +97,12 @@ void fto_blur(const uint8_t* src, int w, int h, uint8_t* dst) {
   gaussian_blur_7x7_s2(s, d);
   memcpy(dst, d.d.data(), d.d.size());
 }
+void fto_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out) {
+  undistort_points(xy, n, K, dist, ndist, out);
+}
+void fto_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* out) {
+  image_bounds(cols, rows, K, dist, ndist, out);
+}
 void fto_remap(const uint8_t* src, int sw, int sh, const float* mapx, const float* mapy, int dw, int dh, uint8_t* dst) {
   Img s, d;
   s.w = sw; s.h = sh; s.d.assign(src, src + (size_t)sw * sh);

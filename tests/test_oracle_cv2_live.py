@@ -83,3 +83,15 @@ def test_remap_live():
     assert np.array_equal(oracle.remap(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
     mx2 = rng.uniform(-8, 760, (100, 120)).astype(np.float32); my2 = rng.uniform(-8, 488, (100, 120)).astype(np.float32)
     assert np.array_equal(oracle.remap(img, mx2, my2), cv2.remap(img, mx2, my2, cv2.INTER_LINEAR))
+
+
+def test_undistort_points_live():
+    rng = np.random.default_rng(8)
+    for K, dist in (([517.3, 516.5, 318.6, 255.3], [0.2624, -0.9531, -0.0054, 0.0026, 1.1633]),
+                    ([458.654, 457.296, 367.215, 248.375], [-0.2834, 0.0740, 0.00019, 1.76e-05]),
+                    ([300.0, 310.0, 320.0, 240.0], [0.1, 0.0, 0.0, 0.0])):
+        K = np.array(K, np.float32); dist = np.array(dist, np.float32)
+        Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+        pts = (rng.random((20000, 2)) * [900, 700] - [80, 80]).astype(np.float32)
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), Km, dist, None, Km).reshape(-1, 2)
+        assert np.array_equal(oracle.undistort_points(pts, K, dist).view(np.uint32), ref.view(np.uint32))

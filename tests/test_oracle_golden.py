@@ -59,3 +59,20 @@ def test_remap_matches_cv2():
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_remap.npz"))
     assert np.array_equal(oracle.remap(g["img"], g["mx"], g["my"]), g["ref"])
+    assert np.array_equal(oracle.remap(g["big"], g["m1l"], g["m2l"]), g["ref_big"])
+
+
+def test_undistort_points_matches_cv2():
+    """cv::undistortPoints(pts, K, distCoef, Mat(), K) of Frame::UndistortKeyPoints / ComputeImageBounds
+    (Frame.cc:771-835): bit-exact incl. the image corners, far outliers and the icdist < 0 bail-out"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_undistort.npz"))
+    for name in ("tum1", "euroc_mono", "strong"):
+        K, dist, pts, ref = g[name + "_K"], g[name + "_dist"], g[name + "_pts"], g[name + "_ref"]
+        got = oracle.undistort_points(pts, K, dist)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
+        w, h = g[name + "_wh"]
+        b = oracle.image_bounds(int(w), int(h), K, dist)
+        assert b[0] == min(ref[0, 0], ref[2, 0]) and b[1] == max(ref[1, 0], ref[3, 0])
+        assert b[2] == min(ref[0, 1], ref[1, 1]) and b[3] == max(ref[2, 1], ref[3, 1])
+    assert np.array_equal(oracle.image_bounds(640, 480, g["tum1_K"], np.zeros(5, np.float32)), [0, 640, 0, 480])
