@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -105,6 +105,7 @@ def load_library():
     L.ft_frame_submit.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_map_store_create.argtypes = [vp, C.c_int]
     L.ft_set_distortion.argtypes = [vp, vp, C.c_int]
+    L.ft_set_input_resize.argtypes = [vp, C.c_int, C.c_int]
     L.ft_image_bounds.argtypes = [vp, vp]
     L.ft_frame_keypoints_undistorted.argtypes = [vp, C.c_int, vp, vp]
     L.ft_map_store_attach.argtypes = [vp, vp]
@@ -258,6 +259,11 @@ class Context:
         if self.fisheye:
             left.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
         return left, right
+
+    def set_input_resize(self, raw_width, raw_height):
+        """cv::resize of the raw input to the camera size in front of the extractor (System.cc:282-285); 0 = off"""
+        self._ck(self.L.ft_set_input_resize(self.h, int(raw_width), int(raw_height)))
+        self._raw = (int(raw_height), int(raw_width)) if raw_width and raw_height else None
 
     # ---- pinhole distortion (Frame::UndistortKeyPoints / ComputeImageBounds) ----
     def set_distortion(self, dist_coef):

@@ -79,6 +79,7 @@ struct ft_context {
   long long pyrBytes = 0;
   // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
   int rectify = 0, rawW = 0, rawH = 0;
+  int inResize = 0;   // cv::resize of the raw input into level 0 (Settings::needToResize)
   uint8_t* dRaw[2] = {nullptr, nullptr};
   int2* dRemapTab = nullptr;
   // resident map-point snapshot + initial holders for ft_search_resident
@@ -221,6 +222,28 @@ static ft_status build_params(ft_context* c) {
   return FT_OK;
 }
 
+// cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp) for one (source, destination) size pair
+static void resize_tables(int sw, int sh, int dw, int dh, int2* xTab, int2* yTab) {
+  const double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+  for (int dx = 0; dx < dw; dx++) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
+    xTab[dx] = make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16)));
+  }
+  for (int dy = 0; dy < dh; dy++) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)std::floor(fy);
+    fy -= sy;
+    const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
+    const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
+    yTab[dy] = make_int2(y0 | (y1 << 16), (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16)));
+  }
+}
+
 static ft_status build_tables(ft_context* c, int cellKpTotal, int candTotal, int lvlKpTotal) {
   const FtParams& P = c->P;
   (void)cellKpTotal; (void)candTotal; (void)lvlKpTotal;
@@ -230,25 +253,7 @@ static ft_status build_tables(ft_context* c, int cellKpTotal, int candTotal, int
   for (int l = 1; l < P.nlevels; l++) {
     const FtLevel& L = P.lv[l];
     const FtLevel& S = P.lv[l - 1];
-    // cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp)
-    const double scale_x = 1. / ((double)L.w / S.w), scale_y = 1. / ((double)L.h / S.h);
-    for (int dx = 0; dx < L.w; dx++) {
-      float fx = (float)((dx + 0.5) * scale_x - 0.5);
-      int sx = (int)std::floor(fx);
-      fx -= sx;
-      if (sx < 0) { fx = 0; sx = 0; }
-      if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
-      const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
-      xTab[L.xTab + dx] = make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16)));
-    }
-    for (int dy = 0; dy < L.h; dy++) {
-      float fy = (float)((dy + 0.5) * scale_y - 0.5);
-      int sy = (int)std::floor(fy);
-      fy -= sy;
-      const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
-      const int y0 = std::min(std::max(sy, 0), S.h - 1), y1 = std::min(std::max(sy + 1, 0), S.h - 1);
-      yTab[L.yTab + dy] = make_int2(y0 | (y1 << 16), (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16)));
-    }
+    resize_tables(S.w, S.h, L.w, L.h, &xTab[L.xTab], &yTab[L.yTab]);
   }
   int2 *dx = nullptr, *dy = nullptr;
   CK(dalloc(c, &dx, xTab.size()));
@@ -505,6 +510,7 @@ static int enqueue_extract(ft_context* c) {
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
   const bool perLevel = !c->timing;
   if (c->rectify) { ft_launch_remap(P, c->B, c->dRaw[0], c->dRaw[1], c->dRemapTab, c->rawW, c->rawH, s); n++; }
+  else if (c->inResize) { ft_launch_resize_input(P, c->B, c->dRaw[0], c->dRaw[1], c->rawW, s); n++; }
   cudaEventRecord(c->evFork, s);
   cudaStreamWaitEvent(s3, c->evFork, 0);
   cudaStreamWaitEvent(s2, c->evFork, 0);
@@ -578,8 +584,9 @@ static ft_status run_extract(ft_context* c) {
 static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
   if (!c || !imgL || !imgR) { set_err("null image (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
   // with rectification the raw image goes to a staging buffer (k_remap writes level 0); otherwise straight into level 0
-  const int w = c->rectify ? c->rawW : c->cfg.width, h = c->rectify ? c->rawH : c->cfg.height;
-  const int dpitch = c->rectify ? w : c->P.lv[0].pitch;
+  const bool raw = c->rectify || c->inResize;
+  const int w = raw ? c->rawW : c->cfg.width, h = raw ? c->rawH : c->cfg.height;
+  const int dpitch = raw ? w : c->P.lv[0].pitch;
   if (stepL < w || stepR < w) { set_err("image step smaller than width"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
   const uint8_t* src[2] = {imgL, imgR};
@@ -588,7 +595,7 @@ static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, co
     cudaPointerAttributes at;
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    uint8_t* dst = c->rectify ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
+    uint8_t* dst = raw ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
     if (pinned && step[e] == w && dpitch == w) {
       CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
     } else if (pinned) {
@@ -610,12 +617,13 @@ extern "C" ft_status ft_extract_stereo(ft_context* c, const uint8_t* imgL, int s
 }
 
 static ft_status copy_device_images(ft_context* c, const uint8_t* dL, int stepL, const uint8_t* dR, int stepR) {
-  const int w = c->rectify ? c->rawW : c->cfg.width, h = c->rectify ? c->rawH : c->cfg.height;
-  const int dpitch = c->rectify ? w : c->P.lv[0].pitch;
+  const bool raw = c->rectify || c->inResize;
+  const int w = raw ? c->rawW : c->cfg.width, h = raw ? c->rawH : c->cfg.height;
+  const int dpitch = raw ? w : c->P.lv[0].pitch;
   const uint8_t* src[2] = {dL, dR};
   const int step[2] = {stepL, stepR};
   for (int e = 0; e < 2; e++) {
-    uint8_t* dst = c->rectify ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
+    uint8_t* dst = raw ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
     if (step[e] == w && dpitch == w) CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
     else CK(cudaMemcpy2DAsync(dst, dpitch, src[e], step[e], w, h, cudaMemcpyDeviceToDevice, c->stream));
   }
@@ -763,6 +771,7 @@ extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_
   if (c->gExtract) { cudaGraphExecDestroy(c->gExtract); c->gExtract = nullptr; }
   if (c->gFrame) { cudaGraphExecDestroy(c->gFrame); c->gFrame = nullptr; }
   if (!M1l || !M2l || !M1r || !M2r) { c->rectify = 0; return FT_OK; }
+  if (c->inResize) { set_err("ft_set_rectification: input resize is active (System.cc:273-285 does one or the other)"); return FT_ERR_STATE; }
   if (raw_width < 8 || raw_height < 8 || raw_width > 8192 || raw_height > 8192) { set_err("ft_set_rectification: bad raw size"); return FT_ERR_INVALID; }
   const int w = c->cfg.width, h = c->cfg.height;
   std::vector<int2> tab((size_t)2 * w * h);
@@ -785,6 +794,34 @@ extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_
     }
   }
   c->rawW = raw_width; c->rawH = raw_height; c->rectify = 1;
+  return FT_OK;
+}
+
+// cv::resize(im, imToFeed, settings_->newImSize()) in front of the extractor (reference src/System.cc:282-285,
+// Settings::needToResize): raw images are raw_width x raw_height and level 0 is their INTER_LINEAR resize.
+// raw_width == 0 switches it off. Mutually exclusive with rectification, as in the reference (if / else if).
+extern "C" ft_status ft_set_input_resize(ft_context* c, int raw_width, int raw_height) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->gExtract) { cudaGraphExecDestroy(c->gExtract); c->gExtract = nullptr; }
+  if (c->gFrame) { cudaGraphExecDestroy(c->gFrame); c->gFrame = nullptr; }
+  if (raw_width == 0 || raw_height == 0) { c->inResize = 0; return FT_OK; }
+  if (c->rectify) { set_err("ft_set_input_resize: rectification is active (the reference resizes only when it does not rectify)"); return FT_ERR_STATE; }
+  if (raw_width < 8 || raw_height < 8 || raw_width > 16384 || raw_height > 16384) { set_err("ft_set_input_resize: bad raw size"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  std::vector<int2> xt(w), yt(h);
+  resize_tables(raw_width, raw_height, w, h, xt.data(), yt.data());
+  CK(cudaMemcpy(const_cast<int2*>(c->B.xTab) + c->P.lv[0].xTab, xt.data(), sizeof(int2) * w, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(const_cast<int2*>(c->B.yTab) + c->P.lv[0].yTab, yt.data(), sizeof(int2) * h, cudaMemcpyHostToDevice));
+  if (c->rawW * c->rawH < raw_width * raw_height || !c->dRaw[0]) {
+    for (int e = 0; e < 2; e++) {
+      CK(dalloc(c, &c->dRaw[e], (size_t)raw_width * raw_height));
+      if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
+      CK(cudaMallocHost((void**)&c->hIn[e], std::max((size_t)raw_width * raw_height, (size_t)w * h)));
+    }
+  }
+  c->rawW = raw_width; c->rawH = raw_height; c->inResize = 1;
   return FT_OK;
 }
 

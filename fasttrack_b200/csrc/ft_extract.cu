@@ -20,21 +20,16 @@ __constant__ __align__(16) int8_t c_pattern[1024] = {
 // Pyramid: level l from level l-1. 4 destination pixels per thread, uchar4 store.
 // Coefficients come from tables built once on the host (they depend on sizes only).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
-                                                int level) {
-  const FtLevel& L = p.lv[level];
-  const FtLevel& S = p.lv[level - 1];
-  const int eye = blockIdx.z;
+__device__ __forceinline__ void ft_resize_rows(const FtBuffers& b, const uint8_t* src, int srcW, int srcPitch, uint8_t* dst,
+                                               const FtLevel& L) {
   const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int dy = blockIdx.y * 8 + threadIdx.y;
   if (dx0 >= L.w || dy >= L.h) return;
-  const uint8_t* src = b.eye[eye].pyr + S.offset;
-  uint8_t* dst = b.eye[eye].pyr + L.offset;
   const int2 yt = b.yTab[L.yTab + dy];
   const int sy0 = yt.x & 0xFFFF, sy1 = yt.x >> 16;
   const int b0 = (short)(yt.y & 0xFFFF), b1 = (short)(yt.y >> 16);
-  const uint8_t* r0 = src + (size_t)sy0 * S.pitch;
-  const uint8_t* r1 = src + (size_t)sy1 * S.pitch;
+  const uint8_t* r0 = src + (size_t)sy0 * srcPitch;
+  const uint8_t* r1 = src + (size_t)sy1 * srcPitch;
   uint32_t out = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -42,7 +37,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams
     if (dx < L.w) {
       const int2 xt = b.xTab[L.xTab + dx];
       const int sx = xt.x;
-      const int sx1 = min(sx + 1, S.w - 1);
+      const int sx1 = min(sx + 1, srcW - 1);
       const int a0 = (short)(xt.y & 0xFFFF), a1 = (short)(xt.y >> 16);
       const int h0 = r0[sx] * a0 + r0[sx1] * a1;
       const int h1 = r1[sx] * a0 + r1[sx1] * a1;
@@ -51,6 +46,23 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams
     }
   }
   *reinterpret_cast<uint32_t*>(dst + (size_t)dy * L.pitch + dx0) = out;
+}
+
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                int level) {
+  const FtLevel& L = p.lv[level];
+  const FtLevel& S = p.lv[level - 1];
+  const int eye = blockIdx.z;
+  ft_resize_rows(b, b.eye[eye].pyr + S.offset, S.w, S.pitch, b.eye[eye].pyr + L.offset, L);
+}
+
+// cv::resize(im, imToFeed, newImSize) of System::TrackStereo (reference src/System.cc:282-285, Settings::needToResize):
+// the raw image is resized straight into level 0 with the level-0 slots of the coefficient tables.
+__global__ void __launch_bounds__(256) k_resize_input(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+                                                      const uint8_t* rawL, const uint8_t* rawR, int rawW) {
+  const FtLevel& L = p.lv[0];
+  const int eye = blockIdx.z;
+  ft_resize_rows(b, eye ? rawR : rawL, rawW, rawW, b.eye[eye].pyr + L.offset, L);
 }
 
 // ------------------------------------------------------------------------------------
@@ -977,6 +989,11 @@ void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL,
                      int rawH, cudaStream_t st) {
   dim3 blk(64, 4), grd((p.lv[0].w + 63) / 64, (p.lv[0].h + 3) / 4, 2);
   k_remap<<<grd, blk, 0, st>>>(p, b, rawL, rawR, tab, rawW, rawH);
+}
+void ft_launch_resize_input(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, int rawW,
+                            cudaStream_t st) {
+  dim3 blk(32, 8), grd((p.lv[0].w + 127) / 128, (p.lv[0].h + 7) / 8, 2);
+  k_resize_input<<<grd, blk, 0, st>>>(p, b, rawL, rawR, rawW);
 }
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
   dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, 2);

@@ -7,6 +7,8 @@ cudaError_t ft_launch_extract_setup(const FtParams& p);
 cudaError_t ft_launch_sbp_setup(const FtParams& p);
 void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,
                      int rawH, cudaStream_t st);
+void ft_launch_resize_input(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, int rawW,
+                            cudaStream_t st);
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st);
 void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st);

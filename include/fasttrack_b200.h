@@ -117,6 +117,12 @@ ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps,
 ft_status ft_set_rectification(ft_context* ctx, int raw_width, int raw_height, const float* M1l, const float* M2l,
                                const float* M1r, const float* M2r);
 
+/* cv::resize(im, imToFeed, newImSize) in front of the extractor (reference src/System.cc:282-285, taken when
+ * Settings::needToResize): raw images are raw_width x raw_height, level 0 of the pyramid is their INTER_LINEAR resize
+ * to the context's camera size. raw_width = 0 switches it off; FT_ERR_STATE while rectification is active (the
+ * reference does one or the other). */
+ft_status ft_set_input_resize(ft_context* ctx, int raw_width, int raw_height);
+
 /* Frame::UndistortKeyPoints + Frame::ComputeImageBounds (reference src/Frame.cc:771-835) for a pinhole camera with
  * distortion: dist_coef = mDistCoef (k1 k2 p1 p2 [k3]; n = 4 or 5, n = 0 or k1 == 0 switches it off as Frame.cc:773
  * does). cv::undistortPoints(pt, K, mDistCoef, Mat(), K) runs per left keypoint inside the frame-grid kernel; the

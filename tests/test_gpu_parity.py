@@ -338,6 +338,31 @@ def test_rectification_fused_into_level0(euroc_pair):
     ctx.close()
 
 
+@pytest.mark.parametrize("raw", [(1504, 960), (1280, 720), (640, 400)])
+def test_input_resize_fused_into_level0(raw):
+    """'next' row 2: cv::resize(im, newImSize) of System::TrackStereo (System.cc:282-285) in front of the extractor;
+    exact 2x (OpenCV's INTER_AREA shortcut, same bytes), a non-integer downscale and an upscale"""
+    rw, rh = raw
+    rawL = synth.texture(rh, rw, 43); rawR = np.roll(rawL, -7, axis=1)
+    ctx, mbf, mb = _ctx(E)
+    ctx.set_input_resize(rw, rh)
+    ctx.extract_stereo(rawL, rawR); ctx.stereo_match()
+    inL, inR = oracle.resize(rawL, E["width"], E["height"]), oracle.resize(rawR, E["width"], E["height"])
+    assert np.array_equal(ctx.level_image(0, 0), inL) and np.array_equal(ctx.level_image(1, 0), inR)
+    exL, exR, oL, oR = _oracle_pair(inL, inR, 1200, 8)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    with pytest.raises(RuntimeError, match="one or the other"):
+        m = np.zeros((E["height"], E["width"]), np.float32)
+        ctx.set_rectification(rw, rh, m, m, m, m)
+    ctx.set_input_resize(0, 0)
+    L2 = synth.texture(E["height"], E["width"], 44)
+    ctx.extract_stereo(L2, L2)
+    assert np.array_equal(ctx.level_image(0, 0), L2)
+    ctx.close()
+
+
 def test_two_contexts_pipelined_match_sequential(euroc_pair):
     """bench.py's throughput leg alternates the frames of one sequence between two contexts (2-deep pipeline):
     every frame's results must equal the one-context, one-frame-at-a-time results"""

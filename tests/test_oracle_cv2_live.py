@@ -95,3 +95,13 @@ def test_undistort_points_live():
         pts = (rng.random((20000, 2)) * [900, 700] - [80, 80]).astype(np.float32)
         ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), Km, dist, None, Km).reshape(-1, 2)
         assert np.array_equal(oracle.undistort_points(pts, K, dist).view(np.uint32), ref.view(np.uint32))
+
+
+def test_input_resize_shapes_live():
+    """cv::resize(im, newImSize) of System::TrackStereo (System.cc:282-285): exact 2x (OpenCV switches to its INTER_AREA
+    shortcut, which yields the same bytes), 3x, non-integer down- and up-scaling"""
+    rng = np.random.default_rng(12)
+    for (sh, sw), (dh, dw) in [((960, 1504), (480, 752)), ((720, 1280), (480, 752)), ((400, 640), (480, 752)),
+                               ((1440, 2256), (480, 752)), ((1024, 1024), (512, 512))]:
+        img = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        assert np.array_equal(oracle.resize(img, dw, dh), cv2.resize(img, (dw, dh)))
