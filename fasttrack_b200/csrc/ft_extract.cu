@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                                                     int levelBegin, int levelEnd) {
   extern __shared__ uint8_t smem[];
   __shared__ int sWarp[FAST_THREADS / 32];
-  __shared__ int sAny;
+  __shared__ int sAny, sPass;
   const int eye = blockIdx.y;
   const int cell = blockIdx.x + p.lv[levelBegin].cellBase;
   int level = levelBegin;
@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   uint8_t* sImg = smem;                         // [rh][rwPad], cell pixel (y, x) at sImg[y*rwPad + ax + x]
   uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // [ih][iw] score (0 below minTh), then NMS survivors
   uint8_t* sMx = sSc + ((iw * ih + 15) & ~15);
+  uint16_t* sList = reinterpret_cast<uint16_t*>(sMx + ((iw * ih + 15) & ~15));   // pixels that pass the quick test
   {
     const uint8_t* srcA = E.pyr + L.offset + (size_t)iniY * L.pitch + (iniX - ax);   // 4-byte aligned
     const int wpr = (ax + rw + 3) >> 2;                                               // words per row
@@ -218,22 +219,40 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
       sW[y * (rwPad >> 2) + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
     }
   }
-  if (tid == 0) sAny = 0;
+  if (tid == 0) { sAny = 0; sPass = 0; }
   __syncthreads();
   const int total = iw * ih;
-  for (int i = tid; i < total; i += FAST_THREADS) {
-    const int y = i / iw, x = i - y * iw;
-    const uint8_t* c = &sImg[(y + 3) * rwPad + ax + (x + 3)];
-    // quick reject at minTh: every 9-arc holds one pixel of each opposite ring pair
-    const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
-    const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
-    const bool dark = (t0 < lo || t8 < lo) && (t4 < lo || t12 < lo);
-    const bool bright = (t0 > hi || t8 > hi) && (t4 > hi || t12 > hi);
-    int s = 0;
-    if (dark || bright) {
-      s = ft_fast_score(c, rwPad);
-      if (s < p.minTh) s = 0;
+  // pass 1, every pixel: quick reject at minTh (every 9-arc holds one pixel of each opposite ring pair); the
+  // survivors are compacted into a list so that the expensive score runs on dense warps
+  for (int i0 = 0; i0 < total; i0 += FAST_THREADS) {
+    const int i = i0 + tid;
+    bool pass = false;
+    if (i < total) {
+      const int y = i / iw, x = i - y * iw;
+      const uint8_t* c = &sImg[(y + 3) * rwPad + ax + (x + 3)];
+      const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
+      const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
+      const bool dark = (t0 < lo || t8 < lo) && (t4 < lo || t12 < lo);
+      const bool bright = (t0 > hi || t8 > hi) && (t4 > hi || t12 > hi);
+      pass = dark || bright;
+      sSc[i] = 0;
     }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+    if (m) {
+      int base = 0;
+      if ((tid & 31) == 0) base = atomicAdd(&sPass, __popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (pass) sList[base + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  // pass 2, survivors only: the exact score (order of the list is irrelevant)
+  const int nPass = sPass;
+  for (int j = tid; j < nPass; j += FAST_THREADS) {
+    const int i = sList[j];
+    const int y = i / iw, x = i - y * iw;
+    int s = ft_fast_score(&sImg[(y + 3) * rwPad + ax + (x + 3)], rwPad);
+    if (s < p.minTh) s = 0;
     sSc[i] = (uint8_t)s;
   }
   __syncthreads();
@@ -966,7 +985,7 @@ size_t ft_fast_smem_bytes(const FtParams& p) {
     const FtLevel& L = p.lv[l];
     const int rw = L.wCell + 6, rh = L.hCell + 6;
     const int rwPad = (rw + 6) & ~3;
-    size_t s = ((rh * rwPad + 15) & ~15) + 2 * ((L.wCell * L.hCell + 15) & ~15);
+    size_t s = ((rh * rwPad + 15) & ~15) + 4 * ((L.wCell * L.hCell + 15) & ~15);
     if (s > mx) mx = s;
   }
   return mx;
