@@ -880,6 +880,11 @@ extern "C" ft_status ft_frame_keypoints_undistorted(ft_context* c, int cap, floa
   return FT_OK;
 }
 
+// Test hook (host arithmetic only, no GPU needed): the cosf/sinf restatement used by the descriptor kernel
+extern "C" void ft_debug_sincosf(int n, const float* angle, float* sin_out, float* cos_out) {
+  for (int i = 0; i < n; i++) ft_glibc_sincosf(angle[i], sin_out[i], cos_out[i]);
+}
+
 extern "C" int ft_max_keypoints(ft_context* c) { return c ? c->P.maxKp : 0; }
 
 // Frame constructor in one call (reference src/Frame.cc:102-223 for pinhole rigs, :1115-1229 for fisheye):

@@ -11,6 +11,7 @@
 
 #include "ft_device.cuh"
 #include "ft_sort.h"
+#include "ft_camera.cuh"
 
 __constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "../../include/ft_orb_pattern.inc"
@@ -912,8 +913,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   // computeOrbDescriptor (ORBextractor.cc:68-108)
   const float factorPI = (float)(3.14159265358979323846 / 180.f);
   const float ang = __fmul_rn(angle, factorPI);
-  // correctly-rounded-in-practice float cos/sin via double (glibc cosf/sinf are < 1 ulp)
-  const float a = (float)cos((double)ang), bb = (float)sin((double)ang);
+  float a, bb;
+  ft_glibc_sincosf(ang, bb, a);
   const uint8_t* bimg = E.blur + L.offset;
   const uint8_t* bc = bimg + (size_t)ky * L.pitch + kx;
   int val = 0;

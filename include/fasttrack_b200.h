@@ -240,6 +240,10 @@ ft_status ft_search_last_frame(ft_context* ctx, int n, const float* pos, const u
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
 
+/* Test hook, host arithmetic only: sinf / cosf as the descriptor kernel evaluates them (glibc's polynomial in double;
+ * the reference calls cos/sin on a float, src/ORBextractor.cc:74). tests/test_abi.py checks it against the host libm. */
+void ft_debug_sincosf(int n, const float* angle, float* sin_out, float* cos_out);
+
 /* ---- diagnostics used by the parity tests (device -> host copies of intermediate stages) ---- */
 ft_status ft_debug_level_dims(ft_context* ctx, int level, int* w, int* h);
 ft_status ft_debug_level_image(ft_context* ctx, int eye, int level, int blurred, uint8_t* out /* w*h tight */);

@@ -71,6 +71,7 @@ def lib():
     L.fto_blur.argtypes = [u8p, C.c_int, C.c_int, u8p]
     L.fto_remap.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, u8p]
     L.fto_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
+    L.fto_libm_sincosf.argtypes = [C.c_int, f32p, f32p, f32p]
     L.fto_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_fast.restype = C.c_int
     L.fto_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
@@ -197,6 +198,14 @@ def remap(src, mapx, mapy):
     dst = np.zeros((dh, dw), np.uint8)
     lib().fto_remap(src, src.shape[1], src.shape[0], mapx, mapy, dw, dh, dst)
     return dst
+
+
+def libm_sincosf(angles):
+    """host libm sinf / cosf of a float32 array (the calls of computeOrbDescriptor, ORBextractor.cc:74)"""
+    a = np.ascontiguousarray(angles, np.float32)
+    s = np.zeros_like(a); c = np.zeros_like(a)
+    lib().fto_libm_sincosf(len(a), a, s, c)
+    return s, c
 
 
 def undistort_points(xy, K, dist):

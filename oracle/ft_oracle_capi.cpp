@@ -2,6 +2,7 @@
 // (TEST INFRASTRUCTURE ONLY; see ft_oracle.h). Keypoints cross this boundary as
 // float[n][6] = {x, y, size, angle, response, octave}.
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <thread>
 
@@ -96,6 +97,10 @@ void fto_blur(const uint8_t* src, int w, int h, uint8_t* dst) {
   s.w = w; s.h = h; s.d.assign(src, src + (size_t)w * h);
   gaussian_blur_7x7_s2(s, d);
   memcpy(dst, d.d.data(), d.d.size());
+}
+// the host libm's cosf / sinf, vectorised (what computeOrbDescriptor calls, ORBextractor.cc:74)
+void fto_libm_sincosf(int n, const float* a, float* s, float* c) {
+  for (int i = 0; i < n; i++) { s[i] = sinf(a[i]); c[i] = cosf(a[i]); }
 }
 void fto_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out) {
   undistort_points(xy, n, K, dist, ndist, out);

@@ -71,3 +71,31 @@ def test_pattern_table_pinned():
         src = "\n".join(open(ref).read().split("\n")[133:391])
         refnums = [int(x) for x in re.findall(r"-?\d+", re.sub(r"/\*.*?\*/", "", src))]
         assert refnums == nums
+
+
+def test_descriptor_sincos_matches_host_libm(lib):
+    """The descriptor kernel rotates the rBRIEF pattern with cosf/sinf of the keypoint angle (reference
+    src/ORBextractor.cc:74). glibc's sinf/cosf are not always correctly rounded, and a rotated sample can land exactly
+    on a .5 rounding boundary, so the kernel evaluates glibc's own polynomial; this pins that restatement (same code,
+    compiled for the host) against the libm of the machine the oracle runs on: 2e6 angles, every degree-grid value the
+    orientation can produce near quadrant boundaries, and the one input that exposed the difference."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    rng = np.random.default_rng(3)
+    deg = np.concatenate([rng.uniform(0, 360, 2_000_000), np.arange(0, 360.5, 0.5), [41.9094352722168, 360.0, 0.0, 1e-5]]).astype(np.float32)
+    ang = (deg * np.float32(np.pi / np.float32(180.0))).astype(np.float32)      # float angle * (float)(CV_PI/180.f)
+    s = np.zeros_like(ang); c = np.zeros_like(ang)
+    lib.ft_debug_sincosf.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ft_debug_sincosf.restype = None
+    lib.ft_debug_sincosf(len(ang), ang.ctypes.data, s.ctypes.data, c.ctypes.data)
+    import oracle
+    rs, rc = oracle.libm_sincosf(ang)                  # the host libm, as the oracle's computeOrbDescriptor calls it
+    assert np.array_equal(s.view(np.uint32), rs.view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), rc.view(np.uint32))
+    libm.sinf.restype = C.c_float; libm.sinf.argtypes = [C.c_float]
+    # the exposed case: libm's sinf(0.73145765f) is 1 ulp above the correctly rounded value
+    a0 = np.float32(0.73145765)
+    assert np.float32(libm.sinf(float(a0))) != np.float32(np.sin(np.float64(a0)))
+    s0 = np.zeros(1, np.float32); c0 = np.zeros(1, np.float32); a1 = np.array([a0], np.float32)
+    lib.ft_debug_sincosf(1, a1.ctypes.data, s0.ctypes.data, c0.ctypes.data)
+    assert s0[0] == np.float32(libm.sinf(float(a0)))
