@@ -462,6 +462,41 @@ def main():
         e2e_collect_and_search_store(ctxs[i % DE], i % N_FRAMES)
     barrier()
     e2e_store_s = time.perf_counter() - t0
+    # ---- timed region 2d: the same three end-to-end loops driven from C++ (fasttrack_b200/host/ft_sequence_driver.cpp,
+    # public C ABI only): what a C++ tracking thread pays, without the Python/ctypes overhead of 2/2b/2c ----
+    drv = C.CDLL(os.path.join(os.path.dirname(ft.library_path()), "libft_sequence_driver.so"))
+
+    class Seq(C.Structure):
+        _fields_ = [("n_frames", C.c_int), ("width", C.c_int), ("height", C.c_int), ("M", C.c_int)] + \
+                   [(k_, C.POINTER(C.c_void_p)) for k_ in ("imgL", "imgR", "pos", "normal", "minmax", "desc", "flags", "rows")]
+    arr = lambda ptrs: (C.c_void_p * len(ptrs))(*ptrs)
+    keep = dict(imgL=arr([t.data_ptr() for t in hL]), imgR=arr([t.data_ptr() for t in hR]),
+                rows=arr([r.ctypes.data for r in rows]))
+    for key in ("pos", "normal", "minmax", "desc", "flags"):
+        keep[key] = arr([m[key].ctypes.data for m in maps])
+    seq = Seq(N_FRAMES, E["width"], E["height"], M_POINTS, *[C.cast(keep[k_], C.POINTER(C.c_void_p)) for k_ in
+                                                           ("imgL", "imgR", "pos", "normal", "minmax", "desc", "flags", "rows")])
+    drv.ftd_run_serial.restype = C.c_double
+    drv.ftd_run_serial.argtypes = [C.c_void_p, C.POINTER(Seq), C.c_int, C.c_float, C.POINTER(C.c_longlong)]
+    drv.ftd_run_pipelined.restype = C.c_double
+    drv.ftd_run_pipelined.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Seq), C.c_int, C.c_float, C.c_int, C.c_int,
+                                      C.POINTER(C.c_longlong)]
+    hctx = (C.c_void_p * DE)(*[c_.h for c_ in ctxs[:DE]])
+    nmatch = [C.c_longlong(), C.c_longlong(), C.c_longlong()]
+
+    def native(fn):
+        barrier()
+        t = fn()
+        if t < 0:
+            raise SystemExit("bench.py: native sequence driver failed: %s" % L_.ft_last_error().decode())
+        (t,) = replicas.reduce_max(dist, world, [t], device="cuda")
+        return t
+    native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), 20, TH, 0, 0, C.byref(nmatch[1])))      # warm-up
+    n_serial_s = native(lambda: drv.ftd_run_serial(ctxs[0].h, C.byref(seq), args.steps, TH, C.byref(nmatch[0])))
+    n_pipe_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 0, 0, C.byref(nmatch[1])))
+    n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[2])))
+    if not (nmatch[0].value == nmatch[1].value == nmatch[2].value) or nmatch[0].value <= 0:
+        raise SystemExit("bench.py: the end-to-end loops disagree on the matches found: %s" % [v.value for v in nmatch])
     clocks = sampler.stop()
     h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + 2 * cap_dev * 5
     d2h = 64 + 2 * cap_dev * (24 + 32) + cap_dev * 8 + 64 + 2 * cap_dev * 5 + M_POINTS * 8
@@ -530,17 +565,22 @@ def main():
                        "pipeline": "%d frames in flight over one sequence (extract t+1.. || search t); searches stay ordered" % D,
                        "pipeline_depth": D,
                        "sequences": world, "parallelism": "independent sequence per GPU, no collective"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_in_flight": DE,
-                    "serial_ms_per_step": e2e_serial_s * 1e3 / args.steps,
-                    "serial_value": replicas.aggregate_throughput(world, args.steps, e2e_serial_s),
-                    "map_store": {"value": replicas.aggregate_throughput(world, args.steps, e2e_store_s),
-                                  "ms_per_step": e2e_store_s * 1e3 / args.steps,
+            "e2e": {"value": replicas.aggregate_throughput(world, args.steps, n_pipe_s), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": n_pipe_s * 1e3 / args.steps, "frames_in_flight": DE,
+                    "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp): ft_frame_submit(t+1..) "
+                              "overlaps marshal + ft_search_staged(t); host wall clock, max over ranks",
+                    "serial_ms_per_step": n_serial_s * 1e3 / args.steps,
+                    "serial_value": replicas.aggregate_throughput(world, args.steps, n_serial_s),
+                    "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s),
+                                  "ms_per_step": n_store_s * 1e3 / args.steps,
                                   "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
                                   "upserts_per_step": STORE_UPSERTS,
                                   "note": "local map named as rows of the persistent device-side store (8f row 3)"},
-                    "note": "value: ft_frame_submit(t+1..) overlaps marshal + ft_search_staged(t) on frames_in_flight contexts, host "
-                            "wall clock; serial_*: ft_frame_construct then ft_search_staged, one frame at a time"},
+                    "matches_per_frame": nmatch[0].value / args.steps,
+                    "python_loop": {"note": "the same calls issued from Python/ctypes (bench.py step functions)",
+                                    "ms_per_step": e2e_s * 1e3 / args.steps, "serial_ms_per_step": e2e_serial_s * 1e3 / args.steps,
+                                    "map_store_ms_per_step": e2e_store_s * 1e3 / args.steps}},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": launches_per_step,
             "clocks": clocks,

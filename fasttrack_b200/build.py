@@ -7,6 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 SO = os.path.join(OUT_DIR, "libfasttrack_b200.so")
+DRIVER_SRC = os.path.join(HERE, "host", "ft_sequence_driver.cpp")
+DRIVER_SO = os.path.join(OUT_DIR, "libft_sequence_driver.so")
 SOURCES = ["ft_context.cu", "ft_extract.cu", "ft_stereo.cu", "ft_sbp.cu"]
 HEADERS = ["ft_device.cuh", "ft_camera.cuh", "ft_internal.h", "ft_sort.h",
            os.path.join("..", "..", "include", "fasttrack_b200.h"),
@@ -24,10 +26,10 @@ def _nvcc():
 
 
 def needs_build():
-    if not os.path.exists(SO):
+    if not os.path.exists(SO) or not os.path.exists(DRIVER_SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [DRIVER_SRC]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -54,6 +56,9 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(log))
     subprocess.check_call([_nvcc(), "-shared", "-o", SO] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    # host-side C++ sequence loop over the public C ABI (used by bench.py's end-to-end legs)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", DRIVER_SRC, "-o", DRIVER_SO, "-L" + OUT_DIR,
+                           "-lfasttrack_b200", "-Wl,-rpath,$ORIGIN"])
     return SO
 
 

@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
       }
     }
     __syncthreads();
-    if (mode == 1) OCT_TICK(22);
+    if (mode == 1) OCT_TICK(22); else OCT_TICK(27);
     // candidates: remap code -> node, count children of nodes being split
     for (int c = tid; c < C; c += OCT_THREADS) {
       const int node = S.map[code[c]];
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     __syncthreads();
     if (usePriv) { oct_count_flush(S.ccnt, sPriv, 4 * n); __syncthreads(); }
 
-    if (mode == 1) OCT_TICK(23);
+    if (mode == 1) OCT_TICK(23); else OCT_TICK(28);
     if (mode == 0) {
       // per node: k = non-empty children, e = children with more than one keypoint
       for (int i = tid; i < n; i += OCT_THREADS) {
@@ -626,9 +626,11 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         S.posA[i] = k; S.posB[i] = nm; S.posC[i] = e;
       }
       __syncthreads();
+      OCT_TICK(29);
       // posA <- children of later nodes (they end up in front), posB <- noMore nodes before i, posC <- vec offset
       oct_scan3(n, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, true);
       __syncthreads();
+      OCT_TICK(30);
       const int totalChildren = sTot[0], nNew = sTot[0] + sTot[1], nToExpand = sTot[2];
       if (nNew > cap) {  // cannot happen (list <= N+3, roots*4); guarded so a logic slip cannot corrupt memory
         if (tid == 0) { atomicOr(b.status, FT_ST_NODE_OVERFLOW); E.lvlKpCount[level] = 0; }
@@ -657,6 +659,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         }
       }
       __syncthreads();
+      OCT_TICK(31);
       if (tid == 0) {
         sN = nNew; sVecN = nToExpand;
         if (nNew >= N || nNew == n) sMode = 2;                 // (:790)

@@ -1,0 +1,117 @@
+// ft_sequence_driver.cpp -- host-side C++ loop over a stereo sequence, written against the public C ABI only
+// (include/fasttrack_b200.h). It is what a C++ tracking thread does per frame with HOST buffers:
+//   Frame constructor   : ft_frame_construct, or ft_frame_submit / ft_frame_collect with several frames in flight
+//   SearchLocalPoints   : marshal the local map into the context's pinned staging (the reference's CudaMapPoint
+//                         loop, src/Kernels/CudaWrappers/CudaMapPoint.cc:15-34) + ft_search_staged, or name the local
+//                         map as rows of the persistent store (ft_map_store_update + ft_search_store)
+// bench.py times these loops for its end-to-end legs (the Python loop around the same calls is reported beside them);
+// every host<->device copy of a step happens inside the timed region. Built by fasttrack_b200/build.py with g++.
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/fasttrack_b200.h"
+
+extern "C" {
+
+typedef struct {
+  int n_frames, width, height, M;
+  const uint8_t* const* imgL;      // [n_frames] host images, row pitch = width
+  const uint8_t* const* imgR;
+  const float* const* pos;         // [n_frames] local map of frame k: pos[M][3] ...
+  const float* const* normal;
+  const float* const* minmax;
+  const uint8_t* const* desc;
+  const int* const* flags;
+  const int* const* rows;          // [n_frames] store rows of the local map (store variant), else NULL
+} ftd_sequence;
+
+static inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct HostFrame {   // the host vectors of ORB_SLAM3::Frame that the constructor fills
+  std::vector<ft_keypoint> kL, kR;
+  std::vector<uint8_t> dL, dR;
+  std::vector<float> ur, dp;
+  std::vector<int> holder; std::vector<uint8_t> hobs; std::vector<int> best;
+  int counts[4];
+  explicit HostFrame(int cap, int M) : kL(cap), kR(cap), dL((size_t)cap * 32), dR((size_t)cap * 32), ur(cap), dp(cap),
+                                       holder(2 * (size_t)cap), hobs(2 * (size_t)cap), best(2 * (size_t)M + 2) {}
+};
+
+static ft_status search_snapshot(ft_context* c, const ftd_sequence* s, int k, int nl, float th, long long* matches) {
+  float *p, *n, *mm; uint8_t* d; int *f, *h; uint8_t* ho;
+  ft_status st = ft_map_point_staging(c, s->M, &p, &n, &mm, &d, &f, &h, &ho);
+  if (st != FT_OK) return st;
+  const size_t M = (size_t)s->M;
+  memcpy(p, s->pos[k], 12 * M); memcpy(n, s->normal[k], 12 * M); memcpy(mm, s->minmax[k], 8 * M);
+  memcpy(d, s->desc[k], 32 * M); memcpy(f, s->flags[k], 4 * M);
+  memset(h, 0xFF, sizeof(int) * (size_t)nl); memset(ho, 0, (size_t)nl);   // F.mvpMapPoints all NULL after the constructor
+  const int *hOut, *bOut; const uint8_t* oOut; int nm = 0;
+  st = ft_search_staged(c, s->M, th, 0, 50.f, 0.8f, &hOut, &oOut, &bOut, &nm);
+  *matches += nm;
+  return st;
+}
+
+#define FTD(call) do { ft_status st_ = (call); if (st_ != FT_OK) return -(double)st_; } while (0)
+
+// one frame at a time on one context: returns wall seconds for `steps` frames, < 0 on error (ft_last_error has the text)
+double ftd_run_serial(ft_context* c, const ftd_sequence* s, int steps, float th, long long* matches) {
+  HostFrame F(ft_max_keypoints(c), s->M);
+  *matches = 0;
+  FTD(ft_synchronize(c));
+  const double t0 = now_s();
+  for (int i = 0; i < steps; i++) {
+    const int k = i % s->n_frames;
+    FTD(ft_frame_construct(c, s->imgL[k], s->width, s->imgR[k], s->width, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(),
+                           F.counts, F.ur.data(), F.dp.data(), nullptr, nullptr, nullptr));
+    FTD(search_snapshot(c, s, k, F.counts[0], th, matches));
+  }
+  FTD(ft_synchronize(c));
+  return now_s() - t0;
+}
+
+// D frames in flight over D contexts of one sequence: frame i+D-1 is submitted (upload + extraction + stereo + result
+// download enqueued) before frame i is collected, marshalled and searched. use_store != 0: the local map is named as
+// rows of the persistent store (created by the caller on ctxs[0], attached to the others), `upserts` rows are
+// re-uploaded per frame.
+double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int steps, float th, int use_store, int upserts,
+                         long long* matches) {
+  if (D < 1) return -1.0;
+  HostFrame F(ft_max_keypoints(ctxs[0]), s->M);
+  *matches = 0;
+  for (int j = 0; j < D; j++) FTD(ft_synchronize(ctxs[j]));
+  const double t0 = now_s();
+  for (int j = 0; j < D - 1 && j < steps; j++) {
+    const int k = j % s->n_frames;
+    FTD(ft_frame_submit(ctxs[j % D], s->imgL[k], s->width, s->imgR[k], s->width));
+  }
+  for (int i = 0; i < steps; i++) {
+    const int j = i + D - 1;
+    if (j < steps) {
+      const int kj = j % s->n_frames;
+      FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
+    }
+    ft_context* c = ctxs[i % D];
+    const int k = i % s->n_frames;
+    FTD(ft_frame_collect(c, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(), F.counts, F.ur.data(), F.dp.data(), nullptr,
+                         nullptr, nullptr));
+    const int nl = F.counts[0];
+    if (!use_store) {
+      FTD(search_snapshot(c, s, k, nl, th, matches));
+    } else {
+      FTD(ft_map_store_update(c, upserts, s->rows[k], s->pos[k], s->normal[k], s->minmax[k], s->desc[k]));
+      std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
+      std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
+      int nm = 0;
+      FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      *matches += nm;
+    }
+  }
+  for (int j = 0; j < D; j++) FTD(ft_synchronize(ctxs[j]));
+  return now_s() - t0;
+}
+
+}  // extern "C"

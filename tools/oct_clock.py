@@ -20,4 +20,5 @@ for lvl in range(8):
     d = np.diff(ticks[:n])
     modes = t[40:40 + max(n - 5, 0)]
     sub = t[20:27]; print("   careful sub-phases", np.diff(sub).tolist(), "m", int(t[63]))
+    print("   last normal pass sub-phases (cand loop, node loop, scan, placement)", np.diff(t[27:32]).tolist())
     print("level", lvl, "C", cand[lvl], "K", kp[lvl], "total cycles", int(ticks[n - 1] - ticks[0]), "phases", d.tolist(), "mode*1e5+n", modes.tolist())
