@@ -168,8 +168,13 @@ __device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const 
 // once: passing keypoints are collected in traversal order into a small per-warp shared-memory buffer
 // (GA_BUF entries; longer lists take a second walk straight into the pool), and the lanes finally split the
 // candidates evenly for the Hamming distances.
+#ifndef GA_WARPS
 #define GA_WARPS 16
+#endif
+#define GA_CTAS_PER_SM (GA_WARPS >= 32 ? 1 : 2)
 #define GA_BUF 96
+#define GA_INLINE 16        // candidate slots every (map point, branch) owns in the pool; longer lists allocate from the overflow area
+#define GA_ACTIVE_CAP 512   // map points one CTA can process: ceil(max_map_points / resident CTAs) + slack
 __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                           const __grid_constant__ FtGridBuffers g,
                                                           const __grid_constant__ FtStereoBuffers st,
@@ -179,8 +184,14 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
   extern __shared__ __align__(16) uint8_t gaSmem[];
   __shared__ unsigned short sBuf[GA_WARPS][GA_BUF];
   __shared__ int sCol[GA_WARPS][FT_GRID_COLS], sPre[GA_WARPS][FT_GRID_COLS];
+  // per-CTA totals, folded into the global cursors once per CTA (thousands of same-address global atomics were the
+  // kernel's critical resource): active map points of this CTA, candidates found, searched non-blocking map points
+  __shared__ int sActive[GA_ACTIVE_CAP];
+  __shared__ int sNActive, sNCand, sNNonBlocking, sActiveBase;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nEyes = a.fisheye ? 2 : 1;
+  if (tid == 0) { sNActive = 0; sNCand = 0; sNNonBlocking = 0; }   // visible after the staging barrier / the one below
+  if (!stage) __syncthreads();
   // The frame-side search structure (grid CSR + 16-byte keypoint records + uRight) is ~40 KB: every CTA stages it
   // in shared memory once, so the window walks below never leave the SM. (stage == 0: structure too large for
   // shared memory, e.g. 10k features; the same code then reads it from L2.)
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
     }
     bool searched = (inView || inViewR) && !(flags & 1);
     if (a.bFar && f[3] > a.thFar) searched = false;   // mTrackDepth > thFarPoints (ORBmatcher.cc:66)
-    if (lane == 0 && searched && !(flags & 2)) atomicAdd(&s.cursor[3], 1);
+    if (lane == 0 && searched && !(flags & 2)) atomicAdd(&sNNonBlocking, 1);
     int2 lens = make_int2(0, 0), offs = make_int2(0, 0);
     if (searched) {
       const uint4* md = reinterpret_cast<const uint4*>(s.desc + (size_t)src * 32);
@@ -363,13 +374,18 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         };
         const int total = walk(nullptr);
         if (total == 0) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s.cursor[0], total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base + total > s.poolCap) {
-          if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
-          continue;
+        // short lists (the common case) live in the slots the (map point, branch) pair owns; only longer ones
+        // allocate from the overflow area behind the M*2*GA_INLINE inline slots
+        int base = (2 * mp + br) * GA_INLINE;
+        if (total > GA_INLINE) {
+          if (lane == 0) base = 2 * M * GA_INLINE + atomicAdd(&s.cursor[0], total);
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          if (base + total > s.poolCap) {
+            if (lane == 0) atomicOr(b.status, FT_ST_SBP_POOL_OVERFLOW);
+            continue;
+          }
         }
+        if (lane == 0) atomicAdd(&sNCand, total);
         if (total > GA_BUF) walk(s.pool + base);
         __syncwarp();
         // Hamming distance + octave per candidate
@@ -386,9 +402,21 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
     if (lane == 0) {
       *reinterpret_cast<int2*>(s.listOff + 2 * mp) = offs;
       *reinterpret_cast<int2*>(s.listLen + 2 * mp) = lens;
-      if (lens.x | lens.y) s.active[atomicAdd(&s.cursor[4], 1)] = mp;
+      if (lens.x | lens.y) {
+        const int k = atomicAdd(&sNActive, 1);
+        if (k < GA_ACTIVE_CAP) sActive[k] = mp; else s.active[atomicAdd(&s.cursor[4], 1)] = mp;   // (cannot happen with the launch geometry)
+      }
     }
   }
+  __syncthreads();
+  const int nAct = min(sNActive, GA_ACTIVE_CAP);
+  if (tid == 0) {
+    sActiveBase = nAct ? atomicAdd(&s.cursor[4], nAct) : 0;
+    if (sNCand) atomicAdd(&s.cursor[9], sNCand);
+    if (sNNonBlocking) atomicAdd(&s.cursor[3], sNNonBlocking);
+  }
+  __syncthreads();
+  for (int i = tid; i < nAct; i += GA_WARPS * 32) s.active[sActiveBase + i] = sActive[i];
 }
 
 // ---- claim resolution ---------------------------------------------------------------------
@@ -625,7 +653,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if (removed) atomicSub(&s.cursor[1], removed);
     cluster.sync();
   }
-  if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status; }
+  if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[9]; s.cursor[9] = 0; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status; }
 }
 
 // In-order execution by one thread (fisheye rigs with non-blocking map points only).
@@ -663,7 +691,7 @@ __global__ void k_resolve_seq(const __grid_constant__ FtBuffers b, const __grid_
       }
     }
   }
-  s.cursor[1] = nm; s.cursor[2] = 0; s.cursor[7] = s.cursor[0]; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status;
+  s.cursor[1] = nm; s.cursor[2] = 0; s.cursor[7] = s.cursor[9]; s.cursor[9] = 0; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status;
 }
 
 // ---- host launchers -----------------------------------------------------------------------
@@ -734,7 +762,7 @@ void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st) {
   const size_t smem = ft_gather_smem(p, ga.fisheye);
   const int stage = smem <= 200 * 1024;
-  const int ctas = min((M + GA_WARPS - 1) / GA_WARPS, 2 * 148);   // two resident CTAs per SM, grid-stride over map points
+  const int ctas = min((M + GA_WARPS - 1) / GA_WARPS, GA_CTAS_PER_SM * 148);   // resident CTAs only, grid-stride over map points
   k_gather<<<ctas, GA_WARPS * 32, stage ? smem : 0, st>>>(p, b, g, stb, s, fa, ga, M, stage);
 }
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
