@@ -22,7 +22,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_debug_sincosf", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_sensor", "ft_extract_mono", "ft_depth_from_rgbd", "ft_debug_sincosf", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -106,6 +106,9 @@ def load_library():
     L.ft_map_store_create.argtypes = [vp, C.c_int]
     L.ft_set_distortion.argtypes = [vp, vp, C.c_int]
     L.ft_set_input_resize.argtypes = [vp, C.c_int, C.c_int]
+    L.ft_set_sensor.argtypes = [vp, C.c_int]
+    L.ft_extract_mono.argtypes = [vp, vp, C.c_int]
+    L.ft_depth_from_rgbd.argtypes = [vp, vp, C.c_int]
     L.ft_debug_sincosf.argtypes = [C.c_int, vp, vp, vp]
     L.ft_debug_sincosf.restype = None
     L.ft_image_bounds.argtypes = [vp, vp]
@@ -261,6 +264,24 @@ class Context:
         if self.fisheye:
             left.update(l2r=l2r[:nl].copy(), r2l=r2l[:nr].copy(), p3d=p3d[:nl].copy())
         return left, right
+
+    # ---- monocular / RGB-D ----
+    def set_sensor(self, sensor):
+        """0 stereo (default), 1 monocular, 2 RGB-D"""
+        self._ck(self.L.ft_set_sensor(self.h, int(sensor)))
+
+    def extract_mono(self, img):
+        assert img.dtype == np.uint8 and img.strides[1] == 1
+        self._ck(self.L.ft_extract_mono(self.h, img.ctypes.data, img.strides[0]))
+
+    def depth_from_rgbd(self, depth=None):
+        """Frame::ComputeStereoFromRGBD with a float32 depth image (None on a monocular context); builds the frame grid"""
+        if depth is None:
+            self._ck(self.L.ft_depth_from_rgbd(self.h, None, 0))
+            return
+        assert depth.dtype == np.float32 and depth.strides[1] == 4
+        self._keep_depth = depth
+        self._ck(self.L.ft_depth_from_rgbd(self.h, depth.ctypes.data, depth.strides[0]))
 
     def set_input_resize(self, raw_width, raw_height):
         """cv::resize of the raw input to the camera size in front of the extractor (System.cc:282-285); 0 = off"""

@@ -80,6 +80,9 @@ struct ft_context {
   // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
   int rectify = 0, rawW = 0, rawH = 0;
   int inResize = 0;   // cv::resize of the raw input into level 0 (Settings::needToResize)
+  // monocular / RGB-D sensors: only eye 0 is extracted; the depth image replaces stereo matching
+  int sensor = FT_SENSOR_STEREO;
+  float* dDepth = nullptr; float* hDepth = nullptr;
   uint8_t* dRaw[2] = {nullptr, nullptr};
   int2* dRemapTab = nullptr;
   // resident map-point snapshot + initial holders for ft_search_resident
@@ -130,6 +133,7 @@ static ft_status build_params(ft_context* c) {
   }
   P.nlevels = nl; P.width = cfg.width; P.height = cfg.height; P.nfeatures = cfg.nfeatures;
   P.iniTh = cfg.ini_th_fast; P.minTh = cfg.min_th_fast; P.camType = cfg.camera_type;
+  P.nEyes = 2;
   P.lap[0][0] = cfg.lap_left[0]; P.lap[0][1] = cfg.lap_left[1];
   P.lap[1][0] = cfg.lap_right[0]; P.lap[1][1] = cfg.lap_right[1];
   // scale tables (ORBextractor.cc:398-411,444-450); scaleFactor is held as double there
@@ -460,6 +464,7 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->hFrame) cudaFreeHost(c->hFrame);
   if (c->hMp) cudaFreeHost(c->hMp);
   if (c->hOut) cudaFreeHost(c->hOut);
+  if (c->hDepth) cudaFreeHost(c->hDepth);
   for (int i = 0; i < FT_STAGE_COUNT; i++) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -582,16 +587,16 @@ static ft_status run_extract(ft_context* c) {
 }
 
 static ft_status upload_images(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR) {
-  if (!c || !imgL || !imgR) { set_err("null image (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
+  if (!c || !imgL || (!imgR && c->P.nEyes == 2)) { set_err("null image (the reference returns -1 on an empty image)"); return FT_ERR_INVALID; }
   // with rectification the raw image goes to a staging buffer (k_remap writes level 0); otherwise straight into level 0
   const bool raw = c->rectify || c->inResize;
   const int w = raw ? c->rawW : c->cfg.width, h = raw ? c->rawH : c->cfg.height;
   const int dpitch = raw ? w : c->P.lv[0].pitch;
-  if (stepL < w || stepR < w) { set_err("image step smaller than width"); return FT_ERR_INVALID; }
+  if (stepL < w || (c->P.nEyes == 2 && stepR < w)) { set_err("image step smaller than width"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));
   const uint8_t* src[2] = {imgL, imgR};
   const int step[2] = {stepL, stepR};
-  for (int e = 0; e < 2; e++) {
+  for (int e = 0; e < c->P.nEyes; e++) {
     cudaPointerAttributes at;
     bool pinned = cudaPointerGetAttributes(&at, src[e]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -622,7 +627,7 @@ static ft_status copy_device_images(ft_context* c, const uint8_t* dL, int stepL,
   const int dpitch = raw ? w : c->P.lv[0].pitch;
   const uint8_t* src[2] = {dL, dR};
   const int step[2] = {stepL, stepR};
-  for (int e = 0; e < 2; e++) {
+  for (int e = 0; e < c->P.nEyes; e++) {
     uint8_t* dst = raw ? c->dRaw[e] : c->B.eye[e].pyr + c->P.lv[0].offset;
     if (step[e] == w && dpitch == w) CK(cudaMemcpyAsync(dst, src[e], (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
     else CK(cudaMemcpy2DAsync(dst, dpitch, src[e], step[e], w, h, cudaMemcpyDeviceToDevice, c->stream));
@@ -662,6 +667,7 @@ extern "C" ft_status ft_stereo_match(ft_context* c) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   if (!c->extracted) { set_err("ft_stereo_match: no extracted frame"); return FT_ERR_STATE; }
   if (c->fisheye) { set_err("ft_stereo_match: context is a KannalaBrandt8 rig; call ft_stereo_match_fisheye"); return FT_ERR_INVALID; }
+  if (c->sensor != FT_SENSOR_STEREO) { set_err("ft_stereo_match: the context is monocular / RGB-D (ft_set_sensor); call ft_depth_from_rgbd"); return FT_ERR_STATE; }
   return run_stereo(c);
 }
 
@@ -731,6 +737,7 @@ extern "C" ft_status ft_frame_download(ft_context* c, int eye, int cap, ft_keypo
 
 // extract + stereo as ONE captured graph (the Frame constructor does both back to back)
 static ft_status run_frame(ft_context* c) {
+  if (c->sensor != FT_SENSOR_STEREO) { set_err("the one-call Frame constructor is stereo only; use ft_extract_mono + ft_depth_from_rgbd"); return FT_ERR_STATE; }
   if (c->useGraph && !c->timing) {
     if (!c->gFrame) {
       cudaGraph_t g = nullptr;
@@ -794,6 +801,70 @@ extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_
     }
   }
   c->rawW = raw_width; c->rawH = raw_height; c->rectify = 1;
+  return FT_OK;
+}
+
+// ---- monocular / RGB-D sensors ("next" row 4 of SURVEY.md 8f, the RGB-D half) ----
+// The monocular and RGB-D Frame constructors (reference src/Frame.cc:226-325, 328-419) run ONE extractor, undistort
+// the keypoints and take depth from the registered depth image (ComputeStereoFromRGBD, :1065-1086) or leave
+// mvuRight / mvDepth at -1 (monocular, :330-331).
+extern "C" ft_status ft_set_sensor(ft_context* c, int sensor) {
+  if (!c || sensor < FT_SENSOR_STEREO || sensor > FT_SENSOR_RGBD) { set_err("ft_set_sensor: bad argument"); return FT_ERR_INVALID; }
+  if (c->fisheye && sensor != FT_SENSOR_STEREO) { set_err("ft_set_sensor: monocular / RGB-D operation is implemented for pinhole cameras"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->gExtract) { cudaGraphExecDestroy(c->gExtract); c->gExtract = nullptr; }
+  if (c->gStereo) { cudaGraphExecDestroy(c->gStereo); c->gStereo = nullptr; }
+  if (c->gFrame) { cudaGraphExecDestroy(c->gFrame); c->gFrame = nullptr; }
+  c->sensor = sensor;
+  c->P.nEyes = sensor == FT_SENSOR_STEREO ? 2 : 1;
+  CK(cudaMemsetAsync(c->B.eye[1].counts, 0, 2 * sizeof(int), c->stream));   // the right eye stays empty
+  c->extracted = false; c->stereoDone = false; c->countsValid = false;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_extract_mono(ft_context* c, const uint8_t* img, int step) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (c->sensor == FT_SENSOR_STEREO) { set_err("ft_extract_mono: the context is a stereo rig (ft_set_sensor first)"); return FT_ERR_STATE; }
+  ft_status st = upload_images(c, img, step, nullptr, 0);
+  if (st != FT_OK) return st;
+  return run_extract(c);
+}
+
+// depth: CV_32F depth image registered to the gray image (after Tracking::GrabImageRGBD's convertTo with
+// mDepthMapFactor, src/Tracking.cc:1552-1553), step in bytes; NULL = monocular frame (mvuRight = mvDepth = -1).
+extern "C" ft_status ft_depth_from_rgbd(ft_context* c, const float* depth, int step_bytes) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (c->sensor == FT_SENSOR_STEREO) { set_err("ft_depth_from_rgbd: the context is a stereo rig (ft_set_sensor first)"); return FT_ERR_STATE; }
+  if (!c->extracted) { set_err("ft_depth_from_rgbd: no extracted frame"); return FT_ERR_STATE; }
+  if (c->sensor == FT_SENSOR_RGBD && !depth) { set_err("ft_depth_from_rgbd: RGB-D context needs a depth image"); return FT_ERR_INVALID; }
+  if (c->sensor == FT_SENSOR_MONOCULAR && depth) { set_err("ft_depth_from_rgbd: monocular context takes no depth image"); return FT_ERR_INVALID; }
+  const int w = c->cfg.width, h = c->cfg.height;
+  if (depth && (step_bytes < w * 4 || step_bytes % 4)) { set_err("ft_depth_from_rgbd: bad step"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  cudaStream_t s = c->stream;
+  if (depth) {
+    if (!c->dDepth) {
+      CK(dalloc(c, &c->dDepth, (size_t)w * h));
+      CK(cudaMallocHost((void**)&c->hDepth, sizeof(float) * (size_t)w * h));
+    }
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, depth) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      CK(cudaMemcpy2DAsync(c->dDepth, sizeof(float) * w, depth, step_bytes, sizeof(float) * w, h, cudaMemcpyHostToDevice, s));
+    } else {
+      CK(cudaStreamSynchronize(s));   // the previous frame may still be reading the staging buffer
+      for (int y = 0; y < h; y++) memcpy(c->hDepth + (size_t)y * w, reinterpret_cast<const uint8_t*>(depth) + (size_t)y * step_bytes, sizeof(float) * w);
+      CK(cudaMemcpyAsync(c->dDepth, c->hDepth, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice, s));
+    }
+  }
+  // frame grid first (it writes mvKeysUn), then the depth lookup
+  { StageScope t(c, FT_STAGE_GRID, s); ft_launch_grid(c->P, c->B, c->G, 0, c->minX, c->minY, c->gridWInv, c->gridHInv, c->und, s); }
+  { StageScope t(c, FT_STAGE_STEREO, s); ft_launch_rgbd_depth(c->P, c->B, c->S, c->G.kpUn, depth ? c->dDepth : nullptr, w, c->mbf, s); }
+  CK(cudaGetLastError());
+  c->nLaunchStereo = 2;
+  c->stereoDone = true; c->countsValid = false;
   return FT_OK;
 }
 

@@ -47,6 +47,7 @@ struct FtParams {
   int totalCells, totalBlurTiles;
   int maxKp;              // capacity of the final per-eye keypoint arrays
   int camType;
+  int nEyes;              // 2 = stereo rig, 1 = monocular / RGB-D (only eye 0 is extracted)
   int lap[2][2];
   int umax[16];
   float scale[FT_MAX_LEVELS], invScale[FT_MAX_LEVELS], sigma2[FT_MAX_LEVELS];

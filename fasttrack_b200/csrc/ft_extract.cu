@@ -1010,31 +1010,31 @@ cudaError_t ft_launch_extract_setup(const FtParams& p) {
 
 void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,
                      int rawH, cudaStream_t st) {
-  dim3 blk(64, 4), grd((p.lv[0].w + 63) / 64, (p.lv[0].h + 3) / 4, 2);
+  dim3 blk(64, 4), grd((p.lv[0].w + 63) / 64, (p.lv[0].h + 3) / 4, p.nEyes);
   k_remap<<<grd, blk, 0, st>>>(p, b, rawL, rawR, tab, rawW, rawH);
 }
 void ft_launch_resize_input(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, int rawW,
                             cudaStream_t st) {
-  dim3 blk(32, 8), grd((p.lv[0].w + 127) / 128, (p.lv[0].h + 7) / 8, 2);
+  dim3 blk(32, 8), grd((p.lv[0].w + 127) / 128, (p.lv[0].h + 7) / 8, p.nEyes);
   k_resize_input<<<grd, blk, 0, st>>>(p, b, rawL, rawR, rawW);
 }
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
-  dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, 2);
+  dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, p.nEyes);
   k_resize<<<grd, blk, 0, st>>>(p, b, level);
 }
 void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   const int tiles = (l1 < p.nlevels ? p.lv[l1].blurTileBase : p.totalBlurTiles) - p.lv[l0].blurTileBase;
-  k_blur<<<dim3(tiles, 2), 256, 0, st>>>(p, b, l0, l1);
+  k_blur<<<dim3(tiles, p.nEyes), 256, 0, st>>>(p, b, l0, l1);
 }
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   const int cells = (l1 < p.nlevels ? p.lv[l1].cellBase : p.totalCells) - p.lv[l0].cellBase;
-  k_fast_cells<<<dim3(cells, 2), FAST_THREADS, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
+  k_fast_cells<<<dim3(cells, p.nEyes), FAST_THREADS, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
 }
 void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   size_t mx = 0;
   for (int l = l0; l < l1; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
-  k_octree<<<dim3(l1 - l0, 2), OCT_THREADS, mx, st>>>(p, b, l0);
+  k_octree<<<dim3(l1 - l0, p.nEyes), OCT_THREADS, mx, st>>>(p, b, l0);
 }
 void ft_launch_orient_desc(const FtParams& p, const FtBuffers& b, cudaStream_t st) {
-  k_orient_desc<<<dim3((p.maxKp + OD_WARPS - 1) / OD_WARPS, 2), OD_WARPS * 32, 0, st>>>(p, b);
+  k_orient_desc<<<dim3((p.maxKp + OD_WARPS - 1) / OD_WARPS, p.nEyes), OD_WARPS * 32, 0, st>>>(p, b);
 }

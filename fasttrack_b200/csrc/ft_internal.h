@@ -18,6 +18,8 @@ void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStere
                             cudaStream_t st);
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st);
+void ft_launch_rgbd_depth(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& st, const float2* kpUn, const float* depth,
+                          int pitchFloats, float mbf, cudaStream_t s);
 void ft_launch_store_scatter(int n, const uint8_t* staged, float* pos, float* normal, float* minmax, uint8_t* desc,
                              cudaStream_t st);
 void ft_launch_grid(const FtParams& p, const FtBuffers& b, const FtGridBuffers& g, int fisheye, float minX, float minY,

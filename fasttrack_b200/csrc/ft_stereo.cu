@@ -396,3 +396,28 @@ void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuff
   k_fisheye_init<<<(p.maxKp + 63) / 64, 64, 0, st>>>(p, b, s);
   k_fisheye_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, 0, st>>>(p, b, s, c1, c2, pose);
 }
+
+// ---- RGB-D / monocular frames ---------------------------------------------------------------------
+// Frame::ComputeStereoFromRGBD (reference src/Frame.cc:1065-1086): d = imDepth.at<float>(kp.pt.y, kp.pt.x) (float
+// coordinates truncated to int); d > 0 -> mvDepth = d, mvuRight = kpU.pt.x - mbf / d, else both stay -1. depth ==
+// nullptr is the monocular Frame constructor (src/Frame.cc:330-331): everything -1. Runs after the frame grid, which
+// writes the undistorted keypoints.
+__global__ void k_rgbd_depth(const __grid_constant__ FtBuffers b, const __grid_constant__ FtStereoBuffers st, const float2* kpUn,
+                             const float* depth, int pitchFloats, int width, int height, float mbf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.eye[0].counts[0]) return;
+  float ur = -1.f, dp = -1.f;
+  if (depth) {
+    const ft_keypoint kp = b.eye[0].kps[i];
+    const int u = (int)kp.x, v = (int)kp.y;
+    if (u >= 0 && u < width && v >= 0 && v < height) {
+      const float d = depth[(size_t)v * pitchFloats + u];
+      if (d > 0) { dp = d; ur = __fsub_rn(kpUn[i].x, __fdiv_rn(mbf, d)); }
+    }
+  }
+  st.uRight[i] = ur; st.depth[i] = dp;
+}
+void ft_launch_rgbd_depth(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& st, const float2* kpUn, const float* depth,
+                          int pitchFloats, float mbf, cudaStream_t s) {
+  k_rgbd_depth<<<(p.maxKp + 255) / 256, 256, 0, s>>>(b, st, kpUn, depth, pitchFloats, p.width, p.height, mbf);
+}

@@ -48,6 +48,7 @@ typedef enum {
 } ft_status;
 
 typedef enum { FT_CAM_PINHOLE = 0, FT_CAM_KB8 = 1 } ft_camera_type;
+typedef enum { FT_SENSOR_STEREO = 0, FT_SENSOR_MONOCULAR = 1, FT_SENSOR_RGBD = 2 } ft_sensor;   /* System::eSensor subset */
 
 /* Settings the reference reads from YAML (src/Settings.cc) plus the rig geometry. */
 typedef struct {
@@ -116,6 +117,17 @@ ft_status ft_frame_download(ft_context* ctx, int eye, int cap, ft_keypoint* kps,
  * images handed to ft_extract_stereo / ft_frame_construct are then raw_width x raw_height. NULL maps switch it off. */
 ft_status ft_set_rectification(ft_context* ctx, int raw_width, int raw_height, const float* M1l, const float* M2l,
                                const float* M1r, const float* M2r);
+
+/* Monocular / RGB-D sensors (RGB-D half). The reference's monocular and RGB-D Frame constructors
+ * (src/Frame.cc:226-325, 328-419) run one ORBextractor::operator(), UndistortKeyPoints, then either
+ * ComputeStereoFromRGBD (src/Frame.cc:1065-1086: depth = imDepth.at<float>(kp.pt.y, kp.pt.x), mvuRight = kpU.pt.x -
+ * mbf / depth where depth > 0) or leave mvuRight / mvDepth at -1. ft_set_sensor switches a pinhole context between
+ * the three modes (default FT_SENSOR_STEREO); ft_extract_mono extracts eye 0 only; ft_depth_from_rgbd takes the CV_32F
+ * depth image (step in bytes; NULL on a monocular context) and also builds the frame grid, after which
+ * ft_frame_download(eye 0), ft_frame_keypoints_undistorted and every projection search work as for a stereo frame. */
+ft_status ft_set_sensor(ft_context* ctx, int sensor);
+ft_status ft_extract_mono(ft_context* ctx, const uint8_t* img, int step);
+ft_status ft_depth_from_rgbd(ft_context* ctx, const float* depth, int step_bytes);
 
 /* cv::resize(im, imToFeed, newImSize) in front of the extractor (reference src/System.cc:282-285, taken when
  * Settings::needToResize): raw images are raw_width x raw_height, level 0 of the pyramid is their INTER_LINEAR resize

@@ -72,6 +72,7 @@ def lib():
     L.fto_remap.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, u8p]
     L.fto_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_libm_sincosf.argtypes = [C.c_int, f32p, f32p, f32p]
+    L.fto_stereo_from_rgbd.argtypes = [f32p, f32p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, f32p, f32p]
     L.fto_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_fast.restype = C.c_int
     L.fto_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
@@ -206,6 +207,19 @@ def libm_sincosf(angles):
     s = np.zeros_like(a); c = np.zeros_like(a)
     lib().fto_libm_sincosf(len(a), a, s, c)
     return s, c
+
+
+def stereo_from_rgbd(keys_xy, keys_un_x, depth, mbf):
+    """Frame::ComputeStereoFromRGBD -> (uRight, depth); depth=None is the monocular frame (all -1)"""
+    xy = np.ascontiguousarray(keys_xy, np.float32).reshape(-1, 2)
+    unx = np.ascontiguousarray(keys_un_x, np.float32)
+    ur = np.zeros(len(xy), np.float32); dp = np.zeros(len(xy), np.float32)
+    if depth is None:
+        lib().fto_stereo_from_rgbd(xy, unx, len(xy), None, 0, 0, float(mbf), ur, dp)
+    else:
+        d = np.ascontiguousarray(depth, np.float32)
+        lib().fto_stereo_from_rgbd(xy, unx, len(xy), d.ctypes.data, d.shape[1], d.shape[0], float(mbf), ur, dp)
+    return ur, dp
 
 
 def undistort_points(xy, K, dist):

@@ -1205,4 +1205,20 @@ void image_bounds(int cols, int rows, const float K[4], const float* dist, int n
   out[2] = std::min(u[1], u[3]); out[3] = std::max(u[5], u[7]);
 }
 
+// Frame::ComputeStereoFromRGBD (Frame.cc:1065-1086): depth image lookup at the RAW keypoint (float coordinates
+// truncated to int by cv::Mat::at<float>(v, u)), mvuRight from the UNDISTORTED x. depth == nullptr: monocular frame
+// (Frame.cc:330-331), everything stays -1.
+void stereo_from_rgbd(const float* keysXY, const float* keysUnX, int n, const float* depth, int w, int h, float mbf,
+                      float* uRight, float* outDepth) {
+  for (int i = 0; i < n; i++) {
+    uRight[i] = -1.f; outDepth[i] = -1.f;
+    if (!depth) continue;
+    const float v = keysXY[2 * i + 1], u = keysXY[2 * i];
+    const int iu = (int)u, iv = (int)v;
+    if (iu < 0 || iu >= w || iv < 0 || iv >= h) continue;
+    const float d = depth[(size_t)iv * w + iu];
+    if (d > 0) { outDepth[i] = d; uRight[i] = keysUnX[i] - mbf / d; }
+  }
+}
+
 }  // namespace fto

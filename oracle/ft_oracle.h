@@ -50,6 +50,10 @@ void remap_linear_u8(const Img& src, const float* mapx, const float* mapy, int d
 void undistort_points(const float* xy, int n, const float K[4], const float* dist, int ndist, float* out);
 void image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float out[4]);  // Frame.cc:806-833
 
+// Frame::ComputeStereoFromRGBD (Frame.cc:1065-1086); depth == nullptr = monocular frame
+void stereo_from_rgbd(const float* keysXY, const float* keysUnX, int n, const float* depth, int w, int h, float mbf,
+                      float* uRight, float* outDepth);
+
 // ---- ORBextractor (ORBextractor.cc CPU branches) ----
 class Extractor {
  public:

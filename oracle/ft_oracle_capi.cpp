@@ -102,6 +102,9 @@ void fto_blur(const uint8_t* src, int w, int h, uint8_t* dst) {
 void fto_libm_sincosf(int n, const float* a, float* s, float* c) {
   for (int i = 0; i < n; i++) { s[i] = sinf(a[i]); c[i] = cosf(a[i]); }
 }
+void fto_stereo_from_rgbd(const float* xy, const float* unx, int n, const float* depth, int w, int h, float mbf, float* ur, float* dp) {
+  stereo_from_rgbd(xy, unx, n, depth, w, h, mbf, ur, dp);
+}
 void fto_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out) {
   undistort_points(xy, n, K, dist, ndist, out);
 }

@@ -76,3 +76,21 @@ def test_undistort_points_matches_cv2():
         assert b[0] == min(ref[0, 0], ref[2, 0]) and b[1] == max(ref[1, 0], ref[3, 0])
         assert b[2] == min(ref[0, 1], ref[1, 1]) and b[3] == max(ref[2, 1], ref[3, 1])
     assert np.array_equal(oracle.image_bounds(640, 480, g["tum1_K"], np.zeros(5, np.float32)), [0, 640, 0, 480])
+
+
+def test_stereo_from_rgbd_restatement():
+    """Frame::ComputeStereoFromRGBD (Frame.cc:1065-1086): float coordinates truncate, depth <= 0 leaves -1, uRight
+    comes from the undistorted x; depth=None is the monocular frame"""
+    rng = np.random.default_rng(2)
+    depth = rng.uniform(-0.5, 6.0, (60, 80)).astype(np.float32)
+    xy = np.stack([rng.uniform(0, 79.99, 500), rng.uniform(0, 59.99, 500)], 1).astype(np.float32)
+    unx = (xy[:, 0] + rng.uniform(-3, 3, 500)).astype(np.float32)
+    mbf = np.float32(40.0)
+    ur, dp = oracle.stereo_from_rgbd(xy, unx, depth, mbf)
+    d = depth[xy[:, 1].astype(np.int32), xy[:, 0].astype(np.int32)]
+    ok = d > 0
+    assert np.array_equal(dp, np.where(ok, d, np.float32(-1))) and ok.sum() > 300 and (~ok).sum() > 10
+    exp = np.where(ok, unx - mbf / np.where(ok, d, np.float32(1)), np.float32(-1)).astype(np.float32)
+    assert np.array_equal(ur, exp)
+    ur0, dp0 = oracle.stereo_from_rgbd(xy, unx, None, mbf)
+    assert np.all(ur0 == -1) and np.all(dp0 == -1)
