@@ -102,8 +102,12 @@ __device__ __forceinline__ int ft_reflect101(int q, int n) {
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                               int levelBegin, int levelEnd) {
-  __shared__ uint8_t sIn[BLUR_TH + 6][BLUR_TW + 8];
-  __shared__ uint16_t sH[BLUR_TH + 6][BLUR_TW];
+  // Word-oriented: the tile (+3 px halo, padded to whole words) is staged with aligned 32-bit loads, a thread of the
+  // horizontal pass produces 4 neighbouring sums from 3 words, a thread of the vertical pass slides a 7-row window
+  // down 4 rows of a column pair. Same integer arithmetic as before (8.8 horizontal, 16.16 vertical, round-half-up).
+  constexpr int WPR = BLUR_TW / 4 + 2;                       // staged words per row: columns [tx-4, tx+TW+4)
+  __shared__ __align__(16) uint32_t sIn[BLUR_TH + 6][WPR];
+  __shared__ __align__(16) uint16_t sH[BLUR_TH + 6][BLUR_TW];
   const int eye = blockIdx.y;
   int level = levelBegin;
   const int tile = blockIdx.x + p.lv[levelBegin].blurTileBase;
@@ -114,33 +118,59 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FtParams p
   const uint8_t* src = b.eye[eye].pyr + L.offset;
   uint8_t* dst = b.eye[eye].blur + L.offset;
   const int tid = threadIdx.x;
-  // stage (TH+6) x (TW+6) input pixels with reflect-101 addressing
-  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-    const int ry = i / (BLUR_TW + 6), rx = i % (BLUR_TW + 6);
-    const int gy = ft_reflect101(ty + ry - 3, L.h), gx = ft_reflect101(tx + rx - 3, L.w);
-    sIn[ry][rx] = src[(size_t)gy * L.pitch + gx];
+  for (int i = tid; i < (BLUR_TH + 6) * WPR; i += 256) {
+    const int ry = i / WPR, wx = i - ry * WPR;
+    const int gy = ft_reflect101(ty + ry - 3, L.h);
+    const int gx0 = tx - 4 + 4 * wx;
+    const uint8_t* row = src + (size_t)gy * L.pitch;
+    uint32_t w;
+    if (gx0 >= 0 && gx0 + 3 < L.w) {
+      w = *reinterpret_cast<const uint32_t*>(row + gx0);       // rows are 64-byte aligned, gx0 is a multiple of 4
+    } else {                                                   // border word: reflect-101 per byte
+      w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) w |= (uint32_t)row[ft_reflect101(gx0 + k, L.w)] << (8 * k);
+    }
+    sIn[ry][wx] = w;
   }
   __syncthreads();
-  for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-    const int ry = i / BLUR_TW, rx = i % BLUR_TW;
-    const uint8_t* s = &sIn[ry][rx];
-    const unsigned acc = 18u * (s[0] + s[6]) + 34u * (s[1] + s[5]) + 48u * (s[2] + s[4]) + 56u * s[3];
-    sH[ry][rx] = (uint16_t)acc;
+  // horizontal: item = (row, group of 4 columns); output column x reads staged bytes x+1 .. x+7
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+    const int ry = i / (BLUR_TW / 4), g = i % (BLUR_TW / 4);
+    const uint32_t w0 = sIn[ry][g], w1 = sIn[ry][g + 1], w2 = sIn[ry][g + 2];
+    unsigned by[10];
+    by[0] = (w0 >> 8) & 0xFF; by[1] = (w0 >> 16) & 0xFF; by[2] = w0 >> 24;
+    by[3] = w1 & 0xFF; by[4] = (w1 >> 8) & 0xFF; by[5] = (w1 >> 16) & 0xFF; by[6] = w1 >> 24;
+    by[7] = w2 & 0xFF; by[8] = (w2 >> 8) & 0xFF; by[9] = (w2 >> 16) & 0xFF;
+    unsigned h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      h[k] = 18u * (by[k] + by[k + 6]) + 34u * (by[k + 1] + by[k + 5]) + 48u * (by[k + 2] + by[k + 4]) + 56u * by[k + 3];
+    *reinterpret_cast<uint2*>(&sH[ry][4 * g]) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
   }
   __syncthreads();
   {
-    const int x = tid % BLUR_TW;
-    const int yg = (tid / BLUR_TW) * 8;   // 4 groups of 8 rows
-    const int gx = tx + x;
+    const int cp = tid & 31;            // column pair
+    const int yg = (tid >> 5) * 4;      // 8 groups of 4 rows
+    const int gx = tx + 2 * cp;
     if (gx < L.w) {
+      unsigned lo[10], hi[10];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int y = yg + k;
-        const int gy = ty + y;
+      for (int r = 0; r < 10; r++) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(&sH[yg + r][2 * cp]);
+        lo[r] = w & 0xFFFFu; hi[r] = w >> 16;
+      }
+      const bool two = gx + 1 < L.w;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int gy = ty + yg + k;
         if (gy < L.h) {
-          const unsigned v = 18u * ((unsigned)sH[y][x] + sH[y + 6][x]) + 34u * ((unsigned)sH[y + 1][x] + sH[y + 5][x]) +
-                             48u * ((unsigned)sH[y + 2][x] + sH[y + 4][x]) + 56u * (unsigned)sH[y + 3][x];
-          dst[(size_t)gy * L.pitch + gx] = (uint8_t)((v + 32768u) >> 16);
+          const unsigned v0 = 18u * (lo[k] + lo[k + 6]) + 34u * (lo[k + 1] + lo[k + 5]) + 48u * (lo[k + 2] + lo[k + 4]) + 56u * lo[k + 3];
+          const unsigned v1 = 18u * (hi[k] + hi[k + 6]) + 34u * (hi[k + 1] + hi[k + 5]) + 48u * (hi[k + 2] + hi[k + 4]) + 56u * hi[k + 3];
+          const unsigned o0 = (v0 + 32768u) >> 16, o1 = (v1 + 32768u) >> 16;
+          uint8_t* q = dst + (size_t)gy * L.pitch + gx;          // gx is even
+          if (two) *reinterpret_cast<uint16_t*>(q) = (uint16_t)(o0 | (o1 << 8));
+          else *q = (uint8_t)o0;
         }
       }
     }
@@ -205,6 +235,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     return;
   }
   const int iw = rw - 6, ih = rh - 6;
+  // row / column of a flat interior index without an integer division per pixel: floor(i / iw) = umulhi(i, ceil(2^32 / iw))
+  // (exact for i < 2^26 with iw <= 64)
+  const unsigned mIw = 0xFFFFFFFFu / (unsigned)iw + 1u;
   const int ax = iniX & 3;                      // the tile is staged with aligned 32-bit loads: ax bytes of slack in front
   const int rwPad = (rw + 6) & ~3;              // >= ax + rw, multiple of 4
   uint8_t* sImg = smem;                         // [rh][rwPad], cell pixel (y, x) at sImg[y*rwPad + ax + x]
@@ -215,8 +248,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const uint8_t* srcA = E.pyr + L.offset + (size_t)iniY * L.pitch + (iniX - ax);   // 4-byte aligned
     const int wpr = (ax + rw + 3) >> 2;                                               // words per row
     uint32_t* sW = reinterpret_cast<uint32_t*>(sImg);
+    const unsigned mWpr = 0xFFFFFFFFu / (unsigned)wpr + 1u;
     for (int i = tid; i < rh * wpr; i += FAST_THREADS) {
-      const int y = i / wpr, wx = i - y * wpr;
+      const int y = (int)__umulhi((unsigned)i, mWpr), wx = i - y * wpr;
       sW[y * (rwPad >> 2) + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
     }
   }
@@ -229,7 +263,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const int i = i0 + tid;
     bool pass = false;
     if (i < total) {
-      const int y = i / iw, x = i - y * iw;
+      const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
       const uint8_t* c = &sImg[(y + 3) * rwPad + ax + (x + 3)];
       const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
       const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
@@ -251,7 +285,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   const int nPass = sPass;
   for (int j = tid; j < nPass; j += FAST_THREADS) {
     const int i = sList[j];
-    const int y = i / iw, x = i - y * iw;
+    const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
     int s = ft_fast_score(&sImg[(y + 3) * rwPad + ax + (x + 3)], rwPad);
     if (s < p.minTh) s = 0;
     sSc[i] = (uint8_t)s;
@@ -260,7 +294,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   // 3x3 strict-maximum NMS inside the interior
   bool any20 = false;
   for (int i = tid; i < total; i += FAST_THREADS) {
-    const int y = i / iw, x = i - y * iw;
+    const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
     const int s = sSc[i];
     int keep = 0;
     if (s) {
@@ -309,7 +343,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   for (int i = beg; i < end; i++) {
     const int s = sMx[i];
     if (s >= th && s > 0) {
-      const int y = i / iw, x = i - y * iw;
+      const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
       if (pos < L.cellCap) out[pos] = ft_pack_xys(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, s);
       pos++;
     }
