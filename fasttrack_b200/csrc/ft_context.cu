@@ -6,6 +6,7 @@
 // sizes and per-level quotas, umax.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,6 +81,7 @@ struct ft_context {
   // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
   int rectify = 0, rawW = 0, rawH = 0;
   int inResize = 0;   // cv::resize of the raw input into level 0 (Settings::needToResize)
+  int grouped = 0;    // launch topology: 0 = one graph branch per pyramid level (lowest latency), 1 = levels 1.. grouped (fewest launches)
   // monocular / RGB-D sensors: only eye 0 is extracted; the depth image replaces stereo matching
   int sensor = FT_SENSOR_STEREO;
   float* dDepth = nullptr; float* hDepth = nullptr;
@@ -417,6 +419,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  { const char* e = getenv("FT_TOPOLOGY"); if (e && !strcmp(e, "grouped")) c->grouped = 1; }
   for (int l = 0; l < P.nlevels; l++) {
     CKF(cudaStreamCreateWithFlags(&c->lvStream[l], cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&c->lvReady[l], cudaEventDisableTiming));
@@ -513,7 +516,7 @@ static int enqueue_extract(ft_context* c) {
   const int nl = P.nlevels;
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
-  const bool perLevel = !c->timing;
+  const bool perLevel = !c->timing && !c->grouped;
   if (c->rectify) { ft_launch_remap(P, c->B, c->dRaw[0], c->dRaw[1], c->dRemapTab, c->rawW, c->rawH, s); n++; }
   else if (c->inResize) { ft_launch_resize_input(P, c->B, c->dRaw[0], c->dRaw[1], c->rawW, s); n++; }
   cudaEventRecord(c->evFork, s);

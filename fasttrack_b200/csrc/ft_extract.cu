@@ -240,10 +240,15 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   const unsigned mIw = 0xFFFFFFFFu / (unsigned)iw + 1u;
   const int ax = iniX & 3;                      // the tile is staged with aligned 32-bit loads: ax bytes of slack in front
   const int rwPad = (rw + 6) & ~3;              // >= ax + rw, multiple of 4
+  const int S = rwPad >> 2;                     // words per staged row
+  // score planes: 1-px zero border so that the 3x3 NMS needs no edge cases, rows a whole number of words;
+  // interior pixel (y, x) lives at [(y + 1) * sS + x + 4]
+  const int sS = (((iw + 3) >> 2) + 3) * 4;
+  const int planeBytes = ((ih + 2) * sS + 15) & ~15;
   uint8_t* sImg = smem;                         // [rh][rwPad], cell pixel (y, x) at sImg[y*rwPad + ax + x]
-  uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // [ih][iw] score (0 below minTh), then NMS survivors
-  uint8_t* sMx = sSc + ((iw * ih + 15) & ~15);
-  uint16_t* sList = reinterpret_cast<uint16_t*>(sMx + ((iw * ih + 15) & ~15));   // pixels that pass the quick test
+  uint8_t* sSc = smem + ((rh * rwPad + 15) & ~15);   // score (0 below minTh)
+  uint8_t* sMx = sSc + planeBytes;                   // NMS survivors
+  uint16_t* sList = reinterpret_cast<uint16_t*>(sMx + planeBytes);   // pixels that pass the quick test (y << 8 | x)
   {
     const uint8_t* srcA = E.pyr + L.offset + (size_t)iniY * L.pitch + (iniX - ax);   // 4-byte aligned
     const int wpr = (ax + rw + 3) >> 2;                                               // words per row
@@ -251,71 +256,103 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const unsigned mWpr = 0xFFFFFFFFu / (unsigned)wpr + 1u;
     for (int i = tid; i < rh * wpr; i += FAST_THREADS) {
       const int y = (int)__umulhi((unsigned)i, mWpr), wx = i - y * wpr;
-      sW[y * (rwPad >> 2) + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
+      sW[y * S + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
     }
+    uint32_t* z = reinterpret_cast<uint32_t*>(sSc);
+    for (int i = tid; i < planeBytes / 4; i += FAST_THREADS) z[i] = 0u;
   }
   if (tid == 0) { sAny = 0; sPass = 0; }
   __syncthreads();
   const int total = iw * ih;
-  // pass 1, every pixel: quick reject at minTh (every 9-arc holds one pixel of each opposite ring pair); the
-  // survivors are compacted into a list so that the expensive score runs on dense warps
-  for (int i0 = 0; i0 < total; i0 += FAST_THREADS) {
-    const int i = i0 + tid;
-    bool pass = false;
-    if (i < total) {
-      const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
-      const uint8_t* c = &sImg[(y + 3) * rwPad + ax + (x + 3)];
-      const int v = c[0], lo = v - p.minTh, hi = v + p.minTh;
-      const int t0 = c[3 * rwPad], t8 = c[-3 * rwPad], t4 = c[3], t12 = c[-3];
-      const bool dark = (t0 < lo || t8 < lo) && (t4 < lo || t12 < lo);
-      const bool bright = (t0 > hi || t8 > hi) && (t4 > hi || t12 > hi);
-      pass = dark || bright;
-      sSc[i] = 0;
-    }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-    if (m) {
-      int base = 0;
-      if ((tid & 31) == 0) base = atomicAdd(&sPass, __popc(m));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (pass) sList[base + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint16_t)i;
+  // pass 1, four pixels per thread (one staged word): quick reject at minTh -- every 9-arc holds one pixel of each
+  // opposite ring pair, so a corner needs (p0 | p8) & (p4 | p12) darker, or brighter, than the centre by more than
+  // minTh. Byte-SIMD compares; saturating +-minTh gives the same predicate as the integer test. Survivors are
+  // compacted into a list so that the expensive score runs on dense warps.
+  {
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(sImg);
+    const int k0 = (ax + 3) >> 2, k1 = (ax + 3 + iw - 1) >> 2, nW = k1 - k0 + 1;
+    const unsigned mNW = 0xFFFFFFFFu / (unsigned)nW + 1u;
+    const unsigned th4 = (unsigned)p.minTh * 0x01010101u;
+    const int items = ih * nW;
+    for (int i0 = 0; i0 < items; i0 += FAST_THREADS) {
+      const int i = i0 + tid;
+      unsigned pass = 0;
+      int y = 0, xb = 0;
+      if (i < items) {
+        y = (int)__umulhi((unsigned)i, mNW);
+        const int k = k0 + (i - y * nW);
+        const uint32_t* r = W + (y + 3) * S + k;
+        const unsigned c = r[0], prev = r[k > 0 ? -1 : 0], next = r[k + 1 < S ? 1 : 0];
+        const unsigned t0 = r[3 * S], t8 = r[-3 * S];
+        const unsigned t12 = __funnelshift_r(prev, c, 8), t4 = __funnelshift_r(c, next, 24);   // columns -3 / +3
+        const unsigned lo = __vsubus4(c, th4), hi = __vaddus4(c, th4);
+        const unsigned dark = (__vcmpltu4(t0, lo) | __vcmpltu4(t8, lo)) & (__vcmpltu4(t4, lo) | __vcmpltu4(t12, lo));
+        const unsigned bright = (__vcmpgtu4(t0, hi) | __vcmpgtu4(t8, hi)) & (__vcmpgtu4(t4, hi) | __vcmpgtu4(t12, hi));
+        pass = dark | bright;
+        xb = 4 * k - ax - 3;                       // interior x of byte 0 of this word
+        // bytes outside the interior columns do not count
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (xb + j < 0 || xb + j >= iw) pass &= ~(0xFFu << (8 * j));
+      }
+      const int cnt = __popc(pass) >> 3;
+      // warp-aggregated append: exclusive prefix of cnt over the lanes
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += n;
+      }
+      const int wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (wtot) {
+        int base = 0;
+        if ((tid & 31) == 31) base = atomicAdd(&sPass, wtot);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        int w = base + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (pass & (0xFFu << (8 * j))) sList[w++] = (uint16_t)((y << 8) | (xb + j));
+      }
     }
   }
   __syncthreads();
   // pass 2, survivors only: the exact score (order of the list is irrelevant)
   const int nPass = sPass;
   for (int j = tid; j < nPass; j += FAST_THREADS) {
-    const int i = sList[j];
-    const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
-    int s = ft_fast_score(&sImg[(y + 3) * rwPad + ax + (x + 3)], rwPad);
-    if (s < p.minTh) s = 0;
-    sSc[i] = (uint8_t)s;
+    const int e = sList[j];
+    const int y = e >> 8, x = e & 0xFF;
+    int sc = ft_fast_score(&sImg[(y + 3) * rwPad + ax + (x + 3)], rwPad);
+    if (sc < p.minTh) sc = 0;
+    sSc[(y + 1) * sS + x + 4] = (uint8_t)sc;
   }
   __syncthreads();
-  // 3x3 strict-maximum NMS inside the interior
+  // 3x3 strict-maximum NMS inside the interior, four pixels per thread; the zero border stands for "no corner"
   bool any20 = false;
-  for (int i = tid; i < total; i += FAST_THREADS) {
-    const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
-    const int s = sSc[i];
-    int keep = 0;
-    if (s) {
-      int m = 0;
-      const bool up = y > 0, dn = y < ih - 1, lf = x > 0, rt = x < iw - 1;
-      if (lf) m = max(m, (int)sSc[i - 1]);
-      if (rt) m = max(m, (int)sSc[i + 1]);
-      if (up) {
-        m = max(m, (int)sSc[i - iw]);
-        if (lf) m = max(m, (int)sSc[i - iw - 1]);
-        if (rt) m = max(m, (int)sSc[i - iw + 1]);
+  {
+    const uint32_t* P = reinterpret_cast<const uint32_t*>(sSc);
+    uint32_t* Q = reinterpret_cast<uint32_t*>(sMx);
+    const int sW4 = sS >> 2;
+    const int nW = ((3 + iw) >> 2);               // words 1 .. nW hold the interior columns 4 .. 3 + iw
+    const unsigned mNW = 0xFFFFFFFFu / (unsigned)nW + 1u;
+    const unsigned ini4 = (unsigned)p.iniTh * 0x01010101u;
+    const int items = ih * nW;
+    for (int i = tid; i < items; i += FAST_THREADS) {
+      const int y = (int)__umulhi((unsigned)i, mNW);
+      const int k = 1 + (i - y * nW);
+      const uint32_t* r = P + (y + 1) * sW4 + k;
+      const unsigned c = r[0];
+      unsigned keep = 0;
+      if (c) {
+        unsigned m = __vmaxu4(__funnelshift_r(r[-1], c, 24), __funnelshift_r(c, r[1], 8));
+        const uint32_t* u = r - sW4;
+        const uint32_t* d = r + sW4;
+        const unsigned uc = u[0], dc = d[0];
+        m = __vmaxu4(m, __vmaxu4(uc, dc));
+        m = __vmaxu4(m, __vmaxu4(__funnelshift_r(u[-1], uc, 24), __funnelshift_r(uc, u[1], 8)));
+        m = __vmaxu4(m, __vmaxu4(__funnelshift_r(d[-1], dc, 24), __funnelshift_r(dc, d[1], 8)));
+        keep = c & __vcmpgtu4(c, m);
+        any20 |= __vcmpgeu4(keep, ini4) != 0;
       }
-      if (dn) {
-        m = max(m, (int)sSc[i + iw]);
-        if (lf) m = max(m, (int)sSc[i + iw - 1]);
-        if (rt) m = max(m, (int)sSc[i + iw + 1]);
-      }
-      if (s > m) keep = s;
+      Q[(y + 1) * sW4 + k] = keep;
     }
-    sMx[i] = (uint8_t)keep;
-    any20 |= keep >= p.iniTh;
   }
   if (any20) sAny = 1;
   __syncthreads();
@@ -324,7 +361,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   const int seg = (total + FAST_THREADS - 1) / FAST_THREADS;
   const int beg = min(tid * seg, total), end = min(beg + seg, total);
   int cnt = 0;
-  for (int i = beg; i < end; i++) cnt += sMx[i] >= th && sMx[i] > 0;
+  {
+    int y = (int)__umulhi((unsigned)beg, mIw), x = beg - y * iw;
+    for (int i = beg; i < end; i++) {
+      const int v = sMx[(y + 1) * sS + x + 4];
+      cnt += v >= th && v > 0;
+      if (++x == iw) { x = 0; y++; }
+    }
+  }
   // block exclusive scan of cnt
   int incl = cnt;
 #pragma unroll
@@ -340,12 +384,15 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   for (int w = 0; w < FAST_THREADS / 32; w++) totalKp += sWarp[w];
   int pos = base + incl - cnt;
   uint32_t* out = E.cellKp + L.cellKpBase + (size_t)(cell - L.cellBase) * L.cellCap;
-  for (int i = beg; i < end; i++) {
-    const int s = sMx[i];
-    if (s >= th && s > 0) {
-      const int y = (int)__umulhi((unsigned)i, mIw), x = i - y * iw;
-      if (pos < L.cellCap) out[pos] = ft_pack_xys(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, s);
-      pos++;
+  if (cnt) {
+    int y = (int)__umulhi((unsigned)beg, mIw), x = beg - y * iw;
+    for (int i = beg; i < end; i++) {
+      const int v = sMx[(y + 1) * sS + x + 4];
+      if (v >= th && v > 0) {
+        if (pos < L.cellCap) out[pos] = ft_pack_xys(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, v);
+        pos++;
+      }
+      if (++x == iw) { x = 0; y++; }
     }
   }
   if (tid == 0) {
@@ -1023,7 +1070,9 @@ size_t ft_fast_smem_bytes(const FtParams& p) {
     const FtLevel& L = p.lv[l];
     const int rw = L.wCell + 6, rh = L.hCell + 6;
     const int rwPad = (rw + 6) & ~3;
-    size_t s = ((rh * rwPad + 15) & ~15) + 4 * ((L.wCell * L.hCell + 15) & ~15);
+    const int sS = (((L.wCell + 3) >> 2) + 3) * 4;
+    const size_t plane = ((size_t)(L.hCell + 2) * sS + 15) & ~(size_t)15;
+    size_t s = ((rh * rwPad + 15) & ~15) + 2 * plane + 2 * ((L.wCell * L.hCell + 15) & ~15);
     if (s > mx) mx = s;
   }
   return mx;
