@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         // order). Lanes first fetch the per-column ranges, then split the flattened element list evenly.
         const int ncol = cx1 - cx0 + 1;
         int T = 0;
+        __syncwarp();   // the previous walk (which may have left through `continue`) has finished reading sCol / sPre
         for (int j0 = 0; j0 < ncol; j0 += 32) {
           const int j = j0 + lane;
           int cs = 0, ce = 0;
