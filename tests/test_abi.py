@@ -99,3 +99,21 @@ def test_descriptor_sincos_matches_host_libm(lib):
     s0 = np.zeros(1, np.float32); c0 = np.zeros(1, np.float32); a1 = np.array([a0], np.float32)
     lib.ft_debug_sincosf(1, a1.ctypes.data, s0.ctypes.data, c0.ctypes.data)
     assert s0[0] == np.float32(libm.sinf(float(a0)))
+
+
+def test_host_mirror_and_driver_compile_and_link(lib, tmp_path):
+    """The C++ host side above the C ABI (fasttrack_b200/host/ft_shim.h via tests/native/shim_demo.cpp, and the sequence
+    driver) compiles with g++ and links against the library here, without a GPU."""
+    import subprocess
+    import fasttrack_b200 as ft
+    libdir = os.path.dirname(ft.library_path())
+    exe = str(tmp_path / "shim_demo")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-Wall", os.path.join(ROOT, "tests", "native", "shim_demo.cpp"),
+                           "-o", exe, "-L" + libdir, "-lfasttrack_b200", "-Wl,-rpath," + libdir])
+    assert os.path.exists(os.path.join(libdir, "libft_sequence_driver.so"))
+    drv = ctypes.CDLL(os.path.join(libdir, "libft_sequence_driver.so"))
+    for name in ("ftd_run_serial", "ftd_run_pipelined"):
+        getattr(drv, name)
+    # without a GPU the demo must fail loudly through the mirror's exception path, not crash or fall back
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode != 0
