@@ -45,3 +45,17 @@ def both():
         c.search_resident(3.0); done[i].record(s)
 for name, fn in (("extract+stereo only", extract_only), ("search chain only", search_only), ("both (bench leg)", both)):
     fn(); print("%-22s %.1f us/frame (depth %d)" % (name, timed(fn), D))
+
+# how long do the two search kernels take while later frames are being extracted? (events inside the pipelined leg)
+def both_timed():
+    done = [torch.cuda.Event() for _ in range(N)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(N)]
+    for i in range(N):
+        c, s = ctxs[i % D], streams[i % D]
+        c.frame_enqueue_device(dL[i % 16].data_ptr(), E["width"], dR[i % 16].data_ptr(), E["width"])
+        if i: s.wait_event(done[i - 1])
+        ev[i][0].record(s); c.search_resident(3.0); ev[i][1].record(s); done[i].record(s)
+    torch.cuda.synchronize()
+    t = np.array([a.elapsed_time(b) for a, b in ev[20:]]) * 1e3
+    print("search (gather + resolve) under load: mean %.1f us, p50 %.1f, p95 %.1f" % (t.mean(), np.percentile(t, 50), np.percentile(t, 95)))
+both_timed()
