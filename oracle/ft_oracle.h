@@ -10,8 +10,10 @@
 // (SURVEY.md section 4), and it cannot be compiled here (needs OpenCV C++, Eigen,
 // Sophus, Pangolin). The OpenCV primitives it calls are therefore pinned
 // bit-exactly against the in-container cv2 4.13.0 (tests/test_oracle_cv2.py and
-// the fixtures under tests/golden/ made by tools/make_cv2_golden.py); the
-// operator-level logic is a line-by-line restatement cited per function.
+// the fixtures under tests/golden/ made by tools/make_cv2_golden.py and
+// tools/make_cv2_golden_geometry.py); the operator-level logic above those primitives
+// is a line-by-line restatement cited per function and is, strictly, PARITY UNPINNED:
+// no output of the reference itself exists to check it against.
 #pragma once
 #include <cstdint>
 #include <vector>
