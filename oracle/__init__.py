@@ -72,6 +72,8 @@ def lib():
     L.fto_remap.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, u8p]
     L.fto_undistort_points.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_libm_sincosf.argtypes = [C.c_int, f32p, f32p, f32p]
+    L.fto_ic_angles.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, f32p, C.c_int, f32p]
+    L.fto_orb_descriptors.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, u8p]
     L.fto_stereo_from_rgbd.argtypes = [f32p, f32p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, f32p, f32p]
     L.fto_image_bounds.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, f32p]
     L.fto_fast.restype = C.c_int
@@ -167,6 +169,13 @@ class Extractor:
         n = self.L.fto_level_keys(self.h, level, cap, kps, desc)
         return kps[:n].copy(), desc[:n].copy()
 
+    def ic_angles(self, img, xy):
+        """IC_Angle (ORBextractor.cc:39-66) of the given integer keypoint positions on `img`"""
+        img = np.ascontiguousarray(img, np.uint8); xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros(len(xy), np.float32)
+        self.L.fto_ic_angles(self.h, img, img.shape[1], img.shape[0], xy, len(xy), out)
+        return out
+
     def desc_borderline(self):
         return int(self.L.fto_desc_borderline(self.h))
 
@@ -199,6 +208,15 @@ def remap(src, mapx, mapy):
     dst = np.zeros((dh, dw), np.uint8)
     lib().fto_remap(src, src.shape[1], src.shape[0], mapx, mapy, dw, dh, dst)
     return dst
+
+
+def orb_descriptors(blurred, xy, angles):
+    """computeOrbDescriptor (ORBextractor.cc:68-108) of the given keypoints on an already blurred image -> [n,32]"""
+    blurred = np.ascontiguousarray(blurred, np.uint8); xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    angles = np.ascontiguousarray(angles, np.float32)
+    out = np.zeros((len(xy), 32), np.uint8)
+    lib().fto_orb_descriptors(blurred, blurred.shape[1], blurred.shape[0], xy, angles, len(xy), out)
+    return out
 
 
 def libm_sincosf(angles):

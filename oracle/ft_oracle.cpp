@@ -1221,4 +1221,19 @@ void stereo_from_rgbd(const float* keysXY, const float* keysUnX, int n, const fl
   }
 }
 
+// Test entry points: orientation and descriptor of given keypoints on given images, so that IC_Angle and
+// computeOrbDescriptor can be pinned against OpenCV's own ORB (cv::ORB::detect / compute use the same two routines;
+// ORB-SLAM's copies derive from them).
+void ic_angles(const Extractor& ex, const uint8_t* img, int w, int h, const float* xy, int n, float* out) {
+  Img im; im.w = w; im.h = h; im.d.assign(img, img + (size_t)w * h);
+  for (int i = 0; i < n; i++) out[i] = ic_angle(im, xy[2 * i], xy[2 * i + 1], ex.umax);
+}
+void orb_descriptors(const uint8_t* blurred, int w, int h, const float* xy, const float* angle, int n, uint8_t* out) {
+  Img im; im.w = w; im.h = h; im.d.assign(blurred, blurred + (size_t)w * h);
+  for (int i = 0; i < n; i++) {
+    KeyPoint kp{xy[2 * i], xy[2 * i + 1], 31.f, angle[i], 0.f, 0};
+    orb_descriptor(kp, im, out + (size_t)32 * i, nullptr);
+  }
+}
+
 }  // namespace fto

@@ -11,7 +11,8 @@
 // Sophus, Pangolin). The OpenCV primitives it calls are therefore pinned
 // bit-exactly against the in-container cv2 4.13.0 (tests/test_oracle_cv2.py and
 // the fixtures under tests/golden/ made by tools/make_cv2_golden.py and
-// tools/make_cv2_golden_geometry.py); the operator-level logic above those primitives
+// tools/make_cv2_golden_geometry.py); IC_Angle and computeOrbDescriptor are pinned against
+// cv::ORB's own orientation / descriptors (tools/make_cv2_golden_orb.py); the remaining operator-level logic
 // is a line-by-line restatement cited per function and is, strictly, PARITY UNPINNED:
 // no output of the reference itself exists to check it against.
 #pragma once
@@ -82,6 +83,10 @@ class Extractor {
   std::vector<Candidate> distributeOctTree(const std::vector<Candidate>& in, int minX, int maxX,
                                            int minY, int maxY, int N) const;
 };
+
+// test entry points: IC_Angle (ORBextractor.cc:39-66) / computeOrbDescriptor (:68-108) of given keypoints
+void ic_angles(const Extractor& ex, const uint8_t* img, int w, int h, const float* xy, int n, float* out);
+void orb_descriptors(const uint8_t* blurred, int w, int h, const float* xy, const float* angle, int n, uint8_t* out);
 
 // ---- pinhole stereo (Frame.cc:835-1005) ----
 struct StereoResult {

@@ -105,6 +105,12 @@ void fto_libm_sincosf(int n, const float* a, float* s, float* c) {
 void fto_stereo_from_rgbd(const float* xy, const float* unx, int n, const float* depth, int w, int h, float mbf, float* ur, float* dp) {
   stereo_from_rgbd(xy, unx, n, depth, w, h, mbf, ur, dp);
 }
+void fto_ic_angles(void* ex, const uint8_t* img, int w, int h, const float* xy, int n, float* out) {
+  ic_angles(*(Extractor*)ex, img, w, h, xy, n, out);
+}
+void fto_orb_descriptors(const uint8_t* blurred, int w, int h, const float* xy, const float* angle, int n, uint8_t* out) {
+  orb_descriptors(blurred, w, h, xy, angle, n, out);
+}
 void fto_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out) {
   undistort_points(xy, n, K, dist, ndist, out);
 }

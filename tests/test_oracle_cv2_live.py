@@ -105,3 +105,21 @@ def test_input_resize_shapes_live():
                                ((1440, 2256), (480, 752)), ((1024, 1024), (512, 512))]:
         img = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
         assert np.array_equal(oracle.resize(img, dw, dh), cv2.resize(img, (dw, dh)))
+
+
+def test_orientation_and_descriptor_against_opencv_orb_live():
+    """oracle IC_Angle / computeOrbDescriptor vs cv2.ORB (nlevels=1) on two images; the descriptor is sampled from the
+    blur cv::ORB applies internally (classic sepFilter2D path on a sub-matrix), reproduced here with sepFilter2D"""
+    ex = oracle.Extractor(1200, 1.2, 8)
+    kx = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    for seed, shape in ((5, (480, 752)), (6, (300, 401))):
+        img = synth.texture(shape[0], shape[1], seed)
+        orb = cv2.ORB_create(nfeatures=3000, scaleFactor=1.2, nlevels=1, edgeThreshold=19, firstLevel=0, WTA_K=2, patchSize=31,
+                             fastThreshold=20)
+        kps = orb.detect(img)
+        xy = np.array([p.pt for p in kps], np.float32); ang = np.array([p.angle for p in kps], np.float32)
+        assert len(kps) > 500 and np.array_equal(xy, np.rint(xy))
+        assert np.array_equal(ex.ic_angles(img, xy).view(np.uint32), ang.view(np.uint32))
+        kps2, desc = orb.compute(img, kps)
+        blurred = cv2.sepFilter2D(img, -1, kx, kx, borderType=cv2.BORDER_REFLECT_101)
+        assert np.array_equal(oracle.orb_descriptors(blurred, xy, ang), desc)

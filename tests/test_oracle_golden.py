@@ -94,3 +94,15 @@ def test_stereo_from_rgbd_restatement():
     assert np.array_equal(ur, exp)
     ur0, dp0 = oracle.stereo_from_rgbd(xy, unx, None, mbf)
     assert np.all(ur0 == -1) and np.all(dp0 == -1)
+
+
+def test_orientation_and_descriptor_match_opencv_orb():
+    """IC_Angle and computeOrbDescriptor (ORBextractor.cc:39-108) against OpenCV's own ORB (ICAngles / computeOrbDescriptors,
+    from which ORB-SLAM copied them): angles bit-exact on the raw image, descriptors bit-exact on the blurred image that
+    cv::ORB sampled (tools/make_cv2_golden_orb.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_orb.npz"))
+    ex = oracle.Extractor(1200, 1.2, 8)
+    assert len(g["xy"]) > 400
+    assert np.array_equal(ex.ic_angles(g["img"], g["xy"]).view(np.uint32), g["angle"].view(np.uint32))
+    assert np.array_equal(oracle.orb_descriptors(g["blurred"], g["xy"], g["angle"]), g["desc"])
