@@ -219,6 +219,26 @@ def orb_descriptors(blurred, xy, angles):
     return out
 
 
+def cam_project(cam_type, params8, P):
+    """GeometricCamera::project (Pinhole.cpp:43-49 / KannalaBrandt8.cpp:67-84) of [n,3] points -> [n,2]"""
+    p8 = np.ascontiguousarray(params8, np.float32); P = np.ascontiguousarray(P, np.float32).reshape(-1, 3)
+    out = np.zeros((len(P), 2), np.float32)
+    L = lib()
+    for i in range(len(P)):
+        L.fto_cam_project(int(cam_type), p8, P[i], out[i])
+    return out
+
+
+def kb8_unproject(params8, uv):
+    """KannalaBrandt8::unproject (KannalaBrandt8.cpp:116-143) of [n,2] pixels -> [n,3] rays (z = 1)"""
+    p8 = np.ascontiguousarray(params8, np.float32); uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    out = np.zeros((len(uv), 3), np.float32)
+    L = lib()
+    for i in range(len(uv)):
+        L.fto_kb8_unproject(p8, float(uv[i, 0]), float(uv[i, 1]), out[i])
+    return out
+
+
 def libm_sincosf(angles):
     """host libm sinf / cosf of a float32 array (the calls of computeOrbDescriptor, ORBextractor.cc:74)"""
     a = np.ascontiguousarray(angles, np.float32)

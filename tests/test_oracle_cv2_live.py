@@ -123,3 +123,24 @@ def test_orientation_and_descriptor_against_opencv_orb_live():
         kps2, desc = orb.compute(img, kps)
         blurred = cv2.sepFilter2D(img, -1, kx, kx, borderType=cv2.BORDER_REFLECT_101)
         assert np.array_equal(oracle.orb_descriptors(blurred, xy, ang), desc)
+
+
+def test_kannala_brandt_model_against_cv2_fisheye():
+    """KannalaBrandt8::project / unproject (KannalaBrandt8.cpp:67-84, 116-143) implement the equidistant model of
+    cv2.fisheye (theta_d = theta (1 + k1 theta^2 + ... + k4 theta^8)); the reference evaluates it in float with atan2 / cos /
+    sin, cv2 in double, so this is a tolerance check of the model and its Newton inverse, not a bit-exact pin."""
+    cam = np.array(synth.TUMVI["cam1"], np.float32)
+    K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float64)
+    D = cam[4:8].astype(np.float64)
+    rng = np.random.default_rng(4)
+    P = np.stack([rng.uniform(-3, 3, 4000), rng.uniform(-3, 3, 4000), rng.uniform(0.5, 6, 4000)], 1).astype(np.float32)
+    uv = oracle.cam_project(1, cam, P)
+    ref, _ = cv2.fisheye.projectPoints(P.astype(np.float64).reshape(1, -1, 3), np.zeros(3), np.zeros(3), K, D)
+    assert np.abs(uv - ref.reshape(-1, 2)).max() < 2e-3            # pixels (float32 evaluation)
+    inside = (uv[:, 0] > 0) & (uv[:, 0] < 512) & (uv[:, 1] > 0) & (uv[:, 1] < 512)
+    ray = oracle.kb8_unproject(cam, uv[inside])
+    und = cv2.fisheye.undistortPoints(uv[inside].astype(np.float64).reshape(1, -1, 2), K, D).reshape(-1, 2)
+    assert inside.sum() > 500
+    assert np.allclose(ray[:, :2], und, rtol=2e-4, atol=2e-4) and np.all(ray[:, 2] == 1)
+    # and the inverse really inverts: unproject(project(P)) is P / z
+    assert np.allclose(ray[:, :2], (P[inside, :2] / P[inside, 2:3]), rtol=2e-4, atol=2e-4)
