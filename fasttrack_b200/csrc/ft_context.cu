@@ -80,6 +80,7 @@ struct ft_context {
   long long pyrBytes = 0;
   // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
   int rectify = 0, rawW = 0, rawH = 0;
+  size_t rawCap = 0;   // pixels the raw-input buffers hold
   int inResize = 0;   // cv::resize of the raw input into level 0 (Settings::needToResize)
   int grouped = 0;    // launch topology: 0 = one graph branch per pyramid level (lowest latency), 1 = levels 1.. grouped (fewest launches)
   // monocular / RGB-D sensors: only eye 0 is extracted; the depth image replaces stereo matching
@@ -120,6 +121,13 @@ static cudaError_t dalloc(ft_context* c, T** p, size_t n) {
   cudaError_t e = cudaMalloc(&v, n * sizeof(T) + 256);
   if (e == cudaSuccess) { c->allocs.push_back(v); *p = (T*)v; cudaMemset(v, 0, n * sizeof(T) + 256); }
   return e;
+}
+
+static void dfree(ft_context* c, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < c->allocs.size(); i++)
+    if (c->allocs[i] == p) { c->allocs.erase(c->allocs.begin() + i); break; }
+  cudaFree(p);
 }
 
 static ft_status build_params(ft_context* c) {
@@ -769,6 +777,22 @@ extern "C" ft_status ft_frame_enqueue_device(ft_context* c, const uint8_t* dL, i
   return run_frame(c);
 }
 
+// Device + pinned staging buffers for raw (pre-rectification / pre-resize) input images; grown on demand, the
+// previous buffers are released (the caller has synchronised the stream).
+static ft_status ensure_raw_buffers(ft_context* c, int raw_width, int raw_height) {
+  const size_t need = (size_t)raw_width * raw_height;
+  if (c->dRaw[0] && c->rawCap >= need) return FT_OK;
+  const size_t hostNeed = std::max(need, (size_t)c->cfg.width * c->cfg.height);
+  for (int e = 0; e < 2; e++) {
+    dfree(c, c->dRaw[e]); c->dRaw[e] = nullptr;
+    CK(dalloc(c, &c->dRaw[e], need));
+    if (c->hIn[e]) { cudaFreeHost(c->hIn[e]); c->hIn[e] = nullptr; }
+    CK(cudaMallocHost((void**)&c->hIn[e], hostNeed));
+  }
+  c->rawCap = need;
+  return FT_OK;
+}
+
 // Stereo rectification in front of the extractor (reference System::TrackStereo, src/System.cc:273-281:
 // cv::remap(im, M1, M2, INTER_LINEAR) with the CV_32F maps of Settings.cc:506-509). Maps are width x height floats
 // (x map, y map) per eye; raw images are raw_width x raw_height. Passing NULL maps switches rectification off.
@@ -796,13 +820,7 @@ extern "C" ft_status ft_set_rectification(ft_context* c, int raw_width, int raw_
     }
   if (!c->dRemapTab) CK(dalloc(c, &c->dRemapTab, tab.size()));
   CK(cudaMemcpy(c->dRemapTab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  if (c->rawW * c->rawH < raw_width * raw_height || !c->dRaw[0]) {
-    for (int e = 0; e < 2; e++) {
-      CK(dalloc(c, &c->dRaw[e], (size_t)raw_width * raw_height));
-      if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
-      CK(cudaMallocHost((void**)&c->hIn[e], std::max((size_t)raw_width * raw_height, (size_t)w * h)));
-    }
-  }
+  { ft_status rs = ensure_raw_buffers(c, raw_width, raw_height); if (rs != FT_OK) return rs; }
   c->rawW = raw_width; c->rawH = raw_height; c->rectify = 1;
   return FT_OK;
 }
@@ -888,13 +906,7 @@ extern "C" ft_status ft_set_input_resize(ft_context* c, int raw_width, int raw_h
   resize_tables(raw_width, raw_height, w, h, xt.data(), yt.data());
   CK(cudaMemcpy(const_cast<int2*>(c->B.xTab) + c->P.lv[0].xTab, xt.data(), sizeof(int2) * w, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(const_cast<int2*>(c->B.yTab) + c->P.lv[0].yTab, yt.data(), sizeof(int2) * h, cudaMemcpyHostToDevice));
-  if (c->rawW * c->rawH < raw_width * raw_height || !c->dRaw[0]) {
-    for (int e = 0; e < 2; e++) {
-      CK(dalloc(c, &c->dRaw[e], (size_t)raw_width * raw_height));
-      if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
-      CK(cudaMallocHost((void**)&c->hIn[e], std::max((size_t)raw_width * raw_height, (size_t)w * h)));
-    }
-  }
+  { ft_status rs = ensure_raw_buffers(c, raw_width, raw_height); if (rs != FT_OK) return rs; }
   c->rawW = raw_width; c->rawH = raw_height; c->inResize = 1;
   return FT_OK;
 }
