@@ -261,3 +261,55 @@ def last_frame_points(keys, desc, n, seed, Rcw, tcw, fx, fy, cx, cy, nlevels=8, 
     flags[rng.random(n) < 0.05] = 0
     flags[rng.random(n) < 0.05] |= 1
     return dict(pos=np.ascontiguousarray(P, np.float32), desc=np.ascontiguousarray(d), octave=octave, angle=angle, flags=flags)
+
+
+# ---- synthetic DBoW2 vocabulary (the real ORBvoc.txt is a 145 MB file that is not in the image) ----
+def make_vocabulary(k=10, L=4, seed=7, stop_fraction=0.02):
+    """A k-ary, depth-L vocabulary tree in DBoW2's text-file node order (depth first, as saveToTextFile writes a tree
+    built by HKmeansStep): returns (parent[n], is_leaf[n], desc[n,32], weight[n]) for nodes 1..n (node 0 = root).
+    A child's descriptor is its parent's with 96 >> level random bits flipped, so descents are decided by real
+    Hamming margins and ties occur; weights look like idf values, a few words are stopped (weight 0)."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight = [], [], [], []
+
+    def grow(pid, pdesc, level):
+        for _ in range(k):
+            d = pdesc.copy()
+            flips = rng.choice(256, size=max(96 >> (level - 1), 3), replace=False)
+            bits = np.unpackbits(d)
+            bits[flips] ^= 1
+            d = np.packbits(bits)
+            parent.append(pid); desc.append(d)
+            nid = len(parent)
+            if level == L:
+                leaf.append(1)
+                weight.append(0.0 if rng.random() < stop_fraction else float(rng.uniform(0.5, 9.0)))
+            else:
+                leaf.append(0); weight.append(0.0)
+                grow(nid, d, level + 1)
+
+    grow(0, rng.integers(0, 256, 32, dtype=np.uint8), 1)
+    return (np.asarray(parent, np.int32), np.asarray(leaf, np.uint8), np.asarray(desc, np.uint8).reshape(-1, 32),
+            np.asarray(weight, np.float64))
+
+
+def write_vocabulary_text(path, k, L, parent, is_leaf, desc, weight, scoring=0, weighting=0, trailing_newline=True):
+    """DBoW2 text format (TemplatedVocabulary::saveToTextFile): header `k L  scoring weighting`, then one line per node:
+    `parent isLeaf d0 .. d31 weight`."""
+    lines = ["%d %d  %d %d" % (k, L, scoring, weighting)]
+    for i in range(len(parent)):
+        lines.append("%d %d %s %r" % (parent[i], is_leaf[i], " ".join(str(int(b)) for b in desc[i]), float(weight[i])))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+        if trailing_newline:
+            f.write("\n")
+
+
+def vocabulary_like_descriptors(desc_nodes, n, seed=8, flips=20):
+    """n query descriptors: random leaves of the tree with `flips` random bit flips (so they descend non-trivially)"""
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, len(desc_nodes), n)
+    bits = np.unpackbits(desc_nodes[pick], axis=1)
+    for i in range(n):
+        bits[i, rng.choice(256, size=flips, replace=False)] ^= 1
+    return np.packbits(bits, axis=1)

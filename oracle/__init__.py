@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "_build", "libft_oracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("ft_oracle.cpp", "ft_oracle_capi.cpp", "ft_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ft_oracle.cpp", "ft_oracle_bow.cpp", "ft_oracle_capi.cpp", "ft_oracle.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "ft_orb_pattern.inc"))
     if not force and os.path.exists(_SO) and all(
         (not os.path.exists(s)) or os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs
@@ -426,3 +426,152 @@ def time_stereo_frame(exL, exR, imgL, imgR, mbf, mb, two_threads=True):
     ms = lib().fto_time_stereo_frame(exL.h, exR.h, imgL, imgR, w, h, w, mbf, mb, int(two_threads), C.byref(nl),
                                      C.byref(nr), C.byref(ns))
     return ms, nl.value, nr.value, ns.value
+
+
+# ---- bag of words (oracle/ft_oracle_bow.cpp) ----
+_REF_SO = os.path.join(_HERE, "_ref", "libft_ref_dbow2.so")
+_REFERENCE = os.environ.get("FT_REFERENCE_DIR", "/root/reference")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+def build_ref():
+    """oracle/_ref/libft_ref_dbow2.so: the REFERENCE's own DBoW2 sources compiled where they lie (make ref). Returns the
+    path, or None when neither the prebuilt library nor the reference tree is available (e.g. on the GPU box before
+    a snapshot carried the .so)."""
+    srcs = [os.path.join(_HERE, "ref_dbow2_capi.cpp"), os.path.join(_HERE, "ref_stubs", "opencv2", "core", "core.hpp")]
+    have_ref = os.path.isdir(os.path.join(_REFERENCE, "Thirdparty", "DBoW2", "DBoW2"))
+    fresh = os.path.exists(_REF_SO) and all(os.path.getmtime(_REF_SO) >= os.path.getmtime(x) for x in srcs)
+    if fresh or (os.path.exists(_REF_SO) and not have_ref):
+        return _REF_SO
+    if not have_ref:
+        return None
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + _REFERENCE])
+    return _REF_SO
+
+
+class Vocabulary:
+    """Oracle restatement of ORBVocabulary (DBoW2::TemplatedVocabulary<FORB>)."""
+
+    def __init__(self, handle):
+        self.h = handle
+        L = lib()
+        info = np.zeros(6, np.int32)
+        L.fto_voc_info(C.c_void_p(self.h), info)
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = [int(x) for x in info]
+
+    @classmethod
+    def load_text(cls, path):
+        L = _voc_lib()
+        h = L.fto_voc_load_text(path.encode())
+        if not h:
+            raise IOError("not a DBoW2 text vocabulary: %s" % path)
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, k, Ldepth, scoring, weighting, parent, is_leaf, desc, weight):
+        L = _voc_lib()
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); weight = np.ascontiguousarray(weight, np.float64)
+        return cls(L.fto_voc_from_arrays(k, Ldepth, scoring, weighting, len(parent), parent, is_leaf, desc, weight))
+
+    def arrays(self):
+        """(parent, is_leaf, desc, weight) without the root: the arguments of ft_vocabulary_create"""
+        n = self.n_nodes - 1
+        parent = np.zeros(n, np.int32); leaf = np.zeros(n, np.uint8); desc = np.zeros((n, 32), np.uint8)
+        weight = np.zeros(n, np.float64)
+        lib().fto_voc_arrays(C.c_void_p(self.h), parent, leaf, desc, weight)
+        return parent, leaf, desc, weight
+
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW: returns dict(node[n] (-1 = stopped word), word[n], bow_ids, bow_vals)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        node = np.zeros(max(n, 1), np.int32); word = np.zeros(max(n, 1), np.int32)
+        ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        m = lib().fto_voc_transform(C.c_void_p(self.h), desc if n else np.zeros((1, 32), np.uint8), n, levelsup, node, word,
+                                    ids, vals, max(n, 1))
+        return dict(node=node[:n], word=word[:n], bow_ids=ids[:m].copy(), bow_vals=vals[:m].copy())
+
+    def __del__(self):
+        try:
+            lib().fto_voc_free(C.c_void_p(self.h))
+        except Exception:
+            pass
+
+
+_voc_bound = False
+
+
+def _voc_lib():
+    global _voc_bound
+    L = lib()
+    if not _voc_bound:
+        L.fto_voc_load_text.restype = C.c_void_p
+        L.fto_voc_load_text.argtypes = [C.c_char_p]
+        L.fto_voc_from_arrays.restype = C.c_void_p
+        L.fto_voc_from_arrays.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p, f64p]
+        L.fto_voc_free.argtypes = [C.c_void_p]
+        L.fto_voc_info.argtypes = [C.c_void_p, i32p]
+        L.fto_voc_arrays.argtypes = [C.c_void_p, i32p, u8p, u8p, f64p]
+        L.fto_voc_transform.restype = C.c_int
+        L.fto_voc_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, i32p, i32p, u32p, f64p, C.c_int]
+        L.fto_search_by_bow.restype = C.c_int
+        L.fto_search_by_bow.argtypes = [C.c_int, u8p, f32p, i32p, u8p, C.c_int, u8p, f32p, i32p, C.c_int, C.c_float, C.c_int,
+                                        i32p]
+        _voc_bound = True
+    return L
+
+
+def search_by_bow(kf_desc, kf_angle, kf_node, kf_has_mp, f_desc, f_angle, f_node, f_nleft=-1, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches): returns (nmatches, match[nF])"""
+    L = _voc_lib()
+    c8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    kf_desc, f_desc, kf_has_mp = c8(kf_desc).reshape(-1, 32), c8(f_desc).reshape(-1, 32), c8(kf_has_mp)
+    kf_angle, f_angle = np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(f_angle, np.float32)
+    kf_node, f_node = np.ascontiguousarray(kf_node, np.int32), np.ascontiguousarray(f_node, np.int32)
+    match = np.full(max(len(f_desc), 1), -1, np.int32)
+    pad = lambda a, dt, shape: a if len(a) else np.zeros(shape, dt)
+    nm = L.fto_search_by_bow(len(kf_desc), pad(kf_desc, np.uint8, (1, 32)), pad(kf_angle, np.float32, 1),
+                             pad(kf_node, np.int32, 1), pad(kf_has_mp, np.uint8, 1), len(f_desc),
+                             pad(f_desc, np.uint8, (1, 32)), pad(f_angle, np.float32, 1), pad(f_node, np.int32, 1),
+                             int(f_nleft), float(nnratio), int(check_ori), match)
+    return nm, match[:len(f_desc)]
+
+
+class RefVocabulary:
+    """The reference's own DBoW2 (oracle/_ref/libft_ref_dbow2.so): used ONLY to pin the oracle's restatement."""
+
+    def __init__(self, path):
+        so = build_ref()
+        if so is None:
+            raise FileNotFoundError("oracle/_ref/libft_ref_dbow2.so is not built and the reference tree is absent")
+        R = C.CDLL(so)
+        R.ftref_voc_load_text.restype = C.c_void_p
+        R.ftref_voc_load_text.argtypes = [C.c_char_p]
+        R.ftref_voc_free.argtypes = [C.c_void_p]
+        R.ftref_voc_words.argtypes = [C.c_void_p]
+        R.ftref_voc_transform.restype = C.c_int
+        R.ftref_voc_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, i32p, u32p, f64p, C.c_int, i32p,
+                                          C.POINTER(C.c_int)]
+        self.R = R
+        self.h = R.ftref_voc_load_text(path.encode())
+        if not self.h:
+            raise IOError("reference loadFromTextFile failed: %s" % path)
+        self.n_words = R.ftref_voc_words(C.c_void_p(self.h))
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        node = np.zeros(max(n, 1), np.int32); order = np.zeros(max(n, 1), np.int32)
+        ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        nf = C.c_int()
+        m = self.R.ftref_voc_transform(C.c_void_p(self.h), desc if n else np.zeros((1, 32), np.uint8), n, levelsup, node, ids,
+                                       vals, max(n, 1), order, C.byref(nf))
+        return dict(node=node[:n], bow_ids=ids[:m].copy(), bow_vals=vals[:m].copy(), featvec_order=order[:nf.value].copy())
+
+    def __del__(self):
+        try:
+            self.R.ftref_voc_free(C.c_void_p(self.h))
+        except Exception:
+            pass

@@ -177,4 +177,40 @@ int search_by_projection_last_frame(FrameModel& F, const std::vector<LastFramePo
                                     bool checkOrientation, float mb, std::vector<int>& holder,
                                     std::vector<uint8_t>& holderObs, std::vector<int>& borderline);
 
+// ---- bag of words: Frame::ComputeBoW (Frame.cc:762-769) -> DBoW2 transform, ORBmatcher::SearchByBoW(KF, F) ----
+// The vocabulary is the reference's vendored DBoW2 (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h, FORB.cpp,
+// BowVector.cpp, FeatureVector.cpp). This restatement is PINNED against that code itself: oracle/Makefile compiles the
+// reference's DBoW2 sources where they lie into oracle/_ref/libft_ref_dbow2.so (tests/test_oracle_bow.py, fixtures in
+// tests/golden/dbow2_ref.npz made by tools/make_dbow2_golden.py).
+struct Vocabulary {
+  int k = 0, L = 0, scoring = 0, weighting = 0;   // ScoringType / WeightingType enums of BowVector.h:39-56
+  std::vector<int> parent;                        // [n] node 0 = root
+  std::vector<std::vector<int>> children;         // in order of appearance (m_nodes[pid].children.push_back)
+  std::vector<uint8_t> desc;                      // [n][32]
+  std::vector<double> weight;                     // [n]
+  std::vector<int> wordId;                        // [n] (0 for inner nodes, as Node() initialises it)
+  int nWords = 0;
+  // loadFromTextFile (TemplatedVocabulary.h:1338-1423), including the node its `while(!f.eof())` loop makes out of
+  // the empty line after a trailing newline: weight 0, parent and leaf flag = the previous line's (uninitialised
+  // locals in the reference), descriptor bytes unspecified in the reference (cv::Mat::create does not initialise) --
+  // zero here, as in the stand-in Mat the _ref build uses.
+  bool loadText(const char* path);
+  // the same tree from arrays: node i+1 has parent[i], is_leaf[i], desc[i], weight[i] (one text line each)
+  void fromArrays(int k_, int L_, int scoring_, int weighting_, int n, const int* parent_, const uint8_t* isLeaf,
+                  const uint8_t* desc_, const double* weight_);
+  // transform(feature, word_id, weight, nid, levelsup) (:1218-1260)
+  void transformOne(const uint8_t* f, int levelsup, unsigned& word, double& w, unsigned& nid) const;
+};
+// transform(features, BowVector, FeatureVector, levelsup) (:1127-1194). featNode[i] = node of feature i in the
+// FeatureVector, -1 when its word is stopped (weight 0); bow = (ids ascending, values) after normalisation.
+void voc_transform(const Vocabulary& v, const uint8_t* desc, int n, int levelsup, std::vector<int>& featNode,
+                   std::vector<int>& featWord, std::vector<unsigned>& bowIds, std::vector<double>& bowVals);
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:322-523). Indices are into the
+// concatenated (left, right) keypoint arrays; nodes are FeatureVector nodes per feature (-1 = not in the FeatureVector).
+// kfHasMp[i] = vpMapPointsKF[i] && !isBad(). match[iF] = KeyFrame feature whose MapPoint the frame keypoint received
+// (-1 none). Returns nmatches.
+int search_by_bow(int nKF, const uint8_t* kfDesc, const float* kfAngle, const int* kfNode, const uint8_t* kfHasMp,
+                  int nF, const uint8_t* fDesc, const float* fAngle, const int* fNode, int fNleft, float nnratio,
+                  bool checkOrientation, std::vector<int>& match);
+
 }  // namespace fto
