@@ -11,7 +11,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["Config", "Context", "FtError", "load_library", "library_path", "KEYPOINT_DTYPE"]
+__all__ = ["Config", "Context", "Vocabulary", "FtError", "load_library", "library_path", "KEYPOINT_DTYPE"]
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4")])
@@ -23,6 +23,8 @@ EXPORTS = [
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
     "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_sensor", "ft_extract_mono", "ft_depth_from_rgbd", "ft_debug_sincosf", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
+    "ft_vocabulary_load_text", "ft_vocabulary_create", "ft_vocabulary_destroy", "ft_vocabulary_info", "ft_vocabulary_transform",
+    "ft_compute_bow", "ft_bow_download", "ft_search_by_bow",
 ]
 
 STAGES = ["copy_level0", "resize", "blur", "fast_cells", "octree", "orient_desc", "grid", "stereo_match",
@@ -117,6 +119,14 @@ def load_library():
     L.ft_map_store_update.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     L.ft_search_store.argtypes = [vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]
     L.ft_frame_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ft_vocabulary_load_text.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.ft_vocabulary_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]
+    L.ft_vocabulary_destroy.argtypes = [vp]
+    L.ft_vocabulary_info.argtypes = [vp, ip, ip, ip, ip, ip, ip]
+    L.ft_vocabulary_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, ip]
+    L.ft_compute_bow.argtypes = [vp, vp, C.c_int]
+    L.ft_bow_download.argtypes = [vp, C.c_int, vp, vp, vp, vp, ip, ip]
+    L.ft_search_by_bow.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, ip]
     for name in EXPORTS:
         if name not in ("ft_last_error", "ft_version", "ft_context_stream"):
             getattr(L, name).restype = C.c_int
@@ -126,6 +136,64 @@ def load_library():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+class Vocabulary:
+    """ORBVocabulary on one device (ft_vocabulary_*): shared read-only by the contexts of that device."""
+
+    def __init__(self, handle):
+        self.L = load_library()
+        self.h = handle
+        v = [C.c_int() for _ in range(6)]
+        self._ck(self.L.ft_vocabulary_info(self.h, *[C.byref(x) for x in v]))
+        self.k, self.depth, self.scoring, self.weighting, self.n_nodes, self.n_words = [x.value for x in v]
+
+    def _ck(self, st):
+        if st != 0:
+            raise FtError(st, self.L.ft_last_error().decode())
+
+    @classmethod
+    def load_text(cls, path, device_id=0):
+        L = load_library()
+        h = C.c_void_p()
+        st = L.ft_vocabulary_load_text(device_id, str(path).encode(), C.byref(h))
+        if st != 0:
+            raise FtError(st, L.ft_last_error().decode())
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, k, depth, scoring, weighting, parent, is_leaf, desc, weight, device_id=0):
+        L = load_library()
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); weight = np.ascontiguousarray(weight, np.float64)
+        h = C.c_void_p()
+        st = L.ft_vocabulary_create(device_id, k, depth, scoring, weighting, len(parent), _ptr(parent), _ptr(is_leaf), _ptr(desc),
+                                    _ptr(weight), C.byref(h))
+        if st != 0:
+            raise FtError(st, L.ft_last_error().decode())
+        return cls(h)
+
+    def transform(self, desc, levelsup=4):
+        """ORBVocabulary::transform on host descriptors: dict(word[n], node[n] (-1 = stopped), bow_ids, bow_vals)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.zeros(max(n, 1), np.int32); node = np.zeros(max(n, 1), np.int32)
+        ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        nb = C.c_int()
+        self._ck(self.L.ft_vocabulary_transform(self.h, _ptr(desc) if n else None, n, levelsup, _ptr(word), _ptr(node), _ptr(ids),
+                                                _ptr(vals), max(n, 1), C.byref(nb)))
+        return dict(word=word[:n], node=node[:n], bow_ids=ids[:nb.value].copy(), bow_vals=vals[:nb.value].copy())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ft_vocabulary_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -425,6 +493,36 @@ class Context:
                                              _ptr(tlw), th, int(b_mono), int(check_ori), _ptr(holder), _ptr(holder_obs),
                                              _ptr(best), C.byref(nm)))
         return nm.value, holder, holder_obs, best[:n]
+
+    # ---- bag of words ----
+    def compute_bow(self, voc, levelsup=4):
+        """Frame::ComputeBoW on the device-resident descriptors (asynchronous)"""
+        self._ck(self.L.ft_compute_bow(self.h, voc.h, int(levelsup)))
+
+    def bow_download(self):
+        """mBowVec / mFeatVec of the frame: dict(word[N], node[N], bow_ids, bow_vals)"""
+        cap = 2 * self.cap
+        word = np.zeros(cap, np.int32); node = np.zeros(cap, np.int32)
+        ids = np.zeros(cap, np.uint32); vals = np.zeros(cap, np.float64)
+        nb, n = C.c_int(), C.c_int()
+        self._ck(self.L.ft_bow_download(self.h, cap, _ptr(word), _ptr(node), _ptr(ids), _ptr(vals), C.byref(nb), C.byref(n)))
+        return dict(word=word[:n.value].copy(), node=node[:n.value].copy(), bow_ids=ids[:nb.value].copy(),
+                    bow_vals=vals[:nb.value].copy())
+
+    def search_by_bow(self, kf_desc, kf_angle, kf_node, kf_has_mp, nnratio=0.7, check_ori=True):
+        """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches): returns (nmatches, match[N])"""
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32); kf_node = np.ascontiguousarray(kf_node, np.int32)
+        kf_has_mp = np.ascontiguousarray(kf_has_mp, np.uint8)
+        n = len(kf_desc)
+        match = np.full(2 * self.cap, -1, np.int32)
+        nm = C.c_int()
+        a = (lambda x: _ptr(x) if n else None)
+        self._ck(self.L.ft_search_by_bow(self.h, n, a(kf_desc), a(kf_angle), a(kf_node), a(kf_has_mp), float(nnratio),
+                                         int(check_ori), _ptr(match), C.byref(nm)))
+        c = self.counts()
+        N = c["n_left"] + (c["n_right"] if self.fisheye else 0)
+        return nm.value, match[:N].copy()
 
     def set_stage_timing(self, enable):
         self._ck(self.L.ft_set_stage_timing(self.h, int(enable)))

@@ -16,6 +16,7 @@
 
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
+void ft_internal_set_err(const char* msg) { g_err = msg ? msg : ""; }
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -98,6 +99,12 @@ struct ft_context {
   bool storeSearchedValid = false, updStagedValid = false;
   uint8_t *hUpd = nullptr, *dUpd = nullptr;
   int updCap = 0;
+  // bag of words (ft_bow.cu): BowVector / FeatureVector of the current frame, SearchByBoW scratch; allocated on first use
+  FtBowFrame W = {};
+  FtBowSearch WQ = {};
+  int bowCap = 0;
+  bool bowValid = false;
+  int nLaunchBow = 0;
   // per-stage CUDA-event timing (direct-launch mode only)
   int timing = 0;
   cudaEvent_t evA[FT_STAGE_COUNT] = {}, evB[FT_STAGE_COUNT] = {};
@@ -593,7 +600,7 @@ static ft_status run_extract(ft_context* c) {
     c->nLaunchExtract = enqueue_extract(c);
     CK(cudaGetLastError());
   }
-  c->extracted = true; c->stereoDone = false; c->countsValid = false;
+  c->extracted = true; c->stereoDone = false; c->countsValid = false; c->bowValid = false;
   return FT_OK;
 }
 
@@ -760,7 +767,7 @@ static ft_status run_frame(ft_context* c) {
       cudaGraphDestroy(g);
     }
     CK(cudaGraphLaunch(c->gFrame, c->stream));
-    c->extracted = true; c->stereoDone = true; c->countsValid = false;
+    c->extracted = true; c->stereoDone = true; c->countsValid = false; c->bowValid = false;
     return FT_OK;
   }
   ft_status st = run_extract(c);
@@ -840,7 +847,7 @@ extern "C" ft_status ft_set_sensor(ft_context* c, int sensor) {
   c->sensor = sensor;
   c->P.nEyes = sensor == FT_SENSOR_STEREO ? 2 : 1;
   CK(cudaMemsetAsync(c->B.eye[1].counts, 0, 2 * sizeof(int), c->stream));   // the right eye stays empty
-  c->extracted = false; c->stereoDone = false; c->countsValid = false;
+  c->extracted = false; c->stereoDone = false; c->countsValid = false; c->bowValid = false;
   return FT_OK;
 }
 
@@ -1394,6 +1401,82 @@ extern "C" ft_status ft_search_last_frame(ft_context* c, int n, const float* pos
   st = search_run(c, th, 0, 0.f, 1.0f, 1, direction, checkOrientation ? 1 : 0);
   if (st != FT_OK) return st;
   return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
+}
+
+// ---- bag of words: Frame::ComputeBoW / ORBmatcher::SearchByBoW on the device-resident frame (kernels in ft_bow.cu) ----
+static FtBowSource bow_source(ft_context* c) {
+  FtBowSource S = {};
+  S.desc0 = c->B.eye[0].desc; S.cnt0 = c->B.eye[0].counts; S.kps0 = c->B.eye[0].kps;
+  if (c->fisheye) { S.desc1 = c->B.eye[1].desc; S.cnt1 = c->B.eye[1].counts; S.kps1 = c->B.eye[1].kps; }
+  return S;
+}
+
+extern "C" ft_status ft_compute_bow(ft_context* c, ft_vocabulary* voc, int levelsup) {
+  if (!c || !voc || levelsup < 0) { set_err("ft_compute_bow: bad argument"); return FT_ERR_INVALID; }
+  if (!c->extracted) { set_err("ft_compute_bow: no extracted frame"); return FT_ERR_STATE; }
+  if (ft_vocabulary_device(voc) != c->cfg.device_id) { set_err("ft_compute_bow: vocabulary lives on another device"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  const int cap = c->fisheye ? 2 * c->P.maxKp : c->P.maxKp;
+  if (cap > 16384) { set_err("ft_compute_bow: more than 16384 features per frame"); return FT_ERR_CAPACITY; }
+  if (!c->bowCap) {
+    CK(ft_bow_frame_alloc(&c->W, cap, c->allocs));
+    c->bowCap = cap;
+  }
+  c->nLaunchBow = ft_launch_bow_transform(voc, bow_source(c), c->W, cap, levelsup, c->stream);
+  CK(cudaGetLastError());
+  c->bowValid = true;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_bow_download(ft_context* c, int cap, int* word_id, int* node_id, uint32_t* bow_ids, double* bow_vals,
+                                     int* n_bow, int* n) {
+  if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (!c->bowValid) { set_err("ft_bow_download: ft_compute_bow has not run on this frame"); return FT_ERR_STATE; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  int meta[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(meta, c->W.meta, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int N = meta[0], nd = meta[2];
+  if (n) *n = N;
+  if (n_bow) *n_bow = nd;
+  if (((word_id || node_id) && cap < N) || ((bow_ids || bow_vals) && cap < nd)) { set_err("ft_bow_download: capacity too small"); return FT_ERR_INVALID; }
+  if (word_id && N) CK(cudaMemcpyAsync(word_id, c->W.word, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+  if (node_id && N) CK(cudaMemcpyAsync(node_id, c->W.node, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+  if (bow_ids && nd) CK(cudaMemcpyAsync(bow_ids, c->W.bowIds, sizeof(uint32_t) * nd, cudaMemcpyDeviceToHost, c->stream));
+  if (bow_vals && nd) CK(cudaMemcpyAsync(bow_vals, c->W.bowVals, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FT_OK;
+}
+
+extern "C" ft_status ft_search_by_bow(ft_context* c, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const int* kf_node,
+                                      const uint8_t* kf_has_mp, float nnratio, int check_orientation, int* match, int* nmatches) {
+  if (!c || n_kf < 0 || !match || (n_kf > 0 && (!kf_desc || !kf_angle || !kf_node || !kf_has_mp))) {
+    set_err("ft_search_by_bow: null argument"); return FT_ERR_INVALID;
+  }
+  if (!c->extracted || !c->bowValid) { set_err("ft_search_by_bow: ft_compute_bow has not run on this frame"); return FT_ERR_STATE; }
+  if (n_kf > 16384) { set_err("ft_search_by_bow: more than 16384 KeyFrame features"); return FT_ERR_CAPACITY; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  ft_status st = fetch_counts(c);
+  if (st != FT_OK) return st;
+  const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
+  if (nmatches) *nmatches = 0;
+  for (int i = 0; i < N; i++) match[i] = -1;
+  if (n_kf == 0 || N == 0) return FT_OK;
+  int capKF = 1024;
+  while (capKF < n_kf) capKF <<= 1;
+  CK(ft_bow_search_alloc(&c->WQ, c->bowCap, capKF, c->allocs));
+  CK(cudaMemcpyAsync(c->WQ.kfDesc, kf_desc, (size_t)32 * n_kf, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->WQ.kfAngle, kf_angle, sizeof(float) * n_kf, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->WQ.kfNode, kf_node, sizeof(int) * n_kf, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->WQ.kfHasMp, kf_has_mp, (size_t)n_kf, cudaMemcpyHostToDevice, c->stream));
+  c->nLaunchBow = ft_launch_bow_search(bow_source(c), c->W, c->WQ, n_kf, c->bowCap, nnratio, check_orientation ? 1 : 0, c->stream);
+  CK(cudaGetLastError());
+  int nm = 0;
+  CK(cudaMemcpyAsync(match, c->WQ.match, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&nm, c->WQ.result, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (nmatches) *nmatches = nm;
+  return FT_OK;
 }
 
 extern "C" ft_status ft_set_stage_timing(ft_context* c, int enable) {

@@ -190,3 +190,49 @@ struct FtResolveArgs {
   int checkOri;    // mode 1: rotation-histogram consistency (ORBmatcher.cc:1884-1900, 2057-2079)
 };
 
+
+// ---- bag of words (ft_bow.cu): vocabulary tree in child order, per-frame BowVector / FeatureVector, SearchByBoW ----
+struct FtVocDevice {
+  int L, nNodes;             // depth levels; nodes including the root (node 0)
+  int scoring, weighting;    // DBoW2 ScoringType / WeightingType
+  const int* firstChild;     // [nNodes] offset of the node's children in the child-order arrays
+  const int* nChild;         // [nNodes]
+  const int* childNode;      // [nNodes-1] node id of each child slot
+  const uint4* childDesc;    // [nNodes-1][2] descriptor of each child slot
+  const double* weight;      // [nNodes] node weight (words: idf)
+  const int* wordId;         // [nNodes]
+  const double* wordWeight;  // [nWords]
+};
+
+// where the features of a transform / search come from: the context's device-resident frame (counts read on the
+// device, second eye appended for fisheye rigs = the vconcat of Frame.cc:1218) or a plain descriptor array (nFixed)
+struct FtBowSource {
+  const uint8_t* desc0; const uint8_t* desc1;
+  const int* cnt0; const int* cnt1;
+  const ft_keypoint* kps0; const ft_keypoint* kps1;
+  int nFixed;
+};
+
+struct FtBowFrame {
+  int* word;                 // [cap] word id per feature
+  int* node;                 // [cap] FeatureVector node per feature, -1 = stopped word
+  uint32_t* bowIds;          // [cap] BowVector ids ascending
+  double* bowVals;           // [cap]
+  int* bowStart;             // [cap+1] scratch: run heads of the sorted words
+  int* fvIdx;                // [cap] features sorted by (node, index)
+  int* fvNode;               // [cap] their nodes
+  int* fvGStart;             // [cap+1] group heads
+  int* fvMeta;               // [0] features in the FeatureVector, [1] groups
+  int* meta;                 // [0] n, [1] nLeft, [2] BowVector size
+};
+
+struct FtBowSearch {
+  int* match;                // [capF] KeyFrame feature matched to each frame keypoint, -1 none
+  int* matchBin;             // [capF] rotation-histogram bin of the match
+  int* hist;                 // [32]
+  int* result;               // [0] nmatches
+  int* kfMeta;               // [0] KeyFrame features in its FeatureVector, [1] groups
+  uint8_t* kfDesc; float* kfAngle; int* kfNode; uint8_t* kfHasMp;   // uploaded KeyFrame side [kfCap]
+  int* kfIdxSorted; int* kfNodeSorted; int* kfGStart;
+  int kfCap;
+};

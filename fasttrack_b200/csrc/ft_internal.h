@@ -1,5 +1,7 @@
 // ft_internal.h -- host-side launch functions shared between the translation units.
 #pragma once
+#include <vector>
+
 #include "ft_device.cuh"
 
 
@@ -28,3 +30,14 @@ void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st);
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st);
+
+// ---- bag of words (ft_bow.cu) ----
+struct ft_vocabulary;
+void ft_internal_set_err(const char* msg);   // the thread-local text behind ft_last_error() (ft_context.cu)
+int ft_vocabulary_device(const ft_vocabulary* v);
+cudaError_t ft_bow_frame_alloc(FtBowFrame* F, int cap, std::vector<void*>& owner);
+cudaError_t ft_bow_search_alloc(FtBowSearch* Q, int capF, int capKF, std::vector<void*>& owner);
+int ft_launch_bow_transform(const ft_vocabulary* voc, const FtBowSource& S, const FtBowFrame& F, int maxN, int levelsup,
+                            cudaStream_t st);
+int ft_launch_bow_search(const FtBowSource& S, const FtBowFrame& F, const FtBowSearch& Q, int nKF, int capF, float nnratio,
+                         int checkOri, cudaStream_t st);

@@ -249,6 +249,43 @@ ft_status ft_search_last_frame(ft_context* ctx, int n, const float* pos, const u
                                int b_mono, int check_orientation, int* holder, uint8_t* holder_obs, int* best_idx,
                                int* nmatches);
 
+/* ---- Bag of words: Frame::ComputeBoW and ORBmatcher::SearchByBoW(KeyFrame*, Frame&) ----
+ * ft_vocabulary is ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (reference include/ORBVocabulary.h:28-29,
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) resident on one device, shared read-only by the contexts of that device.
+ *   ft_vocabulary_load_text  <- ORBVocabulary::loadFromTextFile (TemplatedVocabulary.h:1338-1423; System.cc:118-127 loads
+ *                               ORBvoc.txt with it), incl. the extra stopped node its eof loop makes after a trailing newline
+ *   ft_vocabulary_create     the same tree from arrays: node i+1 (node 0 is the root) has parent[i] (must precede it),
+ *                               is_leaf[i] (the file's flag: leaves get word ids in order), desc[i][32], weight[i]
+ *   ft_vocabulary_transform  <- ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup) (:1127-1194) for HOST
+ *                               descriptors, e.g. KeyFrame::ComputeBoW (src/KeyFrame.cc:98-108). node_id[i] = the FeatureVector
+ *                               node of feature i, -1 when its word is stopped (weight 0); (bow_ids ascending, bow_vals) =
+ *                               the BowVector after the weighting / normalisation the vocabulary's types prescribe.
+ *                               Thread-safe per vocabulary. At most 16384 features per call (FT_ERR_CAPACITY).
+ *   ft_compute_bow           <- Frame::ComputeBoW (src/Frame.cc:762-769) on the context's device-resident descriptors
+ *                               (left eye; left then right for fisheye rigs, the vconcat of Frame.cc:1218); asynchronous.
+ *   ft_bow_download          mBowVec / mFeatVec of that frame: arrays as ft_vocabulary_transform (cap entries each).
+ *   ft_search_by_bow         <- ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:322-523,
+ *                               called by Tracking::TrackReferenceKeyFrame / Relocalization, src/Tracking.cc:2787,3846) after
+ *                               ft_compute_bow. KeyFrame side, HOST arrays over its (left, right) keypoints: kf_desc[n][32],
+ *                               kf_angle[n] (mvKeysUn / mvKeys / mvKeysRight angle), kf_node[n] (its FeatureVector node per
+ *                               feature, -1 none: node_id of ft_vocabulary_transform / ft_bow_download), kf_has_mp[n] =
+ *                               vpMapPointsKF[i] && !isBad(). match[N] out: the KeyFrame feature whose MapPoint frame keypoint
+ *                               i receives (vpMapPointMatches[i] = vpMapPointsKF[match[i]]), -1 none; N = n_left (+ n_right).
+ *                               nnratio = mfNNratio, check_orientation = mbCheckOrientation. *nmatches = the return value. */
+typedef struct ft_vocabulary ft_vocabulary;
+ft_status ft_vocabulary_load_text(int device_id, const char* path, ft_vocabulary** out);
+ft_status ft_vocabulary_create(int device_id, int k, int L, int scoring, int weighting, int n_nodes, const int* parent,
+                               const uint8_t* is_leaf, const uint8_t* desc, const double* weight, ft_vocabulary** out);
+ft_status ft_vocabulary_destroy(ft_vocabulary* voc);
+ft_status ft_vocabulary_info(ft_vocabulary* voc, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words);
+ft_status ft_vocabulary_transform(ft_vocabulary* voc, const uint8_t* desc, int n, int levelsup, int* word_id, int* node_id,
+                                  uint32_t* bow_ids, double* bow_vals, int bow_cap, int* n_bow);
+ft_status ft_compute_bow(ft_context* ctx, ft_vocabulary* voc, int levelsup);
+ft_status ft_bow_download(ft_context* ctx, int cap, int* word_id, int* node_id, uint32_t* bow_ids, double* bow_vals, int* n_bow,
+                          int* n);
+ft_status ft_search_by_bow(ft_context* ctx, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const int* kf_node,
+                           const uint8_t* kf_has_mp, float nnratio, int check_orientation, int* match, int* nmatches);
+
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
 
