@@ -173,6 +173,67 @@ def fast_mappoints(keys, desc, scale_factors, M, seed):
     return dict(pos=f32(P), normal=f32(n), minmax=f32(np.stack([mind, maxd], 1)), desc=np.ascontiguousarray(d), flags=flags)
 
 
+def bench_bow(ctx, ft, torch, stream, frames, device_id, with_cpu):
+    """SURVEY.md 8f row 4 (bag of words) measured beside the headline: Frame::ComputeBoW (device time, CUDA events on the
+    context's stream) and ORBmatcher::SearchByBoW(KeyFrame, Frame) (wall clock through the C ABI with host buffers) on an
+    ORBvoc-shaped vocabulary (k = 10, L = 6, 1,111,110 nodes), with the oracle's CPU time for the same calls."""
+    import fasttrack_b200.synth as synth
+    K, LV, LEVELSUP, REP = 10, 6, 4, 50
+    parent, leaf, vdesc, weight = synth.make_vocabulary_bfs(K, LV, seed=11)
+    ctx.extract_stereo(frames[0][0], frames[0][1]); ctx.stereo_match()
+    kf = ctx.download(0)
+    spread = np.nonzero(leaf)[0][::max(1, int(leaf.sum()) // kf["n"])][:kf["n"]]     # plant the KeyFrame's descriptors as words
+    vdesc[spread] = kf["desc"][:len(spread)]
+    voc = ft.Vocabulary.from_arrays(K, LV, 0, 0, parent, leaf, vdesc, weight, device_id=device_id)
+    kf_node = voc.transform(kf["desc"], LEVELSUP)["node"]
+    kf_has = np.ones(kf["n"], np.uint8)
+    ctx.extract_stereo(frames[1][0], frames[1][1]); ctx.stereo_match()
+    fr = ctx.download(0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(3):
+        ctx.compute_bow(voc, LEVELSUP)
+    ctx.synchronize()
+    with torch.cuda.stream(stream):
+        ev[0].record()
+    for _ in range(REP):
+        ctx.compute_bow(voc, LEVELSUP)
+    with torch.cuda.stream(stream):
+        ev[1].record()
+    ctx.synchronize()
+    bow_ms = ev[0].elapsed_time(ev[1]) / REP
+    nm, _ = ctx.search_by_bow(kf["desc"], kf["kps"]["angle"], kf_node, kf_has, 0.7, True)
+    t0 = time.perf_counter()
+    for _ in range(REP):
+        ctx.search_by_bow(kf["desc"], kf["kps"]["angle"], kf_node, kf_has, 0.7, True)
+    search_ms = (time.perf_counter() - t0) * 1e3 / REP
+    n = fr["n"]
+    alg = n * (LV * K * 32 + 32 + 8)            # descent reads k child descriptors per level + the feature + its outputs
+    pk, _ = peaks()
+    out = {"vocabulary": "synthetic, k=%d L=%d (%d nodes, %.1f MB of descriptors), levelsup=%d" % (K, LV, len(parent) + 1,
+                                                                                                len(parent) * 32 / 1e6, LEVELSUP),
+           "features": int(n), "compute_bow_ms": bow_ms, "compute_bow_launches": 3,
+           "compute_bow_algorithmic_bytes": int(alg), "compute_bow_hbm_frac": alg / (bow_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+           "search_by_bow_ms_e2e": search_ms, "search_by_bow_matches": int(nm), "keyframe_features": int(kf["n"]),
+           "note": "compute_bow: CUDA events around %d asynchronous calls; search_by_bow: host wall clock per call incl. the "
+                   "KeyFrame upload and the match download" % REP}
+    if with_cpu:
+        import oracle
+        vo = oracle.Vocabulary.from_arrays(K, LV, 0, 0, parent, leaf, vdesc, weight)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fo = vo.transform(fr["desc"], LEVELSUP)
+        out["cpu_compute_bow_ms"] = (time.perf_counter() - t0) * 1e3 / 10
+        ang = np.ascontiguousarray(fr["kps"]["angle"]); kang = np.ascontiguousarray(kf["kps"]["angle"])
+        t0 = time.perf_counter()
+        for _ in range(10):
+            nm_o, _ = oracle.search_by_bow(kf["desc"], kang, kf_node, kf_has, fr["desc"], ang, fo["node"], -1, 0.7, True)
+        out["cpu_search_by_bow_ms"] = (time.perf_counter() - t0) * 1e3 / 10
+        if nm_o != nm:
+            raise SystemExit("bench.py: SearchByBoW disagrees with the oracle (%d vs %d matches)" % (nm, nm_o))
+    voc.close()
+    return out
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, restated (oracle port), on the box's host cores with
     the reference's threading: two threads for L/R extraction (Frame.cc:127-130), everything else on one."""
@@ -626,6 +687,8 @@ def main():
                                 "ms_per_frame": cpu_ms,
                                 "sample": "%d frames (extract L/R on 2 threads + stereo) + 6 frames SearchLocalPoints "
                                           "of the same workload; host has %d cores" % (nsample, os.cpu_count())}
+    if rank == 0 and world == 1:
+        line["next_rows"] = {"bow": bench_bow(ctx, ft, torch, stream, frames, local, not args.no_cpu_baseline)}
     if rank == 0:
         print(json.dumps(line))
     for c_ in ctxs:

@@ -9,12 +9,17 @@
 //   ORB_SLAM3::ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
 //                                              (include/ORBmatcher.h:47, src/ORBmatcher.cc:49-312), including the
 //                                              isInFrustum pass of Tracking::SearchLocalPoints (src/Tracking.cc:3504-3522)
+//   ORB_SLAM3::ORBVocabulary::loadFromTextFile / transform, Frame::ComputeBoW, KeyFrame::ComputeBoW,
+//   ORB_SLAM3::ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)
+//                                              (include/ORBVocabulary.h, src/Frame.cc:762-769, src/KeyFrame.cc:98-108,
+//                                              src/ORBmatcher.cc:322-523)
 // Everything is computed on the GPU by libfasttrack_b200; there is no CPU branch here. When the library is
 // compiled into a tree that has OpenCV, define FT_SHIM_USE_OPENCV and the cv:: types are used directly;
 // otherwise the minimal ftcv:: stand-ins below carry the same fields.
 #pragma once
 #include <condition_variable>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -54,6 +59,16 @@ typedef Mat& OutputArray;
 }  // namespace ftcv
 #endif
 
+// The two DBoW2 containers the tracker keeps per frame (reference Thirdparty/DBoW2/DBoW2/BowVector.h:58-60,
+// FeatureVector.h:23-25): plain std::maps, filled from the device results.
+namespace DBoW2 {
+typedef unsigned int WordId;
+typedef unsigned int NodeId;
+typedef double WordValue;
+class BowVector : public std::map<WordId, WordValue> {};
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}  // namespace DBoW2
+
 namespace ORB_SLAM3 {
 
 class FtError : public std::runtime_error {
@@ -62,6 +77,40 @@ class FtError : public std::runtime_error {
   int status;
 };
 inline void ft_check(ft_status st) { if (st != FT_OK) throw FtError((int)st, ft_last_error()); }
+
+// ORBVocabulary (reference include/ORBVocabulary.h:28-29 = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>), resident
+// on one device. Descriptors are passed as rows of 32 bytes.
+class ORBVocabulary {
+ public:
+  explicit ORBVocabulary(int device_id = 0) : device_(device_id) {}
+  ~ORBVocabulary() { if (voc_) ft_vocabulary_destroy(voc_); }
+  ORBVocabulary(const ORBVocabulary&) = delete;
+  bool loadFromTextFile(const std::string& filename) {          // TemplatedVocabulary.h:1338-1423
+    if (voc_) { ft_vocabulary_destroy(voc_); voc_ = nullptr; }
+    return ft_vocabulary_load_text(device_, filename.c_str(), &voc_) == FT_OK;
+  }
+  bool empty() const { return voc_ == nullptr; }
+  ft_vocabulary* get() const { return voc_; }
+  // transform(features, v, fv, levelsup) (:1127-1194) for n host descriptors of 32 bytes
+  void transform(const unsigned char* desc, int n, DBoW2::BowVector& v, DBoW2::FeatureVector& fv, int levelsup) const {
+    std::vector<int> node(n > 0 ? n : 1);
+    std::vector<uint32_t> ids(n > 0 ? n : 1);
+    std::vector<double> vals(n > 0 ? n : 1);
+    int nb = 0;
+    ft_check(ft_vocabulary_transform(voc_, desc, n, levelsup, nullptr, node.data(), ids.data(), vals.data(), (int)ids.size(), &nb));
+    fill(node.data(), n, ids.data(), vals.data(), nb, v, fv);
+  }
+  static void fill(const int* node, int n, const uint32_t* ids, const double* vals, int nb, DBoW2::BowVector& v,
+                   DBoW2::FeatureVector& fv) {
+    v.clear(); fv.clear();
+    for (int i = 0; i < nb; i++) v.insert(v.end(), std::make_pair(ids[i], vals[i]));
+    for (int i = 0; i < n; i++) if (node[i] >= 0) fv[(unsigned)node[i]].push_back((unsigned)i);
+  }
+
+ private:
+  int device_;
+  ft_vocabulary* voc_ = nullptr;
+};
 
 // One GPU context shared by the two extractors of a stereo rig and by the Frame / ORBmatcher mirrors.
 // Replaces KernelController's static singletons (reference include/Kernels/KernelController.h).
@@ -203,6 +252,23 @@ class Frame {
     memcpy(mRcw, Rcw, sizeof(mRcw)); memcpy(mtcw, tcw, sizeof(mtcw));
     ft_check(ft_set_pose(fe_->get(), Rcw, tcw, nullptr, nullptr));
   }
+  // Frame::ComputeBoW (src/Frame.cc:762-769) on the device-resident descriptors of the frame extracted last
+  void ComputeBoW() {
+    if (!mBowVec.empty() || !mpORBvocabulary) return;
+    ft_check(ft_compute_bow(fe_->get(), mpORBvocabulary->get(), 4));
+    const int cap = 2 * ft_max_keypoints(fe_->get());
+    std::vector<int> node(cap);
+    std::vector<uint32_t> ids(cap);
+    std::vector<double> vals(cap);
+    int nb = 0, n = 0;
+    ft_check(ft_bow_download(fe_->get(), cap, nullptr, node.data(), ids.data(), vals.data(), &nb, &n));
+    ORBVocabulary::fill(node.data(), n, ids.data(), vals.data(), nb, mBowVec, mFeatVec);
+    mvFeatNode.assign(node.begin(), node.begin() + n);
+  }
+  ORBVocabulary* mpORBvocabulary = nullptr;
+  DBoW2::BowVector mBowVec;
+  DBoW2::FeatureVector mFeatVec;
+  std::vector<int> mvFeatNode;      // mFeatVec as one node per feature (-1 = none), the form the device search takes
   float mRcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, mtcw[3] = {0, 0, 0};   // Tcw (Frame::SetPose)
   std::vector<bool> mvbOutlier;
 
@@ -234,6 +300,26 @@ class Frame {
     mvbOutlier.assign(N, false);
   }
   std::shared_ptr<FrontEndContext> fe_;
+};
+
+// The fields of KeyFrame that SearchByBoW reads (reference include/KeyFrame.h): descriptors and keypoint angles over the
+// (left, right) keypoints, the map-point matches and the FeatureVector made by KeyFrame::ComputeBoW (src/KeyFrame.cc:98-108).
+struct KeyFrame {
+  int N = 0, NLeft = -1;
+  std::vector<unsigned char> mDescriptors;          // N x 32
+  std::vector<float> mvAngles;                      // mvKeysUn[i].angle (mvKeys / mvKeysRight for two-camera rigs)
+  std::vector<MapPoint*> mvpMapPoints;
+  ORBVocabulary* mpORBvocabulary = nullptr;
+  DBoW2::BowVector mBowVec;
+  DBoW2::FeatureVector mFeatVec;
+  std::vector<int> mvFeatNode;
+  const std::vector<MapPoint*>& GetMapPointMatches() const { return mvpMapPoints; }
+  void ComputeBoW() {
+    if (!mBowVec.empty() || !mpORBvocabulary) return;
+    mpORBvocabulary->transform(mDescriptors.data(), N, mBowVec, mFeatVec, 4);
+    mvFeatNode.assign(N, -1);
+    for (const auto& e : mFeatVec) for (unsigned i : e.second) mvFeatNode[i] = (int)e.first;
+  }
 };
 
 // Host side of the persistent device-side MapPoint store (ft_map_store_*): a MapPoint keeps one row for its lifetime;
@@ -398,6 +484,22 @@ class ORBmatcher {
                                   holder.data(), hobs.data(), nullptr, &nmatches));
     for (int i = 0; i < N; i++)
       CurrentFrame.mvpMapPoints[i] = holder[i] >= 0 ? src[holder[i]] : (holder[i] == -2 ? foreign[i] : nullptr);
+    return nmatches;
+  }
+
+  // Search matches between MapPoints in a KeyFrame and ORB in a Frame, constrained by the vocabulary (reference
+  // src/ORBmatcher.cc:322-523; Tracking::TrackReferenceKeyFrame / Relocalization). F must be the frame the context
+  // extracted last with ComputeBoW() done; pKF->ComputeBoW() done.
+  int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    std::vector<unsigned char> has(pKF->N > 0 ? pKF->N : 1, 0);
+    for (int i = 0; i < pKF->N; i++) has[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+    std::vector<int> match(F.N > 0 ? F.N : 1, -1);
+    int nmatches = 0;
+    ft_check(ft_search_by_bow(F.context()->get(), pKF->N, pKF->mDescriptors.data(), pKF->mvAngles.data(), pKF->mvFeatNode.data(),
+                              has.data(), mfNNratio, mbCheckOrientation ? 1 : 0, match.data(), &nmatches));
+    vpMapPointMatches.assign(F.N, nullptr);
+    for (int i = 0; i < F.N; i++) if (match[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[match[i]];
     return nmatches;
   }
 

@@ -293,6 +293,35 @@ def make_vocabulary(k=10, L=4, seed=7, stop_fraction=0.02):
             np.asarray(weight, np.float64))
 
 
+def make_vocabulary_bfs(k=10, L=6, seed=7, stop_fraction=0.02):
+    """Same kind of tree as make_vocabulary, generated level by level with numpy (seconds for ORBvoc's k = 10, L = 6) and
+    numbered breadth first (parents still precede their children, which is all the array constructor requires)."""
+    rng = np.random.default_rng(seed)
+    parents, leaves, descs, weights = [], [], [], []
+    prev_desc = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    prev_first = 0                                   # node id of the first node of the previous level (root = 0)
+    next_id = 1
+    for level in range(1, L + 1):
+        n = len(prev_desc) * k
+        d = np.repeat(prev_desc, k, axis=0)
+        nflip = max(96 >> (level - 1), 3)
+        pos = rng.integers(0, 256, (n, nflip))
+        rows = np.arange(n)
+        for j in range(nflip):
+            d[rows, pos[:, j] >> 3] ^= (1 << (pos[:, j] & 7)).astype(np.uint8)
+        parents.append(prev_first + np.arange(n) // k)
+        is_leaf = level == L
+        leaves.append(np.full(n, 1 if is_leaf else 0, np.uint8))
+        w = np.zeros(n)
+        if is_leaf:
+            w = rng.uniform(0.5, 9.0, n)
+            w[rng.random(n) < stop_fraction] = 0.0
+        weights.append(w); descs.append(d)
+        prev_desc, prev_first, next_id = d, next_id, next_id + n
+    return (np.concatenate(parents).astype(np.int32), np.concatenate(leaves), np.ascontiguousarray(np.concatenate(descs)),
+            np.concatenate(weights).astype(np.float64))
+
+
 def write_vocabulary_text(path, k, L, parent, is_leaf, desc, weight, scoring=0, weighting=0, trailing_newline=True):
     """DBoW2 text format (TemplatedVocabulary::saveToTextFile): header `k L  scoring weighting`, then one line per node:
     `parent isLeaf d0 .. d31 weight`."""

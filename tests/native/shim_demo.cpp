@@ -82,6 +82,35 @@ int main(int argc, char** argv) {
     for (int i = 0; i < M; i += 7) { mps[i].mWorldPos[0] -= 0.01f; }
     F.mvpMapPoints.assign(F.N, nullptr);
     matcher.SearchByProjection(F, vp, 3.0f, false, 50.0f);
+    // bag of words, when the test provides a vocabulary and a KeyFrame: Frame::ComputeBoW, KeyFrame::ComputeBoW,
+    // ORBmatcher(0.7).SearchByBoW(pKF, F, matches) as Tracking::TrackReferenceKeyFrame drives them
+    std::ifstream vocProbe(dir + "/voc.txt");
+    if (vocProbe.good()) {
+      ORBVocabulary voc(0);
+      if (!voc.loadFromTextFile(dir + "/voc.txt")) { fprintf(stderr, "shim_demo: vocabulary: %s\n", ft_last_error()); return 4; }
+      F.mpORBvocabulary = &voc;
+      F.ComputeBoW();
+      KeyFrame kf;
+      kf.mDescriptors = rd<unsigned char>(dir + "/kf_desc.bin");
+      kf.mvAngles = rd<float>(dir + "/kf_angle.bin");
+      std::vector<unsigned char> kfHas = rd<unsigned char>(dir + "/kf_has.bin");
+      kf.N = (int)kf.mvAngles.size();
+      std::vector<MapPoint> kfMps(kf.N);
+      kf.mvpMapPoints.assign(kf.N, nullptr);
+      for (int i = 0; i < kf.N; i++) if (kfHas[i]) kf.mvpMapPoints[i] = &kfMps[i];
+      kf.mpORBvocabulary = &voc;
+      kf.ComputeBoW();
+      ORBmatcher bowMatcher(0.7f, true);
+      std::vector<MapPoint*> vpMatches;
+      const int nbow = bowMatcher.SearchByBoW(&kf, F, vpMatches);
+      std::vector<int> bowMatch(F.N, -1);
+      for (int i = 0; i < F.N; i++) if (vpMatches[i]) bowMatch[i] = (int)(vpMatches[i] - kfMps.data());
+      bowMatch.push_back(nbow);
+      wr(dir + "/out_bow_match.bin", bowMatch);
+      std::vector<double> bv;
+      for (const auto& e : F.mBowVec) { bv.push_back((double)e.first); bv.push_back(e.second); }
+      wr(dir + "/out_bow_vec.bin", bv);
+    }
     // outputs
     std::vector<float> k;
     for (auto& kp : F.mvKeys) { k.push_back(kp.pt.x); k.push_back(kp.pt.y); k.push_back(kp.size); k.push_back(kp.angle); k.push_back(kp.response); k.push_back((float)kp.octave); }

@@ -69,7 +69,7 @@ def test_transform_matches_oracle(k, L, sc, wt):
 
 def test_full_size_vocabulary_descents():
     """ORBvoc's shape (k = 10, L = 6: 1,111,110 nodes, 35.5 MB of descriptors) -- descents against the oracle"""
-    parent, leaf, desc, weight = synth.make_vocabulary(10, 6, seed=1, stop_fraction=0.01)
+    parent, leaf, desc, weight = synth.make_vocabulary_bfs(10, 6, seed=1, stop_fraction=0.01)
     assert len(parent) == 1111110
     vo = oracle.Vocabulary.from_arrays(10, 6, 0, 0, parent, leaf, desc, weight)
     vg = ft.Vocabulary.from_arrays(10, 6, 0, 0, parent, leaf, desc, weight)

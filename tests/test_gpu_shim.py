@@ -34,8 +34,30 @@ def test_shim_matches_oracle(tmp_path, euroc_pair):
     np.array([E["fx"], E["fy"], E["cx"], E["cy"], mbf], np.float32).tofile(d + "/cam.bin")
     for k in ("pos", "normal", "minmax", "desc", "flags"):
         mp[k].tofile(d + "/mp_%s.bin" % k)
+    # bag of words through the mirror: vocabulary text file + a KeyFrame derived from the left frame
+    parent, leaf, vdesc, weight = synth.make_vocabulary(10, 5, seed=31)
+    leaves = np.nonzero(leaf)[0]
+    vdesc[leaves[:len(dL)]] = dL
+    synth.write_vocabulary_text(d + "/voc.txt", 10, 5, parent, leaf, vdesc, weight)
+    rng = np.random.default_rng(32)
+    pick = rng.integers(0, len(dL), 1000)
+    bits = np.unpackbits(dL[pick], axis=1)
+    for i in range(len(pick)):
+        bits[i, rng.choice(256, size=int(rng.integers(0, 30)), replace=False)] ^= 1
+    kf_desc = np.packbits(bits, axis=1)
+    kf_angle = ((kL[pick, 3] + rng.normal(15, 3, len(pick))) % 360).astype(np.float32)
+    kf_has = (rng.random(len(pick)) < 0.8).astype(np.uint8)
+    kf_desc.tofile(d + "/kf_desc.bin"); kf_angle.tofile(d + "/kf_angle.bin"); kf_has.tofile(d + "/kf_has.bin")
     out = subprocess.run([exe, d], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+    vo = oracle.Vocabulary.load_text(d + "/voc.txt")
+    fo, ko = vo.transform(dL, 4), vo.transform(kf_desc, 4)
+    nm_bow, m_bow = oracle.search_by_bow(kf_desc, kf_angle, ko["node"], kf_has, dL, np.ascontiguousarray(kL[:, 3]), fo["node"],
+                                         -1, 0.7, True)
+    got = np.fromfile(d + "/out_bow_match.bin", np.int32)
+    assert nm_bow > 100 and got[-1] == nm_bow and np.array_equal(got[:-1], m_bow)
+    bv = np.fromfile(d + "/out_bow_vec.bin", np.float64).reshape(-1, 2)
+    assert np.array_equal(bv[:, 0].astype(np.uint32), fo["bow_ids"]) and np.array_equal(bv[:, 1], fo["bow_vals"])
     gk = np.fromfile(d + "/out_kL.bin", np.float32).reshape(-1, 6)
     gd = np.fromfile(d + "/out_dL.bin", np.uint8).reshape(-1, 32)
     meta = np.fromfile(d + "/out_meta.bin", np.int32)
