@@ -435,19 +435,76 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 
 
+_REF_ORB_SO = os.path.join(_HERE, "_ref", "libft_ref_orbextractor.so")
+
+
 def build_ref():
-    """oracle/_ref/libft_ref_dbow2.so: the REFERENCE's own DBoW2 sources compiled where they lie (make ref). Returns the
-    path, or None when neither the prebuilt library nor the reference tree is available (e.g. on the GPU box before
-    a snapshot carried the .so)."""
-    srcs = [os.path.join(_HERE, "ref_dbow2_capi.cpp"), os.path.join(_HERE, "ref_stubs", "opencv2", "core", "core.hpp")]
+    """oracle/_ref/*.so: pieces of the REFERENCE itself compiled where they lie (`make ref`): its vendored DBoW2 and the CPU
+    branch of src/ORBextractor.cc. Returns the directory, or None when neither the prebuilt libraries nor the reference
+    tree are available (e.g. on the GPU box before a snapshot carried the files)."""
+    srcs = [os.path.join(_HERE, f) for f in ("ref_dbow2_capi.cpp", "ref_orbextractor_capi.cpp", "ft_oracle.cpp", "ft_oracle.h",
+                                             os.path.join("ref_stubs", "ft_cv_standin.cpp"),
+                                             os.path.join("ref_stubs", "opencv2", "opencv.hpp"))]
+    outs = [_REF_SO, _REF_ORB_SO]
     have_ref = os.path.isdir(os.path.join(_REFERENCE, "Thirdparty", "DBoW2", "DBoW2"))
-    fresh = os.path.exists(_REF_SO) and all(os.path.getmtime(_REF_SO) >= os.path.getmtime(x) for x in srcs)
-    if fresh or (os.path.exists(_REF_SO) and not have_ref):
-        return _REF_SO
+    built = all(os.path.exists(o) for o in outs)
+    fresh = built and all(os.path.getmtime(o) >= os.path.getmtime(x) for o in outs for x in srcs)
+    if fresh or (built and not have_ref):
+        return os.path.dirname(_REF_SO)
     if not have_ref:
         return None
     subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + _REFERENCE])
-    return _REF_SO
+    return os.path.dirname(_REF_SO)
+
+
+class RefExtractor:
+    """The reference's own ORBextractor (CPU branch of src/ORBextractor.cc, oracle/_ref/libft_ref_orbextractor.so): used
+    ONLY to pin the oracle's restatement and to make golden vectors."""
+
+    def __init__(self, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, width=752, height=480):
+        if build_ref() is None:
+            raise FileNotFoundError("oracle/_ref/libft_ref_orbextractor.so is not built and the reference tree is absent")
+        R = C.CDLL(_REF_ORB_SO)
+        R.ftref_extractor_create.restype = C.c_void_p
+        R.ftref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        R.ftref_extractor_destroy.argtypes = [C.c_void_p]
+        R.ftref_extract.restype = C.c_int
+        R.ftref_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, u8p, C.c_int,
+                                    C.POINTER(C.c_int)]
+        R.ftref_level_image.restype = C.c_int
+        R.ftref_level_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        R.ftref_scale_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p]
+        self.R, self.nlevels, self.cap = R, nlevels, nfeatures + 64 * nlevels
+        self.h = R.ftref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th, width, height)
+
+    def extract(self, img, lap=(0, 0)):
+        """ORBextractor::operator(): returns (monoIndex, kps[n,6], desc[n,32])"""
+        img = np.ascontiguousarray(img, np.uint8)
+        k = np.zeros((self.cap, 6), np.float32); d = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int()
+        mono = self.R.ftref_extract(C.c_void_p(self.h), img, img.shape[1], img.shape[0], img.strides[0], int(lap[0]), int(lap[1]),
+                                    k, d, self.cap, C.byref(n))
+        assert n.value <= self.cap
+        return mono, k[:n.value].copy(), d[:n.value].copy()
+
+    def level_image(self, level):
+        w, h = C.c_int(), C.c_int()
+        if not self.R.ftref_level_image(C.c_void_p(self.h), level, None, C.byref(w), C.byref(h)):
+            return None
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.R.ftref_level_image(C.c_void_p(self.h), level, out.ctypes.data, C.byref(w), C.byref(h))
+        return out
+
+    def scale_tables(self):
+        a = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        self.R.ftref_scale_tables(C.c_void_p(self.h), *a)
+        return dict(scale=a[0], inv_scale=a[1], sigma2=a[2], inv_sigma2=a[3])
+
+    def __del__(self):
+        try:
+            self.R.ftref_extractor_destroy(C.c_void_p(self.h))
+        except Exception:
+            pass
 
 
 class Vocabulary:
@@ -543,10 +600,9 @@ class RefVocabulary:
     """The reference's own DBoW2 (oracle/_ref/libft_ref_dbow2.so): used ONLY to pin the oracle's restatement."""
 
     def __init__(self, path):
-        so = build_ref()
-        if so is None:
+        if build_ref() is None:
             raise FileNotFoundError("oracle/_ref/libft_ref_dbow2.so is not built and the reference tree is absent")
-        R = C.CDLL(so)
+        R = C.CDLL(_REF_SO)
         R.ftref_voc_load_text.restype = C.c_void_p
         R.ftref_voc_load_text.argtypes = [C.c_char_p]
         R.ftref_voc_free.argtypes = [C.c_void_p]

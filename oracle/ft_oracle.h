@@ -16,6 +16,7 @@
 // is a line-by-line restatement cited per function and is, strictly, PARITY UNPINNED:
 // no output of the reference itself exists to check it against.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <vector>
 

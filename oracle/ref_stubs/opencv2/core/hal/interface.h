@@ -1,3 +1,3 @@
 // Stand-in header, TEST INFRASTRUCTURE ONLY: see ../opencv.hpp
 #pragma once
-#include "../opencv.hpp"
+#include "../../opencv.hpp"
