@@ -367,6 +367,9 @@ class Frame:
             d.tcw[i] = tcw[i]; d.Ow[i] = Ow[i]; d.trl[i] = trl[i]; d.tlr[i] = tlr[i]
         self.Rwc, self.Ow = Rwc, Ow
         self.N = len(keys)
+        self._create(d)
+
+    def _create(self, d):
         self.h = C.c_void_p(self.L.fto_frame_create(C.byref(d)))
 
     def __del__(self):
@@ -442,10 +445,12 @@ def build_ref():
     """oracle/_ref/*.so: pieces of the REFERENCE itself compiled where they lie (`make ref`): its vendored DBoW2 and the CPU
     branch of src/ORBextractor.cc. Returns the directory, or None when neither the prebuilt libraries nor the reference
     tree are available (e.g. on the GPU box before a snapshot carried the files)."""
-    srcs = [os.path.join(_HERE, f) for f in ("ref_dbow2_capi.cpp", "ref_orbextractor_capi.cpp", "ft_oracle.cpp", "ft_oracle.h",
+    srcs = [os.path.join(_HERE, f) for f in ("ref_dbow2_capi.cpp", "ref_orbextractor_capi.cpp", "ref_frame_capi.cpp",
+                                             "ref_extract_fns.py", os.path.join("ref_stubs", "ref_frame_shim.h"),
+                                             "ft_oracle.cpp", "ft_oracle.h",
                                              os.path.join("ref_stubs", "ft_cv_standin.cpp"),
                                              os.path.join("ref_stubs", "opencv2", "opencv.hpp"))]
-    outs = [_REF_SO, _REF_ORB_SO]
+    outs = [_REF_SO, _REF_ORB_SO, os.path.join(_HERE, "_ref", "libft_ref_frame.so")]
     have_ref = os.path.isdir(os.path.join(_REFERENCE, "Thirdparty", "DBoW2", "DBoW2"))
     built = all(os.path.exists(o) for o in outs)
     fresh = built and all(os.path.getmtime(o) >= os.path.getmtime(x) for o in outs for x in srcs)
@@ -631,3 +636,136 @@ class RefVocabulary:
             self.R.ftref_voc_free(C.c_void_p(self.h))
         except Exception:
             pass
+
+
+# ---- functions of the reference's Frame.cc / ORBmatcher.cc compiled from their own text (oracle/_ref/libft_ref_frame.so) ----
+_REF_FRAME_SO = os.path.join(_HERE, "_ref", "libft_ref_frame.so")
+
+
+class RefFrameDesc(C.Structure):
+    _fields_ = FrameDesc._fields_ + [("keysUn6", C.c_void_p)]
+
+
+_ref_frame_lib = None
+
+
+def ref_frame_lib():
+    """dlopen oracle/_ref/libft_ref_frame.so; None when it is not built and cannot be built here"""
+    global _ref_frame_lib
+    if _ref_frame_lib is not None:
+        return _ref_frame_lib
+    if build_ref() is None or not os.path.exists(_REF_FRAME_SO):
+        return None
+    R = C.CDLL(_REF_FRAME_SO)
+    vp = C.c_void_p
+    R.ftref_frame_create.restype = vp
+    R.ftref_frame_create.argtypes = [C.POINTER(RefFrameDesc)]
+    R.ftref_frame_destroy.argtypes = [vp]
+    R.ftref_frame_grid.argtypes = [vp, C.c_int, i32p, i32p]
+    R.ftref_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
+    R.ftref_search_local_points.argtypes = [vp, C.c_int, f32p, f32p, f32p, u8p, i32p, C.c_float, C.c_int, C.c_float, C.c_float,
+                                            i32p, u8p, vp, vp]
+    R.ftref_search_last_frame.argtypes = [vp, C.c_int, f32p, u8p, i32p, f32p, i32p, f32p, f32p, C.c_float, C.c_int, C.c_int,
+                                          C.c_float, i32p, u8p]
+    R.ftref_stereo_matches.argtypes = [C.c_int, i32p, i32p, u8p, u8p, f32p, f32p, u8p, C.c_int, f32p, u8p, C.c_int, C.c_float,
+                                       C.c_float, f32p, f32p]
+    R.ftref_stereo_matches.restype = None
+    R.ftref_stereo_from_rgbd.argtypes = [f32p, f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p]
+    R.ftref_stereo_from_rgbd.restype = None
+    R.ftref_search_by_bow.argtypes = [C.c_int, u8p, f32p, i32p, u8p, C.c_int, u8p, f32p, i32p, C.c_int, C.c_float, C.c_int, i32p]
+    _ref_frame_lib = R
+    return R
+
+
+class RefFrame(Frame):
+    """The reference's own Frame::{AssignFeaturesToGrid, GetFeaturesInArea, isInFrustum[Checks]} and
+    ORBmatcher::SearchByProjection functions (text taken from the reference files at build time): same constructor and
+    methods as the oracle's Frame. Used ONLY to pin the oracle's restatement and to make golden vectors."""
+
+    def _create(self, d):
+        self.R = ref_frame_lib()
+        if self.R is None:
+            raise FileNotFoundError("oracle/_ref/libft_ref_frame.so is not built and the reference tree is absent")
+        rd = RefFrameDesc()
+        for name, _ in FrameDesc._fields_:
+            setattr(rd, name, getattr(d, name))
+        rd.keysUn6 = None
+        self.h = C.c_void_p(self.R.ftref_frame_create(C.byref(rd)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self, "R", None):
+            self.R.ftref_frame_destroy(self.h)
+            self.h = None
+
+    def grid(self, right=False):
+        counts = np.zeros(64 * 48, np.int32)
+        idx = np.zeros(max(self.N, 1), np.int32)
+        n = self.R.ftref_frame_grid(self.h, int(right), counts, idx)
+        return counts, idx[:n].copy()
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1, right=False):
+        out = np.zeros(max(self.N, 1), np.int32)
+        n = self.R.ftref_features_in_area(self.h, x, y, r, min_level, max_level, int(right), out, len(out))
+        return out[:n].copy()
+
+    def search_local_points(self, pos, normal, minmax, desc, flags, th, holder, holder_obs, b_far=False, th_far=50.0,
+                            nnratio=0.8):
+        pos, normal, minmax, desc, flags = self._mp(pos, normal, minmax, desc, flags)
+        M = len(pos)
+        holder = np.ascontiguousarray(holder, np.int32).copy()
+        holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        ti = np.zeros((M, 4), np.int32); tf = np.zeros((M, 9), np.float32)
+        n = self.R.ftref_search_local_points(self.h, M, pos, normal, minmax, desc, flags, th, int(b_far), th_far, nnratio,
+                                             holder, holder_obs, ti.ctypes.data, tf.ctypes.data)
+        return n, holder, holder_obs, ti, tf
+
+    def search_last_frame(self, pos, desc, octave, angle, flags, th, Rlw, tlw, mb, holder, holder_obs, b_mono=False,
+                          check_ori=True):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        pos, angle, Rlw, tlw = f(pos), f(angle), f(Rlw).reshape(-1), f(tlw)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        octave = np.ascontiguousarray(octave, np.int32); flags = np.ascontiguousarray(flags, np.int32)
+        holder = np.ascontiguousarray(holder, np.int32).copy(); holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        n = self.R.ftref_search_last_frame(self.h, len(pos), pos, desc, octave, angle, flags, Rlw, tlw, th, int(b_mono),
+                                           int(check_ori), mb, holder, holder_obs)
+        return n, holder, holder_obs
+
+
+def ref_stereo(exL, exR, kL, dL, kR, dR, mbf, mb):
+    """The reference's own Frame::ComputeStereoMatches on the pyramids of two extractors (oracle.Extractor or
+    RefExtractor objects, after extract()): dict(uRight, depth)"""
+    R = ref_frame_lib()
+    nl = exL.nlevels
+    lv = [exL.level_image(l) for l in range(nl)]; rv = [exR.level_image(l) for l in range(nl)]
+    lw = np.array([a.shape[1] for a in lv], np.int32); lh = np.array([a.shape[0] for a in lv], np.int32)
+    pl = np.concatenate([a.reshape(-1) for a in lv]); pr = np.concatenate([a.reshape(-1) for a in rv])
+    scale = np.ascontiguousarray(exL.scale if hasattr(exL, "scale") else exL.scale_tables()["scale"], np.float32)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    ur = np.zeros(max(len(kL), 1), np.float32); dp = np.zeros(max(len(kL), 1), np.float32)
+    R.ftref_stereo_matches(nl, lw, lh, np.ascontiguousarray(pl), np.ascontiguousarray(pr), scale, f(kL),
+                           np.ascontiguousarray(dL, np.uint8), len(kL), f(kR), np.ascontiguousarray(dR, np.uint8), len(kR),
+                           mbf, mb, ur, dp)
+    return dict(uRight=ur[:len(kL)], depth=dp[:len(kL)])
+
+
+def ref_stereo_from_rgbd(keys_xy, keys_un_x, depth, mbf):
+    R = ref_frame_lib()
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    keys_xy, keys_un_x, depth = f(keys_xy), f(keys_un_x), f(depth)
+    n = len(keys_un_x)
+    ur = np.zeros(max(n, 1), np.float32); dp = np.zeros(max(n, 1), np.float32)
+    R.ftref_stereo_from_rgbd(keys_xy, keys_un_x, n, depth, depth.shape[1], depth.shape[0], mbf, ur, dp)
+    return ur[:n], dp[:n]
+
+
+def ref_search_by_bow(kf_desc, kf_angle, kf_node, kf_has_mp, f_desc, f_angle, f_node, f_nleft=-1, nnratio=0.7, check_ori=True):
+    """the reference's own ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) over its own DBoW2::FeatureVector"""
+    R = ref_frame_lib()
+    c8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    kf_desc, f_desc, kf_has_mp = c8(kf_desc).reshape(-1, 32), c8(f_desc).reshape(-1, 32), c8(kf_has_mp)
+    kf_angle, f_angle = np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(f_angle, np.float32)
+    kf_node, f_node = np.ascontiguousarray(kf_node, np.int32), np.ascontiguousarray(f_node, np.int32)
+    match = np.full(max(len(f_desc), 1), -1, np.int32)
+    nm = R.ftref_search_by_bow(len(kf_desc), kf_desc, kf_angle, kf_node, kf_has_mp, len(f_desc), f_desc, f_angle, f_node,
+                               int(f_nleft), float(nnratio), int(check_ori), match)
+    return nm, match[:len(f_desc)]
