@@ -14,9 +14,10 @@
 // 35.5 MB of descriptors and stays L2-resident between frames. Kernels:
 //   k_bow_transform  one warp per feature; lane j scores child j (__popc over two uint4), warp arg-min with the
 //                    first-minimum-wins rule of the reference's strict `<`; L dependent steps.
-//   k_bow_vector     one CTA: bitonic sort of (word, feature) keys in shared memory, run heads -> distinct words, the
-//                    reference's summation order for the weights and for the norm (sequential in ascending word id).
-//   k_bow_group      one CTA: the FeatureVector as a CSR (features sorted by (node, index), group heads).
+//   k_bow_vector     two CTAs side by side. CTA 0: bitonic sort of (word, feature) keys in shared memory, run heads ->
+//                    distinct words, the reference's summation order for the weights and for the norm (sequential in
+//                    ascending word id). CTA 1: the FeatureVector as a CSR (features sorted by (node, index), group heads).
+//   k_bow_group      the same CSR for the uploaded KeyFrame side of a search.
 //   k_bow_search     one warp per KeyFrame node group. Frame features of different nodes are disjoint, so the
 //                    reference's loop-carried "already matched" test only couples KeyFrame features of one node: the
 //                    warp walks them in order and the lanes split the frame features of that node.
@@ -158,12 +159,27 @@ __device__ int bow_run_heads(const unsigned long long* key, int nv, int* start, 
   return total;
 }
 
-// BowVector of the frame: transform(features, v, fv, levelsup) :1127-1194 + BowVector.cpp:34-86
+// FeatureVector as a CSR: features with a node, sorted by (node, feature index); gStart = group heads
+__device__ void bow_group(unsigned long long* key, int* shCnt, int* shScan, const int* node, int n, int* idxOut, int* nodeOut,
+                          int* gStart, int* meta /* [0] nv, [1] groups */, int P) {
+  for (int t = threadIdx.x; t < P; t += blockDim.x)
+    key[t] = (t < n && node[t] >= 0) ? (((unsigned long long)(unsigned)node[t] << 32) | (unsigned)t) : ~0ull;
+  __syncthreads();
+  bow_block_sort(key, P);
+  const int nv = bow_count_valid(key, P, shCnt);
+  const int ng = bow_run_heads(key, nv, gStart, shScan);
+  for (int p = threadIdx.x; p < nv; p += blockDim.x) { idxOut[p] = (int)(unsigned)key[p]; nodeOut[p] = (int)(key[p] >> 32); }
+  if (threadIdx.x == 0) { meta[0] = nv; meta[1] = ng; }
+}
+
+// CTA 0: BowVector of the frame, transform(features, v, fv, levelsup) :1127-1194 + BowVector.cpp:34-86.
+// CTA 1: its FeatureVector (the two sorts are independent and run side by side).
 __global__ void __launch_bounds__(1024) k_bow_vector(FtVocDevice V, FtBowFrame F, int P) {
   extern __shared__ unsigned long long key[];
   __shared__ int shCnt, shScan[33];
   __shared__ double shNorm;
   const int n = F.meta[0];
+  if (blockIdx.x == 1) { bow_group(key, &shCnt, shScan, F.node, n, F.fvIdx, F.fvNode, F.fvGStart, F.fvMeta, P); return; }
   for (int t = threadIdx.x; t < P; t += blockDim.x)
     key[t] = (t < n && F.node[t] >= 0) ? (((unsigned long long)(unsigned)F.word[t] << 32) | (unsigned)t) : ~0ull;
   __syncthreads();
@@ -197,20 +213,11 @@ __global__ void __launch_bounds__(1024) k_bow_vector(FtVocDevice V, FtBowFrame F
   if (threadIdx.x == 0) F.meta[2] = nd;
 }
 
-// FeatureVector as a CSR: features with a node, sorted by (node, feature index); gStart = group heads
-__global__ void __launch_bounds__(1024) k_bow_group(const int* node, const int* nPtr, int nFixed, int* idxOut, int* nodeOut,
-                                                    int* gStart, int* meta /* [0] nv, [1] groups */, int P) {
+// the KeyFrame's FeatureVector, from one node per feature
+__global__ void __launch_bounds__(1024) k_bow_group(const int* node, int n, int* idxOut, int* nodeOut, int* gStart, int* meta, int P) {
   extern __shared__ unsigned long long key[];
   __shared__ int shCnt, shScan[33];
-  const int n = nPtr ? nPtr[0] : nFixed;
-  for (int t = threadIdx.x; t < P; t += blockDim.x)
-    key[t] = (t < n && node[t] >= 0) ? (((unsigned long long)(unsigned)node[t] << 32) | (unsigned)t) : ~0ull;
-  __syncthreads();
-  bow_block_sort(key, P);
-  const int nv = bow_count_valid(key, P, &shCnt);
-  const int ng = bow_run_heads(key, nv, gStart, shScan);
-  for (int p = threadIdx.x; p < nv; p += blockDim.x) { idxOut[p] = (int)(unsigned)key[p]; nodeOut[p] = (int)(key[p] >> 32); }
-  if (threadIdx.x == 0) { meta[0] = nv; meta[1] = ng; }
+  bow_group(key, &shCnt, shScan, node, n, idxOut, nodeOut, gStart, meta, P);
 }
 
 __global__ void k_bow_search_init(FtBowFrame F, FtBowSearch Q, int cap) {
@@ -408,22 +415,21 @@ cudaError_t ft_bow_search_alloc(FtBowSearch* Q, int capF, int capKF, std::vector
   return e;
 }
 
-// transform of up to maxN features (the actual count is read on the device): 3 launches
+// transform of up to maxN features (the actual count is read on the device): 2 launches
 int ft_launch_bow_transform(const ft_vocabulary* voc, const FtBowSource& S, const FtBowFrame& F, int maxN, int levelsup,
                             cudaStream_t st) {
   const int P = pow2_at_least(maxN);
   k_bow_transform<<<(maxN + 7) / 8, 256, 0, st>>>(voc->D, S, F, levelsup);
-  k_bow_vector<<<1, 1024, (size_t)P * 8, st>>>(voc->D, F, P);
-  k_bow_group<<<1, 1024, (size_t)P * 8, st>>>(F.node, F.meta, 0, F.fvIdx, F.fvNode, F.fvGStart, F.fvMeta, P);
-  return 3;
+  k_bow_vector<<<2, 1024, (size_t)P * 8, st>>>(voc->D, F, P);
+  return 2;
 }
 
 // SearchByBoW against nKF uploaded KeyFrame features: 4 (5 with the orientation check) launches
 int ft_launch_bow_search(const FtBowSource& S, const FtBowFrame& F, const FtBowSearch& Q, int nKF, int capF, float nnratio,
                          int checkOri, cudaStream_t st) {
   k_bow_search_init<<<(capF + 255) / 256, 256, 0, st>>>(F, Q, capF);
-  k_bow_group<<<1, 1024, (size_t)pow2_at_least(nKF) * 8, st>>>(Q.kfNode, nullptr, nKF, Q.kfIdxSorted, Q.kfNodeSorted, Q.kfGStart,
-                                                            Q.kfMeta, pow2_at_least(nKF));
+  k_bow_group<<<1, 1024, (size_t)pow2_at_least(nKF) * 8, st>>>(Q.kfNode, nKF, Q.kfIdxSorted, Q.kfNodeSorted, Q.kfGStart, Q.kfMeta,
+                                                            pow2_at_least(nKF));
   k_bow_search<<<(nKF + 3) / 4, 128, 0, st>>>(S, F, Q, nnratio, checkOri);
   if (checkOri) k_bow_finish<<<1, 1024, 0, st>>>(F, Q);
   return checkOri ? 4 : 3;
