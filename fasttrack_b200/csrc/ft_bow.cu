@@ -200,10 +200,23 @@ __global__ void __launch_bounds__(1024) k_bow_vector(FtVocDevice V, FtBowFrame F
   }
   __syncthreads();
   if (must) {
-    if (threadIdx.x == 0) {                                  // BowVector::normalize sums in map order
+    // BowVector::normalize sums in map order: one thread, strictly sequential, so the doubles equal the reference's.
+    // The addends are staged in shared memory (the sort keys are dead by now) to keep the chain at add latency.
+    double* val = reinterpret_cast<double*>(key);
+    for (int r = threadIdx.x; r < nd; r += blockDim.x) {
+      const double v = F.bowVals[r];
+      val[r] = V.scoring != 1 ? fabs(v) : v * v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
       double norm = 0.0;
-      if (V.scoring != 1) { for (int r = 0; r < nd; r++) norm += fabs(F.bowVals[r]); }
-      else { for (int r = 0; r < nd; r++) norm += F.bowVals[r] * F.bowVals[r]; norm = sqrt(norm); }
+      int r = 0;
+      for (; r + 4 <= nd; r += 4) {
+        const double a = val[r], b = val[r + 1], c = val[r + 2], d = val[r + 3];
+        norm += a; norm += b; norm += c; norm += d;
+      }
+      for (; r < nd; r++) norm += val[r];
+      if (V.scoring == 1) norm = sqrt(norm);
       shNorm = norm;
     }
     __syncthreads();
@@ -234,6 +247,11 @@ __device__ __forceinline__ void bow_merge(unsigned& k1, int& d2, unsigned ok1, i
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), src/ORBmatcher.cc:322-523
+// The frame features of the node are loaded once: each lane keeps up to BOW_CACHE of them (index, descriptor, claimed bit)
+// in registers, so the in-order walk over the node's KeyFrame features has no dependent global load on its critical path
+// (the next KeyFrame feature is prefetched while the current one is scored). Nodes with more than 32 * BOW_CACHE frame
+// features continue from global memory with the claim table.
+#define BOW_CACHE 4
 __global__ void __launch_bounds__(128) k_bow_search(FtBowSource S, FtBowFrame F, FtBowSearch Q, float nnratio, int checkOri) {
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -253,18 +271,51 @@ __global__ void __launch_bounds__(128) k_bow_search(FtBowSource S, FtBowFrame F,
   if (lo >= F.fvMeta[1] || F.fvNode[F.fvGStart[lo]] != node) return;
   const int fb = F.fvGStart[lo], fe = F.fvGStart[lo + 1];
   const float factor = 1.0f / FT_BOW_HISTO;
+  // this lane's share of the node's frame features
+  int cIdx[BOW_CACHE];
+  uint4 c0[BOW_CACHE], c1[BOW_CACHE];
+  unsigned claimed = 0;
+#pragma unroll
+  for (int c = 0; c < BOW_CACHE; c++) {
+    const int p = fb + lane + 32 * c;
+    cIdx[c] = p < fe ? F.fvIdx[p] : -1;
+    if (cIdx[c] >= 0) { const uint4* df = bow_frame_desc(S, cIdx[c], nLeft); c0[c] = __ldg(df); c1[c] = __ldg(df + 1); }
+    else { c0[c] = make_uint4(0, 0, 0, 0); c1[c] = c0[c]; }
+  }
+  const int cachedEnd = min(fe, fb + 32 * BOW_CACHE);
+  // software pipeline over the KeyFrame features of the node
+  int realIdxKF = Q.kfIdxSorted[kb];
+  int has = Q.kfHasMp[realIdxKF];
+  const uint4* dk = reinterpret_cast<const uint4*>(Q.kfDesc + 32 * (size_t)realIdxKF);
+  uint4 a0 = __ldg(dk), a1 = __ldg(dk + 1);
+  float kfAngle = Q.kfAngle[realIdxKF];
   for (int q = kb; q < ke; q++) {
-    const int realIdxKF = Q.kfIdxSorted[q];
-    if (!Q.kfHasMp[realIdxKF]) continue;                      // !pMP || pMP->isBad()
-    const uint4* dk = reinterpret_cast<const uint4*>(Q.kfDesc + 32 * (size_t)realIdxKF);
-    const uint4 a0 = __ldg(dk), a1 = __ldg(dk + 1);
+    const int curKF = realIdxKF, curHas = has;
+    const uint4 b0 = a0, b1 = a1;
+    const float curAngle = kfAngle;
+    if (q + 1 < ke) {
+      realIdxKF = Q.kfIdxSorted[q + 1];
+      has = Q.kfHasMp[realIdxKF];
+      dk = reinterpret_cast<const uint4*>(Q.kfDesc + 32 * (size_t)realIdxKF);
+      a0 = __ldg(dk); a1 = __ldg(dk + 1);
+      kfAngle = Q.kfAngle[realIdxKF];
+    }
+    if (!curHas) continue;                                    // !pMP || pMP->isBad()
     unsigned k1 = 256u << 16, k1R = 256u << 16;               // bestDist1 = 256, bestIdxF = -1
     int d2 = 256, d2R = 256;
-    for (int p = fb + lane; p < fe; p += 32) {
+#pragma unroll
+    for (int c = 0; c < BOW_CACHE; c++) {
+      if (cIdx[c] < 0 || ((claimed >> c) & 1)) continue;      // vpMapPointMatches[realIdxF] already set
+      const int dist = ft_hamming256(b0, b1, c0[c], c1[c]);
+      const unsigned key = ((unsigned)dist << 16) | (unsigned)(lane + 32 * c);
+      if (fNleft == -1 || cIdx[c] < fNleft) bow_merge(k1, d2, key, 256);
+      else bow_merge(k1R, d2R, key, 256);
+    }
+    for (int p = cachedEnd + lane; p < fe; p += 32) {         // overflow of very large nodes
       const int realIdxF = F.fvIdx[p];
-      if (((volatile int*)Q.match)[realIdxF] >= 0) continue;  // vpMapPointMatches[realIdxF] already set
+      if (((volatile int*)Q.match)[realIdxF] >= 0) continue;
       const uint4* df = bow_frame_desc(S, realIdxF, nLeft);
-      const int dist = ft_hamming256(a0, a1, __ldg(df), __ldg(df + 1));
+      const int dist = ft_hamming256(b0, b1, __ldg(df), __ldg(df + 1));
       const unsigned key = ((unsigned)dist << 16) | (unsigned)(p - fb);
       if (fNleft == -1 || realIdxF < fNleft) bow_merge(k1, d2, key, 256);
       else bow_merge(k1R, d2R, key, 256);
@@ -276,41 +327,34 @@ __global__ void __launch_bounds__(128) k_bow_search(FtBowSource S, FtBowFrame F,
       bow_merge(k1, d2, ok1, od2);
       bow_merge(k1R, d2R, ok1R, od2R);
     }
-    if (lane == 0) {
-      const int bestDist1 = (int)(k1 >> 16), bestDist1R = (int)(k1R >> 16);
-      if (bestDist1 <= FT_BOW_TH_LOW) {
-        const float kfAngle = Q.kfAngle[realIdxKF];
-        if ((float)bestDist1 < __fmul_rn(nnratio, (float)d2)) {
-          const int bestIdxF = F.fvIdx[fb + (int)(k1 & 0xFFFFu)];
-          Q.match[bestIdxF] = realIdxKF;
-          if (checkOri) {
-            const float fa = bestIdxF < nLeft ? S.kps0[bestIdxF].angle : S.kps1[bestIdxF - nLeft].angle;
-            float rot = __fsub_rn(kfAngle, fa);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            int bin = (int)roundf(__fmul_rn(rot, factor));
-            if (bin == FT_BOW_HISTO) bin = 0;
-            Q.matchBin[bestIdxF] = bin;
-            atomicAdd(&Q.hist[bin], 1);
-          }
-          atomicAdd(&Q.result[0], 1);
+    // every lane holds the same (best, second) pairs: the decisions are uniform, lane 0 publishes them
+    const int bestDist1 = (int)(k1 >> 16), bestDist1R = (int)(k1R >> 16);
+    int posL = -1, posR = -1;
+    if (bestDist1 <= FT_BOW_TH_LOW) {
+      if ((float)bestDist1 < __fmul_rn(nnratio, (float)d2)) posL = (int)(k1 & 0xFFFFu);
+      if (bestDist1R <= FT_BOW_TH_LOW) posR = (int)(k1R & 0xFFFFu);                       // `ratio test || true` (:451)
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int pos = side ? posR : posL;
+      if (pos < 0) continue;
+      if (pos < 32 * BOW_CACHE && (pos & 31) == lane) claimed |= 1u << (pos >> 5);
+      if (lane == 0) {
+        const int bestIdxF = F.fvIdx[fb + pos];
+        Q.match[bestIdxF] = curKF;
+        if (checkOri) {
+          const float fa = bestIdxF < nLeft ? S.kps0[bestIdxF].angle : S.kps1[bestIdxF - nLeft].angle;
+          float rot = __fsub_rn(curAngle, fa);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          int bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == FT_BOW_HISTO) bin = 0;
+          Q.matchBin[bestIdxF] = bin;
+          atomicAdd(&Q.hist[bin], 1);
         }
-        if (bestDist1R <= FT_BOW_TH_LOW) {                    // `ratio test || true` (:451)
-          const int bestIdxFR = F.fvIdx[fb + (int)(k1R & 0xFFFFu)];
-          Q.match[bestIdxFR] = realIdxKF;
-          if (checkOri) {
-            const float fa = bestIdxFR < nLeft ? S.kps0[bestIdxFR].angle : S.kps1[bestIdxFR - nLeft].angle;
-            float rot = __fsub_rn(kfAngle, fa);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            int bin = (int)roundf(__fmul_rn(rot, factor));
-            if (bin == FT_BOW_HISTO) bin = 0;
-            Q.matchBin[bestIdxFR] = bin;
-            atomicAdd(&Q.hist[bin], 1);
-          }
-          atomicAdd(&Q.result[0], 1);
-        }
+        atomicAdd(&Q.result[0], 1);
       }
     }
-    __syncwarp();   // the claims written by lane 0 are visible to the next KeyFrame feature of this node
+    if (fe > cachedEnd) __syncwarp();   // claims of overflow features travel through the global table
   }
 }
 
@@ -386,33 +430,41 @@ cudaError_t ft_bow_frame_alloc(FtBowFrame* F, int cap, std::vector<void*>& owner
   return e;
 }
 
+// Device side of a search. `result` and `match` are one allocation ([0] nmatches, 3 pad, match[capF]) so that one D2H
+// brings the answer back; the uploaded KeyFrame side is one blob (desc | angle | node | hasMp, laid out for the call's nKF
+// by ft_bow_search_bind) so that one H2D carries it.
 cudaError_t ft_bow_search_alloc(FtBowSearch* Q, int capF, int capKF, std::vector<void*>& owner) {
   cudaError_t e = cudaSuccess;
-  if (!Q->match) {
-    e = balloc(owner, &Q->match, capF);
+  if (!Q->result) {
+    e = balloc(owner, &Q->result, (size_t)capF + 4);
+    if (e == cudaSuccess) Q->match = Q->result + 4;
     if (e == cudaSuccess) e = balloc(owner, &Q->matchBin, capF);
     if (e == cudaSuccess) e = balloc(owner, &Q->hist, 32);
-    if (e == cudaSuccess) e = balloc(owner, &Q->result, 4);
     if (e == cudaSuccess) e = balloc(owner, &Q->kfMeta, 4);
   }
   if (e == cudaSuccess && capKF > Q->kfCap) {   // KeyFrame-side arrays grow with the largest KeyFrame seen
-    void** old[] = {(void**)&Q->kfDesc, (void**)&Q->kfAngle, (void**)&Q->kfNode, (void**)&Q->kfHasMp, (void**)&Q->kfIdxSorted,
-                    (void**)&Q->kfNodeSorted, (void**)&Q->kfGStart};
+    void** old[] = {(void**)&Q->kfBlob, (void**)&Q->kfIdxSorted, (void**)&Q->kfNodeSorted, (void**)&Q->kfGStart};
     for (void** p : old) {
       if (!*p) continue;
       for (size_t i = 0; i < owner.size(); i++) if (owner[i] == *p) { owner.erase(owner.begin() + i); break; }
       cudaFree(*p); *p = nullptr;
     }
-    e = balloc(owner, &Q->kfDesc, (size_t)capKF * 32);
-    if (e == cudaSuccess) e = balloc(owner, &Q->kfAngle, capKF);
-    if (e == cudaSuccess) e = balloc(owner, &Q->kfNode, capKF);
-    if (e == cudaSuccess) e = balloc(owner, &Q->kfHasMp, capKF);
+    e = balloc(owner, &Q->kfBlob, (size_t)capKF * 41 + 64);
     if (e == cudaSuccess) e = balloc(owner, &Q->kfIdxSorted, capKF);
     if (e == cudaSuccess) e = balloc(owner, &Q->kfNodeSorted, capKF);
     if (e == cudaSuccess) e = balloc(owner, &Q->kfGStart, capKF + 1);
     if (e == cudaSuccess) Q->kfCap = capKF;
   }
   return e;
+}
+
+// blob layout for nKF features: desc[nKF][32] | angle[nKF] | node[nKF] | hasMp[nKF]; returns its size in bytes
+size_t ft_bow_search_bind(FtBowSearch* Q, int nKF) {
+  Q->kfDesc = Q->kfBlob;
+  Q->kfAngle = reinterpret_cast<float*>(Q->kfBlob + (size_t)32 * nKF);
+  Q->kfNode = reinterpret_cast<int*>(Q->kfBlob + (size_t)36 * nKF);
+  Q->kfHasMp = Q->kfBlob + (size_t)40 * nKF;
+  return (size_t)41 * nKF;
 }
 
 // transform of up to maxN features (the actual count is read on the device): 2 launches

@@ -4,6 +4,7 @@
 // Host-side constants are computed exactly the way ORBextractor's constructor does
 // (reference src/ORBextractor.cc:393-499): running float32 scale products, cvRound'ed level
 // sizes and per-level quotas, umax.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +106,8 @@ struct ft_context {
   int bowCap = 0;
   bool bowValid = false;
   int nLaunchBow = 0;
+  uint8_t* hBow = nullptr;   // pinned staging of ft_search_by_bow
+  size_t hBowBytes = 0;
   // per-stage CUDA-event timing (direct-launch mode only)
   int timing = 0;
   cudaEvent_t evA[FT_STAGE_COUNT] = {}, evB[FT_STAGE_COUNT] = {};
@@ -483,6 +486,7 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->hMp) cudaFreeHost(c->hMp);
   if (c->hOut) cudaFreeHost(c->hOut);
   if (c->hDepth) cudaFreeHost(c->hDepth);
+  if (c->hBow) cudaFreeHost(c->hBow);
   for (int i = 0; i < FT_STAGE_COUNT; i++) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -1465,16 +1469,28 @@ extern "C" ft_status ft_search_by_bow(ft_context* c, int n_kf, const uint8_t* kf
   int capKF = 1024;
   while (capKF < n_kf) capKF <<= 1;
   CK(ft_bow_search_alloc(&c->WQ, c->bowCap, capKF, c->allocs));
-  CK(cudaMemcpyAsync(c->WQ.kfDesc, kf_desc, (size_t)32 * n_kf, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->WQ.kfAngle, kf_angle, sizeof(float) * n_kf, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->WQ.kfNode, kf_node, sizeof(int) * n_kf, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->WQ.kfHasMp, kf_has_mp, (size_t)n_kf, cudaMemcpyHostToDevice, c->stream));
+  // pinned staging: the KeyFrame side goes up in one H2D, (nmatches, match[N]) comes back in one D2H
+  const size_t need = std::max((size_t)41 * capKF + 64, sizeof(int) * ((size_t)c->bowCap + 4));
+  if (need > c->hBowBytes) {
+    if (c->hBow) cudaFreeHost(c->hBow);
+    c->hBow = nullptr; c->hBowBytes = 0;
+    CK(cudaMallocHost((void**)&c->hBow, need));
+    c->hBowBytes = need;
+  }
+  const size_t blob = ft_bow_search_bind(&c->WQ, n_kf);
+  CK(cudaStreamSynchronize(c->stream));   // the staging buffer may still feed an earlier search
+  memcpy(c->hBow, kf_desc, (size_t)32 * n_kf);
+  memcpy(c->hBow + (size_t)32 * n_kf, kf_angle, sizeof(float) * n_kf);
+  memcpy(c->hBow + (size_t)36 * n_kf, kf_node, sizeof(int) * n_kf);
+  memcpy(c->hBow + (size_t)40 * n_kf, kf_has_mp, (size_t)n_kf);
+  CK(cudaMemcpyAsync(c->WQ.kfBlob, c->hBow, blob, cudaMemcpyHostToDevice, c->stream));
   c->nLaunchBow = ft_launch_bow_search(bow_source(c), c->W, c->WQ, n_kf, c->bowCap, nnratio, check_orientation ? 1 : 0, c->stream);
   CK(cudaGetLastError());
-  int nm = 0;
-  CK(cudaMemcpyAsync(match, c->WQ.match, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&nm, c->WQ.result, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->hBow, c->WQ.result, sizeof(int) * ((size_t)N + 4), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  const int* out = reinterpret_cast<const int*>(c->hBow);
+  const int nm = out[0];
+  memcpy(match, out + 4, sizeof(int) * N);
   if (nmatches) *nmatches = nm;
   return FT_OK;
 }

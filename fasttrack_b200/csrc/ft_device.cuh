@@ -227,12 +227,13 @@ struct FtBowFrame {
 };
 
 struct FtBowSearch {
+  int* result;               // [0] nmatches, [1..3] pad; match follows in the same allocation (one D2H)
   int* match;                // [capF] KeyFrame feature matched to each frame keypoint, -1 none
   int* matchBin;             // [capF] rotation-histogram bin of the match
   int* hist;                 // [32]
-  int* result;               // [0] nmatches
   int* kfMeta;               // [0] KeyFrame features in its FeatureVector, [1] groups
-  uint8_t* kfDesc; float* kfAngle; int* kfNode; uint8_t* kfHasMp;   // uploaded KeyFrame side [kfCap]
+  uint8_t* kfBlob;           // uploaded KeyFrame side, one H2D: desc | angle | node | hasMp, bound per call
+  uint8_t* kfDesc; float* kfAngle; int* kfNode; uint8_t* kfHasMp;
   int* kfIdxSorted; int* kfNodeSorted; int* kfGStart;
   int kfCap;
 };

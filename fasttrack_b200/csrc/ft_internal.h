@@ -37,6 +37,7 @@ void ft_internal_set_err(const char* msg);   // the thread-local text behind ft_
 int ft_vocabulary_device(const ft_vocabulary* v);
 cudaError_t ft_bow_frame_alloc(FtBowFrame* F, int cap, std::vector<void*>& owner);
 cudaError_t ft_bow_search_alloc(FtBowSearch* Q, int capF, int capKF, std::vector<void*>& owner);
+size_t ft_bow_search_bind(FtBowSearch* Q, int nKF);
 int ft_launch_bow_transform(const ft_vocabulary* voc, const FtBowSource& S, const FtBowFrame& F, int maxN, int levelsup,
                             cudaStream_t st);
 int ft_launch_bow_search(const FtBowSource& S, const FtBowFrame& F, const FtBowSearch& Q, int nKF, int capF, float nnratio,

@@ -534,11 +534,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   // Round r reads the stamps of buffer r%3 (all empty in round 0), scatters the decisions it makes into buffer
   // (r+1)%3 and clears buffer (r+2)%3: one cluster barrier per round.
   int rounds = 0;
+  for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = 0x7FFFFFFF;   // round 0: buffer 0 is empty, no need to read it back
   for (;;) {
-    int* mk = s.minKey + (rounds % 3) * stride;
     int* mkNext = s.minKey + ((rounds + 1) % 3) * stride;
     int* mkClear = s.minKey + ((rounds + 2) % 3) * stride;
-    for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = __ldcg(&mk[i]);
     __syncthreads();
     for (int i = gtid; i < nS; i += nThreads) mkClear[i] = 0x7FFFFFFF;
     if (gtid == 0) s.cursor[5 + ((rounds + 2) % 3)] = 0;
@@ -585,7 +584,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     }
     if (changed) s.cursor[5 + (rounds % 3)] = 1;
     cluster.sync();
+    // the "anything changed" flag and the stamps the next round reads are fetched together (one L2 round trip, not two);
+    // every thread of the CTA is past its scans, so the shared copy may be overwritten
     const int ch = __ldcg(&s.cursor[5 + (rounds % 3)]);
+    for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = __ldcg(&mkNext[i]);
     rounds++;
     if (!ch) break;
     if (rounds > a.M + 2) { if (gtid == 0) atomicOr(b.status, FT_ST_RESOLVE_NOCONV); break; }
