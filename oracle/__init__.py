@@ -670,6 +670,9 @@ def ref_frame_lib():
     R.ftref_stereo_matches.argtypes = [C.c_int, i32p, i32p, u8p, u8p, f32p, f32p, u8p, C.c_int, f32p, u8p, C.c_int, C.c_float,
                                        C.c_float, f32p, f32p]
     R.ftref_stereo_matches.restype = None
+    R.ftref_stereo_fisheye.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int, f32p, u8p, C.c_int, C.c_int, f32p, u8p, C.c_int, C.c_int,
+                                       i32p, i32p, f32p, f32p]
+    R.ftref_stereo_fisheye.restype = None
     R.ftref_stereo_from_rgbd.argtypes = [f32p, f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p]
     R.ftref_stereo_from_rgbd.restype = None
     R.ftref_search_by_bow.argtypes = [C.c_int, u8p, f32p, i32p, u8p, C.c_int, u8p, f32p, i32p, C.c_int, C.c_float, C.c_int, i32p]
@@ -746,6 +749,20 @@ def ref_stereo(exL, exR, kL, dL, kR, dR, mbf, mb):
                            np.ascontiguousarray(dL, np.uint8), len(kL), f(kR), np.ascontiguousarray(dR, np.uint8), len(kR),
                            mbf, mb, ur, dp)
     return dict(uRight=ur[:len(kL)], depth=dp[:len(kL)])
+
+
+def ref_fisheye(cam1, cam2, Rlr, tlr, sigma2, kL, dL, mono_left, kR, dR, mono_right):
+    """The reference's own Frame::ComputeStereoFishEyeMatches + KannalaBrandt8::TriangulateMatches (BFMatcher = the oracle's
+    cv2-pinned knn, JacobiSVD = the oracle's Jacobi routine): dict(l2r, r2l, depth, p3d)"""
+    R = ref_frame_lib()
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    nL, nR = len(kL), len(kR)
+    l2r = np.zeros(max(nL, 1), np.int32); r2l = np.zeros(max(nR, 1), np.int32)
+    depth = np.zeros(max(nL, 1), np.float32); p3d = np.zeros((max(nL, 1), 3), np.float32)
+    sigma2 = f(sigma2)
+    R.ftref_stereo_fisheye(f(cam1), f(cam2), f(Rlr).reshape(-1), f(tlr), sigma2, len(sigma2), f(kL), np.ascontiguousarray(dL, np.uint8),
+                           nL, int(mono_left), f(kR), np.ascontiguousarray(dR, np.uint8), nR, int(mono_right), l2r, r2l, depth, p3d)
+    return dict(l2r=l2r[:nL], r2l=r2l[:nR], depth=depth[:nL], p3d=p3d[:nL])
 
 
 def ref_stereo_from_rgbd(keys_xy, keys_un_x, depth, mbf):

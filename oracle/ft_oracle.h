@@ -15,8 +15,9 @@
 //   * the vendored DBoW2.
 // This restatement equals that code bit for bit on every input of tests/test_oracle_ref_extractor.py,
 // tests/test_oracle_ref_frame.py and tests/test_oracle_bow.py (golden fixtures tests/golden/ref_*.npz, dbow2_ref.npz).
-// Still restated only: ComputeStereoFishEyeMatches / TriangulateMatches (BFMatcher order pinned against cv2, SVD with a
-// tolerance), UndistortKeyPoints, remap / input resize (pinned against cv2). See DESIGN.md section 2.
+// Eigen::JacobiSVD (KannalaBrandt8::Triangulate) has no independent pin: the compiled reference function and this file
+// share one Jacobi routine. Still restated only: UndistortKeyPoints, remap / input resize (each pinned against cv2).
+// See DESIGN.md section 2.
 #pragma once
 #include <cstddef>
 #include <cstdint>

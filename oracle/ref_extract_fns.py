@@ -12,6 +12,7 @@ RANGES = [  # file, first line, last line, text expected on the first line
     ("src/Frame.cc", 749, 759, "bool Frame::PosInGrid("),
     ("src/Frame.cc", 835, 1005, "void Frame::ComputeStereoMatches()"),
     ("src/Frame.cc", 1065, 1086, "void Frame::ComputeStereoFromRGBD("),
+    ("src/Frame.cc", 1231, 1271, "void Frame::ComputeStereoFishEyeMatches()"),
     ("src/Frame.cc", 1308, 1382, "bool Frame::isInFrustumChecks("),
     ("src/MapPoint.cc", 502, 512, "float MapPoint::GetMinDistanceInvariance()"),
     ("src/MapPoint.cc", 531, 546, "int MapPoint::PredictScale(const float &currentDist, Frame* pF)"),
@@ -23,6 +24,10 @@ RANGES = [  # file, first line, last line, text expected on the first line
     ("src/ORBmatcher.cc", 2256, 2272, "int ORBmatcher::DescriptorDistance("),
     ("src/CameraModels/Pinhole.cpp", 43, 49, "Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)"),
     ("src/CameraModels/KannalaBrandt8.cpp", 67, 93, "Eigen::Vector2f KannalaBrandt8::project(const Eigen::Vector3f &v3D)"),
+    ("src/CameraModels/KannalaBrandt8.cpp", 111, 114, "Eigen::Vector3f KannalaBrandt8::unprojectEig(const cv::Point2f &p2D)"),
+    ("src/CameraModels/KannalaBrandt8.cpp", 116, 143, "cv::Point3f KannalaBrandt8::unproject(const cv::Point2f &p2D)"),
+    ("src/CameraModels/KannalaBrandt8.cpp", 306, 375, "float KannalaBrandt8::TriangulateMatches("),
+    ("src/CameraModels/KannalaBrandt8.cpp", 394, 406, "void KannalaBrandt8::Triangulate("),
 ]
 
 

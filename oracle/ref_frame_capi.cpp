@@ -1,7 +1,8 @@
 // ref_frame_capi.cpp -- C entry points over FUNCTIONS OF THE REFERENCE compiled from their own text (TEST INFRASTRUCTURE
 // ONLY). oracle/_ref/gen_frame_fns.inc is written at build time by oracle/ref_extract_fns.py: the verbatim text of
 //   Frame::{AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum, isInFrustumChecks, ComputeStereoMatches,
-//          ComputeStereoFromRGBD}, MapPoint::{Get*DistanceInvariance, PredictScale}, Pinhole / KannalaBrandt8::project,
+//          ComputeStereoFishEyeMatches, ComputeStereoFromRGBD}, MapPoint::{Get*DistanceInvariance, PredictScale},
+//   Pinhole::project, KannalaBrandt8::{project, unproject, unprojectEig, TriangulateMatches, Triangulate},
 //   ORBmatcher::{SearchByProjection (local map), SearchByProjection (last frame), SearchByBoW, RadiusByViewingCos,
 //               ComputeThreeMaxima, DescriptorDistance}
 // taken from the reference files where they lie; it is compiled against ref_stubs/ref_frame_shim.h. The entry points
@@ -239,6 +240,28 @@ void ftref_stereo_matches(int nlevels, const int* lw, const int* lh, const unsig
   F.ComputeStereoMatches();
   memcpy(uRight, F.mvuRight.data(), sizeof(float) * nL);
   memcpy(depth, F.mvDepth.data(), sizeof(float) * nL);
+}
+
+// Frame::ComputeStereoFishEyeMatches (+ KannalaBrandt8::TriangulateMatches / Triangulate / unproject / project)
+void ftref_stereo_fisheye(const float* cam1, const float* cam2, const float* Rlr, const float* tlr, const float* sigma2, int nlevels,
+                          const float* keysL6, const unsigned char* descL, int nL, int monoLeft, const float* keysR6,
+                          const unsigned char* descR, int nR, int monoRight, int* l2r, int* r2l, float* depth, float* p3d) {
+  RefFrame r;
+  Frame& F = r.F;
+  r.kb1.mvParameters.assign(cam1, cam1 + 8); r.kb2.mvParameters.assign(cam2, cam2 + 8);
+  F.mpCamera = &r.kb1; F.mpCamera2 = &r.kb2;
+  F.Nleft = nL; F.Nright = nR; F.N = nL + nR;
+  F.monoLeft = monoLeft; F.monoRight = monoRight;
+  F.mvKeys = keys_from(keysL6, nL); F.mvKeysRight = keys_from(keysR6, nR);
+  F.mDescriptors = desc_from(descL, nL); F.mDescriptorsRight = desc_from(descR, nR);
+  F.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+  set9(F.mRlr, Rlr); set3(F.mtlr, tlr);
+  F.ComputeStereoFishEyeMatches();
+  for (int i = 0; i < nL; i++) {
+    l2r[i] = F.mvLeftToRightMatch[i]; depth[i] = F.mvDepth[i];
+    for (int k = 0; k < 3; k++) p3d[3 * i + k] = F.mvStereo3Dpoints[i](k);
+  }
+  for (int i = 0; i < nR; i++) r2l[i] = F.mvRightToLeftMatch[i];
 }
 
 // Frame::ComputeStereoFromRGBD

@@ -104,3 +104,19 @@ def test_cuda_search_by_bow_matches_reference_golden(euroc_ctx):
         n, m = ctx.search_by_bow(kf_desc, kf_angle, kf_node, kf_has, ratio, ori)
         assert n == int(g["bow_%d_n" % ci]) and np.array_equal(m, g["bow_%d_match" % ci])
     vg.close()
+
+
+def test_cuda_fisheye_stereo_matches_reference_golden():
+    """ComputeStereoFishEyeMatches on the TUM-VI-shaped rig against the reference function's output: match tables exact,
+    depth within the tolerance the un-vendored Eigen::JacobiSVD leaves (DESIGN.md section 2)"""
+    g = np.load(GOLD_FRAME)
+    T = synth.TUMVI
+    L, R = synth.fisheye_pair(seed=3)
+    Rlr, tlr, _, _ = synth.tumvi_extrinsics()
+    ctx = ft.Context(T["width"], T["height"], nfeatures=1000, camera_type=1, cam1=T["cam1"], cam2=T["cam2"], lap_left=T["lap"],
+                     lap_right=T["lap"], bf=T["bf"], Tlr=np.hstack([Rlr, tlr[:, None]]))
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    r = ctx.download(0, stereo=True)
+    assert np.array_equal(r["l2r"], g["fisheye_stereo_l2r"]) and np.array_equal(r["r2l"], g["fisheye_stereo_r2l"])
+    assert np.allclose(r["depth"], g["fisheye_stereo_depth"], rtol=1e-4, atol=1e-5)
+    ctx.close()

@@ -85,6 +85,28 @@ def test_fisheye_local_map_search_matches_reference_golden():
         assert np.array_equal(ti[:, :4], g[p + "track_i"])
 
 
+def test_fisheye_stereo_matches_reference_golden():
+    """ComputeStereoFishEyeMatches + TriangulateMatches: match tables exact; depth and 3-D points within the tolerance of the
+    SVD stand-in (the reference's x/w is a float division, the oracle's a double one: one ulp)"""
+    g = np.load(GOLD)
+    exL, kL, dL, kR, dR, fo, _ = G.fisheye_frame()
+    assert np.array_equal(fo["l2r"], g["fisheye_stereo_l2r"]) and np.array_equal(fo["r2l"], g["fisheye_stereo_r2l"])
+    acc = fo["l2r"] >= 0
+    assert acc.sum() > 100
+    assert np.allclose(fo["depth"], g["fisheye_stereo_depth"], rtol=1e-6, atol=0)
+    assert np.allclose(fo["p3d"][acc], g["fisheye_stereo_p3d"][acc], rtol=1e-5, atol=1e-6)
+    if oracle.ref_frame_lib() is not None:   # live, with a partial lapping area (mono and stereo keypoints mixed)
+        L, R = synth.fisheye_pair(seed=8)
+        Rlr, tlr, Rrl, trl = synth.tumvi_extrinsics()
+        exL, exR = oracle.Extractor(800), oracle.Extractor(800)
+        mL, kL, dL = exL.extract(L, lap=(150, 511)); mR, kR, dR = exR.extract(R, lap=(0, 360))
+        a = oracle.fisheye(T["cam1"], T["cam2"], Rlr, tlr, exL.sigma2, kL, dL, mL, kR, dR, mR)
+        b = oracle.ref_fisheye(T["cam1"], T["cam2"], Rlr, tlr, exL.sigma2, kL, dL, mL, kR, dR, mR)
+        assert 0 < mL < len(kL) and (a["l2r"] >= 0).sum() > 50
+        assert np.array_equal(a["l2r"], b["l2r"]) and np.array_equal(a["r2l"], b["r2l"])
+        assert np.allclose(a["depth"], b["depth"], rtol=1e-6, atol=0)
+
+
 def test_search_by_bow_matches_reference_golden(euroc):
     g = np.load(GOLD)
     kL, dL = euroc["kL"], euroc["dL"]

@@ -110,6 +110,11 @@ def main():
         p = "fisheye_%d_" % int(all_obs)
         g[p + "n"], g[p + "holder"], g[p + "holder_obs"], g[p + "track_i"], g[p + "track_f"] = np.int32(n), h, ho, ti, tf
         print("fisheye local map all_obs=%s: %d matches" % (all_obs, n))
+    # Frame::ComputeStereoFishEyeMatches on the same rig (tables exact; depth / 3-D points carry the SVD stand-in's tolerance)
+    fr = oracle.ref_fisheye(T["cam1"], T["cam2"], Rlr, tlr, fexL.sigma2, fkL, fdL, 0, fkR, fdR, 0)
+    g["fisheye_stereo_l2r"], g["fisheye_stereo_r2l"] = fr["l2r"], fr["r2l"]
+    g["fisheye_stereo_depth"], g["fisheye_stereo_p3d"] = fr["depth"], fr["p3d"]
+    print("fisheye stereo: %d matches" % int((fr["l2r"] >= 0).sum()))
     # SearchByBoW, monocular-style and two-camera frames
     angle = np.ascontiguousarray(kL[:, 3])
     voc, kf_desc, kf_angle, kf_has = bow_case(dL, angle, 5, 1100)
