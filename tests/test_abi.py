@@ -60,6 +60,39 @@ def test_create_without_gpu_fails_loudly(lib):
     assert e.value.status == 2 and "no CPU fallback" in str(e.value)
 
 
+def test_vocabulary_host_side_errors(lib, tmp_path):
+    """ft_vocabulary_load_text / ft_vocabulary_create validate on the host before touching the device; with a valid tree
+    and no GPU they fail with FT_ERR_CUDA (no CPU fallback for the bag-of-words path either)."""
+    import numpy as np
+    import fasttrack_b200 as ft
+    from fasttrack_b200 import synth
+    from conftest import _has_gpu
+    with pytest.raises(ft.FtError) as e:
+        ft.Vocabulary.load_text(str(tmp_path / "missing.txt"))
+    assert e.value.status == 1
+    bad = tmp_path / "bad.txt"
+    bad.write_text("this is not a vocabulary\n1 2 3\n")
+    with pytest.raises(ft.FtError) as e:
+        ft.Vocabulary.load_text(str(bad))
+    assert e.value.status == 1 and "DBoW2" in str(e.value)
+    parent, leaf, desc, weight = synth.make_vocabulary(3, 2, seed=1)
+    broken = parent.copy(); broken[2] = 7                      # a parent that does not exist yet
+    with pytest.raises(ft.FtError) as e:
+        ft.Vocabulary.from_arrays(3, 2, 0, 0, broken, leaf, desc, weight)
+    assert e.value.status == 1
+    fwd = tmp_path / "fwd.txt"
+    synth.write_vocabulary_text(str(fwd), 3, 2, broken, leaf, desc, weight)
+    with pytest.raises(ft.FtError) as e:
+        ft.Vocabulary.load_text(str(fwd))
+    assert e.value.status == 1
+    if not _has_gpu():
+        good = tmp_path / "good.txt"
+        synth.write_vocabulary_text(str(good), 3, 2, parent, leaf, desc, weight)
+        with pytest.raises(ft.FtError) as e:
+            ft.Vocabulary.load_text(str(good))
+        assert e.value.status == 2
+
+
 def test_pattern_table_pinned():
     txt = open(os.path.join(ROOT, "include", "ft_orb_pattern.inc")).read()
     nums = [int(x) for x in re.findall(r"-?\d+", re.sub(r"//.*", "", txt))]
