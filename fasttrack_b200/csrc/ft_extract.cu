@@ -210,7 +210,7 @@ __device__ __forceinline__ int ft_fast_score(const uint8_t* c, int stride) {
 }
 
 #define FAST_THREADS 256
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+__global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                     int levelBegin, int levelEnd) {
   extern __shared__ uint8_t smem[];
   __shared__ int sWarp[FAST_THREADS / 32];
@@ -264,15 +264,21 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   if (tid == 0) { sAny = 0; sPass = 0; }
   __syncthreads();
   const int total = iw * ih;
-  // pass 1, four pixels per thread (one staged word): quick reject at minTh -- every 9-arc holds one pixel of each
+  // The reference runs cv::FAST(iniTh) and, only when that leaves the cell empty AFTER non-maximum suppression, cv::FAST(minTh)
+  // (:1157-1177). Same order here: on textured images nearly every cell is done after the first attempt, whose quick test
+  // passes a third fewer pixels to the expensive score than a single pass at minTh would.
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; attempt++) {
+  const int thr = attempt ? p.minTh : p.iniTh;
+  // pass 1, four pixels per thread (one staged word): quick reject at thr -- every 9-arc holds one pixel of each
   // opposite ring pair, so a corner needs (p0 | p8) & (p4 | p12) darker, or brighter, than the centre by more than
-  // minTh. Byte-SIMD compares; saturating +-minTh gives the same predicate as the integer test. Survivors are
+  // thr. Byte-SIMD compares; saturating +-thr gives the same predicate as the integer test. Survivors are
   // compacted into a list so that the expensive score runs on dense warps.
   {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(sImg);
     const int k0 = (ax + 3) >> 2, k1 = (ax + 3 + iw - 1) >> 2, nW = k1 - k0 + 1;
     const unsigned mNW = 0xFFFFFFFFu / (unsigned)nW + 1u;
-    const unsigned th4 = (unsigned)p.minTh * 0x01010101u;
+    const unsigned th4 = (unsigned)thr * 0x01010101u;
     const int items = ih * nW;
     for (int i0 = 0; i0 < items; i0 += FAST_THREADS) {
       const int i = i0 + tid;
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const int e = sList[j];
     const int y = e >> 8, x = e & 0xFF;
     int sc = ft_fast_score(&sImg[(y + 3) * rwPad + ax + (x + 3)], rwPad);
-    if (sc < p.minTh) sc = 0;
+    if (sc < thr) sc = 0;
     sSc[(y + 1) * sS + x + 4] = (uint8_t)sc;
   }
   __syncthreads();
@@ -356,6 +362,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
   }
   if (any20) sAny = 1;
   __syncthreads();
+  if (sAny || attempt) break;                 // block-uniform
+  // nothing survived at iniTh: again at minTh. Scores written above belong to pixels that pass at minTh too and are
+  // rewritten with the same values; the NMS plane is rewritten completely.
+  if (tid == 0) sPass = 0;
+  __syncthreads();
+  }
   const int th = sAny ? p.iniTh : p.minTh;
   // ordered compaction: thread t owns the contiguous pixel range [t*seg, (t+1)*seg) in row-major order
   const int seg = (total + FAST_THREADS - 1) / FAST_THREADS;
