@@ -673,6 +673,8 @@ def ref_frame_lib():
     R.ftref_stereo_fisheye.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int, f32p, u8p, C.c_int, C.c_int, f32p, u8p, C.c_int, C.c_int,
                                        i32p, i32p, f32p, f32p]
     R.ftref_stereo_fisheye.restype = None
+    R.ftref_undistort.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_int, f32p, f32p]
+    R.ftref_undistort.restype = None
     R.ftref_stereo_from_rgbd.argtypes = [f32p, f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p]
     R.ftref_stereo_from_rgbd.restype = None
     R.ftref_search_by_bow.argtypes = [C.c_int, u8p, f32p, i32p, u8p, C.c_int, u8p, f32p, i32p, C.c_int, C.c_float, C.c_int, i32p]
@@ -763,6 +765,18 @@ def ref_fisheye(cam1, cam2, Rlr, tlr, sigma2, kL, dL, mono_left, kR, dR, mono_ri
     R.ftref_stereo_fisheye(f(cam1), f(cam2), f(Rlr).reshape(-1), f(tlr), sigma2, len(sigma2), f(kL), np.ascontiguousarray(dL, np.uint8),
                            nL, int(mono_left), f(kR), np.ascontiguousarray(dR, np.uint8), nR, int(mono_right), l2r, r2l, depth, p3d)
     return dict(l2r=l2r[:nL], r2l=r2l[:nR], depth=depth[:nL], p3d=p3d[:nL])
+
+
+def ref_undistort(xy, cols, rows, K, dist):
+    """The reference's own Frame::UndistortKeyPoints + ComputeImageBounds (cv::undistortPoints = the oracle's cv2-pinned one):
+    returns (mvKeysUn xy [n,2], bounds [mnMinX, mnMaxX, mnMinY, mnMaxY])"""
+    R = ref_frame_lib()
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    xy, K, dist = f(xy).reshape(-1, 2), f(K), f(dist)
+    out = np.zeros((max(len(xy), 1), 2), np.float32); b = np.zeros(4, np.float32)
+    R.ftref_undistort(xy if len(xy) else np.zeros((1, 2), np.float32), len(xy), int(cols), int(rows), K,
+                      dist if len(dist) else np.zeros(1, np.float32), len(dist), out, b)
+    return out[:len(xy)], b
 
 
 def ref_stereo_from_rgbd(keys_xy, keys_un_x, depth, mbf):

@@ -10,6 +10,8 @@ RANGES = [  # file, first line, last line, text expected on the first line
     ("src/Frame.cc", 536, 610, "bool Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit)"),
     ("src/Frame.cc", 681, 747, "vector<size_t> Frame::GetFeaturesInArea("),
     ("src/Frame.cc", 749, 759, "bool Frame::PosInGrid("),
+    ("src/Frame.cc", 771, 804, "void Frame::UndistortKeyPoints()"),
+    ("src/Frame.cc", 806, 833, "void Frame::ComputeImageBounds(const cv::Mat &imLeft)"),
     ("src/Frame.cc", 835, 1005, "void Frame::ComputeStereoMatches()"),
     ("src/Frame.cc", 1065, 1086, "void Frame::ComputeStereoFromRGBD("),
     ("src/Frame.cc", 1231, 1271, "void Frame::ComputeStereoFishEyeMatches()"),

@@ -1,7 +1,7 @@
 // ref_frame_capi.cpp -- C entry points over FUNCTIONS OF THE REFERENCE compiled from their own text (TEST INFRASTRUCTURE
 // ONLY). oracle/_ref/gen_frame_fns.inc is written at build time by oracle/ref_extract_fns.py: the verbatim text of
 //   Frame::{AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum, isInFrustumChecks, ComputeStereoMatches,
-//          ComputeStereoFishEyeMatches, ComputeStereoFromRGBD}, MapPoint::{Get*DistanceInvariance, PredictScale},
+//          ComputeStereoFishEyeMatches, ComputeStereoFromRGBD, UndistortKeyPoints, ComputeImageBounds}, MapPoint::{Get*DistanceInvariance, PredictScale},
 //   Pinhole::project, KannalaBrandt8::{project, unproject, unprojectEig, TriangulateMatches, Triangulate},
 //   ORBmatcher::{SearchByProjection (local map), SearchByProjection (last frame), SearchByBoW, RadiusByViewingCos,
 //               ComputeThreeMaxima, DescriptorDistance}
@@ -262,6 +262,26 @@ void ftref_stereo_fisheye(const float* cam1, const float* cam2, const float* Rlr
     for (int k = 0; k < 3; k++) p3d[3 * i + k] = F.mvStereo3Dpoints[i](k);
   }
   for (int i = 0; i < nR; i++) r2l[i] = F.mvRightToLeftMatch[i];
+}
+
+// Frame::UndistortKeyPoints (mvKeysUn) and Frame::ComputeImageBounds (mnMinX, mnMaxX, mnMinY, mnMaxY)
+void ftref_undistort(const float* keysXY, int n, int cols, int rows, const float* K4, const float* dist, int ndist, float* outXY,
+                     float* bounds4) {
+  RefFrame r;
+  Frame& F = r.F;
+  r.pin1.mvParameters.assign(K4, K4 + 4);
+  F.mpCamera = &r.pin1;
+  F.mK = r.pin1.toK();
+  F.mDistCoef = cv::Mat(ndist > 0 ? ndist : 1, 1, CV_32F);
+  for (int i = 0; i < ndist; i++) F.mDistCoef.at<float>(i, 0) = dist[i];
+  F.N = n;
+  F.mvKeys.resize(n);
+  for (int i = 0; i < n; i++) { F.mvKeys[i].pt.x = keysXY[2 * i]; F.mvKeys[i].pt.y = keysXY[2 * i + 1]; }
+  F.UndistortKeyPoints();
+  for (int i = 0; i < n; i++) { outXY[2 * i] = F.mvKeysUn[i].pt.x; outXY[2 * i + 1] = F.mvKeysUn[i].pt.y; }
+  cv::Mat im(rows, cols, CV_8U);
+  F.ComputeImageBounds(im);
+  bounds4[0] = F.mnMinX; bounds4[1] = F.mnMaxX; bounds4[2] = F.mnMinY; bounds4[3] = F.mnMaxY;
 }
 
 // Frame::ComputeStereoFromRGBD

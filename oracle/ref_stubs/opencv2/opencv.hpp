@@ -101,12 +101,15 @@ class Mat {
   Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
   Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
   Mat row(int y) const { return rowRange(y, y + 1); }
+  Mat reshape(int /*channels*/) const { return *this; }   // N x 2 floats <-> N two-channel points: same bytes
   uchar* ptr(int y = 0) { return data + (size_t)y * step; }
   const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
   template <typename T> T* ptr(int y = 0) { return reinterpret_cast<T*>(data + (size_t)y * step); }
   template <typename T> const T* ptr(int y = 0) const { return reinterpret_cast<const T*>(data + (size_t)y * step); }
   template <typename T> T& at(int y, int x) { return reinterpret_cast<T*>(data + (size_t)y * step)[x]; }
   template <typename T> const T& at(int y, int x) const { return reinterpret_cast<const T*>(data + (size_t)y * step)[x]; }
+  template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }   // single-index access of a vector
+  template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
  private:
   int type_;
   size_t esz() const { return type_ == CV_32F ? 4 : 1; }

@@ -52,6 +52,20 @@ inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {   // 8U: integ
   for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) s += std::abs((int)a.ptr(y)[x] - (int)b.ptr(y)[x]);
   return (double)s;
 }
+// cv::undistortPoints(src, dst, K, distCoeffs, R = Mat(), P) for N x 2 float points with P == K: the oracle's restatement,
+// pinned bit-exactly against cv2.undistortPoints on 80k points (tests/golden/cv2_undistort.npz + live test)
+inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& dist, const Mat& /*R*/, const Mat& P) {
+  const float k4[4] = {K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2)};
+  const float p4[4] = {P.at<float>(0, 0), P.at<float>(1, 1), P.at<float>(0, 2), P.at<float>(1, 2)};
+  for (int i = 0; i < 4; i++) if (k4[i] != p4[i]) throw std::runtime_error("stand-in undistortPoints: P must equal K");
+  const int n = src.rows, nd = dist.rows * dist.cols;
+  std::vector<float> in((size_t)2 * n), out((size_t)2 * n), d(nd);
+  for (int i = 0; i < n; i++) { in[2 * i] = src.at<float>(i, 0); in[2 * i + 1] = src.at<float>(i, 1); }
+  for (int i = 0; i < nd; i++) d[i] = dist.ptr<float>()[i];
+  fto::undistort_points(in.data(), n, k4, d.data(), nd, out.data());
+  dst.create(n, 2, CV_32F);
+  for (int i = 0; i < n; i++) { dst.at<float>(i, 0) = out[2 * i]; dst.at<float>(i, 1) = out[2 * i + 1]; }
+}
 }  // namespace cv
 
 namespace Eigen {
@@ -201,6 +215,12 @@ class GeometricCamera {
 class Pinhole : public GeometricCamera {
  public:
   Eigen::Vector2f project(const Eigen::Vector3f& v3D);
+  cv::Mat toK() {   // Pinhole::toK (src/CameraModels/Pinhole.cpp): fx 0 cx; 0 fy cy; 0 0 1
+    cv::Mat K = cv::Mat::zeros(3, 3, CV_32F);
+    K.at<float>(0, 0) = mvParameters[0]; K.at<float>(1, 1) = mvParameters[1];
+    K.at<float>(0, 2) = mvParameters[2]; K.at<float>(1, 2) = mvParameters[3]; K.at<float>(2, 2) = 1.f;
+    return K;
+  }
   Eigen::Vector3f unprojectEig(const cv::Point2f&) { abort(); }
 };
 class KannalaBrandt8 : public GeometricCamera {   // include/CameraModels/KannalaBrandt8.h
@@ -251,6 +271,9 @@ class Frame {   // include/Frame.h
   vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
                                    const bool bRight = false) const;
   bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+  void UndistortKeyPoints();
+  void ComputeImageBounds(const cv::Mat& imLeft);
+  cv::Mat mK, mDistCoef;
   void ComputeStereoMatches();
   void ComputeStereoFishEyeMatches();
   void ComputeStereoFromRGBD(const cv::Mat& imDepth);

@@ -128,6 +128,20 @@ def test_search_by_bow_matches_reference_golden(euroc):
         assert (m[len(fkL):] >= 0).any()
 
 
+def test_undistortion_matches_reference_live():
+    """Frame::UndistortKeyPoints / ComputeImageBounds (the reference's text over the cv2-pinned undistortPoints)"""
+    if oracle.ref_frame_lib() is None:
+        pytest.skip("oracle/_ref/libft_ref_frame.so not built and no reference tree here")
+    rng = np.random.default_rng(3)
+    K = np.array([E["fx"], E["fy"], E["cx"], E["cy"]], np.float32)
+    for dist in ([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], [-0.28, 0.07, 0.0002, 1.8e-05, 0.01], [0.0, 0.1, 0, 0]):
+        xy = np.stack([rng.uniform(0, E["width"], 3000), rng.uniform(0, E["height"], 3000)], 1).astype(np.float32)
+        want = oracle.undistort_points(xy, K, np.array(dist, np.float32)) if dist[0] != 0 else xy   # Frame.cc:773
+        got, bounds = oracle.ref_undistort(xy, E["width"], E["height"], K, dist)
+        assert np.array_equal(got, want)
+        assert np.array_equal(bounds, oracle.image_bounds(E["width"], E["height"], K, np.array(dist, np.float32)))
+
+
 def test_reference_functions_live():
     """other seeds, sizes and thresholds than the golden, against the compiled reference functions themselves"""
     if oracle.ref_frame_lib() is None:
