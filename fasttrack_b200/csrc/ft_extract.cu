@@ -209,6 +209,12 @@ __device__ __forceinline__ int ft_fast_score(const uint8_t* c, int stride) {
   return max(pos, neg) - 1;
 }
 
+// floor(i / n) for the small run-time divisors of the cell geometry (interior width, words per row, cell columns):
+// c_recip[n] = ceil(2^32 / n), exact for i * n < 2^32; n = 1 has no 32-bit reciprocal and is passed through.
+#define FT_RECIP_N 256
+__constant__ unsigned c_recip[FT_RECIP_N];
+__device__ __forceinline__ int ft_div_small(int i, int n, unsigned m) { return n == 1 ? i : (int)__umulhi((unsigned)i, m); }
+
 #define FAST_THREADS 256
 __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                     int levelBegin, int levelEnd) {
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   int level = levelBegin;
   while (level + 1 < levelEnd && cell >= p.lv[level + 1].cellBase) level++;
   const FtLevel& L = p.lv[level];
-  const int ci = (cell - L.cellBase) / L.nCols, cj = (cell - L.cellBase) % L.nCols;
+  const int ci = ft_div_small(cell - L.cellBase, L.nCols, c_recip[L.nCols]), cj = (cell - L.cellBase) - ci * L.nCols;
   const FtEye& E = b.eye[eye];
   const int tid = threadIdx.x;
   // cell window (ORBextractor.cc:1136-1153); all quantities are integers held in floats there
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   const int iw = rw - 6, ih = rh - 6;
   // row / column of a flat interior index without an integer division per pixel: floor(i / iw) = umulhi(i, ceil(2^32 / iw))
   // (exact for i < 2^26 with iw <= 64)
-  const unsigned mIw = 0xFFFFFFFFu / (unsigned)iw + 1u;
+  const unsigned mIw = c_recip[iw];
   const int ax = iniX & 3;                      // the tile is staged with aligned 32-bit loads: ax bytes of slack in front
   const int rwPad = (rw + 6) & ~3;              // >= ax + rw, multiple of 4
   const int S = rwPad >> 2;                     // words per staged row
@@ -253,9 +259,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
     const uint8_t* srcA = E.pyr + L.offset + (size_t)iniY * L.pitch + (iniX - ax);   // 4-byte aligned
     const int wpr = (ax + rw + 3) >> 2;                                               // words per row
     uint32_t* sW = reinterpret_cast<uint32_t*>(sImg);
-    const unsigned mWpr = 0xFFFFFFFFu / (unsigned)wpr + 1u;
+    const unsigned mWpr = c_recip[wpr];
     for (int i = tid; i < rh * wpr; i += FAST_THREADS) {
-      const int y = (int)__umulhi((unsigned)i, mWpr), wx = i - y * wpr;
+      const int y = ft_div_small(i, wpr, mWpr), wx = i - y * wpr;
       sW[y * S + wx] = *reinterpret_cast<const uint32_t*>(srcA + (size_t)y * L.pitch + 4 * wx);
     }
     uint32_t* z = reinterpret_cast<uint32_t*>(sSc);
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(sImg);
     const int k0 = (ax + 3) >> 2, k1 = (ax + 3 + iw - 1) >> 2, nW = k1 - k0 + 1;
-    const unsigned mNW = 0xFFFFFFFFu / (unsigned)nW + 1u;
+    const unsigned mNW = c_recip[nW];
     const unsigned th4 = (unsigned)thr * 0x01010101u;
     const int items = ih * nW;
     for (int i0 = 0; i0 < items; i0 += FAST_THREADS) {
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
       unsigned pass = 0;
       int y = 0, xb = 0;
       if (i < items) {
-        y = (int)__umulhi((unsigned)i, mNW);
+        y = ft_div_small(i, nW, mNW);
         const int k = k0 + (i - y * nW);
         const uint32_t* r = W + (y + 3) * S + k;
         const unsigned c = r[0], prev = r[k > 0 ? -1 : 0], next = r[k + 1 < S ? 1 : 0];
@@ -337,11 +343,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
     uint32_t* Q = reinterpret_cast<uint32_t*>(sMx);
     const int sW4 = sS >> 2;
     const int nW = ((3 + iw) >> 2);               // words 1 .. nW hold the interior columns 4 .. 3 + iw
-    const unsigned mNW = 0xFFFFFFFFu / (unsigned)nW + 1u;
+    const unsigned mNW = c_recip[nW];
     const unsigned ini4 = (unsigned)p.iniTh * 0x01010101u;
     const int items = ih * nW;
     for (int i = tid; i < items; i += FAST_THREADS) {
-      const int y = (int)__umulhi((unsigned)i, mNW);
+      const int y = ft_div_small(i, nW, mNW);
       const int k = 1 + (i - y * nW);
       const uint32_t* r = P + (y + 1) * sW4 + k;
       const unsigned c = r[0];
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   const int beg = min(tid * seg, total), end = min(beg + seg, total);
   int cnt = 0;
   {
-    int y = (int)__umulhi((unsigned)beg, mIw), x = beg - y * iw;
+    int y = ft_div_small(beg, iw, mIw), x = beg - y * iw;
     for (int i = beg; i < end; i++) {
       const int v = sMx[(y + 1) * sS + x + 4];
       cnt += v >= th && v > 0;
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   int pos = base + incl - cnt;
   uint32_t* out = E.cellKp + L.cellKpBase + (size_t)(cell - L.cellBase) * L.cellCap;
   if (cnt) {
-    int y = (int)__umulhi((unsigned)beg, mIw), x = beg - y * iw;
+    int y = ft_div_small(beg, iw, mIw), x = beg - y * iw;
     for (int i = beg; i < end; i++) {
       const int v = sMx[(y + 1) * sS + x + 4];
       if (v >= th && v > 0) {
@@ -1096,6 +1102,13 @@ size_t ft_octree_smem_bytes(const FtParams& p, int level) {
 }
 
 cudaError_t ft_launch_extract_setup(const FtParams& p) {
+  {
+    unsigned recip[FT_RECIP_N];
+    recip[0] = 0; recip[1] = 0;
+    for (unsigned n = 2; n < FT_RECIP_N; n++) recip[n] = 0xFFFFFFFFu / n + 1u;
+    cudaError_t e0 = cudaMemcpyToSymbol(c_recip, recip, sizeof(recip));
+    if (e0 != cudaSuccess) return e0;
+  }
   size_t mx = 0;
   for (int l = 0; l < p.nlevels; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
   cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);

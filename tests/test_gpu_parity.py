@@ -204,7 +204,10 @@ def test_edge_images(kind):
     ctx.close()
 
 
-@pytest.mark.parametrize("shape,nf,nl", [((480, 640), 1000, 8), ((376, 1241), 2000, 8), ((512, 512), 1000, 8), ((240, 376), 300, 5)])
+# (480, 978) and (400, 1083): the last FAST cell column of level 0 is 4 / 1 interior pixels wide (one staged word per row),
+# (360, 1344): the same at level 1 (1120 px) -- the degenerate divisors of the per-cell index arithmetic
+@pytest.mark.parametrize("shape,nf,nl", [((480, 640), 1000, 8), ((376, 1241), 2000, 8), ((512, 512), 1000, 8), ((240, 376), 300, 5),
+                                         ((480, 978), 1500, 8), ((400, 1083), 1500, 6), ((360, 1344), 1500, 4)])
 def test_other_resolutions(shape, nf, nl):
     h, w = shape
     sc = synth.StereoScene(seed=31 + h, width=w, height=h, dmin=1.0, dmax=30.0, margin_x=96, margin_y=8)
