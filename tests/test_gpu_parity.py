@@ -224,6 +224,34 @@ def test_other_resolutions(shape, nf, nl):
     ctx.close()
 
 
+FUZZ_SHAPES = [(241, 320), (255, 443), (300, 599), (333, 641), (401, 753), (479, 851), (487, 999), (512, 1001), (350, 1119),
+               (377, 1153), (600, 800), (721, 1279), (384, 700), (297, 529), (450, 451), (613, 613)]
+
+
+@pytest.mark.parametrize("shape", FUZZ_SHAPES)
+def test_resolution_fuzz(shape):
+    """odd widths / heights, pitches that are no multiple of 4, square and wide images, 4-8 levels: every intermediate
+    stage of the extractor against the oracle (the FAST cell geometry, the resize tables and the blur tiles all depend on
+    the size)"""
+    h, w = shape
+    nl = 4 + (h + w) % 5
+    nf = 300 + (h * 7 + w) % 900
+    img = synth.StereoScene(seed=h + w, width=w, height=h, dmin=1.0, dmax=20.0, margin_x=64, margin_y=8).pair()[0]
+    ctx = ft.Context(w, h, nfeatures=nf, nlevels=nl, cam1=[400.0, 400.0, w / 2.0, h / 2.0], bf=40.0)
+    ctx.extract_stereo(img, img)
+    ex = oracle.Extractor(nf, 1.2, nl)
+    mono, k, d = ex.extract(img)
+    for eye in (0, 1):
+        for l in range(nl):
+            assert np.array_equal(ctx.level_image(eye, l), ex.level_image(l)), (shape, eye, l, "pyramid")
+            assert np.array_equal(ctx.level_image(eye, l, blurred=True), ex.level_image(l, blurred=True)) or \
+                ex.level_image(l, blurred=True) is None, (shape, eye, l, "blur")
+            assert np.array_equal(ctx.level_candidates(eye, l), ex.level_candidates(l)), (shape, eye, l, "FAST candidates")
+        r = ctx.download(eye)
+        assert np.array_equal(ft.keypoints_as_array(r["kps"]), k) and np.array_equal(r["desc"], d), (shape, eye)
+    ctx.close()
+
+
 def test_octree_fuzz_many_seeds():
     """the order-sensitive octree (incl. the std::sort tie order) on many different textures / quotas"""
     for seed in range(12):
