@@ -449,8 +449,17 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evJoin3, cudaEventDisableTiming));
+  for (int l = 0; l < P.nlevels; l++)
+    if (ft_octree_smem_bytes(P, l) + 4608 > 227 * 1024) {   // the per-level octree keeps its node list in shared memory
+      char buf[200];
+      snprintf(buf, sizeof(buf), "ft_context_create: %d features put %d octree nodes on level %d (%zu KB of shared memory, 227 KB available); "
+               "reduce nfeatures (about 6500 at scale factor 1.2)", cfg->nfeatures, P.lv[l].nodeCap, l, ft_octree_smem_bytes(P, l) >> 10);
+      set_err(buf);
+      return fail(FT_ERR_CAPACITY);
+    }
   CKF(ft_launch_extract_setup(P));
   CKF(ft_launch_sbp_setup(P));
+  CKF(ft_launch_stereo_setup(P));
   *out = c;
   return FT_OK;
 }

@@ -6,7 +6,9 @@
 
 
 cudaError_t ft_launch_extract_setup(const FtParams& p);
+size_t ft_octree_smem_bytes(const FtParams& p, int level);   // dynamic shared memory of k_octree for one level
 cudaError_t ft_launch_sbp_setup(const FtParams& p);
+cudaError_t ft_launch_stereo_setup(const FtParams& p);
 void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,
                      int rawH, cudaStream_t st);
 void ft_launch_resize_input(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, int rawW,

@@ -387,6 +387,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_fisheye_match(const __grid_co
   }
 }
 
+// the right-keypoint table staged by every CTA is 12 bytes per keypoint: above ~4000 features it exceeds the 48 KB a kernel
+// gets without opting in
+cudaError_t ft_launch_stereo_setup(const FtParams& p) {
+  return cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FtRightKp) * p.maxKp));
+}
+
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
                             cudaStream_t st) {
   k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, sizeof(FtRightKp) * p.maxKp, st>>>(p, b, s, mbf, mb);

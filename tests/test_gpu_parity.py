@@ -252,6 +252,41 @@ def test_resolution_fuzz(shape):
     ctx.close()
 
 
+@pytest.mark.parametrize("nf", [5000, 6500])
+def test_many_features(nf):
+    """the documented upper end (10000 features on a 1280x720 pair): octree levels with thousands of nodes, the gather
+    kernel's path without the shared-memory copy of the frame structure (more than ~7800 keypoints), stereo and a
+    25000-point local-map search"""
+    w, h = 1280, 720
+    L, R = synth.StereoScene(seed=77, width=w, height=h, dmin=1.0, dmax=48.0, margin_x=96, margin_y=8).pair()
+    c = dict(width=w, height=h, nfeatures=nf, nlevels=8, fx=700.0, fy=700.0, cx=w / 2.0, cy=h / 2.0, baseline=0.1)
+    ctx, mbf, mb = _ctx(c)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR, oL, oR = _oracle_pair(L, R, nf, 8)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert len(oL[1]) > 0.8 * nf
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    assert np.array_equal(gl["u_right"], st["uRight"]) and np.array_equal(gl["depth"], st["depth"])
+    M = 25000
+    mp = synth.mappoints(oL[1], oL[2], exL.scale, M, seed=5, width=w, height=h, fx=700.0, fy=700.0, cx=w / 2.0, cy=h / 2.0)
+    F = oracle.Frame(oL[1], oL[2], exL.scale, w, h, cam1=[700.0, 700.0, w / 2.0, h / 2.0, 0, 0, 0, 0], mbf=float(mbf),
+                     u_right=st["uRight"])
+    n_o, h_o, ho_o, ti, tf = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, mp["holder"],
+                                                   mp["holder_obs"])
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n_g, h_g, ho_g, _ = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, mp["holder"],
+                                                mp["holder_obs"])
+    gi, gf = ctx.track(M)
+    assert n_o > 1000
+    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
+        assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    else:
+        assert (ti[:, 4] != 0).sum() > 0 and abs(n_g - n_o) <= 5
+    ctx.close()
+
+
 def test_octree_fuzz_many_seeds():
     """the order-sensitive octree (incl. the std::sort tie order) on many different textures / quotas"""
     for seed in range(12):
