@@ -130,3 +130,45 @@ def test_fisheye_store_search_equals_snapshot_search(tum):
         assert ref[0] == got[0] and ref[0] > 20
         for a, b in zip(ref[1:], got[1:]):
             assert np.array_equal(a, b)
+
+
+def test_fisheye_many_features_search():
+    """4000 features per eye on the fisheye rig: the frame-side search structure of both eyes no longer fits the gather
+    kernel's shared memory, so the window walks read it from L2 (the kernel's other code path)"""
+    nf = 4000
+    L, R = synth.fisheye_pair(seed=5)
+    Rlr, tlr, Rrl, trl = synth.tumvi_extrinsics()
+    ctx = ft.Context(T["width"], T["height"], nfeatures=nf, camera_type=1, cam1=T["cam1"], cam2=T["cam2"], lap_left=T["lap"],
+                     lap_right=T["lap"], bf=T["bf"], Tlr=np.hstack([Rlr, tlr[:, None]]))
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR = oracle.Extractor(nf), oracle.Extractor(nf)
+    mL, kL, dL = exL.extract(L, lap=T["lap"]); mR, kR, dR = exR.extract(R, lap=T["lap"])
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert len(kL) > 3000
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), kL) and np.array_equal(gl["desc"], dL)
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), kR) and np.array_equal(gr["desc"], dR)
+    fo = oracle.fisheye(T["cam1"], T["cam2"], Rlr, tlr, exL.sigma2, kL, dL, mL, kR, dR, mR)
+    # ~600 ratio-test survivors go through TriangulateMatches here; its accept / reject thresholds (parallax, depth signs,
+    # chi-square) are evaluated on values that come out of device tanf / atan2f and the Jacobi SVD, so a decision that sits on
+    # a threshold may differ from the host's (the non-pinnable residue of DESIGN.md section 2): counted, not tolerated silently
+    dl = int((gl["l2r"] != fo["l2r"]).sum()); dr = int((gl["r2l"] != fo["r2l"]).sum())
+    assert dl <= 3 and dr <= 3, "fisheye match tables differ in %d / %d entries" % (dl, dr)
+    tables_equal = dl == 0 and dr == 0
+    c1 = T["cam1"]
+    M = 8000
+    mp = synth.mappoints(kL, dL, exL.scale, M, seed=17, width=512, height=512, fx=c1[0], fy=c1[1], cx=c1[2], cy=c1[3])
+    mp["flags"] |= 2
+    N = len(kL) + len(kR)
+    holder = np.full(N, -1, np.int32); hobs = np.zeros(N, np.uint8)
+    F = oracle.Frame(np.vstack([kL, kR]), np.vstack([dL, dR]), exL.scale, 512, 512, cam_type=1, cam1=T["cam1"], cam2=T["cam2"],
+                     mbf=T["bf"], n_left=len(kL), n_right=len(kR), l2r=fo["l2r"], r2l=fo["r2l"], Rrl=Rrl, trl=trl, tlr=tlr)
+    n_o, h_o, ho_o, ti, tf = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, holder, hobs)
+    ctx.set_pose(np.eye(3), np.zeros(3))
+    n_g, h_g, ho_g, _ = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, holder, hobs)
+    gi, gf = ctx.track(M)
+    assert n_o > 100
+    if tables_equal and np.array_equal(gi, ti[:, :4]) and np.array_equal(gf, tf):
+        assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    else:   # KB8 projection through device atan2f / sinf / cosf: last-ulp differences may move a borderline decision
+        assert abs(n_g - n_o) <= 0.02 * n_o + 2
+    ctx.close()

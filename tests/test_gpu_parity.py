@@ -287,6 +287,27 @@ def test_many_features(nf):
     ctx.close()
 
 
+@pytest.mark.parametrize("shape,nf", [((1080, 1920), 3000), ((1440, 2560), 2000)])
+def test_large_images(shape, nf):
+    """1080p / 1440p: more FAST candidates per level than the octree keeps in shared memory (its HBM scratch path), 50+ cell
+    columns, pyramid slabs of several MB"""
+    h, w = shape
+    L, R = synth.StereoScene(seed=h, width=w, height=h, dmin=1.0, dmax=60.0, margin_x=128, margin_y=8).pair()
+    c = dict(width=w, height=h, nfeatures=nf, nlevels=8, fx=1000.0, fy=1000.0, cx=w / 2.0, cy=h / 2.0, baseline=0.1)
+    ctx, mbf, mb = _ctx(c)
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR, oL, oR = _oracle_pair(L, R, nf, 8)
+    assert len(exL.level_candidates(0)) > 16384
+    for l in range(8):
+        assert np.array_equal(ctx.level_candidates(0, l), exL.level_candidates(l)), (shape, l)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), oL[1]) and np.array_equal(gl["desc"], oL[2])
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), oR[1]) and np.array_equal(gr["desc"], oR[2])
+    st = oracle.stereo(exL, exR, oL[1], oL[2], oR[1], oR[2], float(mbf), float(mb))
+    assert np.array_equal(gl["u_right"], st["uRight"]) and np.array_equal(gl["depth"], st["depth"])
+    ctx.close()
+
+
 def test_octree_fuzz_many_seeds():
     """the order-sensitive octree (incl. the std::sort tie order) on many different textures / quotas"""
     for seed in range(12):
