@@ -252,6 +252,27 @@ def test_resolution_fuzz(shape):
     ctx.close()
 
 
+@pytest.mark.parametrize("shape,nl,sf", [((480, 752), 1, 1.2), ((480, 752), 2, 1.2), ((360, 500), 3, 1.5), ((640, 480), 8, 1.2),
+                                         ((700, 400), 5, 1.2), ((300, 300), 2, 2.0)])
+def test_few_levels_portrait_and_scale_factors(shape, nl, sf):
+    """1-3 pyramid levels (the per-level branches of the launch graph), portrait images (one octree root) and other scale
+    factors, both eyes against the oracle incl. stereo"""
+    h, w = shape
+    nf = 600
+    L, R = synth.StereoScene(seed=h * 3 + w + nl, width=w, height=h, dmin=1.0, dmax=24.0, margin_x=64, margin_y=8).pair()
+    mbf = np.float32(40.0)
+    ctx = ft.Context(w, h, nfeatures=nf, nlevels=nl, scale_factor=sf, cam1=[400.0, 400.0, w / 2.0, h / 2.0], bf=float(mbf))
+    ctx.extract_stereo(L, R); ctx.stereo_match()
+    exL, exR = oracle.Extractor(nf, sf, nl), oracle.Extractor(nf, sf, nl)
+    _, kL, dL = exL.extract(L); _, kR, dR = exR.extract(R)
+    gl, gr = ctx.download(0, stereo=True), ctx.download(1)
+    assert np.array_equal(ft.keypoints_as_array(gl["kps"]), kL) and np.array_equal(gl["desc"], dL)
+    assert np.array_equal(ft.keypoints_as_array(gr["kps"]), kR) and np.array_equal(gr["desc"], dR)
+    st = oracle.stereo(exL, exR, kL, dL, kR, dR, float(mbf), float(mbf / np.float32(400.0)))
+    assert np.array_equal(gl["u_right"], st["uRight"]) and np.array_equal(gl["depth"], st["depth"])
+    ctx.close()
+
+
 @pytest.mark.parametrize("nf", [5000, 6500])
 def test_many_features(nf):
     """the documented upper end (10000 features on a 1280x720 pair): octree levels with thousands of nodes, the gather
