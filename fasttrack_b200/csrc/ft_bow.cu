@@ -398,12 +398,16 @@ __global__ void __launch_bounds__(1024) k_bow_finish(FtBowFrame F, FtBowSearch Q
 
 static int pow2_at_least(int n) { int p = 32; while (p < n) p <<= 1; return p; }
 
-static bool g_bowAttr = false;
+// function attributes are per device: opt the two sort kernels into large dynamic shared memory once on every device used
+static bool g_bowAttr[64] = {};
 static cudaError_t bow_kernel_attributes() {
-  if (g_bowAttr) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_bow_vector, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_BOW_MAX_FEATURES * 8);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && g_bowAttr[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(k_bow_vector, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_BOW_MAX_FEATURES * 8);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bow_group, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_BOW_MAX_FEATURES * 8);
-  g_bowAttr = e == cudaSuccess;
+  if (e == cudaSuccess && dev >= 0 && dev < 64) g_bowAttr[dev] = true;
   return e;
 }
 
