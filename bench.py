@@ -614,6 +614,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                 "algorithmic_bytes_per_launch": alg_bytes[top], "launch_ms": stage_ms[top]}
+    # every kernel against the same roofline: algorithmic bytes of the launch(es) / CUDA-event time, as a fraction of the HBM peak
+    stages_roofline = {k_: {"algorithmic_bytes": int(alg_bytes[k_]), "ms": stage_ms[k_],
+                            "achieved_gbs": alg_bytes[k_] / (stage_ms[k_] * 1e-3) / 1e9,
+                            "frac": alg_bytes[k_] / (stage_ms[k_] * 1e-3) / 1e9 / pk["hbm_gbs"]}
+                       for k_ in stage_ms if k_ in alg_bytes and stage_ms[k_] > 0}
     frame_bytes = sum(alg_bytes.values())
     lat_ms = float(step_ms.mean())
 
@@ -647,6 +652,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "stages_ms": stage_ms,
+            "stages_roofline": stages_roofline,
             "frame_algorithmic_bytes": int(frame_bytes),
             "frame_hbm_roofline_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
             "frame_hbm_roofline_frac_latency": frame_bytes / (lat_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
