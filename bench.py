@@ -279,6 +279,36 @@ def run_reference(args, rank, world):
                              "sample": "%d frames of the bench workload; L/R extraction on 2 threads as Frame.cc:127-130, "
                                        "stereo + SearchLocalPoints on 1; host has %d cores" % (args.steps, os.cpu_count())},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # Beside it, when oracle/_ref travelled with the snapshot: the reference's OWN code (src/ORBextractor.cc compiled as a whole,
+    # ComputeStereoMatches / isInFrustum / SearchByProjection compiled from their text) on the same frames. It runs on the
+    # OpenCV stand-in (scalar primitives, extra copies), so it is slower than the port above; the port stays the baseline.
+    try:
+        if oracle.ref_frame_lib() is not None:
+            import threading
+            rL, rR = oracle.RefExtractor(), oracle.RefExtractor()
+            n_ref = max(3, min(args.steps, 8))
+            t_ref = []
+            for i in range(n_ref + 1):
+                L, R = frames[i % len(frames)]
+                out = {}
+                t0 = time.perf_counter()
+                th = [threading.Thread(target=lambda key, ex, im: out.__setitem__(key, ex.extract(im)), args=a)
+                      for a in (("L", rL, L), ("R", rR, R))]
+                [x.start() for x in th]; [x.join() for x in th]
+                (_, kL, dL), (_, kR, dR) = out["L"], out["R"]
+                st = oracle.ref_stereo(rL, rR, kL, dL, kR, dR, float(mbf), float(mb))
+                F = oracle.RefFrame(kL, dL, exL.scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                                    mbf=float(mbf), u_right=st["uRight"])
+                mp = maps[i % len(frames)]
+                F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], TH,
+                                      np.full(len(kL), -1, np.int32), np.zeros(len(kL), np.uint8))
+                if i:
+                    t_ref.append((time.perf_counter() - t0) * 1e3)
+            line["reference_compiled"] = {"ms_per_step": float(np.mean(t_ref)), "value": 1000.0 / float(np.mean(t_ref)), "frames": n_ref,
+                                          "note": "oracle/_ref: the reference's own ORBextractor.cc + Frame / ORBmatcher function text on the "
+                                                  "OpenCV stand-in (includes the pyramid hand-over through Python); informational"}
+    except Exception as e:   # never let the extra leg break the arm
+        line["reference_compiled"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
 
 
