@@ -309,6 +309,32 @@ def run_reference(args, rank, world):
                                                   "OpenCV stand-in (includes the pyramid hand-over through Python); informational"}
     except Exception as e:   # never let the extra leg break the arm
         line["reference_compiled"] = {"unavailable": str(e)[:200]}
+    # What the real reference's OpenCV (SIMD / IPP) spends on the image primitives alone -- a lower bound for its extractor that
+    # the scalar port above cannot show: pyramid resize chain, the 8 Gaussian blurs and cv::FAST at iniThFAST on whole levels,
+    # for both eyes on one thread (no octree, orientation, descriptors, stereo or search). Informational.
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        sizes = [(exL.level_image(l).shape[1], exL.level_image(l).shape[0]) for l in range(E["nlevels"])]
+        fast = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True)
+        t_cv = []
+        for i in range(6):
+            L, R = frames[i % len(frames)]
+            t0 = time.perf_counter()
+            for im in (L, R):
+                lv = im
+                for l in range(E["nlevels"]):
+                    if l:
+                        lv = cv2.resize(lv, sizes[l], interpolation=cv2.INTER_LINEAR)
+                    cv2.GaussianBlur(lv, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+                    fast.detect(lv, None)
+            if i:
+                t_cv.append((time.perf_counter() - t0) * 1e3)
+        line["opencv_primitives"] = {"ms_per_step": float(np.mean(t_cv)), "cv2": cv2.__version__, "threads": 1,
+                                     "note": "cv2 resize chain + 8 GaussianBlur + FAST(20) on whole levels, both eyes; lower bound of the "
+                                             "reference's extractor with a SIMD OpenCV; informational"}
+    except Exception as e:
+        line["opencv_primitives"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
 
 
