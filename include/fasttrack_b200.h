@@ -50,7 +50,10 @@ typedef enum {
 typedef enum { FT_CAM_PINHOLE = 0, FT_CAM_KB8 = 1 } ft_camera_type;
 typedef enum { FT_SENSOR_STEREO = 0, FT_SENSOR_MONOCULAR = 1, FT_SENSOR_RGBD = 2 } ft_sensor;   /* System::eSensor subset */
 
-/* Settings the reference reads from YAML (src/Settings.cc) plus the rig geometry. */
+/* Settings the reference reads from YAML (src/Settings.cc) plus the rig geometry.
+ * Limits checked by ft_context_create (FT_ERR_INVALID / FT_ERR_CAPACITY with the numbers in ft_last_error): image at most
+ * 4000 x 4000; every pyramid level at least one 35-px FAST cell; aspect ratio at least 1:2; about 6500 features at scale
+ * factor 1.2 (the per-level octree keeps its node list in shared memory). */
 typedef struct {
   int device_id;
   int width, height;        /* Camera.width / Camera.height */
