@@ -4,7 +4,8 @@
   (tests/golden/dbow2_ref.npz, made by tools/make_dbow2_golden.py through oracle/_ref/libft_ref_dbow2.so).
 * test_transform_matches_reference_live: the same comparison against the compiled reference code itself, on fresh
   inputs, whenever oracle/_ref is built or can be built (skipped on a machine with neither the .so nor /root/reference).
-* test_search_by_bow_*: properties of the SearchByBoW restatement (no reference build of ORBmatcher.cc exists).
+* test_search_by_bow_*: properties of the SearchByBoW restatement (its comparison with the reference's own function text is in
+  tests/test_oracle_ref_frame.py).
 """
 import os
 
