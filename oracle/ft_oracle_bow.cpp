@@ -10,7 +10,8 @@
 //   FeatureVector::addFeature                          Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)    src/ORBmatcher.cc:322-523
 //   ORBmatcher::ComputeThreeMaxima                     src/ORBmatcher.cc:2210-2254
-// The transform is pinned against the reference's own DBoW2 compiled into oracle/_ref (tests/test_oracle_bow.py).
+// The transform is pinned against the reference's own DBoW2 compiled into oracle/_ref (tests/test_oracle_bow.py), SearchByBoW
+// against the reference's own function text compiled into oracle/_ref/libft_ref_frame.so (tests/test_oracle_ref_frame.py).
 #include <cmath>
 #include <cstring>
 #include <fstream>
