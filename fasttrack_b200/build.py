@@ -9,7 +9,7 @@ OUT_DIR = os.path.join(HERE, "_build")
 SO = os.path.join(OUT_DIR, "libfasttrack_b200.so")
 DRIVER_SRC = os.path.join(HERE, "host", "ft_sequence_driver.cpp")
 DRIVER_SO = os.path.join(OUT_DIR, "libft_sequence_driver.so")
-SOURCES = ["ft_context.cu", "ft_extract.cu", "ft_stereo.cu", "ft_sbp.cu", "ft_bow.cu"]
+SOURCES = ["ft_context.cu", "ft_extract.cu", "ft_octree.cu", "ft_stereo.cu", "ft_sbp.cu", "ft_bow.cu"]
 HEADERS = ["ft_device.cuh", "ft_camera.cuh", "ft_internal.h", "ft_sort.h",
            os.path.join("..", "..", "include", "fasttrack_b200.h"),
            os.path.join("..", "..", "include", "ft_orb_pattern.inc")]

@@ -80,6 +80,7 @@ struct ft_context {
   int lastM = 0;
   int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
   long long pyrBytes = 0;
+  int octDenseTotal = 0;   // dense octree cells per eye (all levels)
   // stereo rectification (optional): raw images are uploaded to dRaw and remapped into level 0 by k_remap
   int rectify = 0, rawW = 0, rawH = 0;
   size_t rawCap = 0;   // pixels the raw-input buffers hold
@@ -193,7 +194,7 @@ static ft_status build_params(ft_context* c) {
     }
     for (int i = 0; i < 16; i++) P.umax[i] = umax[i];
   }
-  int off = 0, cellBase = 0, cellKp = 0, cand = 0, lvlKp = 0, xt = 0, yt = 0, tiles = 0;
+  int off = 0, cellBase = 0, cellKp = 0, cand = 0, lvlKp = 0, xt = 0, yt = 0, tiles = 0, octX = 0, octY = 0;
   for (int l = 0; l < nl; l++) {
     FtLevel& L = P.lv[l];
     L.w = cv_round_f((float)cfg.width * c->invScale[l]);     // (:1500)
@@ -228,12 +229,15 @@ static ft_status build_params(ft_context* c) {
       return FT_ERR_INVALID;
     }
     L.hX = (float)(L.maxBorderX - FT_MIN_BORDER) / L.nIni;
-    L.nodeCap = L.quota + 4 * L.nIni + 8;
+    if (L.nIni > 8) { set_err("ft_context_create: aspect ratio above 8:1 is not supported"); return FT_ERR_INVALID; }
+    L.nodeCap = std::max(L.quota + 4 * L.nIni + 8, 32);
     L.lvlKpBase = lvlKp;
     L.lvlKpCap = L.nodeCap;
     lvlKp += L.lvlKpCap;
     L.xTab = xt; L.yTab = yt;
     xt += L.w; yt += L.h;
+    L.octTabX = octX; L.octTabY = octY;
+    octX += L.maxBorderX - FT_MIN_BORDER + 1; octY += L.maxBorderY - FT_MIN_BORDER + 1;
     L.blurTileBase = tiles;
     L.blurTilesX = (L.w + 63) / 64;
     tiles += L.blurTilesX * ((L.h + 31) / 32);
@@ -285,6 +289,17 @@ static ft_status build_tables(ft_context* c, int cellKpTotal, int candTotal, int
   CK(cudaMemcpy(dx, xTab.data(), xTab.size() * sizeof(int2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dy, yTab.data(), yTab.size() * sizeof(int2), cudaMemcpyHostToDevice));
   c->B.xTab = dx; c->B.yTab = dy;
+  // quadtree path tables of the octree kernel (they depend on the level geometry only)
+  int ox = 0, oy = 0;
+  for (int l = 0; l < P.nlevels; l++) { ox += P.lv[l].maxBorderX - FT_MIN_BORDER + 1; oy += P.lv[l].maxBorderY - FT_MIN_BORDER + 1; }
+  std::vector<uint32_t> octX(ox), octY(oy);
+  for (int l = 0; l < P.nlevels; l++) ft_octree_tables(P.lv[l], &octX[P.lv[l].octTabX], &octY[P.lv[l].octTabY]);
+  uint32_t *dox = nullptr, *doy = nullptr;
+  CK(dalloc(c, &dox, octX.size()));
+  CK(dalloc(c, &doy, octY.size()));
+  CK(cudaMemcpy(dox, octX.data(), octX.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(doy, octY.data(), octY.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  c->B.octTabX = dox; c->B.octTabY = doy;
   return FT_OK;
 }
 
@@ -303,6 +318,30 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   ft_status st = build_params(c);
   if (st != FT_OK) { delete c; return st; }
   FtParams& P = c->P;
+  {
+    // the per-level octree keeps its node list (and, when they fit, the level's candidates) in shared memory
+    const size_t budget = ft_octree_smem_budget();
+    const char* denseEnv = getenv("FT_OCT_DENSE");      // "0": general (sort-based) octree path only (tests, A/B runs)
+    int denseTotal = 0;
+    for (int l = 0; l < P.nlevels; l++) {
+      const bool ok = ft_octree_plan(P.lv[l], budget);
+      if (ok) {
+        if (denseEnv && denseEnv[0] == '0') P.lv[l].octDenseDepth = 0;
+        P.lv[l].octDenseBase = denseTotal;
+        if (P.lv[l].octDenseDepth > 0) denseTotal += P.lv[l].nIni << (2 * P.lv[l].octDenseDepth);
+        c->octDenseTotal = denseTotal;
+        continue;
+      }
+      {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "ft_context_create: %d features put %d octree nodes on level %d (60 B each, %zu KB of shared memory available); "
+                 "reduce nfeatures", cfg->nfeatures, P.lv[l].nodeCap, l, budget >> 10);
+        set_err(buf);
+        delete c;
+        return FT_ERR_CAPACITY;
+      }
+    }
+  }
   c->fisheye = cfg->camera_type == FT_CAM_KB8;
   c->cam1.type = c->cam2.type = cfg->camera_type;
   memcpy(c->cam1.p, cfg->cam1, 32); memcpy(c->cam2.p, cfg->cam2, 32);
@@ -378,7 +417,9 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
     CKF(dalloc(c, &E.cellKp, (size_t)cellKpTotal));
     CKF(dalloc(c, &E.cellCount, (size_t)P.totalCells));
     CKF(dalloc(c, &E.cand, (size_t)candTotal));
-    CKF(dalloc(c, &E.candNode, (size_t)candTotal));
+    CKF(dalloc(c, &E.octScratch, (size_t)candTotal * 20));
+    CKF(dalloc(c, &E.octCnt, (size_t)c->octDenseTotal + 4));
+    CKF(dalloc(c, &E.octBest, (size_t)c->octDenseTotal + 4));
     CKF(dalloc(c, &E.lvlCandCount, (size_t)FT_MAX_LEVELS));
     CKF(dalloc(c, &E.lvlKp, (size_t)lvlKpTotal));
     CKF(dalloc(c, &E.lvlKpCount, (size_t)FT_MAX_LEVELS));
@@ -449,14 +490,6 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
   CKF(cudaEventCreateWithFlags(&c->evJoin3, cudaEventDisableTiming));
-  for (int l = 0; l < P.nlevels; l++)
-    if (ft_octree_smem_bytes(P, l) + 4608 > 227 * 1024) {   // the per-level octree keeps its node list in shared memory
-      char buf[200];
-      snprintf(buf, sizeof(buf), "ft_context_create: %d features put %d octree nodes on level %d (%zu KB of shared memory, 227 KB available); "
-               "reduce nfeatures (about 6500 at scale factor 1.2)", cfg->nfeatures, P.lv[l].nodeCap, l, ft_octree_smem_bytes(P, l) >> 10);
-      set_err(buf);
-      return fail(FT_ERR_CAPACITY);
-    }
   CKF(ft_launch_extract_setup(P));
   CKF(ft_launch_sbp_setup(P));
   CKF(ft_launch_stereo_setup(P));
@@ -1576,9 +1609,18 @@ extern "C" ft_status ft_debug_level_candidates(ft_context* c, int eye, int level
   CK(cudaStreamSynchronize(c->stream));
   *n = cnt;
   if (!xyr || cap < cnt || cnt == 0) return FT_OK;
-  std::vector<uint32_t> tmp(cnt);
-  CK(cudaMemcpy(tmp.data(), c->B.eye[eye].cand + L.candBase, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < cnt; i++) { xyr[3 * i] = (float)ft_px(tmp[i]); xyr[3 * i + 1] = (float)ft_py(tmp[i]); xyr[3 * i + 2] = (float)ft_ps(tmp[i]); }
+  // canonical order = cell row-major, then the order inside the cell's slab (ORBextractor.cc:1131-1203)
+  const int nCells = L.nCols * L.nRows;
+  std::vector<int> cc(nCells);
+  std::vector<uint32_t> slab((size_t)nCells * L.cellCap);
+  CK(cudaMemcpy(cc.data(), c->B.eye[eye].cellCount + L.cellBase, sizeof(int) * nCells, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(slab.data(), c->B.eye[eye].cellKp + L.cellKpBase, sizeof(uint32_t) * slab.size(), cudaMemcpyDeviceToHost));
+  int i = 0;
+  for (int cell = 0; cell < nCells; cell++)
+    for (int k = 0; k < cc[cell] && i < cnt; k++, i++) {
+      const uint32_t w = slab[(size_t)cell * L.cellCap + k];
+      xyr[3 * i] = (float)ft_px(w); xyr[3 * i + 1] = (float)ft_py(w); xyr[3 * i + 2] = (float)ft_ps(w);
+    }
   return FT_OK;
 }
 

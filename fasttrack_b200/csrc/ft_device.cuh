@@ -16,6 +16,8 @@
 #define FT_HALF_PATCH 15       // :30
 #define FT_PATCH 31            // :29
 #define FT_MIN_BORDER 16       // EDGE_THRESHOLD-3 (ORBextractor.cc:1120)
+#define FT_OCT_D 12            // quadrant digits of an octree path key (ft_octree.cu)
+#define FT_OCT_EVEN_MASK 0x333333u   // digits of even depth are stored complemented
 
 struct FtLevel {
   int w, h;               // level size (cvRound(width * invScale))
@@ -38,6 +40,11 @@ struct FtLevel {
   int xTab, yTab;         // offsets into the resize coefficient tables
   int blurTileBase;       // first blur tile id
   int blurTilesX;
+  int octBinDepth;        // k_octree: leading quadrant digits that index the bins of its sort
+  int octCandSmem;        // k_octree: candidates the level keeps in shared memory (more -> HBM scratch)
+  int octTabX, octTabY;   // offsets into the octree path tables
+  int octDenseDepth;      // k_octree dense path: depth of the cells k_fast_cells counts into (0 = path off)
+  int octDenseBase;       // entry offset of this level's dense cells
   int pad;
 };
 
@@ -61,7 +68,9 @@ struct FtEye {
   uint32_t* cellKp;        // per-cell candidates: x:12 | y:12 | score:8 (relative to minBorder)
   int* cellCount;          // [totalCells]
   uint32_t* cand;          // flat per-level candidate lists in canonical order (same packing)
-  uint16_t* candNode;      // octree scratch: node code per candidate
+  uint8_t* octScratch;     // octree scratch (20 B per candidate slot) for levels whose candidates exceed shared memory
+  int* octCnt;             // dense cells of every level: keypoints per cell (filled by k_fast_cells, consumed + zeroed by k_octree)
+  unsigned* octBest;       // dense cells: response << 20 | (0xFFFFF - (cell << 9 | slot)) of the best keypoint
   int* lvlCandCount;       // [nlevels]
   uint32_t* lvlKp;         // kept keypoints per level after the octree (level coords, absolute): x:12|y:12|score:8
   int* lvlKpCount;         // [nlevels]
@@ -75,6 +84,8 @@ struct FtBuffers {
   FtEye eye[2];
   const int2* xTab;        // per level, per dst column: {sx, a0 | a1<<16}
   const int2* yTab;        // per level, per dst row:    {sy0 | sy1<<16, b0 | b1<<16}
+  const uint32_t* octTabX; // per level, per keypoint-area column: root << 24 | x half of the quadtree path (even bits)
+  const uint32_t* octTabY; // per level, per keypoint-area row: y half of the quadtree path (odd bits)
   int* status;             // device-side status word (capacity overflow flags)
   unsigned long long* stereoStats;   // FtStereoBuffers::stats (cleared by k_orient_desc for the stereo kernel)
 };

@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "ft_device.cuh"
+#include "ft_internal.h"
 #include "ft_sort.h"
 #include "ft_camera.cuh"
 
@@ -407,7 +408,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
     for (int i = beg; i < end; i++) {
       const int v = sMx[(y + 1) * sS + x + 4];
       if (v >= th && v > 0) {
-        if (pos < L.cellCap) out[pos] = ft_pack_xys(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, v);
+        if (pos < L.cellCap) {
+          const int X = x + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
+          out[pos] = ft_pack_xys(X, Y, v);
+          if (L.octDenseDepth > 0) {
+            // the octree's dense path (ft_octree.cu): count and best (response, canonical position) of the quadtree
+            // cell of depth octDenseDepth that holds this corner
+            const uint32_t q = (b.octTabX[L.octTabX + X] | b.octTabY[L.octTabY + Y]) ^ FT_OCT_EVEN_MASK;
+            const int di = L.octDenseBase + (int)(q >> (2 * (FT_OCT_D - L.octDenseDepth)));
+            atomicAdd(&E.octCnt[di], 1);
+            atomicMax(&E.octBest[di], ((unsigned)v << 20) | (0xFFFFFu - (((unsigned)(cell - L.cellBase) << 9) | (unsigned)pos)));
+          }
+        }
         pos++;
       }
       if (++x == iw) { x = 0; y++; }
@@ -417,474 +429,6 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
     E.cellCount[cell] = min(totalKp, L.cellCap);
     if (totalKp > L.cellCap) atomicOr(b.status, FT_ST_CELL_OVERFLOW);
   }
-}
-
-// ------------------------------------------------------------------------------------
-// Octree distribution. One CTA per (eye, level). The std::list of nodes becomes an array in
-// list order that is rebuilt every pass; a node's keypoints are not moved: every candidate
-// carries a 16-bit code (node slot * 4 + quadrant) that is remapped through a table.
-// ------------------------------------------------------------------------------------
-#define OCT_THREADS 512
-#ifdef FT_OCT_CLOCK
-#define OCT_TICK(slot) do { if (tid == 0 && E.octClock && (slot) < 64) E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + (slot)] = clock64(); } while (0)
-#else
-#define OCT_TICK(slot) do {} while (0)
-#endif
-#define OCT_SMEM_CANDS 16384   // candidates of one level held in shared memory (6 B each); larger levels use HBM scratch
-
-struct OctSmem {
-  // carved from dynamic shared memory, all arrays sized nodeCap
-  short4* bnd[2];      // ULx, ULy, BRx, BRy  (ping-pong)
-  int* cnt[2];         // keypoints per node
-  int* ccnt;           // [cap][4] child counts of the pass
-  int* posA;           // scan scratch
-  int* posB;
-  int* posC;
-  int* map;            // [cap*4] code -> node index in the current list
-  unsigned long long* vec[2];  // expandable nodes (key<<32 | node index), ping-pong
-  int* vecPos;         // node index -> position in processing order, -1 when not in vec
-};
-
-// exclusive scans of three per-node quantities by warp 0; returns totals through smem
-__device__ void oct_scan3(int n, const int* a, const int* b3, const int* c3, int* oa, int* ob, int* oc, int* totals,
-                          bool reverseA) {
-  // reverseA: oa[i] = sum of a[j] for j > i (children of later nodes go in front of earlier ones)
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int ra = 0, rb = 0, rc = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int ia = reverseA ? (n - 1 - i) : i;
-      int va = (i < n) ? a[ia] : 0, vb = (i < n) ? b3[i] : 0, vc = (i < n) ? c3[i] : 0;
-      int sa = va, sb = vb, sc = vc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o),
-                  tc = __shfl_up_sync(0xFFFFFFFFu, sc, o);
-        if (lane >= o) { sa += ta; sb += tb; sc += tc; }
-      }
-      if (i < n) { oa[ia] = ra + sa - va; ob[i] = rb + sb - vb; oc[i] = rc + sc - vc; }
-      ra += __shfl_sync(0xFFFFFFFFu, sa, 31); rb += __shfl_sync(0xFFFFFFFFu, sb, 31); rc += __shfl_sync(0xFFFFFFFFu, sc, 31);
-    }
-    if (lane == 0) { totals[0] = ra; totals[1] = rb; totals[2] = rc; }
-  }
-}
-
-// Counter increments of the candidate loops. While a pass has at most OCT_PRIV counters (the first passes funnel
-// thousands of candidates into a handful of counters and same-address shared atomics serialise) every warp
-// counts into its own private copy; oct_count_flush folds the copies into the real counters.
-#define OCT_PRIV 64
-__device__ __forceinline__ void oct_count(int* counters, int* priv, bool usePriv, int key) {
-  if (usePriv) atomicAdd(&priv[(threadIdx.x >> 5) * OCT_PRIV + key], 1);
-  else atomicAdd(&counters[key], 1);
-}
-__device__ __forceinline__ void oct_priv_clear(int* priv) {
-  for (int i = threadIdx.x; i < (OCT_THREADS / 32) * OCT_PRIV; i += OCT_THREADS) priv[i] = 0;
-}
-__device__ __forceinline__ void oct_count_flush(int* counters, const int* priv, int nCounters) {
-  for (int k = threadIdx.x; k < nCounters; k += OCT_THREADS) {
-    int sum = 0;
-#pragma unroll
-    for (int w = 0; w < OCT_THREADS / 32; w++) sum += priv[w * OCT_PRIV + k];
-    counters[k] += sum;
-  }
-}
-
-__device__ __forceinline__ void oct_child_bounds(short4 bd, int q, short4& out) {
-  // DivideNode (ORBextractor.cc:510-538): halfX = ceil((UR.x-UL.x)/2.f), halfY = ceil((BR.y-UL.y)/2.f)
-  const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
-  const int mx = bd.x + halfX, my = bd.y + halfY;
-  out.x = (q & 1) ? mx : bd.x;
-  out.z = (q & 1) ? bd.z : mx;
-  out.y = (q & 2) ? my : bd.y;
-  out.w = (q & 2) ? bd.w : my;
-}
-
-__global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
-                                                        int levelBegin) {
-  extern __shared__ __align__(16) uint8_t smemRaw[];
-  __shared__ int sTot[4];
-  __shared__ int sN, sMode, sVecN, sP, sCellTot;
-  __shared__ int sScan[OCT_THREADS / 32];
-  __shared__ int sChildP, sGrowP, sVecP;
-  __shared__ int sPriv[(OCT_THREADS / 32) * OCT_PRIV];
-  const int level = levelBegin + blockIdx.x;
-  const int eye = blockIdx.y;
-  const FtLevel& L = p.lv[level];
-  const FtEye& E = b.eye[eye];
-  const int tid = threadIdx.x;
-  const int cap = L.nodeCap;
-  const int N = L.quota;
-  const int nCells = L.nCols * L.nRows;
-
-  OctSmem S;
-  int* cellOff;          // [nCells + 1] exclusive prefix of the per-cell candidate counts
-  uint32_t* candS;       // [OCT_SMEM_CANDS]
-  uint16_t* codeS;       // [OCT_SMEM_CANDS]
-  {
-    uint8_t* q = smemRaw;
-    S.vec[0] = (unsigned long long*)q; q += sizeof(unsigned long long) * cap;
-    S.vec[1] = (unsigned long long*)q; q += sizeof(unsigned long long) * cap;
-    S.bnd[0] = (short4*)q; q += sizeof(short4) * cap;
-    S.bnd[1] = (short4*)q; q += sizeof(short4) * cap;
-    S.cnt[0] = (int*)q; q += 4 * cap;
-    S.cnt[1] = (int*)q; q += 4 * cap;
-    S.ccnt = (int*)q; q += 16 * cap;
-    S.posA = (int*)q; q += 4 * cap;
-    S.posB = (int*)q; q += 4 * cap;
-    S.posC = (int*)q; q += 4 * cap;
-    S.map = (int*)q; q += 16 * cap;
-    S.vecPos = (int*)q; q += 4 * cap;
-    cellOff = (int*)q; q += 4 * (nCells + 1);
-    q = (uint8_t*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
-    candS = (uint32_t*)q; q += 4 * OCT_SMEM_CANDS;
-    codeS = (uint16_t*)q;
-  }
-
-  OCT_TICK(0);
-  // ---- flat canonical order (cell row-major, then row-major inside the cell) ----
-  // exclusive scan of the per-cell counts, then every candidate finds its cell by binary search: the copy out of
-  // the per-cell slabs is one coalesced pass instead of a per-cell serial loop.
-  {
-    int running = 0;
-    for (int c0 = 0; c0 < nCells; c0 += OCT_THREADS) {
-      const int c = c0 + tid;
-      const int cnt = c < nCells ? E.cellCount[L.cellBase + c] : 0;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((tid & 31) >= o) incl += n;
-      }
-      if ((tid & 31) == 31) sScan[tid >> 5] = incl;
-      __syncthreads();
-      int off = running;
-      for (int w = 0; w < (tid >> 5); w++) off += sScan[w];
-      if (c < nCells) cellOff[c] = off + incl - cnt;
-      int tot = 0;
-      for (int w = 0; w < OCT_THREADS / 32; w++) tot += sScan[w];
-      running += tot;
-      __syncthreads();
-    }
-    if (tid == 0) {
-      int C = running;
-      cellOff[nCells] = C;
-      if (C > L.candCap) { C = L.candCap; atomicOr(b.status, FT_ST_CAND_OVERFLOW); }
-      sCellTot = C;
-      E.lvlCandCount[level] = C;
-    }
-    __syncthreads();
-  }
-  const int C = sCellTot;
-  OCT_TICK(1);
-  uint32_t* outKp = E.lvlKp + L.lvlKpBase;
-  if (C == 0) {
-    if (tid == 0) E.lvlKpCount[level] = 0;
-    return;
-  }
-  uint32_t* candG = E.cand + L.candBase;          // global copy: read back by ft_debug_level_candidates
-  const bool inSmem = C <= OCT_SMEM_CANDS;
-  uint32_t* cand = inSmem ? candS : candG;
-  uint16_t* code = inSmem ? codeS : (E.candNode + L.candBase);
-  {
-    // one warp per cell, four cells in flight per warp so the slab reads overlap
-    const int lane = tid & 31, warp = tid >> 5, nWarps = OCT_THREADS / 32;
-    for (int cell0 = warp * 4; cell0 < nCells; cell0 += nWarps * 4) {
-      uint32_t v[4]; int off[4], cnt[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int cell = cell0 + u;
-        off[u] = 0; cnt[u] = 0; v[u] = 0;
-        if (cell < nCells) {
-          off[u] = cellOff[cell]; cnt[u] = min(cellOff[cell + 1], C) - off[u];
-          if (lane < cnt[u]) v[u] = E.cellKp[L.cellKpBase + (size_t)cell * L.cellCap + lane];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (lane < cnt[u]) { candG[off[u] + lane] = v[u]; if (inSmem) candS[off[u] + lane] = v[u]; }
-        for (int k = 32 + lane; k < cnt[u]; k += 32) {   // rare: more than 32 survivors in one cell
-          const uint32_t w = E.cellKp[L.cellKpBase + (size_t)(cell0 + u) * L.cellCap + k];
-          candG[off[u] + k] = w; if (inSmem) candS[off[u] + k] = w;
-        }
-      }
-    }
-  }
-
-  OCT_TICK(2);
-  // ---- roots (ORBextractor.cc:664-706) ----
-  int cur = 0;  // ping-pong index of the current list
-  const int nIni = L.nIni;
-  const float hX = L.hX;
-  const int H = L.maxBorderY - FT_MIN_BORDER;
-  for (int i = tid; i < nIni; i += OCT_THREADS) {
-    short4 bd;
-    bd.x = (short)(int)__fmul_rn(hX, (float)i);
-    bd.z = (short)(int)__fmul_rn(hX, (float)(i + 1));
-    bd.y = 0; bd.w = (short)H;
-    S.bnd[0][i] = bd;
-    S.cnt[0][i] = 0;
-  }
-  const bool privRoots = nIni <= OCT_PRIV;
-  if (privRoots) oct_priv_clear(sPriv);
-  __syncthreads();
-  for (int c = tid; c < C; c += OCT_THREADS) {
-    const uint32_t pk = cand[c];
-    int r = (int)__fdiv_rn((float)ft_px(pk), hX);
-    if (r >= nIni) r = nIni - 1;
-    code[c] = (uint16_t)(r * 4);
-    oct_count(S.cnt[0], sPriv, privRoots, r);
-  }
-  __syncthreads();
-  if (privRoots) { oct_count_flush(S.cnt[0], sPriv, nIni); __syncthreads(); }
-  // drop empty roots
-  if (tid == 0) {
-    int n = 0;
-    for (int i = 0; i < nIni; i++) {
-      if (S.cnt[0][i] > 0) {
-        S.bnd[1][n] = S.bnd[0][i]; S.cnt[1][n] = S.cnt[0][i];
-        for (int q = 0; q < 4; q++) S.map[i * 4 + q] = n;
-        n++;
-      } else {
-        for (int q = 0; q < 4; q++) S.map[i * 4 + q] = -1;
-      }
-    }
-    sN = n; sMode = 0; sVecN = 0;
-  }
-  cur = 1;
-  __syncthreads();
-
-  OCT_TICK(3);
-  int tick = 4;
-  // ---- main loop ----
-  // sMode: 0 = normal pass, 1 = careful pass (largest-first with early break), 2 = finished
-  int vcur = 0;  // ping-pong of the expandable-node vector
-  for (int iter = 0; iter < 64; iter++) {
-    const int n = sN;
-    const int mode = sMode;
-    if (mode == 2) break;
-    OCT_TICK(tick); tick++;
-    if (tid == 0 && E.octClock && tick < 60) E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + 40 + (tick - 5)] = mode * 100000 + n;
-    short4* bnd = S.bnd[cur]; int* cnt = S.cnt[cur];
-    short4* bnd2 = S.bnd[cur ^ 1]; int* cnt2 = S.cnt[cur ^ 1];
-    const int m = sVecN;                 // size of the vector entering a careful pass
-    unsigned long long* vecPrev = S.vec[vcur];
-    unsigned long long* vecNew = S.vec[vcur ^ 1];
-
-    const bool usePriv = 4 * n <= OCT_PRIV;
-    if (usePriv) oct_priv_clear(sPriv);
-    // which nodes are split (speculatively, in careful mode) this pass
-    for (int i = tid; i < n; i += OCT_THREADS) {
-      S.vecPos[i] = -1;
-      S.ccnt[4 * i] = 0; S.ccnt[4 * i + 1] = 0; S.ccnt[4 * i + 2] = 0; S.ccnt[4 * i + 3] = 0;
-    }
-    if (mode == 1) {
-      // std::sort(..., compareNodes) (ORBextractor.cc:805): warp 0 replays libstdc++'s introsort loop, then the
-      // final insertion sort (= stable sort of what the loop leaves) is a parallel rank computation
-      OCT_TICK(20);
-      __syncthreads();   // the loop above initialises vecPos/ccnt; posC doubles as the range queue of the sort
-      ftsort::cta_introsort_loop(vecPrev, m, S.posA, S.posB, S.posC);
-      __syncthreads();
-      OCT_TICK(21);
-      ftsort::stable_rank(vecPrev, vecNew, m, tid, OCT_THREADS);
-      __syncthreads();
-      // processing order r = 0..m-1 walks the sorted vector from the back (:806)
-      for (int r = tid; r < m; r += OCT_THREADS) {
-        const unsigned long long e = vecNew[m - 1 - r];
-        vecPrev[m - 1 - r] = e;
-        S.vecPos[(int)(e & 0xFFFFFFFFu)] = r;
-      }
-    }
-    __syncthreads();
-    if (mode == 1) OCT_TICK(22); else OCT_TICK(27);
-    // candidates: remap code -> node, count children of nodes being split
-    for (int c = tid; c < C; c += OCT_THREADS) {
-      const int node = S.map[code[c]];
-      const bool split = (mode == 0) ? (cnt[node] > 1) : (S.vecPos[node] >= 0);
-      int q = 0;
-      if (split) {
-        const uint32_t pk = cand[c];
-        const short4 bd = bnd[node];
-        const int halfX = (bd.z - bd.x + 1) >> 1, halfY = (bd.w - bd.y + 1) >> 1;
-        q = (ft_px(pk) < bd.x + halfX ? 0 : 1) | (ft_py(pk) < bd.y + halfY ? 0 : 2);
-        oct_count(S.ccnt, sPriv, usePriv, 4 * node + q);
-      }
-      code[c] = (uint16_t)(node * 4 + q);
-    }
-    __syncthreads();
-    if (usePriv) { oct_count_flush(S.ccnt, sPriv, 4 * n); __syncthreads(); }
-
-    if (mode == 1) OCT_TICK(23); else OCT_TICK(28);
-    if (mode == 0) {
-      // per node: k = non-empty children, e = children with more than one keypoint
-      for (int i = tid; i < n; i += OCT_THREADS) {
-        int k = 0, e = 0, nm = 0;
-        if (cnt[i] > 1) {
-          for (int q = 0; q < 4; q++) { k += S.ccnt[4 * i + q] > 0; e += S.ccnt[4 * i + q] > 1; }
-        } else nm = 1;
-        S.posA[i] = k; S.posB[i] = nm; S.posC[i] = e;
-      }
-      __syncthreads();
-      OCT_TICK(29);
-      // posA <- children of later nodes (they end up in front), posB <- noMore nodes before i, posC <- vec offset
-      oct_scan3(n, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, true);
-      __syncthreads();
-      OCT_TICK(30);
-      const int totalChildren = sTot[0], nNew = sTot[0] + sTot[1], nToExpand = sTot[2];
-      if (nNew > cap) {  // cannot happen (list <= N+3, roots*4); guarded so a logic slip cannot corrupt memory
-        if (tid == 0) { atomicOr(b.status, FT_ST_NODE_OVERFLOW); E.lvlKpCount[level] = 0; }
-        return;
-      }
-      for (int i = tid; i < n; i += OCT_THREADS) {
-        if (cnt[i] > 1) {
-          const short4 bd = bnd[i];
-          int after = 0;   // non-empty children with a higher quadrant index are pushed later => sit in front
-          int vpos = S.posC[i];
-          int pos[4];
-          for (int q = 3; q >= 0; q--) { pos[q] = S.posA[i] + after; after += S.ccnt[4 * i + q] > 0; }
-          for (int q = 0; q < 4; q++) {
-            const int cc = S.ccnt[4 * i + q];
-            if (cc > 0) {
-              short4 cb; oct_child_bounds(bd, q, cb);
-              bnd2[pos[q]] = cb; cnt2[pos[q]] = cc;
-              S.map[4 * i + q] = pos[q];
-              if (cc > 1) vecNew[vpos++] = ((unsigned long long)(((unsigned)cc << 12) | (unsigned)cb.x) << 32) | (unsigned)pos[q];
-            } else S.map[4 * i + q] = -1;
-          }
-        } else {
-          const int np = totalChildren + S.posB[i];
-          bnd2[np] = bnd[i]; cnt2[np] = cnt[i];
-          S.map[4 * i] = np; S.map[4 * i + 1] = np; S.map[4 * i + 2] = np; S.map[4 * i + 3] = np;
-        }
-      }
-      __syncthreads();
-      OCT_TICK(31);
-      if (tid == 0) {
-        sN = nNew; sVecN = nToExpand;
-        if (nNew >= N || nNew == n) sMode = 2;                 // (:790)
-        else if (nNew + nToExpand * 3 > N) sMode = 1;          // (:794)
-      }
-      cur ^= 1; vcur ^= 1;
-      __syncthreads();
-    } else {
-      // careful pass: nodes of the sorted vector are split from the back until the list reaches N (:806-853)
-      // posA[r] = non-empty children of the r-th processed node, posB[r] = growth (children - 1), posC[r] = expandable
-      for (int r = tid; r < m; r += OCT_THREADS) {
-        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
-        int k = 0, e = 0;
-        for (int q = 0; q < 4; q++) { k += S.ccnt[4 * node + q] > 0; e += S.ccnt[4 * node + q] > 1; }
-        S.posA[r] = k; S.posB[r] = k - 1; S.posC[r] = e;
-      }
-      if (tid == 0) sP = m;
-      __syncthreads();
-      // exclusive prefix over processing order: posA -> children before r, posB -> growth before r, posC -> vec offset
-      oct_scan3(m, S.posA, S.posB, S.posC, S.posA, S.posB, S.posC, sTot, false);
-      __syncthreads();
-      // number processed P: first r with n + growthBefore(r) + growth(r) >= N, else m
-      for (int r = tid; r < m; r += OCT_THREADS) {
-        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
-        int k = 0;
-        for (int q = 0; q < 4; q++) k += S.ccnt[4 * node + q] > 0;
-        if (n + S.posB[r] + (k - 1) >= N) atomicMin(&sP, r + 1);
-      }
-      __syncthreads();
-      const int P = sP;
-      OCT_TICK(24);
-      // totals restricted to the processed prefix
-      if (tid == 0) {
-        if (P == m) { sChildP = sTot[0]; sGrowP = sTot[1]; sVecP = sTot[2]; }
-        else { sChildP = S.posA[P]; sGrowP = S.posB[P]; sVecP = S.posC[P]; }
-      }
-      __syncthreads();
-      const int childP = sChildP, nNew = n + sGrowP, vecP = sVecP;
-      if (nNew > cap) {
-        if (tid == 0) { atomicOr(b.status, FT_ST_NODE_OVERFLOW); E.lvlKpCount[level] = 0; }
-        return;
-      }
-      // processed nodes: children go to the front, later-processed first
-      for (int r = tid; r < P; r += OCT_THREADS) {
-        const int node = (int)(vecPrev[m - 1 - r] & 0xFFFFFFFFu);
-        const short4 bd = bnd[node];
-        int k = 0;
-        for (int q = 0; q < 4; q++) k += S.ccnt[4 * node + q] > 0;
-        const int start = childP - S.posA[r] - k;   // children of nodes processed after r sit in front
-        int after = 0, vpos = S.posC[r];
-        int pos[4];
-        for (int q = 3; q >= 0; q--) { pos[q] = start + after; after += S.ccnt[4 * node + q] > 0; }
-        for (int q = 0; q < 4; q++) {
-          const int cc = S.ccnt[4 * node + q];
-          if (cc > 0) {
-            short4 cb; oct_child_bounds(bd, q, cb);
-            bnd2[pos[q]] = cb; cnt2[pos[q]] = cc;
-            S.map[4 * node + q] = pos[q];
-            if (cc > 1) vecNew[vpos++] = ((unsigned long long)(((unsigned)cc << 12) | (unsigned)cb.x) << 32) | (unsigned)pos[q];
-          } else S.map[4 * node + q] = -1;
-        }
-      }
-      __syncthreads();   // posA/posB of the processed prefix are consumed; they are reused below
-      OCT_TICK(25);
-      // surviving old nodes keep their relative order behind the new children
-      for (int i = tid; i < n; i += OCT_THREADS) {
-        const int r = S.vecPos[i];
-        S.posB[i] = (r >= 0 && r < P) ? 0 : 1;
-      }
-      __syncthreads();
-      if (tid < 32) {
-        // exclusive scan of the survive flags into posA
-        const int lane = tid;
-        int run = 0;
-        for (int base = 0; base < n; base += 32) {
-          const int i = base + lane;
-          const int v = i < n ? S.posB[i] : 0;
-          int s = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += t; }
-          if (i < n) S.posA[i] = run + s - v;
-          run += __shfl_sync(0xFFFFFFFFu, s, 31);
-        }
-      }
-      __syncthreads();
-      for (int i = tid; i < n; i += OCT_THREADS) {
-        if (S.posB[i]) {
-          const int np = childP + S.posA[i];
-          bnd2[np] = bnd[i]; cnt2[np] = cnt[i];
-          S.map[4 * i] = np; S.map[4 * i + 1] = np; S.map[4 * i + 2] = np; S.map[4 * i + 3] = np;
-        }
-      }
-      __syncthreads();
-      OCT_TICK(26);
-      if (tid == 0) {
-        sN = nNew; sVecN = vecP; E.octClock ? (void)(E.octClock[(eye * FT_MAX_LEVELS + level) * 64 + 63] = m) : (void)0;
-        if (nNew >= N || nNew == n) sMode = 2;   // (:855)
-      }
-      cur ^= 1; vcur ^= 1;
-      __syncthreads();
-    }
-  }
-
-  OCT_TICK(tick); tick++;
-  // ---- best keypoint per node: highest response, first in input order wins ties (:862-881) ----
-  const int n = sN;
-  unsigned* best = (unsigned*)S.posA;
-  for (int i = tid; i < n; i += OCT_THREADS) best[i] = 0;
-  __syncthreads();
-  for (int c = tid; c < C; c += OCT_THREADS) {
-    const int node = S.map[code[c]];
-    const unsigned key = ((unsigned)ft_ps(cand[c]) << 20) | (unsigned)(0xFFFFF - c);
-    atomicMax(&best[node], key);
-  }
-  __syncthreads();
-  if (n > L.lvlKpCap) {
-    if (tid == 0) { atomicOr(b.status, FT_ST_KP_OVERFLOW); E.lvlKpCount[level] = 0; }
-    return;
-  }
-  for (int i = tid; i < n; i += OCT_THREADS) {
-    const int c = 0xFFFFF - (int)(best[i] & 0xFFFFFu);
-    const uint32_t pk = cand[c];
-    outKp[i] = ft_pack_xys(ft_px(pk) + FT_MIN_BORDER, ft_py(pk) + FT_MIN_BORDER, ft_ps(pk));
-  }
-  if (tid == 0) E.lvlKpCount[level] = n;
-  OCT_TICK(tick);
 }
 
 // ------------------------------------------------------------------------------------
@@ -912,6 +456,7 @@ __device__ __forceinline__ float ft_fast_atan2(float y, float x) {
   return a;
 }
 
+#define OCT_THREADS 512      // k_debug_sort (the octree kernel itself lives in ft_octree.cu)
 #define OD_WARPS 8
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_constant__ FtParams p,
                                                                const __grid_constant__ FtBuffers b) {
@@ -1095,12 +640,6 @@ size_t ft_fast_smem_bytes(const FtParams& p) {
   }
   return mx;
 }
-size_t ft_octree_smem_bytes(const FtParams& p, int level) {
-  const FtLevel& L = p.lv[level];
-  return (size_t)L.nodeCap * (8 + 8 + 8 + 8 + 4 + 4 + 16 + 4 + 4 + 4 + 16 + 4) + 4 * (size_t)(L.nCols * L.nRows + 1) + 16 +
-         (size_t)OCT_SMEM_CANDS * 6 + 64;
-}
-
 cudaError_t ft_launch_extract_setup(const FtParams& p) {
   {
     unsigned recip[FT_RECIP_N];
@@ -1109,11 +648,9 @@ cudaError_t ft_launch_extract_setup(const FtParams& p) {
     cudaError_t e0 = cudaMemcpyToSymbol(c_recip, recip, sizeof(recip));
     if (e0 != cudaSuccess) return e0;
   }
-  size_t mx = 0;
-  for (int l = 0; l < p.nlevels; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
-  cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  cudaError_t e = ft_launch_octree_setup();
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_fast_smem_bytes(p));
+  return ft_set_max_dynamic_smem((const void*)k_fast_cells);
 }
 
 void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,
@@ -1137,11 +674,6 @@ void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaS
 void ft_launch_fast(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   const int cells = (l1 < p.nlevels ? p.lv[l1].cellBase : p.totalCells) - p.lv[l0].cellBase;
   k_fast_cells<<<dim3(cells, p.nEyes), FAST_THREADS, ft_fast_smem_bytes(p), st>>>(p, b, l0, l1);
-}
-void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
-  size_t mx = 0;
-  for (int l = l0; l < l1; l++) mx = ft_octree_smem_bytes(p, l) > mx ? ft_octree_smem_bytes(p, l) : mx;
-  k_octree<<<dim3(l1 - l0, p.nEyes), OCT_THREADS, mx, st>>>(p, b, l0);
 }
 void ft_launch_orient_desc(const FtParams& p, const FtBuffers& b, cudaStream_t st) {
   k_orient_desc<<<dim3((p.maxKp + OD_WARPS - 1) / OD_WARPS, p.nEyes), OD_WARPS * 32, 0, st>>>(p, b);

@@ -7,6 +7,25 @@
 
 cudaError_t ft_launch_extract_setup(const FtParams& p);
 size_t ft_octree_smem_bytes(const FtParams& p, int level);   // dynamic shared memory of k_octree for one level
+size_t ft_octree_smem_budget();                              // dynamic shared memory k_octree may use on this device
+bool ft_octree_plan(FtLevel& L, size_t smemBudget);          // fills octBinDepth / octCandSmem; false: node list too large
+void ft_octree_tables(const FtLevel& L, uint32_t* tabX, uint32_t* tabY);
+cudaError_t ft_launch_octree_setup();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function AND per device: a context must never lower what a live,
+// larger context needs. Every kernel with dynamic shared memory gets the device's opt-in maximum (minus its static
+// part) once; the launches pass what they actually use.
+inline cudaError_t ft_set_max_dynamic_smem(const void* func) {
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, func);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
 cudaError_t ft_launch_sbp_setup(const FtParams& p);
 cudaError_t ft_launch_stereo_setup(const FtParams& p);
 void ft_launch_remap(const FtParams& p, const FtBuffers& b, const uint8_t* rawL, const uint8_t* rawR, const int2* tab, int rawW,

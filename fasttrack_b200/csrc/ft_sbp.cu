@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "ft_device.cuh"
+#include "ft_internal.h"
 #include "ft_camera.cuh"
 
 #define GRID_CELLS (FT_GRID_COLS * FT_GRID_ROWS)
@@ -705,12 +706,10 @@ static size_t ft_gather_smem(const FtParams& p, int fisheye) {
 }
 static size_t ft_resolve_smem(int slotCap) { return (size_t)slotCap * 4 + (size_t)((slotCap + 3) / 4) * 4 + 2 * RS_LCAP * RS_THREADS * 4 + 16; }
 cudaError_t ft_launch_sbp_setup(const FtParams& p) {
-  cudaError_t e = cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_resolve_smem(2 * p.maxKp));
+  // per function and per device: the opt-in maximum once, never lowered by a later, smaller context
+  cudaError_t e = ft_set_max_dynamic_smem((const void*)k_resolve);
   if (e != cudaSuccess) return e;
-  {
-    const size_t g1 = ft_gather_smem(p, 1);
-    e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(g1 <= 200 * 1024 ? g1 : ft_gather_smem(p, 0) <= 200 * 1024 ? ft_gather_smem(p, 0) : 0));
-  }
+  e = ft_set_max_dynamic_smem((const void*)k_gather);
   if (e != cudaSuccess) return e;
   // 16-CTA clusters are a non-portable size: opt in, and fall back to the portable 8 when the device cannot place one
   g_resolveCluster = 8;

@@ -8,6 +8,7 @@
 //   k_fisheye_match    Frame::ComputeStereoFishEyeMatches (:1231-1271): brute-force 2-NN Hamming with Lowe
 //                      ratio, then KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:306-406).
 #include "ft_device.cuh"
+#include "ft_internal.h"
 #include "ft_camera.cuh"
 
 #define ST_WARPS 8
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_fisheye_match(const __grid_co
 // the right-keypoint table staged by every CTA is 12 bytes per keypoint: above ~4000 features it exceeds the 48 KB a kernel
 // gets without opting in
 cudaError_t ft_launch_stereo_setup(const FtParams& p) {
-  return cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FtRightKp) * p.maxKp));
+  (void)p;
+  return ft_set_max_dynamic_smem((const void*)k_stereo_match);   // per function and per device: never lowered by a smaller context
 }
 
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,

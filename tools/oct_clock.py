@@ -1,4 +1,6 @@
-"""Debug: per-phase clock64 deltas of the octree kernel (library must be built with FT_EXTRA_NVCC_FLAGS=-DFT_OCT_CLOCK)."""
+"""Debug: per-phase clock64 deltas of the octree kernel (library must be built with FT_EXTRA_NVCC_FLAGS=-DFT_OCT_CLOCK).
+Slots: 0 start, 1 cell scan, 2 copy + keys + bin histogram, 3 bin scan + scatter, 4 rank, 5 neighbour stats + decision,
+6 list construction, 7.. careful passes, 20 careful done, 21 end."""
 import os, sys, ctypes as C
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,11 +16,18 @@ buf = np.zeros((2, 16, 64), np.int64)
 ctx.L.ft_debug_oct_clock.argtypes = [C.c_void_p, C.c_void_p]
 ctx.L.ft_debug_oct_clock(ctx.h, buf.ctypes.data)
 cand, kp = ctx.level_counts(0)
+names = {0: "start", 1: "cellscan|dense-load", 2: "copy+key|pyramid", 3: "binscan+scatter", 4: "rank", 5: "stats", 6: "list", 20: "careful_done", 21: "end"}
 for lvl in range(8):
     t = buf[0, lvl]
-    ticks = t[:40]; n = int((ticks > 0).sum())
-    d = np.diff(ticks[:n])
-    modes = t[40:40 + max(n - 5, 0)]
-    sub = t[20:27]; print("   careful sub-phases", np.diff(sub).tolist(), "m", int(t[63]))
-    print("   last normal pass sub-phases (cand loop, node loop, scan, placement)", np.diff(t[27:32]).tolist())
-    print("level", lvl, "C", cand[lvl], "K", kp[lvl], "total cycles", int(ticks[n - 1] - ticks[0]), "phases", d.tolist(), "mode*1e5+n", modes.tolist())
+    slots = [s for s in range(30) if t[s] > 0]
+    prev = None
+    out = []
+    for s in slots:
+        if prev is not None:
+            out.append("%s:%d" % (names.get(s, "careful%d" % (s - 7)), t[s] - t[prev]))
+        prev = s
+    sub = [s for s in range(30, 36) if t[s] > 0]
+    if len(sub) > 1:
+        out.append("| first careful pass (sort loop, rank, splits, scan+P, children): " + " ".join(str(int(t[sub[i + 1]] - t[sub[i]])) for i in range(len(sub) - 1)))
+    if t[40]: out.append("| FELL BACK to the general path")
+    print("level", lvl, "C", cand[lvl], "K", kp[lvl], "total", int(t[slots[-1]] - t[slots[0]]), " ".join(out))
