@@ -415,7 +415,9 @@ template <typename T>
 static cudaError_t balloc(std::vector<void*>& owner, T** p, size_t n) {
   void* v = nullptr;
   cudaError_t e = cudaMalloc(&v, (n ? n : 1) * sizeof(T) + 256);
-  if (e == cudaSuccess) { owner.push_back(v); *p = (T*)v; e = cudaMemset(v, 0, (n ? n : 1) * sizeof(T) + 256); }
+  if (e == cudaSuccess) { owner.push_back(v); *p = (T*)v; e = cudaMemset(v, 0, (n ? n : 1) * sizeof(T) + 256);
+    // the memset runs on the legacy default stream, which the context's non-blocking stream does not wait for
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy); }
   return e;
 }
 

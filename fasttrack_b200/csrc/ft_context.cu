@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -37,9 +38,10 @@ struct ft_map_store {
   int cap = 0, device = 0;
   float *pos = nullptr, *normal = nullptr, *minmax = nullptr;
   uint8_t* desc = nullptr;
-  cudaEvent_t updated = nullptr;      // recorded after every scatter; a search on any context waits for it
-  bool everUpdated = false;
-  std::vector<ft_context*> users;     // attached contexts (an update waits for the last search of each)
+  std::vector<ft_context*> users;     // attached contexts: a search waits for the last update of each (ft_context::storeUpdated),
+                                      // an update for the last search (storeSearched) and the last update of each
+  std::mutex mu;                      // the mapping side updates while a tracking context searches: guards `users` and the
+                                      // event bookkeeping of the attached contexts
 };
 
 struct ft_context {
@@ -75,8 +77,11 @@ struct ft_context {
   uint8_t* dOut = nullptr; uint8_t* hOut = nullptr;
   size_t offOutHolder = 0, offOutObs = 0, offOutSel = 0;
   cudaGraphExec_t gExtract = nullptr, gStereo = nullptr, gFrame = nullptr;
+  FtSearchGraph gSearch;   // gather -> resolve, parameters refreshed per call
   int useGraph = 1;
+  int searchGraph = 1;     // FT_SEARCH_GRAPH=0: direct launches of gather / resolve (A/B runs)
   bool extracted = false, stereoDone = false, countsValid = false, framePending = false;
+  int frameStatus = 0;   // device status bits seen for the current frame (latched until the next extraction)
   int lastM = 0;
   int nLaunchExtract = 0, nLaunchStereo = 0, nLaunchSearch = 0;
   long long pyrBytes = 0;
@@ -97,8 +102,8 @@ struct ft_context {
   uint8_t* holderObsInit = nullptr;
   // persistent map store (optional)
   ft_map_store* store = nullptr;
-  cudaEvent_t storeSearched = nullptr, updStaged = nullptr;
-  bool storeSearchedValid = false, updStagedValid = false;
+  cudaEvent_t storeSearched = nullptr, updStaged = nullptr, storeUpdated = nullptr;
+  bool storeSearchedValid = false, updStagedValid = false, storeUpdatedValid = false;
   uint8_t *hUpd = nullptr, *dUpd = nullptr;
   int updCap = 0;
   // bag of words (ft_bow.cu): BowVector / FeatureVector of the current frame, SearchByBoW scratch; allocated on first use
@@ -130,7 +135,13 @@ template <typename T>
 static cudaError_t dalloc(ft_context* c, T** p, size_t n) {
   void* v = nullptr;
   cudaError_t e = cudaMalloc(&v, n * sizeof(T) + 256);
-  if (e == cudaSuccess) { c->allocs.push_back(v); *p = (T*)v; cudaMemset(v, 0, n * sizeof(T) + 256); }
+  if (e == cudaSuccess) {
+    c->allocs.push_back(v); *p = (T*)v;
+    // the memset runs on the legacy default stream, which the context's non-blocking streams do not wait for: finish it
+    // here so that no later (lazy) allocation can be zeroed after a kernel has already written into it
+    e = cudaMemset(v, 0, n * sizeof(T) + 256);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+  }
   return e;
 }
 
@@ -479,6 +490,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   { const char* e = getenv("FT_TOPOLOGY"); if (e && !strcmp(e, "grouped")) c->grouped = 1; }
+  { const char* e = getenv("FT_SEARCH_GRAPH"); if (e && e[0] == '0') c->searchGraph = 0; }
   for (int l = 0; l < P.nlevels; l++) {
     CKF(cudaStreamCreateWithFlags(&c->lvStream[l], cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&c->lvReady[l], cudaEventDisableTiming));
@@ -501,11 +513,13 @@ static void store_detach(ft_context* c) {
   ft_map_store* st = c->store;
   if (!st) return;
   c->store = nullptr;
-  for (size_t i = 0; i < st->users.size(); i++)
-    if (st->users[i] == c) { st->users.erase(st->users.begin() + i); break; }
-  if (!st->users.empty()) return;
+  {
+    std::lock_guard<std::mutex> lk(st->mu);
+    for (size_t i = 0; i < st->users.size(); i++)
+      if (st->users[i] == c) { st->users.erase(st->users.begin() + i); break; }
+    if (!st->users.empty()) return;
+  }
   cudaFree(st->pos); cudaFree(st->normal); cudaFree(st->minmax); cudaFree(st->desc);
-  if (st->updated) cudaEventDestroy(st->updated);
   delete st;
 }
 
@@ -516,10 +530,12 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->gExtract) cudaGraphExecDestroy(c->gExtract);
   if (c->gStereo) cudaGraphExecDestroy(c->gStereo);
   if (c->gFrame) cudaGraphExecDestroy(c->gFrame);
+  ft_search_graph_destroy(&c->gSearch);
   store_detach(c);
   if (c->hUpd) cudaFreeHost(c->hUpd);
   if (c->dUpd) cudaFree(c->dUpd);
   if (c->storeSearched) cudaEventDestroy(c->storeSearched);
+  if (c->storeUpdated) cudaEventDestroy(c->storeUpdated);
   if (c->updStaged) cudaEventDestroy(c->updStaged);
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
@@ -646,7 +662,7 @@ static ft_status run_extract(ft_context* c) {
     c->nLaunchExtract = enqueue_extract(c);
     CK(cudaGetLastError());
   }
-  c->extracted = true; c->stereoDone = false; c->countsValid = false; c->bowValid = false;
+  c->extracted = true; c->stereoDone = false; c->countsValid = false; c->bowValid = false; c->frameStatus = 0;
   return FT_OK;
 }
 
@@ -754,12 +770,16 @@ static ft_status check_device_status(ft_context* c, int status) {
   return FT_ERR_CAPACITY;
 }
 
+// A capacity overflow stays latched for the frame it happened in: every later call on that frame (downloads, searches)
+// reports it again instead of handing out clamped counts; the next extraction starts clean.
 static ft_status fetch_counts(ft_context* c) {
-  if (c->countsValid) return FT_OK;
-  CK(cudaMemcpyAsync(c->hCounts, c->dFrame, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // counts + status header
-  CK(cudaStreamSynchronize(c->stream));
-  c->countsValid = true;
-  return check_device_status(c, c->hCounts[4]);
+  if (!c->countsValid) {
+    CK(cudaMemcpyAsync(c->hCounts, c->dFrame, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // counts + status header
+    CK(cudaStreamSynchronize(c->stream));
+    c->countsValid = true;
+    c->frameStatus |= c->hCounts[4];
+  }
+  return check_device_status(c, c->frameStatus);
 }
 
 extern "C" ft_status ft_frame_counts(ft_context* c, int* nL, int* nR, int* monoL, int* monoR) {
@@ -813,7 +833,7 @@ static ft_status run_frame(ft_context* c) {
       cudaGraphDestroy(g);
     }
     CK(cudaGraphLaunch(c->gFrame, c->stream));
-    c->extracted = true; c->stereoDone = true; c->countsValid = false; c->bowValid = false;
+    c->extracted = true; c->stereoDone = true; c->countsValid = false; c->bowValid = false; c->frameStatus = 0;
     return FT_OK;
   }
   ft_status st = run_extract(c);
@@ -893,7 +913,7 @@ extern "C" ft_status ft_set_sensor(ft_context* c, int sensor) {
   c->sensor = sensor;
   c->P.nEyes = sensor == FT_SENSOR_STEREO ? 2 : 1;
   CK(cudaMemsetAsync(c->B.eye[1].counts, 0, 2 * sizeof(int), c->stream));   // the right eye stays empty
-  c->extracted = false; c->stereoDone = false; c->countsValid = false; c->bowValid = false;
+  c->extracted = false; c->stereoDone = false; c->countsValid = false; c->bowValid = false; c->frameStatus = 0;
   return FT_OK;
 }
 
@@ -1068,7 +1088,8 @@ extern "C" ft_status ft_frame_collect(ft_context* c, ft_keypoint* kpsL, uint8_t*
     if (p3d) memcpy(p3d, c->hFrame + c->offP3D, sizeof(float) * 3 * nl);
   }
   for (int i = 0; i < 4; i++) counts4[i] = c->hCounts[i];
-  return check_device_status(c, c->hCounts[4]);
+  c->frameStatus |= c->hCounts[4];
+  return check_device_status(c, c->frameStatus);
 }
 
 extern "C" ft_status ft_frame_construct(ft_context* c, const uint8_t* imgL, int stepL, const uint8_t* imgR, int stepR,
@@ -1211,8 +1232,12 @@ static ft_status search_run(ft_context* c, float th, int bFar, float thFar, floa
   FtResolveArgs ra;
   ra.M = M; ra.nLeft = 0; ra.nSlots = 2 * c->P.maxKp; ra.fisheye = c->fisheye; ra.nnratio = nnratio;   // nSlots: smem sizing bound
   ra.mode = mode; ra.checkOri = checkOri;
-  { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s); }
-  { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
+  if (c->useGraph && !c->timing && c->searchGraph) {
+    CK(ft_search_graph_run(&c->gSearch, c->P, c->B, c->G, c->S, Q, fa, ga, ra, M, s));
+  } else {
+    { StageScope t(c, FT_STAGE_GATHER, s); ft_launch_gather(c->P, c->B, c->G, c->S, Q, fa, ga, M, s); }
+    { StageScope t(c, FT_STAGE_RESOLVE, s); ft_launch_resolve(c->B, Q, c->S, ra, s); }
+  }
   c->nLaunchSearch = 2 + (c->fisheye ? 1 : 0);
   CK(cudaGetLastError());
   return FT_OK;
@@ -1310,7 +1335,7 @@ extern "C" ft_status ft_map_store_create(ft_context* c, int capacity) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&st->normal, (size_t)12 * capacity);
   if (e == cudaSuccess) e = cudaMalloc((void**)&st->minmax, (size_t)8 * capacity);
   if (e == cudaSuccess) e = cudaMalloc((void**)&st->desc, (size_t)32 * capacity);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->updated, cudaEventDisableTiming);
+  if (e == cudaSuccess && !c->storeUpdated) e = cudaEventCreateWithFlags(&c->storeUpdated, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     cudaFree(st->pos); cudaFree(st->normal); cudaFree(st->minmax); cudaFree(st->desc);
     delete st;
@@ -1319,8 +1344,8 @@ extern "C" ft_status ft_map_store_create(ft_context* c, int capacity) {
   }
   cudaMemsetAsync(st->pos, 0, (size_t)12 * capacity, c->stream); cudaMemsetAsync(st->normal, 0, (size_t)12 * capacity, c->stream);
   cudaMemsetAsync(st->minmax, 0, (size_t)8 * capacity, c->stream); cudaMemsetAsync(st->desc, 0, (size_t)32 * capacity, c->stream);
-  CK(cudaEventRecord(st->updated, c->stream));
-  st->everUpdated = true;
+  CK(cudaEventRecord(c->storeUpdated, c->stream));
+  c->storeUpdatedValid = true;
   st->users.push_back(c);
   c->store = st;
   return FT_OK;
@@ -1332,7 +1357,10 @@ extern "C" ft_status ft_map_store_attach(ft_context* c, ft_context* owner) {
   if (c->store) { set_err("ft_map_store_attach: the context already has a map store"); return FT_ERR_STATE; }
   if (owner->store->device != c->cfg.device_id) { set_err("ft_map_store_attach: contexts live on different devices"); return FT_ERR_INVALID; }
   c->store = owner->store;
-  c->store->users.push_back(c);
+  {
+    std::lock_guard<std::mutex> lk(c->store->mu);
+    c->store->users.push_back(c);
+  }
   return FT_OK;
 }
 
@@ -1363,12 +1391,21 @@ extern "C" ft_status ft_map_store_update(ft_context* c, int n, const int* slots,
   CK(cudaMemcpyAsync(c->dUpd, h, (size_t)68 * n + (size_t)4 * n, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(c->updStaged, s));
   c->updStagedValid = true;
-  // rows may be read by a search in flight on another context of the sequence: wait for the last search of each
-  for (ft_context* u : st->users)
-    if (u != c && u->storeSearchedValid) CK(cudaStreamWaitEvent(s, u->storeSearched, 0));
-  ft_launch_store_scatter(n, c->dUpd, st->pos, st->normal, st->minmax, st->desc, s);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(st->updated, s));
+  {
+    std::lock_guard<std::mutex> lk(st->mu);
+    if (!c->storeUpdated) CK(cudaEventCreateWithFlags(&c->storeUpdated, cudaEventDisableTiming));
+    // rows may be read by a search in flight on another context of the sequence, or written by an update still in flight
+    // on another context's stream: wait for the last search and the last update of each
+    for (ft_context* u : st->users) {
+      if (u == c) continue;
+      if (u->storeSearchedValid) CK(cudaStreamWaitEvent(s, u->storeSearched, 0));
+      if (u->storeUpdatedValid) CK(cudaStreamWaitEvent(s, u->storeUpdated, 0));
+    }
+    ft_launch_store_scatter(n, c->dUpd, st->pos, st->normal, st->minmax, st->desc, s);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->storeUpdated, s));
+    c->storeUpdatedValid = true;
+  }
   return FT_OK;
 }
 
@@ -1402,12 +1439,17 @@ extern "C" ft_status ft_search_store(ft_context* c, int M, const int* slots, con
   Q.slot = reinterpret_cast<const int*>(c->dMp + c->mpHolderBytes);
   Q.flags = reinterpret_cast<int*>(c->dMp + c->mpHolderBytes + (size_t)4 * M);
   c->residentM = M;
-  if (st->everUpdated) CK(cudaStreamWaitEvent(s, st->updated, 0));
-  rs = ft_search_resident(c, th, bFar, thFar, nnratio);
-  if (rs != FT_OK) return rs;
-  if (!c->storeSearched) CK(cudaEventCreateWithFlags(&c->storeSearched, cudaEventDisableTiming));
-  CK(cudaEventRecord(c->storeSearched, s));
-  c->storeSearchedValid = true;
+  {
+    std::lock_guard<std::mutex> lk(st->mu);
+    // every update outstanding on any attached context's stream lands before the search reads the rows
+    for (ft_context* u : st->users)
+      if (u != c && u->storeUpdatedValid) CK(cudaStreamWaitEvent(s, u->storeUpdated, 0));
+    rs = ft_search_resident(c, th, bFar, thFar, nnratio);
+    if (rs != FT_OK) return rs;
+    if (!c->storeSearched) CK(cudaEventCreateWithFlags(&c->storeSearched, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->storeSearched, s));
+    c->storeSearchedValid = true;
+  }
   return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
 }
 

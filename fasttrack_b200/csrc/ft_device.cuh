@@ -16,6 +16,12 @@
 #define FT_HALF_PATCH 15       // :30
 #define FT_PATCH 31            // :29
 #define FT_MIN_BORDER 16       // EDGE_THRESHOLD-3 (ORBextractor.cc:1120)
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; FT_PDL_WAIT() blocks until that predecessor has completed
+// and its writes are visible (a no-op for a normal launch). Every such kernel executes it on every path before it
+// touches anything the predecessor writes. FT_PDL_TRIGGER() in the predecessor lets the dependent be scheduled early.
+#define FT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define FT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define FT_OCT_D 12            // quadrant digits of an octree path key (ft_octree.cu)
 #define FT_OCT_EVEN_MASK 0x333333u   // digits of even depth are stored complemented
 

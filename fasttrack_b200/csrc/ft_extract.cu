@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FtParams
   const FtLevel& L = p.lv[level];
   const FtLevel& S = p.lv[level - 1];
   const int eye = blockIdx.z;
+  FT_PDL_TRIGGER();     // the next level's resize may be scheduled; it waits for this grid before it reads
+  FT_PDL_WAIT();        // levels >= 2 are launched as programmatic dependents of the previous level's resize
   ft_resize_rows(b, b.eye[eye].pyr + S.offset, S.w, S.pitch, b.eye[eye].pyr + L.offset, L);
 }
 
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   extern __shared__ uint8_t smem[];
   __shared__ int sWarp[FAST_THREADS / 32];
   __shared__ int sAny, sPass;
+  FT_PDL_TRIGGER();     // the level's octree kernel may be scheduled; it waits for this grid before it reads
   const int eye = blockIdx.y;
   const int cell = blockIdx.x + p.lv[levelBegin].cellBase;
   int level = levelBegin;
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   const int eye = blockIdx.y;
   const FtEye& E = b.eye[eye];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  FT_PDL_TRIGGER();     // the stereo kernel may be scheduled; it waits for this grid before it reads
   sPat[tid] = reinterpret_cast<const int*>(c_pattern)[tid];
   if (tid == 0) {
     int o = 0;
@@ -665,7 +669,8 @@ void ft_launch_resize_input(const FtParams& p, const FtBuffers& b, const uint8_t
 }
 void ft_launch_resize(const FtParams& p, const FtBuffers& b, int level, cudaStream_t st) {
   dim3 blk(32, 8), grd((p.lv[level].w + 127) / 128, (p.lv[level].h + 7) / 8, p.nEyes);
-  k_resize<<<grd, blk, 0, st>>>(p, b, level);
+  if (level >= 2) ft_launch_pdl(k_resize, grd, blk, 0, st, p, b, level);   // predecessor in the stream: resize of level - 1
+  else k_resize<<<grd, blk, 0, st>>>(p, b, level);
 }
 void ft_launch_blur(const FtParams& p, const FtBuffers& b, int l0, int l1, cudaStream_t st) {
   const int tiles = (l1 < p.nlevels ? p.lv[l1].blurTileBase : p.totalBlurTiles) - p.lv[l0].blurTileBase;

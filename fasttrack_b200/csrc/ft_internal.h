@@ -1,5 +1,7 @@
 // ft_internal.h -- host-side launch functions shared between the translation units.
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "ft_device.cuh"
@@ -51,6 +53,34 @@ void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers
                       const FtSbpBuffers& s, const FtFrustumArgs& fa, const FtGatherArgs& ga, int M, cudaStream_t st);
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st);
+
+// gather -> resolve as one CUDA graph whose kernel-node parameters are refreshed per call (ft_sbp.cu)
+struct FtSearchGraph {
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphNode_t gather = nullptr, resolve = nullptr, seq = nullptr;
+};
+cudaError_t ft_search_graph_run(FtSearchGraph* G, const FtParams& p, const FtBuffers& b, const FtGridBuffers& g,
+                                const FtStereoBuffers& stb, const FtSbpBuffers& s, const FtFrustumArgs& fa,
+                                const FtGatherArgs& ga, const FtResolveArgs& ra, int M, cudaStream_t st);
+void ft_search_graph_destroy(FtSearchGraph* G);
+
+// Launch `k` as a programmatic dependent of the previous kernel in the stream (FT_PDL=0 in the environment: plain launch).
+inline bool ft_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FT_PDL"); v = !(e && e[0] == '0'); }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t ft_launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = ft_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
 
 // ---- bag of words (ft_bow.cu) ----
 struct ft_vocabulary;

@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) k_octree(const __grid_constan
 #else
   long long* clk = nullptr;
 #endif
+  FT_PDL_WAIT();        // launched as a programmatic dependent of the level's k_fast_cells
   if (L.octDenseDepth > 0) {
     if (oct_dense_path(b, L, E, level, nd, area, sh, clk)) return;
     __syncthreads();
@@ -896,5 +897,5 @@ void ft_launch_octree(const FtParams& p, const FtBuffers& b, int l0, int l1, cud
     const int want = p.lv[l].candCap / 48;
     while (threads < OCT_MAX_THREADS && threads < want) threads *= 2;
   }
-  k_octree<<<dim3(l1 - l0, p.nEyes), threads, mx, st>>>(p, b, l0);
+  ft_launch_pdl(k_octree, dim3(l1 - l0, p.nEyes), dim3(threads), mx, st, p, b, l0);   // predecessor in the stream: k_fast_cells
 }

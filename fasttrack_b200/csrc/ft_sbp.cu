@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
   // kernel's critical resource): active map points of this CTA, candidates found, searched non-blocking map points
   __shared__ int sActive[GA_ACTIVE_CAP];
   __shared__ int sNActive, sNCand, sNNonBlocking, sActiveBase;
+  FT_PDL_TRIGGER();     // the claim-resolution cluster may be scheduled; it waits for this grid before it reads
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nEyes = a.fisheye ? 2 : 1;
   if (tid == 0) { sNActive = 0; sNCand = 0; sNNonBlocking = 0; }   // visible after the staging barrier / the one below
@@ -309,7 +310,12 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
         const int cx1 = min(FT_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.minX), rr), a.gridWInv)));
         const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
         const int cy1 = min(FT_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.minY), rr), a.gridHInv)));
-        if (!(cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0)) continue;
+        // an empty LEFT window ends the last-frame search of this point before its right-eye half:
+        // `if(vIndices2.empty()) continue;` (ORBmatcher.cc:1836-1837) sits in front of the Nleft != -1 block (:1915)
+        if (!(cx0 < FT_GRID_COLS && cx1 >= 0 && cy0 < FT_GRID_ROWS && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0)) {
+          if (a.mode == 1 && br == 0) break;
+          continue;
+        }
         const int* cellStart = cellStartP[br];
         const int* cellIdx = cellIdxP[br];
         const float4* rec = recP[br];
@@ -375,7 +381,10 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
           return run;
         };
         const int total = walk(nullptr);
-        if (total == 0) continue;
+        if (total == 0) {
+          if (a.mode == 1 && br == 0) break;     // (:1836-1837), see above
+          continue;
+        }
         // short lists (the common case) live in the slots the (map point, branch) pair owns; only longer ones
         // allocate from the overflow area behind the M*2*GA_INLINE inline slots
         int base = (2 * mp + br) * GA_INLINE;
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
   // map points are dealt round-robin over the CTAs of the cluster so that every SM gets an equal share of the
   // candidate-list scans (the active list is usually shorter than the cluster's thread count)
   const int vid = tid * gridDim.x + blockIdx.x;
+  FT_PDL_WAIT();        // launched as a programmatic dependent of k_gather
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
@@ -771,10 +781,79 @@ void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereo
                        cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(ra.nSlots); cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = g_resolveCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // predecessor in the stream: k_gather
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = ft_pdl_enabled() ? 2 : 1;
   cudaLaunchKernelEx(&cfg, k_resolve, b, s, stb, ra);
   if (ra.fisheye) k_resolve_seq<<<1, 32, 0, st>>>(b, s, stb, ra);   // exits immediately unless it is needed
+}
+
+// ---- the search chain as a CUDA graph ------------------------------------------------------------------------------
+// gather -> resolve (-> resolve_seq on fisheye rigs) captured once per context; the pose, M, th and the map-point
+// pointers change with every call, so the kernel nodes get their parameters (and the gather grid) through
+// cudaGraphExecKernelNodeSetParams: the arguments stay in the constant bank, one cudaGraphLaunch per search.
+cudaError_t ft_search_graph_run(FtSearchGraph* G, const FtParams& p, const FtBuffers& b, const FtGridBuffers& g,
+                                const FtStereoBuffers& stb, const FtSbpBuffers& s, const FtFrustumArgs& fa,
+                                const FtGatherArgs& ga, const FtResolveArgs& ra, int M, cudaStream_t st) {
+  cudaError_t e;
+  if (!G->exec) {
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return e;
+    ft_launch_gather(p, b, g, stb, s, fa, ga, M, st);
+    ft_launch_resolve(b, s, stb, ra, st);
+    e = cudaStreamEndCapture(st, &graph);
+    if (e != cudaSuccess) return e;
+    e = cudaGraphInstantiate(&G->exec, graph, 0);
+    if (e == cudaSuccess) {
+      cudaGraphNode_t nodes[8];
+      size_t n = 8;
+      e = cudaGraphGetNodes(graph, nodes, &n);
+      for (size_t i = 0; e == cudaSuccess && i < n; i++) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+        if (kp.func == (void*)k_gather) G->gather = nodes[i];
+        else if (kp.func == (void*)k_resolve) G->resolve = nodes[i];
+        else if (kp.func == (void*)k_resolve_seq) G->seq = nodes[i];
+      }
+      if (e == cudaSuccess && (!G->gather || !G->resolve || (ra.fisheye && !G->seq))) e = cudaErrorUnknown;
+    }
+    // the exec graph keeps the node handles of the graph it was instantiated from: the template stays alive with it
+    G->graph = graph;
+    if (e != cudaSuccess) return e;
+  } else {
+    const size_t smem = ft_gather_smem(p, ga.fisheye);
+    int stage = smem <= 200 * 1024;
+    int Marg = M;
+    const int ctas = min((M + GA_WARPS - 1) / GA_WARPS, GA_CTAS_PER_SM * 148);
+    void* ka[9] = {(void*)&p, (void*)&b, (void*)&g, (void*)&stb, (void*)&s, (void*)&fa, (void*)&ga, (void*)&Marg, (void*)&stage};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_gather; kp.gridDim = dim3(ctas); kp.blockDim = dim3(GA_WARPS * 32);
+    kp.sharedMemBytes = (unsigned)(stage ? smem : 0); kp.kernelParams = ka;
+    e = cudaGraphExecKernelNodeSetParams(G->exec, G->gather, &kp);
+    if (e != cudaSuccess) return e;
+    void* kr[4] = {(void*)&b, (void*)&s, (void*)&stb, (void*)&ra};
+    cudaKernelNodeParams kq = {};
+    kq.func = (void*)k_resolve; kq.gridDim = dim3(g_resolveCluster); kq.blockDim = dim3(RS_THREADS);
+    kq.sharedMemBytes = (unsigned)ft_resolve_smem(ra.nSlots); kq.kernelParams = kr;
+    e = cudaGraphExecKernelNodeSetParams(G->exec, G->resolve, &kq);
+    if (e != cudaSuccess) return e;
+    if (G->seq) {
+      cudaKernelNodeParams ks = {};
+      ks.func = (void*)k_resolve_seq; ks.gridDim = dim3(1); ks.blockDim = dim3(32); ks.sharedMemBytes = 0; ks.kernelParams = kr;
+      e = cudaGraphExecKernelNodeSetParams(G->exec, G->seq, &ks);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaGraphLaunch(G->exec, st);
+}
+void ft_search_graph_destroy(FtSearchGraph* G) {
+  if (G->exec) cudaGraphExecDestroy(G->exec);
+  if (G->graph) cudaGraphDestroy(G->graph);
+  *G = FtSearchGraph();
 }

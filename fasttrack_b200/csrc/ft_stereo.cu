@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   __shared__ int sHist[256];
   __shared__ int sLast, sCount, sBin, sBefore, sMedian;
   const int tid = threadIdx.x, lane = tid & 31;
+  FT_PDL_WAIT();        // launched as a programmatic dependent of k_orient_desc
   const int nL = b.eye[0].counts[0], nR = b.eye[1].counts[0];
   const int iL = blockIdx.x * ST_WARPS + (tid >> 5);
   if (blockIdx.x * ST_WARPS < nL) {
@@ -331,6 +332,7 @@ __device__ float ft_triangulate_matches(const FtCamera& c1, const FtCamera& c2, 
 __global__ void __launch_bounds__(64) k_fisheye_init(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                      const __grid_constant__ FtStereoBuffers s) {
   const int i = blockIdx.x * 64 + threadIdx.x;
+  FT_PDL_WAIT();        // launched as a programmatic dependent of k_orient_desc
   if (i < p.maxKp) {
     s.l2r[i] = -1; s.r2l[i] = -1; s.depth[i] = -1.0f; s.uRight[i] = -1.0f; s.code[i] = 0;
     s.p3d[3 * i] = 0; s.p3d[3 * i + 1] = 0; s.p3d[3 * i + 2] = 0;
@@ -397,11 +399,12 @@ cudaError_t ft_launch_stereo_setup(const FtParams& p) {
 
 void ft_launch_stereo_match(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, float mbf, float mb,
                             cudaStream_t st) {
-  k_stereo_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, sizeof(FtRightKp) * p.maxKp, st>>>(p, b, s, mbf, mb);
+  ft_launch_pdl(k_stereo_match, dim3((p.maxKp + ST_WARPS - 1) / ST_WARPS), dim3(ST_WARPS * 32), sizeof(FtRightKp) * p.maxKp, st,
+                p, b, s, mbf, mb);
 }
 void ft_launch_fisheye(const FtParams& p, const FtBuffers& b, const FtStereoBuffers& s, const FtCamera& c1,
                        const FtCamera& c2, const FtPose& pose, cudaStream_t st) {
-  k_fisheye_init<<<(p.maxKp + 63) / 64, 64, 0, st>>>(p, b, s);
+  ft_launch_pdl(k_fisheye_init, dim3((p.maxKp + 63) / 64), dim3(64), 0, st, p, b, s);
   k_fisheye_match<<<(p.maxKp + ST_WARPS - 1) / ST_WARPS, ST_WARPS * 32, 0, st>>>(p, b, s, c1, c2, pose);
 }
 

@@ -121,6 +121,9 @@ class FrontEndContext {
   FrontEndContext(const FrontEndContext&) = delete;
   ft_context* get() const { return ctx_; }
   const ft_config& config() const { return cfg_; }
+  // Calls on one ft_context are single-threaded (include/fasttrack_b200.h): the two extractor threads of a stereo rig
+  // take this lock around every C-ABI call they make after the rendezvous in submit().
+  std::mutex& api_mutex() { return api_mu_; }
 
   // Frame::ExtractORB runs the two extractors on two std::threads (src/Frame.cc:127-130). The first eye to
   // arrive parks its image; the second one launches the stereo extraction for both and wakes the first.
@@ -129,6 +132,7 @@ class FrontEndContext {
     img_[eye] = img; step_[eye] = step;
     const unsigned gen = gen_;
     if (++arrived_ == 2) {
+      std::lock_guard<std::mutex> api(api_mu_);
       ft_status st = ft_extract_stereo(ctx_, img_[0], step_[0], img_[1], step_[1]);
       if (st == FT_OK) st = ft_synchronize(ctx_);
       status_ = st; err_ = st == FT_OK ? "" : ft_last_error();
@@ -143,7 +147,7 @@ class FrontEndContext {
  private:
   ft_config cfg_;
   ft_context* ctx_ = nullptr;
-  std::mutex mu_;
+  std::mutex mu_, api_mu_;
   std::condition_variable cv_;
   const unsigned char* img_[2] = {nullptr, nullptr};
   int step_[2] = {0, 0};
@@ -179,7 +183,10 @@ class ORBextractor {
     std::vector<ft_keypoint> k(cap);
     std::vector<unsigned char> d((size_t)cap * 32);
     int n = 0, mono = 0;
-    ft_check(ft_frame_download(fe_->get(), eye_, cap, k.data(), d.data(), &n, &mono, nullptr, nullptr, nullptr, nullptr, nullptr));
+    {
+      std::lock_guard<std::mutex> api(fe_->api_mutex());     // the other eye's thread downloads from the same context
+      ft_check(ft_frame_download(fe_->get(), eye_, cap, k.data(), d.data(), &n, &mono, nullptr, nullptr, nullptr, nullptr, nullptr));
+    }
     keypoints.assign(n, ftcv::KeyPoint());
     for (int i = 0; i < n; i++) {
       ftcv::KeyPoint& o = keypoints[i];
@@ -332,6 +339,7 @@ class MapStore {
   }
   // gives pMP a row (no-op when it has one) and queues it for the next Flush()
   void Insert(MapPoint* pMP) {
+    std::lock_guard<std::mutex> lk(mu_);     // LocalMapping inserts / culls while Tracking flushes
     if (pMP->mnStoreRow < 0) {
       if (!free_.empty()) { pMP->mnStoreRow = free_.back(); free_.pop_back(); }
       else if (next_ < cap_) pMP->mnStoreRow = next_++;
@@ -341,10 +349,12 @@ class MapStore {
     if (pMP->mbStoreDirty) pending_.push_back(pMP);
   }
   void Erase(MapPoint* pMP) {   // MapPoint::SetBadFlag / culling
+    std::lock_guard<std::mutex> lk(mu_);
     if (pMP->mnStoreRow >= 0) free_.push_back(pMP->mnStoreRow);
     pMP->mnStoreRow = -1;
   }
   void Flush() {
+    std::lock_guard<std::mutex> lk(mu_);
     std::vector<int> rows; std::vector<float> pos, nrm, mm; std::vector<unsigned char> desc;
     for (MapPoint* p : pending_) {
       if (!p->mbStoreDirty || p->mnStoreRow < 0) continue;
@@ -363,6 +373,7 @@ class MapStore {
  private:
   std::shared_ptr<FrontEndContext> fe_;
   int cap_, next_ = 0;
+  std::mutex mu_;
   std::vector<int> free_;
   std::vector<MapPoint*> pending_;
 };

@@ -83,3 +83,53 @@ def test_last_frame_search_fisheye():
     same = np.array_equal(h_g, h_o)
     assert same or (np.mean(h_g != h_o) < 0.01 and abs(n_g - n_o) <= 3)
     ctx.close()
+
+
+def test_last_frame_fisheye_empty_left_window_skips_right_eye():
+    """`if(vIndices2.empty()) continue;` (ORBmatcher.cc:1836-1837) stands in front of the right-eye block (:1915): a
+    last-frame point whose LEFT window holds no keypoint is never searched in the right image, even when right keypoints
+    lie inside its right window. Points are planted where the left image has no keypoints (the 19-px border) but whose
+    right projection lands on right keypoints, carrying those keypoints' descriptors; holders must be equal, exactly."""
+    T = synth.TUMVI
+    L, R = synth.fisheye_pair(seed=3)
+    Rlr, tlr, Rrl, trl = synth.tumvi_extrinsics()
+    ctx = ft.Context(512, 512, nfeatures=1000, camera_type=1, cam1=T["cam1"], cam2=T["cam2"], lap_left=T["lap"], lap_right=T["lap"],
+                     bf=T["bf"], Tlr=np.hstack([Rlr, tlr[:, None]]))
+    ctx.frame_construct(L, R)
+    exL, exR = oracle.Extractor(1000), oracle.Extractor(1000)
+    mL, kL, dL = exL.extract(L, lap=T["lap"]); mR, kR, dR = exR.extract(R, lap=T["lap"])
+    fo = oracle.fisheye(T["cam1"], T["cam2"], Rlr, tlr, exL.sigma2, kL, dL, mL, kR, dR, mR)
+    keys = np.vstack([kL, kR]); desc = np.vstack([dL, dR])
+    Rcw = np.eye(3, dtype=np.float32); tcw = np.zeros(3, np.float32)
+    c1 = np.asarray(T["cam1"], np.float64)
+    th = 7.0
+    # for every right keypoint: the camera-1 point (several depths) whose right-eye projection (Trl * x, LEFT camera model,
+    # as the reference does) is that keypoint; keep those whose LEFT projection falls where no left keypoint is within reach
+    pts, dsc, octs, angs = [], [], [], []
+    for z in (0.6, 1.0, 2.0, 5.0):
+        ray = synth.kb8_unproject(c1, kR[:, 0].astype(np.float64), kR[:, 1].astype(np.float64))
+        Pr = ray * z / np.maximum(ray[:, 2:3], 1e-9)
+        Pc = (Pr - trl.astype(np.float64)) @ Rrl.astype(np.float64)       # x3Dc = Rrl^T (x3Dr - trl)
+        ul, vl = synth.kb8_project(c1, Pc)
+        inside = (ul > 0.5) & (ul < 511.5) & (vl > 0.5) & (vl < 511.5) & (Pc[:, 2] > 0)
+        for j in np.nonzero(inside)[0]:
+            o = int(kR[j, 5])
+            rad = th * float(exL.scale[o]) + 1.0
+            near = (np.abs(kL[:, 0] - ul[j]) < rad) & (np.abs(kL[:, 1] - vl[j]) < rad)
+            if not near.any():
+                pts.append(Pc[j]); dsc.append(dR[j]); octs.append(o); angs.append(kR[j, 3])
+    assert len(pts) >= 5, "the synthetic pair offers too few right keypoints whose left window is empty"
+    n = len(pts)
+    lf = dict(pos=np.ascontiguousarray(pts, np.float32), desc=np.ascontiguousarray(dsc, np.uint8), octave=np.asarray(octs, np.int32),
+              angle=np.asarray(angs, np.float32), flags=np.full(n, 2, np.int32))
+    F = oracle.Frame(keys, desc, exL.scale, 512, 512, cam_type=1, cam1=T["cam1"], cam2=T["cam2"], mbf=T["bf"], n_left=len(kL),
+                     n_right=len(kR), l2r=fo["l2r"], r2l=fo["r2l"], Rcw=Rcw, tcw=tcw, Rrl=Rrl, trl=trl, tlr=tlr)
+    N = len(keys)
+    holder0 = np.full(N, -1, np.int32); hobs0 = np.zeros(N, np.uint8)
+    n_o, h_o, ho_o, bl = F.search_last_frame(lf["pos"], lf["desc"], lf["octave"], lf["angle"], lf["flags"], th, 0, holder0, hobs0, False)
+    ctx.set_pose(Rcw, tcw, F.Rwc, F.Ow)
+    n_g, h_g, ho_g, _ = ctx.search_last_frame(lf["pos"], lf["desc"], lf["octave"], lf["angle"], lf["flags"], np.eye(3), np.zeros(3), th,
+                                              holder0, hobs0, b_mono=False, check_ori=False)
+    assert n_o == 0 and not (h_o >= 0).any(), "the planted points must stay unmatched in the reference's order of tests"
+    assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    ctx.close()
