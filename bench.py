@@ -6,8 +6,11 @@
 
 A step = one synthetic EuRoC-shaped stereo frame (752x480, 1200 features, 8 levels, x1.2) through
 extract(L,R) -> ComputeStereoMatches -> SearchLocalPoints(M map points). One independent sequence per GPU
-(no collective on the data path; torch.distributed is only used for the barrier and the max-over-ranks time).
-Prints ONE JSON line on rank 0.
+(no collective on the data path; torch.distributed over gloo is only used for the barrier and the max-over-ranks
+time: no NCCL anywhere). Prints ONE JSON line on rank 0. Besides the headline the line carries `configs` (every
+BASELINE.json configuration: CPU-extractor image, pinhole stereo pair, fisheye pair at 1000 / 2000 features, projection
+search at M = 5k / 10k / 20k x th = 1 / 2 / 6 / 10), `next_rows` (last-frame search, rectification / input resize /
+undistortion front, bag of words) and `reference_gpu` (the reference's own CUDA kernels timed on the same GPU).
 """
 import argparse
 import json
@@ -32,6 +35,15 @@ STORE_UPSERTS = 400     # rows the mapping side changes per frame in the map-sto
 WORKLOAD = ("euroc_752x480_stereo_sequence: extract(L,R; 1200 features, 8 levels, x1.2) + ComputeStereoMatches + "
             "SearchLocalPoints(M=%d, th=%g)" % (M_POINTS, TH))
 METRIC = "frames/sec (ORB extract L+R + stereo match + projection search)"
+
+
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """progress on stderr with FT_BENCH_LOG=1 (which leg takes how long)"""
+    if os.environ.get("FT_BENCH_LOG"):
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg)); sys.stderr.flush()
 
 
 def peaks():
@@ -234,24 +246,333 @@ def bench_bow(ctx, ft, torch, stream, frames, device_id, with_cpu):
     return out
 
 
+def _dev_ms(torch, stream, fn, reps, flush=None, warm=3):
+    """mean CUDA-event ms of fn() enqueued on `stream` (events recorded on that stream, synchronised per repetition)"""
+    for _ in range(warm):
+        fn()
+    stream.synchronize()
+    t = []
+    for _ in range(reps):
+        if flush:
+            flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); fn(); e1.record(stream)
+        stream.synchronize()
+        t.append(e0.elapsed_time(e1))
+    return float(np.mean(t))
+
+
+def _extract_bytes(ctx, st):
+    """SURVEY.md 8d algorithmic bytes of one extraction (both eyes) with the measured counts"""
+    px = [w * h for w, h in (ctx.level_dims(l) for l in range(ctx.nlevels))]
+    sumP = sum(px)
+    C_ = st["cand_left"] + st["cand_right"]; K_ = st["kp_left"] + st["kp_right"]
+    return (2 * (sum(px[:-1]) + sum(px[1:])) + 2 * 2 * sumP + 2 * sumP + 16 * C_ + 16 * C_ + 20 * K_ + (749 + 4 + 512 + 32) * K_)
+
+
+def bench_configs(ft, torch, local, frames, with_cpu, flush_l2):
+    """Every BASELINE.json configuration and every built 'next' row of SURVEY.md 8f, each with its device time (CUDA events on
+    the context's stream), its algorithmic bytes / HBM fraction and the oracle's CPU time beside it. Side legs never break the
+    headline: a failing leg reports {"unavailable": ...}."""
+    import fasttrack_b200.synth as synth
+    pk, _ = peaks()
+    dev = torch.device("cuda", local)
+    mbf = np.float32(E["fx"] * E["baseline"]); mb = np.float32(mbf / np.float32(E["fx"]))
+    oracle = None
+    if with_cpu:
+        import oracle as _o
+        oracle = _o
+    out = {}
+    frac = lambda b, ms: b / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    def leg(name, fn):
+        log("config " + name)
+        try:
+            out[name] = fn()
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+    L0, R0 = frames[0]
+
+    # ---- BASELINE config 0: one 752x480 image through the extractor alone (monocular Frame) ----
+    def cfg_mono():
+        c = ft.Context(E["width"], E["height"], nfeatures=E["nfeatures"], nlevels=E["nlevels"], scale_factor=E["scale"],
+                       cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), device_id=local)
+        c.set_sensor(1)     # FT_SENSOR_MONOCULAR
+        st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        hp = pin(L0)
+        ms = _dev_ms(torch, st_, lambda: c._ck(c.L.ft_extract_mono(c.h, hp.data_ptr(), E["width"])), 30, flush_l2)
+        n = c.counts()[0]
+        r = {"workload": "ORBextractor::operator() on one 752x480 image (1200 features, 8 levels): upload + extraction",
+             "gpu_ms": ms, "keypoints": int(n), "timing": "CUDA events on the context's stream around ft_extract_mono (pinned host image, H2D inside)"}
+        if oracle:
+            ex = oracle.Extractor()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ex.extract(L0)
+            r["cpu_ms"] = (time.perf_counter() - t0) * 1e3 / 5
+            r["cpu"] = "oracle port, 1 thread"
+        c.close()
+        return r
+    leg("cpu_extractor_image_752x480", cfg_mono)
+
+    # ---- BASELINE config 1: EuRoC-shaped pair, extract + ComputeStereoMatches ----
+    def cfg_pinhole():
+        c = ft.Context(E["width"], E["height"], nfeatures=E["nfeatures"], nlevels=E["nlevels"], scale_factor=E["scale"],
+                       cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), device_id=local)
+        st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        dl, dr = torch.from_numpy(L0).to(dev), torch.from_numpy(R0).to(dev)
+        ms = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dl.data_ptr(), E["width"], dr.data_ptr(), E["width"]), 30, flush_l2)
+        s_ = c.stats()
+        b = _extract_bytes(c, s_) + 44 * (s_["kp_left"] + s_["kp_right"]) + 44 * s_["stereo_tested"] + 352 * s_["stereo_refined"] + 12 * s_["kp_left"]
+        r = {"workload": "752x480 pair: extract(L,R) + ComputeStereoMatches (one CUDA graph)", "gpu_ms": ms,
+             "algorithmic_bytes": int(b), "hbm_frac": frac(b, ms), "stereo_matches": int(s_.get("stereo_refined", 0)),
+             "timing": "CUDA events around ft_frame_enqueue_device, images resident in HBM, L2 flushed"}
+        if oracle:
+            exL, exR = oracle.Extractor(), oracle.Extractor()
+            t = [oracle.time_stereo_frame(exL, exR, L0, R0, float(mbf), float(mb), two_threads=True)[0] for _ in range(4)]
+            r["cpu_ms"] = float(np.mean(t[1:])); r["cpu"] = "oracle port, 2 extraction threads (Frame.cc:127-130)"
+        c.close()
+        return r
+    leg("stereo_pinhole_euroc_752x480", cfg_pinhole)
+
+    # ---- BASELINE config 2: TUM-VI-shaped fisheye pair, extract + ComputeStereoFishEyeMatches ----
+    def cfg_fisheye(nf):
+        T = synth.TUMVI
+        Lf, Rf = synth.fisheye_pair(seed=3)
+        Rlr, tlr, Rrl, trl = synth.tumvi_extrinsics()
+        c = ft.Context(512, 512, nfeatures=nf, camera_type=1, cam1=T["cam1"], cam2=T["cam2"], lap_left=T["lap"], lap_right=T["lap"],
+                       bf=T["bf"], Tlr=np.hstack([Rlr, tlr[:, None]]), device_id=local)
+        st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        dl, dr = torch.from_numpy(Lf).to(dev), torch.from_numpy(Rf).to(dev)
+        ms = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dl.data_ptr(), 512, dr.data_ptr(), 512), 30, flush_l2)
+        c.set_stage_timing(True)
+        acc = []
+        for _ in range(10):
+            flush_l2(); c.frame_enqueue_device(dl.data_ptr(), 512, dr.data_ptr(), 512); acc.append(c.stage_times())
+        c.set_stage_timing(False)
+        s_ = c.stats()
+        nl, nr = s_["kp_left"], s_["kp_right"]
+        b = _extract_bytes(c, s_) + 32 * (nl + nr) + 28 * nl
+        r = {"workload": "512x512 KB8 pair, %d features: extract(L,R) + ComputeStereoFishEyeMatches" % nf, "gpu_ms": ms,
+             "algorithmic_bytes": int(b), "hbm_frac": frac(b, ms), "keypoints": [int(nl), int(nr)], "hamming_pairs": int(nl) * int(nr),
+             "fisheye_match_kernel_ms": float(np.mean([a.get("stereo_match", 0.0) for a in acc])),
+             "timing": "CUDA events around ft_frame_enqueue_device, images resident in HBM, L2 flushed"}
+        if oracle:
+            exL, exR = oracle.Extractor(nf), oracle.Extractor(nf)
+            t0 = time.perf_counter()
+            mL, kL, dL_ = exL.extract(Lf, lap=T["lap"]); mR, kR, dR_ = exR.extract(Rf, lap=T["lap"])
+            t1 = time.perf_counter()
+            oracle.fisheye(T["cam1"], T["cam2"], Rlr, tlr, exL.sigma2, kL, dL_, mL, kR, dR_, mR)
+            t2 = time.perf_counter()
+            r["cpu_ms"] = (t2 - t0) * 1e3; r["cpu_extract_ms"] = (t1 - t0) * 1e3; r["cpu_match_ms"] = (t2 - t1) * 1e3
+            r["cpu"] = "oracle port, 1 thread (both extractions back to back)"
+        c.close()
+        return r
+    leg("stereo_fisheye_tumvi_512_1000", lambda: cfg_fisheye(1000))
+    leg("stereo_fisheye_tumvi_512_2000", lambda: cfg_fisheye(2000))
+
+    # ---- BASELINE config 3: SearchByProjection alone, 5k-20k local MapPoints against a 1200-keypoint frame ----
+    def cfg_sbp():
+        c = ft.Context(E["width"], E["height"], nfeatures=E["nfeatures"], nlevels=E["nlevels"], scale_factor=E["scale"],
+                       cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), max_map_points=25000, device_id=local)
+        st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        c.frame_construct(L0, R0)
+        g = c.download(0, stereo=True)
+        keys = ft.keypoints_as_array(g["kps"])
+        scale = c.scale_tables()["scale"]
+        c.set_pose(np.eye(3), np.zeros(3)); c.upload_holders(None, None)
+        F = None
+        if oracle:
+            exL = oracle.Extractor()
+            F = oracle.Frame(keys, g["desc"], exL.scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                             mbf=float(mbf), u_right=g["u_right"])
+        res = {}
+        for M in (5000, 10000, 20000):
+            mp = fast_mappoints(keys, g["desc"], scale, M, 4242 + M)
+            dm = {k: torch.from_numpy(v).to(dev) for k, v in mp.items()}
+            c.bind_map_points_device(M, dm["pos"].data_ptr(), dm["normal"].data_ptr(), dm["minmax"].data_ptr(), dm["desc"].data_ptr(),
+                                     dm["flags"].data_ptr())
+            for th in (1.0, 2.0, 6.0, 10.0):
+                ms = _dev_ms(torch, st_, lambda: c.search_resident(th), 20, flush_l2)
+                s_ = c.stats()
+                b = 68 * M + 52 * s_["sbp_candidates"] + 4 * s_["sbp_candidates"] + 8 * M
+                e = {"gpu_ms": ms, "algorithmic_bytes": int(b), "hbm_frac": frac(b, ms), "candidates": int(s_["sbp_candidates"]),
+                     "resolve_rounds": int(s_.get("sbp_rounds", 0))}
+                if F is not None:
+                    t0 = time.perf_counter()
+                    nm = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], th,
+                                               np.full(len(keys), -1, np.int32), np.zeros(len(keys), np.uint8))[0]
+                    e["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+                    e["matches"] = int(nm)
+                res["M%d_th%g" % (M, th)] = e
+        c.close()
+        return {"workload": "SearchLocalPoints (isInFrustum + SearchByProjection) against one 1200-keypoint EuRoC frame, map points resident "
+                            "in HBM", "timing": "CUDA events around ft_search_resident (gather + resolve), L2 flushed", "cpu": "oracle port, 1 thread",
+                "cases": res}
+    leg("search_by_projection_5k_20k", cfg_sbp)
+
+    nxt = {}
+
+    def nleg(name, fn):
+        log("next row " + name)
+        try:
+            nxt[name] = fn()
+        except Exception as e:   # noqa: BLE001
+            nxt[name] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+    # ---- next row 1: frame-to-last-frame SearchByProjection (TrackWithMotionModel) ----
+    def row_last_frame():
+        c = ft.Context(E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), device_id=local)
+        c.frame_construct(L0, R0)
+        g = c.download(0, stereo=True)
+        keys = ft.keypoints_as_array(g["kps"])
+        a = 0.02
+        Rcw = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        tcw = np.array([0.03, -0.02, -0.05], np.float32)
+        lf = synth.last_frame_points(keys, g["desc"], 1000, seed=100, Rcw=Rcw, tcw=tcw, fx=E["fx"], fy=E["fy"], cx=E["cx"], cy=E["cy"])
+        c.set_pose(Rcw, tcw)
+        N = len(keys)
+        h0 = np.full(N, -1, np.int32); ho0 = np.zeros(N, np.uint8)
+        call = lambda: c.search_last_frame(lf["pos"], lf["desc"], lf["octave"], lf["angle"], lf["flags"], np.eye(3, dtype=np.float32),
+                                           np.zeros(3, np.float32), 7.0, h0, ho0, b_mono=False, check_ori=True)
+        for _ in range(3):
+            nm = call()[0]
+        t0 = time.perf_counter()
+        for _ in range(50):
+            call()
+        ms = (time.perf_counter() - t0) * 1e3 / 50
+        r = {"workload": "SearchByProjection(CurrentFrame, LastFrame, th=7) + rotation histogram, 1000 last-frame map points",
+             "gpu_ms_e2e": ms, "matches": int(nm), "timing": "host wall clock per ft_search_last_frame call (H2D of the points, gather + resolve, D2H)"}
+        if oracle:
+            exL = oracle.Extractor()
+            F = oracle.Frame(keys, g["desc"], exL.scale, E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"], 0, 0, 0, 0],
+                             mbf=float(mbf), u_right=g["u_right"], Rcw=Rcw, tcw=tcw)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                F.search_last_frame(lf["pos"], lf["desc"], lf["octave"], lf["angle"], lf["flags"], 7.0, 0, h0, ho0, True)
+            r["cpu_ms"] = (time.perf_counter() - t0) * 1e3 / 5
+        c.close()
+        return r
+    nleg("last_frame_search", row_last_frame)
+
+    # ---- next row 2: rectification remap / input resize / keypoint undistortion in front of / behind the extractor ----
+    def row_front():
+        mk = lambda: ft.Context(E["width"], E["height"], cam1=[E["fx"], E["fy"], E["cx"], E["cy"]], bf=float(mbf), device_id=local)
+        W, H = E["width"], E["height"]
+        r = {}
+        c = mk(); st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        dl, dr = torch.from_numpy(L0).to(dev), torch.from_numpy(R0).to(dev)
+        base = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dl.data_ptr(), W, dr.data_ptr(), W), 20, flush_l2)
+        r["plain_frame_gpu_ms"] = base
+        # cv::remap with a mild radial map (System.cc:273-281)
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        rr2 = ((xx - E["cx"]) / E["fx"]) ** 2 + ((yy - E["cy"]) / E["fy"]) ** 2
+        mx = (xx + (xx - E["cx"]) * 0.05 * rr2).astype(np.float32); my = (yy + (yy - E["cy"]) * 0.05 * rr2).astype(np.float32)
+        c.set_rectification(W, H, mx, my, mx, my)
+        ms = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dl.data_ptr(), W, dr.data_ptr(), W), 20, flush_l2)
+        r["rectify_remap"] = {"gpu_ms_frame": ms, "gpu_ms_added": ms - base, "algorithmic_bytes": int(2 * (W * H * 8 + 2 * W * H)),
+                              "note": "k_remap writes level 0 from the raw pair (fixed-point map table 8 B / pixel)"}
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                cv2.remap(L0, mx, my, cv2.INTER_LINEAR); cv2.remap(R0, mx, my, cv2.INTER_LINEAR)
+            r["rectify_remap"]["cpu_ms"] = (time.perf_counter() - t0) * 1e3 / 10
+            r["rectify_remap"]["cpu"] = "cv2.remap x2, 1 thread"
+        except Exception:   # noqa: BLE001
+            pass
+        c.close()
+        # cv::resize of a 2x larger raw pair (System.cc:282-285)
+        c = mk(); st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        raw = np.ascontiguousarray(np.kron(L0, np.ones((2, 2), np.uint8)))
+        dlr = torch.from_numpy(raw).to(dev)
+        c.set_input_resize(2 * W, 2 * H)
+        ms = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dlr.data_ptr(), 2 * W, dlr.data_ptr(), 2 * W), 20, flush_l2)
+        r["input_resize"] = {"gpu_ms_frame": ms, "gpu_ms_added": ms - base, "algorithmic_bytes": int(2 * (4 * W * H + W * H)),
+                             "note": "1504x960 raw pair resized into level 0 by k_resize_input"}
+        try:
+            import cv2
+            t0 = time.perf_counter()
+            for _ in range(10):
+                cv2.resize(raw, (W, H), interpolation=cv2.INTER_LINEAR); cv2.resize(raw, (W, H), interpolation=cv2.INTER_LINEAR)
+            r["input_resize"]["cpu_ms"] = (time.perf_counter() - t0) * 1e3 / 10
+        except Exception:   # noqa: BLE001
+            pass
+        c.close()
+        # Frame::UndistortKeyPoints (Frame.cc:771-835) inside the frame-grid kernel
+        c = mk(); st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
+        dist = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]
+        c.set_distortion(dist)
+        ms = _dev_ms(torch, st_, lambda: c.frame_enqueue_device(dl.data_ptr(), W, dr.data_ptr(), W), 20, flush_l2)
+        r["undistort_keypoints"] = {"gpu_ms_frame": ms, "gpu_ms_added": ms - base,
+                                    "note": "EuRoC distortion coefficients; the undistortion runs per left keypoint inside k_grid_build (parallel branch)"}
+        if oracle:
+            g = c.download(0)
+            xy = np.ascontiguousarray(ft.keypoints_as_array(g["kps"])[:, :2], np.float32)
+            K = np.array([[E["fx"], 0, E["cx"]], [0, E["fy"], E["cy"]], [0, 0, 1]], np.float64)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                oracle.undistort_points(xy, K, np.asarray(dist, np.float64))
+            r["undistort_keypoints"]["cpu_ms"] = (time.perf_counter() - t0) * 1e3 / 20
+        c.close()
+        return r
+    nleg("front_end_preprocessing", row_front)
+    return out, nxt
+
+
+def reference_gpu_legs(frames, mbf, mb):
+    """FastTrack's OWN CUDA kernels on this box's GPU (oracle/_ref/libft_ref_orbextractor_gpu.so = the reference's
+    src/{resize,gaussian_blur,fast,orientation,descriptor}.cu + src/Kernels/StereoMatchKernel.cu compiled from where they lie):
+    per-launcher CUDA-event times, ORBextractor::operator() in GPU run mode end to end, and the GPU stereo matching call.
+    The performance bar of SURVEY.md 2.1, never a correctness oracle. SearchLocalPointsKernel.cu / PoseEstimationKernel.cu
+    include Frame.h / MapPoint.h (Eigen, Sophus, g2o: not installed), so they cannot be compiled here."""
+    try:
+        import oracle
+        if oracle.ref_gpu_lib() is None:
+            return {"unavailable": "oracle/_ref/libft_ref_orbextractor_gpu.so did not travel with the snapshot"}
+        L, R = frames[0]
+        st = oracle.ref_gpu_stage_times(L, E["nlevels"], E["scale"], 20, 7, reps=20)
+        ms_img, nkp = oracle.ref_gpu_extract_ms([f[0] for f in frames[:6]] + [frames[0][0]], E["nfeatures"], E["scale"], E["nlevels"], 20, 7)
+        exL, exR = oracle.Extractor(), oracle.Extractor()
+        _, kL, dL = exL.extract(L); _, kR, dR = exR.extract(R)
+        ms_st, kept = oracle.ref_gpu_stereo_ms(L, R, kL, dL, kR, dR, float(mbf), float(mb), E["nlevels"], E["scale"], reps=10)
+        return {"per_image_launcher_ms": {k: v for k, v in st.items() if k != "corners"}, "corners_all_levels": st["corners"],
+                "extract_operator_ms_per_image": ms_img, "extract_keypoints": nkp,
+                "stereo_match_ms_per_call": ms_st, "stereo_matches": kept,
+                "note": "one 752x480 image per launcher chain (the reference runs one ORBextractor per eye); operator() = H2D + kernels + "
+                        "D2H of every corner + DistributeOctTreeGPU on the host, wall clock; stereo = Frame::ComputeStereoMatchesGPU "
+                        "(row table, StereoMatchKernel::launch with its per-call cudaMemcpy's, host sort + median filter), wall clock; "
+                        "SearchLocalPointsKernel.cu / PoseEstimationKernel.cu need Eigen / Sophus headers: not buildable here"}
+    except Exception as e:   # never let the extra leg break the arm
+        return {"unavailable": str(e)[:300]}
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, restated (oracle port), on the box's host cores with
-    the reference's threading: two threads for L/R extraction (Frame.cc:127-130), everything else on one."""
+    the reference's threading: two threads for L/R extraction (Frame.cc:127-130), everything else on one. Under torchrun
+    rank 0 alone runs and prints; it drives `world` independent CPU sequences concurrently (one Python thread each; the
+    oracle calls release the GIL), so the line is like-for-like with the N-GPU arm: N sequences, whole-job frames/s."""
     if rank != 0:
         return
     import oracle
+    n_seq = max(1, world)
     frames = make_frames(5, min(N_FRAMES, 6))
     mbf = np.float32(E["fx"] * E["baseline"]); mb = np.float32(mbf / np.float32(E["fx"]))
-    exL, exR = oracle.Extractor(), oracle.Extractor()
+    exs = [(oracle.Extractor(), oracle.Extractor()) for _ in range(n_seq)]
+    exL, exR = exs[0]
     maps = []
     for (L, R) in frames:
         _, kL, dL = exL.extract(L)
         maps.append(fast_mappoints(kL, dL, exL.scale, M_POINTS, 99))
-    def step(i):
+    def step(i, seq=0):
         k = i % len(frames)
         L, R = frames[k]
+        a, b = exs[seq]
         # Frame ctor: two extractor threads, then ComputeStereoMatches (timed inside the oracle in C++)
-        ms, nl, nr, ns = oracle.time_stereo_frame(exL, exR, L, R, float(mbf), float(mb), two_threads=True)
+        ms, nl, nr, ns = oracle.time_stereo_frame(a, b, L, R, float(mbf), float(mb), two_threads=True)
         # Tracking::SearchLocalPoints on that frame (frame model incl. AssignFeaturesToGrid is rebuilt per step)
         _, kL, dL = pre[k]
         t0 = time.perf_counter()
@@ -268,16 +589,31 @@ def run_reference(args, rank, world):
         pre_ur.append(oracle.stereo(exL, exR, kL, dL, kR, dR, float(mbf), float(mb))["uRight"])
     for i in range(args.warmup):
         step(i)
-    t = [step(i) for i in range(args.steps)]
-    ms = float(np.mean(t))
-    val = 1000.0 / ms
+    if n_seq == 1:
+        t = [step(i) for i in range(args.steps)]
+        ms = float(np.mean(t))
+        val = 1000.0 / ms
+        cores = 2
+    else:
+        # N independent sequences at once: whole-job rate = N * steps / wall time of the slowest
+        def run_seq(q):
+            for i in range(args.steps):
+                step(i, q)
+        th_ = [threading.Thread(target=run_seq, args=(q,)) for q in range(n_seq)]
+        t0 = time.perf_counter()
+        [x.start() for x in th_]; [x.join() for x in th_]
+        wall = time.perf_counter() - t0
+        ms = wall * 1e3 / args.steps
+        val = n_seq * args.steps / wall
+        cores = min(2 * n_seq, os.cpu_count() or 1)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": 2, "kind": "port",
-                             "sample": "%d frames of the bench workload; L/R extraction on 2 threads as Frame.cc:127-130, "
-                                       "stereo + SearchLocalPoints on 1; host has %d cores" % (args.steps, os.cpu_count())},
+            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)", "sequences": n_seq},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames of the bench workload on each of %d concurrent sequences; L/R extraction on 2 threads "
+                                       "per sequence as Frame.cc:127-130, stereo + SearchLocalPoints on 1; host has %d cores"
+                                       % (args.steps, n_seq, os.cpu_count())},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     # Beside it, when oracle/_ref travelled with the snapshot: the reference's OWN code (src/ORBextractor.cc compiled as a whole,
     # ComputeStereoMatches / isInFrustum / SearchByProjection compiled from their text) on the same frames. It runs on the
@@ -335,6 +671,7 @@ def run_reference(args, rank, world):
                                              "reference's extractor with a SIMD OpenCV; informational"}
     except Exception as e:
         line["opencv_primitives"] = {"unavailable": str(e)[:200]}
+    line["reference_gpu"] = reference_gpu_legs(frames, mbf, mb)
     print(json.dumps(line))
 
 
@@ -345,10 +682,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=0.3, help="the K-step timed region is repeated until this much device time is measured")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration / next-row / reference-GPU legs")
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
     ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight in the end-to-end legs (<= pipeline depth)")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight in the throughput leg (contexts/streams)")
+    ap.add_argument("--watchdog", type=float, default=900.0, help="dump every thread's Python stack to stderr and exit if the run takes longer (s)")
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.enable()
+    if args.watchdog > 0:
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank, local, world = replicas.env_rank()
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -360,9 +704,21 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
+    pinned_cores = None
     if world > 1:
+        # one rank per GPU on one node: give every rank its own slice of the host cores (the end-to-end legs are bound by the
+        # tracker thread's memcpy + submit path; eight unpinned ranks migrate and collide on the same cores)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[(local % world) * per:(local % world) * per + per] or cores
+            os.sched_setaffinity(0, mine)
+            pinned_cores = mine
+        except (AttributeError, OSError):
+            pass
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        # barrier + MAX of the per-rank times only: gloo on the host, no NCCL (the data path has no collective)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
 
     mbf = np.float32(E["fx"] * E["baseline"])
     def make_ctx():
@@ -377,6 +733,7 @@ def main():
     stream = streams[0]
     scale = ctx.scale_tables()["scale"]
 
+    log("contexts created")
     # ---- inputs: one independent synthetic sequence per GPU (seed = 5 + rank), prepared outside the timed region ----
     frames = make_frames(replicas.sequence_seed(rank), N_FRAMES)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -470,6 +827,7 @@ def main():
     for i in range(3):
         step_e2e(i)
 
+    log("warm-up done")
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None))
     # ---- timed region 1a: per-frame LATENCY, one frame at a time, CUDA events per step, L2 flushed between steps ----
     n_lat = min(args.steps, 100)
@@ -487,29 +845,47 @@ def main():
     # 2-deep pipeline over one sequence: frames alternate between two contexts (streams); frame t+1 is extracted
     # while frame t is searched, and the search of frame t+1 still waits for the search of frame t (tracking is
     # frame-sequential: pose(t+1) follows from the matches of frame t).
-    done = [torch.cuda.Event(enable_timing=False) for _ in range(args.steps)]
-    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.perf_counter()
-    ev_start.record(streams[0])
-    for s_ in streams[1:]:
-        s_.wait_event(ev_start)
-    for i in range(args.steps):
-        c_, s_ = ctxs[i % D], streams[i % D]
-        k = i % N_FRAMES
-        c_.frame_enqueue_device(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"])
-        if i > 0:
-            s_.wait_event(done[i - 1])
-        bind_map(c_, k)
-        c_.search_resident(TH)
-        done[i].record(s_)
-    for j in range(1, min(D, args.steps) + 1):
-        streams[0].wait_event(done[args.steps - j])
-    host_submit_s = time.perf_counter() - wall0
-    ev_end.record(streams[0])
-    barrier()
-    wall1 = time.perf_counter()
-    dev_ms_total = float(ev_start.elapsed_time(ev_end))
+    # `--steps K` times EXACTLY K steps per region (barrier + synchronize on both sides). A region of a few milliseconds is
+    # mostly pipeline fill and drain, so the region is repeated until about --min-seconds of device time have been
+    # measured; ms_per_step = total device time / (regions x K).
+    def throughput_region():
+        done = [torch.cuda.Event(enable_timing=False) for _ in range(args.steps)]
+        ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.perf_counter()
+        ev_start.record(streams[0])
+        for s_ in streams[1:]:
+            s_.wait_event(ev_start)
+        for i in range(args.steps):
+            c_, s_ = ctxs[i % D], streams[i % D]
+            k = i % N_FRAMES
+            c_.frame_enqueue_device(dL[k].data_ptr(), E["width"], dR[k].data_ptr(), E["width"])
+            if i > 0:
+                s_.wait_event(done[i - 1])
+            bind_map(c_, k)
+            c_.search_resident(TH)
+            done[i].record(s_)
+        for j in range(1, min(D, args.steps) + 1):
+            streams[0].wait_event(done[args.steps - j])
+        submit_s = time.perf_counter() - w0
+        ev_end.record(streams[0])
+        barrier()
+        return float(ev_start.elapsed_time(ev_end)), submit_s, time.perf_counter() - w0
+
+    log("latency leg done")
+    dev_ms_total, host_submit_s, wall_total = throughput_region()
+    n_regions = 1
+    est = dev_ms_total / 1e3
+    target_regions = int(min(64, max(1, np.ceil(args.min_seconds / max(est, 1e-6)))))
+    if world > 1:   # every rank must run the same number of regions (they contain barriers)
+        (tr,) = replicas.reduce_max(dist, world, [float(target_regions)])
+        target_regions = int(tr)
+    while n_regions < target_regions:
+        a_, b_, c2_ = throughput_region()
+        dev_ms_total += a_; host_submit_s += b_; wall_total += c2_
+        n_regions += 1
+    steps_timed = n_regions * args.steps
+    log("throughput leg done (%d regions)" % n_regions)
     ext_l, st_l, se_l = ctx.launch_counts()
     launches_per_step = ext_l + st_l + se_l
 
@@ -581,6 +957,7 @@ def main():
     e2e_store_s = time.perf_counter() - t0
     # ---- timed region 2d: the same three end-to-end loops driven from C++ (fasttrack_b200/host/ft_sequence_driver.cpp,
     # public C ABI only): what a C++ tracking thread pays, without the Python/ctypes overhead of 2/2b/2c ----
+    log("python e2e legs done")
     drv = C.CDLL(os.path.join(os.path.dirname(ft.library_path()), "libft_sequence_driver.so"))
 
     class Seq(C.Structure):
@@ -601,19 +978,42 @@ def main():
     hctx = (C.c_void_p * DE)(*[c_.h for c_ in ctxs[:DE]])
     nmatch = [C.c_longlong(), C.c_longlong(), C.c_longlong()]
 
-    def native(fn):
+    def native_once(fn):
         barrier()
         t = fn()
         if t < 0:
             raise SystemExit("bench.py: native sequence driver failed: %s" % L_.ft_last_error().decode())
-        (t,) = replicas.reduce_max(dist, world, [t], device="cuda")
+        (t,) = replicas.reduce_max(dist, world, [t])
         return t
+
+    def native(fn):
+        """seconds per K-step call (max over ranks), averaged over enough calls to cover --min-seconds (each call is exactly
+        K steps, synchronised on both sides, so a 20-step run is not one 3 ms interval of pipeline fill and drain)"""
+        t = native_once(fn)
+        reps = int(min(64, max(1, np.ceil(args.min_seconds / max(t, 1e-6)))))
+        if world > 1:
+            (r_,) = replicas.reduce_max(dist, world, [float(reps)])
+            reps = int(r_)
+        tot = t
+        for _ in range(reps - 1):
+            tot += native_once(fn)
+        return tot / reps
     native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), 20, TH, 0, 0, C.byref(nmatch[1])))      # warm-up
     n_serial_s = native(lambda: drv.ftd_run_serial(ctxs[0].h, C.byref(seq), args.steps, TH, C.byref(nmatch[0])))
     n_pipe_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 0, 0, C.byref(nmatch[1])))
     n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[2])))
+    # the same store loop with PAGEABLE input images (what a caller holding a plain cv::Mat hands over): upload_images stages
+    # them through the context's pinned buffer (ft_context.cu), one extra host copy of both images per frame
+    pg = dict(imgL=arr([f[0].ctypes.data for f in frames]), imgR=arr([f[1].ctypes.data for f in frames]))
+    seq_pg = Seq(N_FRAMES, E["width"], E["height"], M_POINTS, C.cast(pg["imgL"], C.POINTER(C.c_void_p)), C.cast(pg["imgR"], C.POINTER(C.c_void_p)),
+                 *[C.cast(keep[k_], C.POINTER(C.c_void_p)) for k_ in ("pos", "normal", "minmax", "desc", "flags", "rows")])
+    nmatch.append(C.c_longlong())
+    n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[3])))
+    if nmatch[3].value != nmatch[2].value:
+        raise SystemExit("bench.py: pageable-input loop disagrees on the matches found")
     if not (nmatch[0].value == nmatch[1].value == nmatch[2].value) or nmatch[0].value <= 0:
         raise SystemExit("bench.py: the end-to-end loops disagree on the matches found: %s" % [v.value for v in nmatch])
+    log("native e2e legs done")
     clocks = sampler.stop()
     h2d = 2 * E["width"] * E["height"] + M_POINTS * (12 + 12 + 8 + 32 + 4) + 2 * cap_dev * 5
     d2h = 64 + 2 * cap_dev * (24 + 32) + cap_dev * 8 + 64 + 2 * cap_dev * 5 + M_POINTS * 8
@@ -629,10 +1029,12 @@ def main():
     stage_ms = {k_: float(np.mean(v)) for k_, v in acc.items()}
     st = ctx.stats()
 
+    log("per-kernel pass done")
     # ---- reductions over ranks (max time) ----
-    dev_ms_total, e2e_s, wall_s, e2e_serial_s, e2e_store_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall1 - wall0, e2e_serial_s, e2e_store_s], device="cuda")
-    ms_per_step = dev_ms_total / args.steps
-    value = replicas.aggregate_throughput(world, args.steps, dev_ms_total / 1e3)
+    dev_ms_total, e2e_s, wall_total, e2e_serial_s, e2e_store_s = replicas.reduce_max(dist, world, [dev_ms_total, e2e_s, wall_total, e2e_serial_s, e2e_store_s])
+    ms_per_step = dev_ms_total / steps_timed
+    value = replicas.aggregate_throughput(world, steps_timed, dev_ms_total / 1e3)
+    wall_s = wall_total
     e2e_value = replicas.aggregate_throughput(world, args.steps, e2e_s)
 
     # ---- roofline of the dominant kernel (SURVEY.md 8d byte formulas with the measured counts) ----
@@ -645,7 +1047,6 @@ def main():
     C_ = st["cand_left"] + st["cand_right"]; K_ = st["kp_left"] + st["kp_right"]
     # per launch (both eyes): bytes each kernel has to move at minimum (SURVEY.md 8d formulas, measured counts)
     alg_bytes = {
-        "copy_level0": 2 * 2 * px[0],
         "resize": 2 * (sum(px[:-1]) + sum(px[1:])),
         "blur_l0": 2 * 2 * px[0],
         "blur": 2 * 2 * (sumP - px[0]),
@@ -656,7 +1057,6 @@ def main():
         "orient_desc": (749 + 4 + 512 + 32) * K_,
         "grid": 24 * st["kp_left"] + 4 * st["kp_left"] + 4 * 3073,
         "stereo_match": 44 * K_ + 44 * st["stereo_tested"] + 352 * st["stereo_refined"] + 12 * st["kp_left"],
-        "frustum": (12 + 12 + 8 + 4 + 52) * M_POINTS,
         "gather": 68 * M_POINTS + 52 * st["sbp_candidates"],
         "resolve": 4 * st["sbp_candidates"] + 8 * M_POINTS,
     }
@@ -664,11 +1064,14 @@ def main():
     top = max((k_ for k_ in stage_ms if k_ in alg_bytes and k_ != "resize"), key=lambda k_: stage_ms[k_])
     ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this workload
-        traffic = json.load(open(tp))["dram_bytes_per_launch"].get(top)
+    traffic_src = None
+    for tp in (os.path.join(ROOT, "profiles", "r2_traffic.json"), os.path.join(ROOT, "profiles", "r1_traffic.json")):
+        if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this workload
+            traffic = json.load(open(tp))["dram_bytes_per_launch"].get(top)
+            traffic_src = os.path.basename(tp)
+            break
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_kind,
                 "algorithmic_bytes_per_launch": alg_bytes[top], "launch_ms": stage_ms[top]}
     # every kernel against the same roofline: algorithmic bytes of the launch(es) / CUDA-event time, as a fraction of the HBM peak
     stages_roofline = {k_: {"algorithmic_bytes": int(alg_bytes[k_]), "ms": stage_ms[k_],
@@ -686,24 +1089,36 @@ def main():
                              "between steps (256 MiB write)" % (N_FRAMES, N_FRAMES * (2 * E["width"] * E["height"] + 68 * M_POINTS) / 1e6),
                        "pipeline": "%d frames in flight over one sequence (extract t+1.. || search t); searches stay ordered" % D,
                        "pipeline_depth": D,
-                       "sequences": world, "parallelism": "independent sequence per GPU, no collective"},
-            "e2e": {"value": replicas.aggregate_throughput(world, args.steps, n_pipe_s), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": n_pipe_s * 1e3 / args.steps, "frames_in_flight": DE,
+                       "sequences": world, "parallelism": "independent sequence per GPU, no collective (gloo barrier + MAX only)",
+                       "pinned_cores": pinned_cores},
+            # headline end-to-end path = the design's answer to the per-frame CudaMapPoint marshalling of the reference:
+            # host images in, every host vector of the Frame out, the local map named as rows of the persistent device-side
+            # store (8 B / point + the rows the mapping side changed). The 68 B / point snapshot variant is reported beside it.
+            "e2e": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
+                    "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": n_store_s * 1e3 / args.steps, "frames_in_flight": DE,
+                    "path": "ft_frame_submit / ft_frame_collect + ft_map_store_update(%d rows) + ft_search_store (SURVEY 8f row 3)" % STORE_UPSERTS,
                     "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp): ft_frame_submit(t+1..) "
-                              "overlaps marshal + ft_search_staged(t); host wall clock, max over ranks",
+                              "overlaps marshal + search(t); host wall clock, max over ranks; pinned host images",
+                    "upserts_per_step": STORE_UPSERTS,
+                    "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s), "ms_per_step": n_store_s * 1e3 / args.steps},
+                    "pageable_images": {"value": replicas.aggregate_throughput(world, args.steps, n_store_pg_s),
+                                        "ms_per_step": n_store_pg_s * 1e3 / args.steps,
+                                        "note": "same loop, input images in pageable host memory (a plain cv::Mat): staged through the "
+                                                "context's pinned buffer inside ft_frame_submit"},
+                    "snapshot": {"value": replicas.aggregate_throughput(world, args.steps, n_pipe_s),
+                                 "ms_per_step": n_pipe_s * 1e3 / args.steps, "h2d_bytes_per_step": int(h2d),
+                                 "note": "local map re-marshalled and uploaded every frame (68 B / point), as the reference's "
+                                         "CudaMapPoint loop does"},
                     "serial_ms_per_step": n_serial_s * 1e3 / args.steps,
                     "serial_value": replicas.aggregate_throughput(world, args.steps, n_serial_s),
-                    "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s),
-                                  "ms_per_step": n_store_s * 1e3 / args.steps,
-                                  "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
-                                  "upserts_per_step": STORE_UPSERTS,
-                                  "note": "local map named as rows of the persistent device-side store (8f row 3)"},
                     "matches_per_frame": nmatch[0].value / args.steps,
                     "python_loop": {"note": "the same calls issued from Python/ctypes (bench.py step functions)",
                                     "ms_per_step": e2e_s * 1e3 / args.steps, "serial_ms_per_step": e2e_serial_s * 1e3 / args.steps,
                                     "map_store_ms_per_step": e2e_store_s * 1e3 / args.steps}},
-            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches": int(launches_per_step * steps_timed),
+            "timed_regions": n_regions,
             "launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": roofline,
@@ -749,8 +1164,39 @@ def main():
                                 "ms_per_frame": cpu_ms,
                                 "sample": "%d frames (extract L/R on 2 threads + stereo) + 6 frames SearchLocalPoints "
                                           "of the same workload; host has %d cores" % (nsample, os.cpu_count())}
+    log("cpu baseline done")
     if rank == 0 and world == 1:
         line["next_rows"] = {"bow": bench_bow(ctx, ft, torch, stream, frames, local, not args.no_cpu_baseline)}
+        if not args.no_configs:
+            cfgs, nxt = bench_configs(ft, torch, local, frames, not args.no_cpu_baseline, flush_l2)
+            cfgs["sequence_2000_frames_per_gpu"] = {"workload": WORKLOAD, "see": "value / ms_per_step / latency / e2e of this line (the headline)"}
+            line["configs"] = cfgs
+            line["next_rows"].update(nxt)
+            log("reference gpu legs")
+            rg = reference_gpu_legs(frames, mbf, np.float32(mbf / np.float32(E["fx"])))
+            line["reference_gpu"] = rg
+            if "per_image_launcher_ms" in rg:
+                # FastTrack's own kernels process ONE image per launcher chain (one ORBextractor per eye, two streams); this repo's
+                # launches process BOTH eyes. vs_ref_gpu = reference ms for one image / this repo's ms for both eyes (>= 1: faster even
+                # if the reference overlapped its two eyes perfectly); vs_ref_gpu_two_images assumes they run back to back.
+                rs = rg["per_image_launcher_ms"]
+                mine = {"resize": stage_ms.get("resize", 0.0),
+                        "gaussian_blur": stage_ms.get("blur", 0.0) + stage_ms.get("blur_l0", 0.0),
+                        "fast_extract": stage_ms.get("fast_cells", 0.0) + stage_ms.get("fast_cells_l0", 0.0),
+                        "orientation_descriptor": stage_ms.get("orient_desc", 0.0)}
+                ref = {"resize": rs["resize"], "gaussian_blur": rs["gaussian_blur"], "fast_extract": rs["fast_extract"],
+                       "orientation_descriptor": rs["compute_orientation"] + rs["compute_descriptor"]}
+                line["stages_vs_ref_gpu"] = {k_: {"ref_ms_one_image": ref[k_], "ms_both_eyes": mine[k_],
+                                                  "vs_ref_gpu": ref[k_] / mine[k_] if mine[k_] > 0 else None,
+                                                  "vs_ref_gpu_two_images": 2 * ref[k_] / mine[k_] if mine[k_] > 0 else None}
+                                             for k_ in mine}
+                ext_ms = cfgs.get("stereo_pinhole_euroc_752x480", {}).get("gpu_ms")
+                if ext_ms:
+                    line["stages_vs_ref_gpu"]["extract_plus_stereo_pair"] = {
+                        "ref_ms": 2 * rg["extract_operator_ms_per_image"] + rg["stereo_match_ms_per_call"], "ms": ext_ms,
+                        "vs_ref_gpu": (2 * rg["extract_operator_ms_per_image"] + rg["stereo_match_ms_per_call"]) / ext_ms,
+                        "note": "reference: two ORBextractor::operator() calls in GPU run mode (host octree included) + "
+                                "ComputeStereoMatchesGPU, wall clock; this repo: extract + stereo graph, device time"}
     if rank == 0:
         print(json.dumps(line))
     for c_ in ctxs:

@@ -439,18 +439,19 @@ u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 
 
 _REF_ORB_SO = os.path.join(_HERE, "_ref", "libft_ref_orbextractor.so")
+_REF_GPU_SO = os.path.join(_HERE, "_ref", "libft_ref_orbextractor_gpu.so")
 
 
 def build_ref():
     """oracle/_ref/*.so: pieces of the REFERENCE itself compiled where they lie (`make ref`): its vendored DBoW2 and the CPU
     branch of src/ORBextractor.cc. Returns the directory, or None when neither the prebuilt libraries nor the reference
     tree are available (e.g. on the GPU box before a snapshot carried the files)."""
-    srcs = [os.path.join(_HERE, f) for f in ("ref_dbow2_capi.cpp", "ref_orbextractor_capi.cpp", "ref_frame_capi.cpp",
+    srcs = [os.path.join(_HERE, f) for f in ("ref_dbow2_capi.cpp", "ref_orbextractor_capi.cpp", "ref_frame_capi.cpp", "ref_gpu_capi.cpp",
                                              "ref_extract_fns.py", os.path.join("ref_stubs", "ref_frame_shim.h"),
                                              "ft_oracle.cpp", "ft_oracle.h",
                                              os.path.join("ref_stubs", "ft_cv_standin.cpp"),
                                              os.path.join("ref_stubs", "opencv2", "opencv.hpp"))]
-    outs = [_REF_SO, _REF_ORB_SO, os.path.join(_HERE, "_ref", "libft_ref_frame.so")]
+    outs = [_REF_SO, _REF_ORB_SO, os.path.join(_HERE, "_ref", "libft_ref_frame.so"), _REF_GPU_SO]
     have_ref = os.path.isdir(os.path.join(_REFERENCE, "Thirdparty", "DBoW2", "DBoW2"))
     built = all(os.path.exists(o) for o in outs)
     fresh = built and all(os.path.getmtime(o) >= os.path.getmtime(x) for o in outs for x in srcs)
@@ -460,6 +461,82 @@ def build_ref():
         return None
     subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + _REFERENCE])
     return os.path.dirname(_REF_SO)
+
+
+_ref_gpu = None
+
+
+def ref_gpu_lib():
+    """oracle/_ref/libft_ref_orbextractor_gpu.so: the reference's OWN CUDA kernels (src/{resize,gaussian_blur,fast,orientation,
+    descriptor}.cu, src/Kernels/StereoMatchKernel.cu) compiled with nvcc from where they lie, plus src/ORBextractor.cc in GPU run
+    mode. Bench infrastructure only (the performance bar); None when the library did not travel with the snapshot."""
+    global _ref_gpu
+    if _ref_gpu is None:
+        if build_ref() is None or not os.path.exists(_REF_GPU_SO):
+            return None
+        R = C.CDLL(_REF_GPU_SO)
+        R.ftrefgpu_extractor_create.restype = C.c_void_p
+        R.ftrefgpu_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        R.ftrefgpu_extractor_destroy.argtypes = [C.c_void_p]
+        R.ftrefgpu_extract.restype = C.c_int
+        R.ftrefgpu_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int]
+        R.ftrefgpu_stage_times.restype = C.c_int
+        R.ftrefgpu_stage_times.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, f32p]
+        R.ftrefgpu_stereo_time.restype = C.c_int
+        R.ftrefgpu_stereo_time.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, C.c_int, u8p, f32p, C.c_int,
+                                           u8p, C.c_float, C.c_float, C.c_int, f32p]
+        _ref_gpu = R
+    return _ref_gpu
+
+
+def ref_gpu_stage_times(img, nlevels=8, scale_factor=1.2, ini_th=20, min_th=7, reps=20):
+    """CUDA-event ms of the reference's five extractor launchers on one image (both resize..descriptor chains as
+    ComputePyramidGPU / ComputeKeyPointsOctTreeGPU issue them): dict(resize, gaussian_blur, fast_extract, compute_orientation,
+    compute_descriptor, corners)"""
+    R = ref_gpu_lib()
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros(8, np.float32)
+    rc = R.ftrefgpu_stage_times(img, img.shape[1], img.shape[0], img.strides[0], nlevels, scale_factor, ini_th, min_th, reps, out)
+    if rc != 0:
+        raise RuntimeError("ftrefgpu_stage_times failed (%d)" % rc)
+    names = ("resize", "gaussian_blur", "fast_extract", "compute_orientation", "compute_descriptor")
+    d = {k: float(out[i]) for i, k in enumerate(names)}
+    d["corners"] = int(out[5])
+    return d
+
+
+def ref_gpu_extract_ms(imgs, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """wall-clock ms per image of the reference's ORBextractor::operator() in GPU run mode (H2D, its kernels, D2H of all
+    corners, DistributeOctTreeGPU on the host); first image is a warm-up. Returns (ms_per_image, keypoints of the last)"""
+    import time
+    R = ref_gpu_lib()
+    h, w = imgs[0].shape
+    ex = R.ftrefgpu_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th, w, h)
+    t = []
+    n = 0
+    for i, im in enumerate(imgs):
+        im = np.ascontiguousarray(im, np.uint8)
+        t0 = time.perf_counter()
+        n = R.ftrefgpu_extract(C.c_void_p(ex), im, w, h, im.strides[0])
+        if i:
+            t.append((time.perf_counter() - t0) * 1e3)
+    R.ftrefgpu_extractor_destroy(C.c_void_p(ex))
+    return float(np.mean(t)), int(n)
+
+
+def ref_gpu_stereo_ms(imgL, imgR, kL, dL, kR, dR, mbf, mb, nlevels=8, scale_factor=1.2, reps=10):
+    """wall-clock ms per call of the reference's GPU stereo matching (Frame::ComputeStereoMatchesGPU -> StereoMatchKernel::launch)
+    on an extracted pair (kL / kR: oracle keypoint rows x, y, size, angle, response, octave). Returns (ms, matches kept)"""
+    R = ref_gpu_lib()
+    imgL = np.ascontiguousarray(imgL, np.uint8); imgR = np.ascontiguousarray(imgR, np.uint8)
+    a = np.ascontiguousarray(kL[:, [0, 1, 5]], np.float32); b = np.ascontiguousarray(kR[:, [0, 1, 5]], np.float32)
+    out = np.zeros(4, np.float32)
+    rc = R.ftrefgpu_stereo_time(imgL, imgR, imgL.shape[1], imgL.shape[0], imgL.strides[0], nlevels, scale_factor, a, len(a),
+                                np.ascontiguousarray(dL, np.uint8), b, len(b), np.ascontiguousarray(dR, np.uint8), float(mbf), float(mb),
+                                reps, out)
+    if rc != 0:
+        raise RuntimeError("ftrefgpu_stereo_time failed (%d)" % rc)
+    return float(out[0]), int(out[1])
 
 
 class RefExtractor:

@@ -7,6 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import oracle
+from sbp_check import assert_search_matches
 import fasttrack_b200 as ft
 from fasttrack_b200 import synth
 
@@ -62,8 +63,12 @@ def test_mono_and_rgbd_frames(euroc_pair, sensor):
     n_g, h_g, ho_g, _ = ctx.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0,
                                                 mp["holder"], mp["holder_obs"])
     gi, gf = ctx.track(M)
-    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
-        assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    def prefix(k_):
+        a = {key: v[:k_] for key, v in mp.items() if key not in ("holder", "holder_obs")}
+        o = F.search_local_points(a["pos"], a["normal"], a["minmax"], a["desc"], a["flags"], 3.0, mp["holder"], mp["holder_obs"])
+        g_ = ctx.search_local_points(a["pos"], a["normal"], a["minmax"], a["desc"], a["flags"], 3.0, mp["holder"], mp["holder_obs"])
+        return g_[:3], o[:3]
+    assert_search_matches((n_g, h_g, ho_g), (n_o, h_o, ho_o), gi, ti, prefix)
     assert n_o > 100
     # call-order errors
     with pytest.raises(RuntimeError, match="monocular / RGB-D"):

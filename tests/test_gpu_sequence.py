@@ -14,6 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import oracle
+from sbp_check import assert_search_matches
 import fasttrack_b200 as ft
 from fasttrack_b200 import synth
 
@@ -139,8 +140,12 @@ def test_sequence_2000_frames():
                 n_o, h_o, ho_o, ti, tf = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0,
                                                                np.full(len(kL), -1, np.int32), np.zeros(len(kL), np.uint8))
                 gi, gf = seq.track(M)
-                if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
-                    assert res[0] == n_o and np.array_equal(res[1], h_o) and np.array_equal(res[2], ho_o)
+                def prefix(k_):
+                    h0, o0 = np.full(len(kL), -1, np.int32), np.zeros(len(kL), np.uint8)
+                    o = F.search_local_points(mp["pos"][:k_], mp["normal"][:k_], mp["minmax"][:k_], mp["desc"][:k_], mp["flags"][:k_], 3.0, h0, o0)
+                    g_ = seq.search_local_points(mp["pos"][:k_], mp["normal"][:k_], mp["minmax"][:k_], mp["desc"][:k_], mp["flags"][:k_], 3.0, h0, o0)
+                    return g_[:3], o[:3]
+                assert_search_matches(res[:3], (n_o, h_o, ho_o), gi, ti, prefix)
                 checked_exact.append(t)
         # (b) pipelined run: frame t is submitted, frame t-(D-1) is collected and searched
         maps[t] = mp

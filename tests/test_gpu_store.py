@@ -7,6 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import oracle
+from sbp_check import assert_search_matches
 import fasttrack_b200 as ft
 from fasttrack_b200 import synth
 
@@ -51,8 +52,12 @@ def test_store_search_equals_snapshot_search_and_oracle(frame):
     n_o, h_o, ho_o, ti, tf = F.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0,
                                                    mp["holder"], mp["holder_obs"])
     gi, gf = ctx.track(M)
-    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
-        assert got[0] == n_o and np.array_equal(got[1], h_o) and np.array_equal(got[2], ho_o)
+    def prefix(k):
+        o = F.search_local_points(mp["pos"][:k], mp["normal"][:k], mp["minmax"][:k], mp["desc"][:k], mp["flags"][:k], 3.0,
+                                  mp["holder"], mp["holder_obs"])
+        g = ctx.search_store(slots[:k], mp["flags"][:k], 3.0, mp["holder"], mp["holder_obs"])
+        return g[:3], o[:3]
+    assert_search_matches(got[:3], (n_o, h_o, ho_o), gi, ti, prefix)
 
     # incremental update: LocalMapping moved / re-described 700 of the points; a sub-list of the map is searched
     ch = rng.choice(M, 700, replace=False)

@@ -8,6 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import oracle
+from sbp_check import assert_search_matches
 import fasttrack_b200 as ft
 from fasttrack_b200 import synth
 
@@ -50,8 +51,12 @@ def test_undistorted_keypoints_grid_and_search(euroc_pair, which):
     gi, gf = ctx.track(M)
     clean = ti[:, 4] == 0
     assert np.array_equal(gi[clean, 0], ti[clean, 0]) and np.array_equal(gi[clean, 2], ti[clean, 2])
-    if np.array_equal(gi[:, 0], ti[:, 0]) and np.array_equal(gi[:, 2], ti[:, 2]):
-        assert n_g == n_o and np.array_equal(h_g, h_o) and np.array_equal(ho_g, ho_o)
+    def prefix(k):
+        a = {key: v[:k] for key, v in mp.items() if key not in ("holder", "holder_obs")}
+        o = F.search_local_points(a["pos"], a["normal"], a["minmax"], a["desc"], a["flags"], 3.0, mp["holder"], mp["holder_obs"])
+        g = ctx.search_local_points(a["pos"], a["normal"], a["minmax"], a["desc"], a["flags"], 3.0, mp["holder"], mp["holder_obs"])
+        return g[:3], o[:3]
+    assert_search_matches((n_g, h_g, ho_g), (n_o, h_o, ho_o), gi, ti, prefix)
     assert n_o > 100
     # k1 == 0 switches it off (Frame.cc:773): mvKeysUn = mvKeys, bounds = the image
     ctx.set_distortion([0.0, 0.1, 0, 0])
