@@ -551,7 +551,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     int* mkClear = s.minKey + ((rounds + 2) % 3) * stride;
     __syncthreads();
     for (int i = gtid; i < nS; i += nThreads) mkClear[i] = 0x7FFFFFFF;
-    if (gtid == 0) s.cursor[5 + ((rounds + 2) % 3)] = 0;
+    // The "changed" flag of round r lives in cursor[5 + r % 3]. Clear the flag of round r + 1 here: it was last read at the
+    // end of round r - 2, and the cluster barrier of round r - 1 lies in between. (Clearing the flag of round r + 2 = r - 1
+    // would race with CTAs that have not read it yet at the end of round r - 1: a CTA reading 0 leaves the loop while the
+    // others continue, and the cluster deadlocks in its next barrier.)
+    if (gtid == 0) s.cursor[5 + ((rounds + 1) % 3)] = 0;
     int changed = 0;
     for (int k = vid; k < nA; k += nThreads) {
       const bool mine = (k == vid);
