@@ -246,7 +246,7 @@ def bench_bow(ctx, ft, torch, stream, frames, device_id, with_cpu):
     return out
 
 
-def _dev_ms(torch, stream, fn, reps, flush=None, warm=3):
+def _dev_ms(torch, stream, fn, reps, flush=None, warm=3):   # flush(stream): L2 flush enqueued on the SAME stream as fn
     """mean CUDA-event ms of fn() enqueued on `stream` (events recorded on that stream, synchronised per repetition)"""
     for _ in range(warm):
         fn()
@@ -254,7 +254,7 @@ def _dev_ms(torch, stream, fn, reps, flush=None, warm=3):
     t = []
     for _ in range(reps):
         if flush:
-            flush()
+            flush(stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream); fn(); e1.record(stream)
         stream.synchronize()
@@ -303,7 +303,7 @@ def bench_configs(ft, torch, local, frames, with_cpu, flush_l2):
         st_ = torch.cuda.ExternalStream(c.stream(), device=dev)
         hp = pin(L0)
         ms = _dev_ms(torch, st_, lambda: c._ck(c.L.ft_extract_mono(c.h, hp.data_ptr(), E["width"])), 30, flush_l2)
-        n = c.counts()[0]
+        n = c.counts()["n_left"]
         r = {"workload": "ORBextractor::operator() on one 752x480 image (1200 features, 8 levels): upload + extraction",
              "gpu_ms": ms, "keypoints": int(n), "timing": "CUDA events on the context's stream around ft_extract_mono (pinned host image, H2D inside)"}
         if oracle:
@@ -350,7 +350,7 @@ def bench_configs(ft, torch, local, frames, with_cpu, flush_l2):
         c.set_stage_timing(True)
         acc = []
         for _ in range(10):
-            flush_l2(); c.frame_enqueue_device(dl.data_ptr(), 512, dr.data_ptr(), 512); acc.append(c.stage_times())
+            flush_l2(st_); c.frame_enqueue_device(dl.data_ptr(), 512, dr.data_ptr(), 512); acc.append(c.stage_times())
         c.set_stage_timing(False)
         s_ = c.stats()
         nl, nr = s_["kp_left"], s_["kp_right"]
@@ -761,8 +761,8 @@ def main():
     L_ = ctx.L
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-    def flush_l2():
-        with torch.cuda.stream(stream):
+    def flush_l2(on=None):
+        with torch.cuda.stream(on or stream):
             flush_buf.add_(1)
 
     # ---- step variants ----
@@ -1011,6 +1011,16 @@ def main():
     n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[3])))
     if nmatch[3].value != nmatch[2].value:
         raise SystemExit("bench.py: pageable-input loop disagrees on the matches found")
+    # ... and with the same pageable buffers registered once (ft_host_register): what INTEGRATION.md recommends for a caller
+    # that keeps its camera buffers
+    for f_ in frames:
+        for im in f_:
+            ctx._ck(L_.ft_host_register(im.ctypes.data, im.nbytes))
+    nmatch.append(C.c_longlong())
+    n_store_reg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[4])))
+    for f_ in frames:
+        for im in f_:
+            L_.ft_host_unregister(im.ctypes.data)
     if not (nmatch[0].value == nmatch[1].value == nmatch[2].value) or nmatch[0].value <= 0:
         raise SystemExit("bench.py: the end-to-end loops disagree on the matches found: %s" % [v.value for v in nmatch])
     log("native e2e legs done")
@@ -1107,6 +1117,9 @@ def main():
                                         "ms_per_step": n_store_pg_s * 1e3 / args.steps,
                                         "note": "same loop, input images in pageable host memory (a plain cv::Mat): staged through the "
                                                 "context's pinned buffer inside ft_frame_submit"},
+                    "registered_images": {"value": replicas.aggregate_throughput(world, args.steps, n_store_reg_s),
+                                          "ms_per_step": n_store_reg_s * 1e3 / args.steps,
+                                          "note": "same pageable buffers after one ft_host_register each (camera ring buffers are reused)"},
                     "snapshot": {"value": replicas.aggregate_throughput(world, args.steps, n_pipe_s),
                                  "ms_per_step": n_pipe_s * 1e3 / args.steps, "h2d_bytes_per_step": int(h2d),
                                  "note": "local map re-marshalled and uploaded every frame (68 B / point), as the reference's "

@@ -17,6 +17,7 @@ KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle"
                            ("octave", "<i4")])
 
 EXPORTS = [
+    "ft_host_alloc", "ft_host_free", "ft_host_register", "ft_host_unregister",
     "ft_last_error", "ft_version", "ft_context_create", "ft_context_destroy", "ft_get_scale_tables",
     "ft_extract_stereo", "ft_extract_stereo_device", "ft_stereo_match", "ft_stereo_match_fisheye", "ft_frame_counts",
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
@@ -67,6 +68,10 @@ def load_library():
     L.ft_version.restype = C.c_char_p
     L.ft_context_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.ft_context_destroy.argtypes = [vp]
+    L.ft_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.ft_host_free.argtypes = [vp]
+    L.ft_host_register.argtypes = [vp, C.c_size_t]
+    L.ft_host_unregister.argtypes = [vp]
     L.ft_get_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ft_extract_stereo.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.ft_extract_stereo_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]

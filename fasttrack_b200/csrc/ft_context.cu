@@ -1602,6 +1602,25 @@ extern "C" ft_status ft_get_stage_times(ft_context* c, float* ms, int n) {
   return FT_OK;
 }
 
+extern "C" ft_status ft_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) { set_err("ft_host_alloc: bad argument"); return FT_ERR_INVALID; }
+  CK(cudaMallocHost(out, bytes));
+  return FT_OK;
+}
+extern "C" ft_status ft_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return FT_OK;
+}
+extern "C" ft_status ft_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) { set_err("ft_host_register: bad argument"); return FT_ERR_INVALID; }
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return FT_OK;
+}
+extern "C" ft_status ft_host_unregister(void* p) {
+  if (p) CK(cudaHostUnregister(p));
+  return FT_OK;
+}
+
 extern "C" ft_status ft_synchronize(ft_context* c) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   CK(cudaSetDevice(c->cfg.device_id));

@@ -29,6 +29,7 @@
 #ifndef FASTTRACK_B200_H
 #define FASTTRACK_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -291,6 +292,16 @@ ft_status ft_search_by_bow(ft_context* ctx, int n_kf, const uint8_t* kf_desc, co
 
 /* Block until everything enqueued on this context has finished. */
 ft_status ft_synchronize(ft_context* ctx);
+
+/* Host image buffers. The extractor takes any host pointer; pageable memory (a plain cv::Mat) is first copied row by row
+ * into the context's pinned staging buffer, which costs one extra pass over both images per frame. A caller that owns its
+ * frame buffers avoids that copy by allocating them here (page-locked, the DMA reads them directly) or by registering the
+ * buffers it already has once (camera ring buffers are reused frame after frame). The reference has no counterpart: its
+ * ORBextractor::ComputePyramidGPU issues cudaMemcpyAsync on the cv::Mat as it comes (src/ORBextractor.cc:1524). */
+ft_status ft_host_alloc(size_t bytes, void** out);
+ft_status ft_host_free(void* p);
+ft_status ft_host_register(void* p, size_t bytes);
+ft_status ft_host_unregister(void* p);
 
 /* Test hook, host arithmetic only: sinf / cosf as the descriptor kernel evaluates them (glibc's polynomial in double;
  * the reference calls cos/sin on a float, src/ORBextractor.cc:74). tests/test_abi.py checks it against the host libm. */

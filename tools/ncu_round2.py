@@ -20,8 +20,9 @@ acc = collections.OrderedDict()
 for r in rows[1:]:
     acc.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
 tot = sum(sum(v) for v in acc.values())
+frames = max(1, len(acc.get("k_resolve", [])) or frames)     # one claim resolution per frame: the list's own frame count
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sectors.sum",
@@ -92,8 +93,8 @@ with open(out_md, "w") as f:
     for k, v in sorted(acc.items(), key=lambda kv: -sum(kv[1])):
         f.write("| %s | %.0f | %.2f | %.1f%% |\n" % (k, len(v) / frames, sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
     f.write("\nSum of kernel time per frame: %.1f us\n\n" % (tot / frames / 1e3))
-    f.write("Full capture (`ncu --set full --metrics lts__t_bytes.sum,lts__t_sectors.sum,lts__t_sector_hit_rate.pct --clock-control none "
-            "--import-source on`), first launch of each (kernel, grid). HBM GB/s = (DRAM read + write) / duration, L2 GB/s = lts__t_bytes / "
+    f.write("Full capture (`ncu --set full --metrics lts__t_bytes.sum,lts__t_sectors.sum,lts__t_sector_hit_rate.pct --clock-control none`, one frame), "
+            "first launch of each (kernel, grid). HBM GB/s = (DRAM read + write) / duration, L2 GB/s = lts__t_bytes / "
             "duration, both against the measured HBM copy peak of %.1f GB/s (MEASURED_PEAKS.json); under ncu every launch runs alone with a "
             "cold L2, so these are per-launch figures, not the pipelined frame's.\n\n" % peak)
     f.write("| kernel | grid x block | regs | us | DRAM rd B | DRAM wr B | HBM GB/s | % of HBM peak | L2 bytes | L2 GB/s | L2 hit % | warp insts | warps active % |\n")
