@@ -523,30 +523,45 @@ def bench_configs(ft, torch, local, frames, with_cpu, flush_l2):
     return out, nxt
 
 
-def reference_gpu_legs(frames, mbf, mb):
+def _reference_gpu_worker():
+    """child process of reference_gpu_legs: the reference's GPU code calls exit() on any CUDA error (CudaUtils.cu:17-22), so it
+    never runs inside the bench process itself"""
+    import oracle
+    if oracle.ref_gpu_lib() is None:
+        print(json.dumps({"unavailable": "oracle/_ref/libft_ref_orbextractor_gpu.so did not travel with the snapshot"}))
+        return
+    frames = make_frames(5, 6)
+    mbf = np.float32(E["fx"] * E["baseline"]); mb = np.float32(mbf / np.float32(E["fx"]))
+    L, R = frames[0]
+    st = oracle.ref_gpu_stage_times(L, E["nlevels"], E["scale"], 20, 7, reps=20)
+    ms_img, nkp = oracle.ref_gpu_extract_ms([f[0] for f in frames] + [frames[0][0]], E["nfeatures"], E["scale"], E["nlevels"], 20, 7)
+    exL, exR = oracle.Extractor(), oracle.Extractor()
+    _, kL, dL = exL.extract(L); _, kR, dR = exR.extract(R)
+    ms_st, kept = oracle.ref_gpu_stereo_ms(L, R, kL, dL, kR, dR, float(mbf), float(mb), E["nlevels"], E["scale"], reps=10)
+    print(json.dumps({
+        "per_image_launcher_ms": {k: v for k, v in st.items() if k != "corners"}, "corners_all_levels": st["corners"],
+        "extract_operator_ms_per_image": ms_img, "extract_keypoints": nkp,
+        "stereo_match_ms_per_call": ms_st, "stereo_matches": kept,
+        "note": "one 752x480 image per launcher chain (the reference runs one ORBextractor per eye); its resize kernel computes every "
+                "level straight from level 0 in one launch (not what its CPU ComputePyramid does: SURVEY.md 2.3), this repo's pyramid "
+                "is the bit-exact chain; operator() = H2D + kernels + D2H of every corner + DistributeOctTreeGPU on the host, wall clock; "
+                "stereo = Frame::ComputeStereoMatchesGPU (row table, StereoMatchKernel::launch with its per-call cudaMemcpy's, host sort "
+                "+ median filter), wall clock; SearchLocalPointsKernel.cu / PoseEstimationKernel.cu need Eigen / Sophus headers: not "
+                "buildable here"}))
+
+
+def reference_gpu_legs(frames=None, mbf=None, mb=None):
     """FastTrack's OWN CUDA kernels on this box's GPU (oracle/_ref/libft_ref_orbextractor_gpu.so = the reference's
     src/{resize,gaussian_blur,fast,orientation,descriptor}.cu + src/Kernels/StereoMatchKernel.cu compiled from where they lie):
     per-launcher CUDA-event times, ORBextractor::operator() in GPU run mode end to end, and the GPU stereo matching call.
-    The performance bar of SURVEY.md 2.1, never a correctness oracle. SearchLocalPointsKernel.cu / PoseEstimationKernel.cu
-    include Frame.h / MapPoint.h (Eigen, Sophus, g2o: not installed), so they cannot be compiled here."""
+    The performance bar of SURVEY.md 2.1, never a correctness oracle. Runs in a child process (see _reference_gpu_worker)."""
     try:
-        import oracle
-        if oracle.ref_gpu_lib() is None:
-            return {"unavailable": "oracle/_ref/libft_ref_orbextractor_gpu.so did not travel with the snapshot"}
-        L, R = frames[0]
-        st = oracle.ref_gpu_stage_times(L, E["nlevels"], E["scale"], 20, 7, reps=20)
-        ms_img, nkp = oracle.ref_gpu_extract_ms([f[0] for f in frames[:6]] + [frames[0][0]], E["nfeatures"], E["scale"], E["nlevels"], 20, 7)
-        exL, exR = oracle.Extractor(), oracle.Extractor()
-        _, kL, dL = exL.extract(L); _, kR, dR = exR.extract(R)
-        ms_st, kept = oracle.ref_gpu_stereo_ms(L, R, kL, dL, kR, dR, float(mbf), float(mb), E["nlevels"], E["scale"], reps=10)
-        return {"per_image_launcher_ms": {k: v for k, v in st.items() if k != "corners"}, "corners_all_levels": st["corners"],
-                "extract_operator_ms_per_image": ms_img, "extract_keypoints": nkp,
-                "stereo_match_ms_per_call": ms_st, "stereo_matches": kept,
-                "note": "one 752x480 image per launcher chain (the reference runs one ORBextractor per eye); operator() = H2D + kernels + "
-                        "D2H of every corner + DistributeOctTreeGPU on the host, wall clock; stereo = Frame::ComputeStereoMatchesGPU "
-                        "(row table, StereoMatchKernel::launch with its per-call cudaMemcpy's, host sort + median filter), wall clock; "
-                        "SearchLocalPointsKernel.cu / PoseEstimationKernel.cu need Eigen / Sophus headers: not buildable here"}
-    except Exception as e:   # never let the extra leg break the arm
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-gpu-worker"], capture_output=True, text=True, timeout=240)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": ("exit code %d: " % r.returncode) + (r.stderr.strip().splitlines() or ["no output"])[-1][:240]}
+        return json.loads(lines[-1])
+    except Exception as e:   # noqa: BLE001 -- never let the extra leg break the arm
         return {"unavailable": str(e)[:300]}
 
 
@@ -620,7 +635,6 @@ def run_reference(args, rank, world):
     # OpenCV stand-in (scalar primitives, extra copies), so it is slower than the port above; the port stays the baseline.
     try:
         if oracle.ref_frame_lib() is not None:
-            import threading
             rL, rR = oracle.RefExtractor(), oracle.RefExtractor()
             n_ref = max(3, min(args.steps, 8))
             t_ref = []
@@ -687,12 +701,16 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
     ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight in the end-to-end legs (<= pipeline depth)")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight in the throughput leg (contexts/streams)")
+    ap.add_argument("--ref-gpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--watchdog", type=float, default=900.0, help="dump every thread's Python stack to stderr and exit if the run takes longer (s)")
     args = ap.parse_args()
     import faulthandler
     faulthandler.enable()
     if args.watchdog > 0:
         faulthandler.dump_traceback_later(args.watchdog, exit=True)
+    if args.ref_gpu_worker:
+        _reference_gpu_worker()
+        return
     rank, local, world = replicas.env_rank()
     if args.impl == "reference":
         run_reference(args, rank, world)
