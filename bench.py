@@ -1053,8 +1053,16 @@ def main():
         flush_l2(); step_resident(i)
         for k_, v in ctx.stage_times().items():
             acc.setdefault(k_, []).append(v)
-    ctx.set_stage_timing(False)
     stage_ms = {k_: float(np.mean(v)) for k_, v in acc.items()}
+    # the same pass with every launch on ONE stream: each stage alone on the GPU (what a per-kernel comparison needs)
+    ctx.set_stage_timing(2)
+    acc2 = {}
+    for i in range(args.profile_steps):
+        flush_l2(); step_resident(i)
+        for k_, v in ctx.stage_times().items():
+            acc2.setdefault(k_, []).append(v)
+    ctx.set_stage_timing(False)
+    stage_iso_ms = {k_: float(np.mean(v)) for k_, v in acc2.items()}
     st = ctx.stats()
 
     log("per-kernel pass done")
@@ -1154,6 +1162,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "stages_ms": stage_ms,
+            "stages_isolated_ms": stage_iso_ms,
             "stages_roofline": stages_roofline,
             "frame_algorithmic_bytes": int(frame_bytes),
             "frame_hbm_roofline_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
@@ -1211,10 +1220,11 @@ def main():
                 # launches process BOTH eyes. vs_ref_gpu = reference ms for one image / this repo's ms for both eyes (>= 1: faster even
                 # if the reference overlapped its two eyes perfectly); vs_ref_gpu_two_images assumes they run back to back.
                 rs = rg["per_image_launcher_ms"]
-                mine = {"resize": stage_ms.get("resize", 0.0),
-                        "gaussian_blur": stage_ms.get("blur", 0.0) + stage_ms.get("blur_l0", 0.0),
-                        "fast_extract": stage_ms.get("fast_cells", 0.0) + stage_ms.get("fast_cells_l0", 0.0),
-                        "orientation_descriptor": stage_ms.get("orient_desc", 0.0)}
+                # both sides timed the same way: every launch alone on the GPU, CUDA events around it
+                mine = {"resize": stage_iso_ms.get("resize", 0.0),
+                        "gaussian_blur": stage_iso_ms.get("blur", 0.0) + stage_iso_ms.get("blur_l0", 0.0),
+                        "fast_extract": stage_iso_ms.get("fast_cells", 0.0) + stage_iso_ms.get("fast_cells_l0", 0.0),
+                        "orientation_descriptor": stage_iso_ms.get("orient_desc", 0.0)}
                 ref = {"resize": rs["resize"], "gaussian_blur": rs["gaussian_blur"], "fast_extract": rs["fast_extract"],
                        "orientation_descriptor": rs["compute_orientation"] + rs["compute_descriptor"]}
                 line["stages_vs_ref_gpu"] = {k_: {"ref_ms_one_image": ref[k_], "ms_both_eyes": mine[k_],

@@ -593,6 +593,7 @@ static int enqueue_extract(ft_context* c) {
   const int nl = P.nlevels;
   int n = 0;
   cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3;
+  if (c->timing == 2) { s2 = s; s3 = s; }     // isolated stage timing: every launch on one stream, nothing overlaps
   const bool perLevel = !c->timing && !c->grouped;
   if (c->rectify) { ft_launch_remap(P, c->B, c->dRaw[0], c->dRaw[1], c->dRemapTab, c->rawW, c->rawH, s); n++; }
   else if (c->inResize) { ft_launch_resize_input(P, c->B, c->dRaw[0], c->dRaw[1], c->rawW, s); n++; }
@@ -636,6 +637,7 @@ static int enqueue_extract(ft_context* c) {
 // Stereo matching with the frame grid (only read by the projection search) built on a parallel branch.
 static int enqueue_stereo(ft_context* c) {
   cudaStream_t s = c->stream, s2 = c->stream2;
+  if (c->timing == 2) s2 = s;
   cudaEventRecord(c->evFork2, s);
   cudaStreamWaitEvent(s2, c->evFork2, 0);
   { StageScope t(c, FT_STAGE_GRID, s2); ft_launch_grid(c->P, c->B, c->G, c->fisheye, c->minX, c->minY, c->gridWInv, c->gridHInv, c->und, s2); }

@@ -463,7 +463,7 @@ __device__ __forceinline__ float ft_fast_atan2(float y, float x) {
 #define OD_WARPS 8
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_constant__ FtParams p,
                                                                const __grid_constant__ FtBuffers b) {
-  __shared__ int sLvlOff[FT_MAX_LEVELS + 1];
+  __shared__ int sLvlOff[FT_MAX_LEVELS + 1], sLvlCnt[FT_MAX_LEVELS];
   __shared__ int sScan[OD_WARPS];
   __shared__ int sMonoBefore;   // mono (non-lapping) keypoints before this block's first keypoint
   __shared__ int sMonoTotal;
@@ -473,9 +473,12 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   FT_PDL_TRIGGER();     // the stereo kernel may be scheduled; it waits for this grid before it reads
   sPat[tid] = reinterpret_cast<const int*>(c_pattern)[tid];
+  // per-level keypoint counts: one load per thread (all in flight at once), then the prefix by one thread
+  if (tid < FT_MAX_LEVELS) sLvlCnt[tid] = tid < p.nlevels ? E.lvlKpCount[tid] : 0;
+  __syncthreads();
   if (tid == 0) {
     int o = 0;
-    for (int l = 0; l < p.nlevels; l++) { sLvlOff[l] = o; o += E.lvlKpCount[l]; }
+    for (int l = 0; l < p.nlevels; l++) { sLvlOff[l] = o; o += sLvlCnt[l]; }
     sLvlOff[p.nlevels] = o;
     sMonoBefore = 0; sMonoTotal = 0;
   }

@@ -328,7 +328,9 @@ ft_status ft_debug_grid(ft_context* ctx, int right, int* counts, int* indices, i
 ft_status ft_debug_stats(ft_context* ctx, long long* stats, int n);
 
 /* Per-stage device timing with CUDA events recorded around every kernel on the stream it is launched on.
- * Enabling it switches the context to direct launches (events cannot be read out of a replayed graph). */
+ * Enabling it switches the context to direct launches (events cannot be read out of a replayed graph).
+ * enable = 1: the launch topology of the product path (branches on several streams: stage times include the contention
+ * between concurrent kernels); enable = 2: every launch on one stream, so each stage is timed in isolation. */
 #define FT_STAGE_COPY0 0
 #define FT_STAGE_RESIZE 1
 #define FT_STAGE_BLUR 2
