@@ -379,17 +379,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   __syncthreads();
   }
   const int th = sAny ? p.iniTh : p.minTh;
-  // ordered compaction: thread t owns the contiguous pixel range [t*seg, (t+1)*seg) in row-major order
-  const int seg = (total + FAST_THREADS - 1) / FAST_THREADS;
-  const int beg = min(tid * seg, total), end = min(beg + seg, total);
+  // ordered compaction, four pixels at a time: the items are the words of the NMS plane in row-major order, thread t owns
+  // the contiguous item range [t*per, (t+1)*per); a byte-SIMD compare marks the survivors of a word
+  const int nWc = (3 + iw) >> 2;                  // words 1 .. nWc of a plane row hold the interior columns
+  const unsigned mNWc = c_recip[nWc];
+  const int itemsC = ih * nWc;
+  const int per = (itemsC + FAST_THREADS - 1) / FAST_THREADS;
+  const int ibeg = min(tid * per, itemsC), iend = min(ibeg + per, itemsC);
+  const unsigned th4c = (unsigned)th * 0x01010101u;     // th >= 1: a survivor is a byte >= th
+  const uint32_t* Pm = reinterpret_cast<const uint32_t*>(sMx);
+  const int sW4c = sS >> 2;
   int cnt = 0;
-  {
-    int y = ft_div_small(beg, iw, mIw), x = beg - y * iw;
-    for (int i = beg; i < end; i++) {
-      const int v = sMx[(y + 1) * sS + x + 4];
-      cnt += v >= th && v > 0;
-      if (++x == iw) { x = 0; y++; }
-    }
+  for (int i = ibeg; i < iend; i++) {
+    const int y = ft_div_small(i, nWc, mNWc), k = 1 + (i - y * nWc);
+    cnt += __popc(__vcmpgeu4(Pm[(y + 1) * sW4c + k], th4c)) >> 3;
   }
   // block exclusive scan of cnt
   int incl = cnt;
@@ -400,32 +403,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_con
   }
   if ((tid & 31) == 31) sWarp[tid >> 5] = incl;
   __syncthreads();
-  int base = 0;
-  for (int w = 0; w < (tid >> 5); w++) base += sWarp[w];
-  int totalKp = 0;
-  for (int w = 0; w < FAST_THREADS / 32; w++) totalKp += sWarp[w];
+  int base = 0, totalKp = 0;
+#pragma unroll
+  for (int w = 0; w < FAST_THREADS / 32; w++) { const int v = sWarp[w]; if (w < (tid >> 5)) base += v; totalKp += v; }
   int pos = base + incl - cnt;
   uint32_t* out = E.cellKp + L.cellKpBase + (size_t)(cell - L.cellBase) * L.cellCap;
   if (cnt) {
-    int y = ft_div_small(beg, iw, mIw), x = beg - y * iw;
-    for (int i = beg; i < end; i++) {
-      const int v = sMx[(y + 1) * sS + x + 4];
-      if (v >= th && v > 0) {
-        if (pos < L.cellCap) {
-          const int X = x + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
-          out[pos] = ft_pack_xys(X, Y, v);
-          if (L.octDenseDepth > 0) {
-            // the octree's dense path (ft_octree.cu): count and best (response, canonical position) of the quadtree
-            // cell of depth octDenseDepth that holds this corner
-            const uint32_t q = (b.octTabX[L.octTabX + X] | b.octTabY[L.octTabY + Y]) ^ FT_OCT_EVEN_MASK;
-            const int di = L.octDenseBase + (int)(q >> (2 * (FT_OCT_D - L.octDenseDepth)));
-            atomicAdd(&E.octCnt[di], 1);
-            atomicMax(&E.octBest[di], ((unsigned)v << 20) | (0xFFFFFu - (((unsigned)(cell - L.cellBase) << 9) | (unsigned)pos)));
-          }
-        }
+    for (int i = ibeg; i < iend; i++) {
+      const int y = ft_div_small(i, nWc, mNWc), k = 1 + (i - y * nWc);
+      const unsigned w = Pm[(y + 1) * sW4c + k];
+      unsigned m = __vcmpgeu4(w, th4c);
+      while (m) {
+        const int j = (__ffs(m) - 1) >> 3;
+        m &= ~(0xFFu << (8 * j));
+        if (pos < L.cellCap) out[pos] = ft_pack_xys(4 * (k - 1) + j + 3 + cj * L.wCell, y + 3 + ci * L.hCell, (w >> (8 * j)) & 0xFFu);
         pos++;
       }
-      if (++x == iw) { x = 0; y++; }
+    }
+  }
+  if (L.octDenseDepth > 0) {
+    // the octree's dense path (ft_octree.cu): count and best (response, canonical position) of the quadtree cell of depth
+    // octDenseDepth that holds each corner -- one corner per lane, read back from the slab this CTA just wrote
+    __syncthreads();
+    const int nOut = min(totalKp, L.cellCap);
+    for (int j = tid; j < nOut; j += FAST_THREADS) {
+      const uint32_t w = out[j];
+      const uint32_t q = (b.octTabX[L.octTabX + ft_px(w)] | b.octTabY[L.octTabY + ft_py(w)]) ^ FT_OCT_EVEN_MASK;
+      const int di = L.octDenseBase + (int)(q >> (2 * (FT_OCT_D - L.octDenseDepth)));
+      atomicAdd(&E.octCnt[di], 1);
+      atomicMax(&E.octBest[di], ((unsigned)ft_ps(w) << 20) | (0xFFFFFu - (((unsigned)(cell - L.cellBase) << 9) | (unsigned)j)));
     }
   }
   if (tid == 0) {
