@@ -281,7 +281,7 @@ def test_few_levels_portrait_and_scale_factors(shape, nl, sf):
     ctx.close()
 
 
-@pytest.mark.parametrize("nf", [5000, 6500])
+@pytest.mark.parametrize("nf", [5000, 6500, 10000])
 def test_many_features(nf):
     """the documented upper end (10000 features on a 1280x720 pair): octree levels with thousands of nodes, the gather
     kernel's path without the shared-memory copy of the frame structure (more than ~7800 keypoints), stereo and a
