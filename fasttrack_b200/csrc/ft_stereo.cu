@@ -161,11 +161,20 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   if (!sLast) return;
   __threadfence();
   // ---- outlier filter, 256 threads ----
+  // The SADs are fetched from L2 once and kept in registers across the three passes (up to ST_KEEP per thread; frames with
+  // more keypoints re-read the tail).
+  constexpr int ST_KEEP = 8;
+  const int NT = ST_WARPS * 32;
   sHist[tid] = 0;
   if (tid == 0) { sCount = 0; reinterpret_cast<unsigned*>(&s.stats[7])[0] = 0; }
+  int keep[ST_KEEP];
+#pragma unroll
+  for (int k = 0; k < ST_KEEP; k++) { const int i = tid + k * NT; keep[k] = i < nL ? __ldcg(&s.sad[i]) : -1; }
   __syncthreads();
   int local = 0;
-  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+#pragma unroll
+  for (int k = 0; k < ST_KEEP; k++) if (keep[k] >= 0) { local++; atomicAdd(&sHist[keep[k] >> 7], 1); }
+  for (int i = tid + ST_KEEP * NT; i < nL; i += NT) {
     const int v = __ldcg(&s.sad[i]);
     if (v >= 0) { local++; atomicAdd(&sHist[v >> 7], 1); }
   }
@@ -195,7 +204,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   const int bin = sBin, rem = target - sBefore;
   if (tid < 128) sHist[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+#pragma unroll
+  for (int k = 0; k < ST_KEEP; k++) if (keep[k] >= 0 && (keep[k] >> 7) == bin) atomicAdd(&sHist[keep[k] & 127], 1);
+  for (int i = tid + ST_KEEP * NT; i < nL; i += NT) {
     const int v = __ldcg(&s.sad[i]);
     if (v >= 0 && (v >> 7) == bin) atomicAdd(&sHist[v & 127], 1);
   }
@@ -207,7 +218,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
   }
   __syncthreads();
   const float thDist = __fmul_rn(1.5f * 1.4f, (float)sMedian);
-  for (int i = tid; i < nL; i += ST_WARPS * 32) {
+#pragma unroll
+  for (int k = 0; k < ST_KEEP; k++) {
+    const int i = tid + k * NT;
+    if (keep[k] >= 0 && !((float)keep[k] < thDist)) { s.uRight[i] = -1.0f; s.depth[i] = -1.0f; }
+  }
+  for (int i = tid + ST_KEEP * NT; i < nL; i += NT) {
     const int v = __ldcg(&s.sad[i]);
     if (v >= 0 && !((float)v < thDist)) { s.uRight[i] = -1.0f; s.depth[i] = -1.0f; }
   }
