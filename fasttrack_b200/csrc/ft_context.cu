@@ -486,13 +486,19 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &Q.rotHist, (size_t)32));
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
-  CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CKF(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  CKF(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  // Launch priorities (captured into the graph's kernel nodes): the blur is only read by the orientation + descriptor kernel
+  // that closes the extraction, so it has the whole FAST -> octree phase to hide in; at t = 0 it would otherwise compete
+  // with FAST of level 0 and the first resizes, which are on the critical path. FT_PRIORITIES=0: all streams equal.
+  int prLeast = 0, prGreatest = 0;
+  CKF(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+  { const char* e = getenv("FT_PRIORITIES"); if (e && e[0] == '0') prLeast = prGreatest = 0; }
+  CKF(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest));
+  CKF(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prLeast));      // blur
+  CKF(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prGreatest));   // FAST -> octree of level 0
   { const char* e = getenv("FT_TOPOLOGY"); if (e && !strcmp(e, "grouped")) c->grouped = 1; }
   { const char* e = getenv("FT_SEARCH_GRAPH"); if (e && e[0] == '0') c->searchGraph = 0; }
   for (int l = 0; l < P.nlevels; l++) {
-    CKF(cudaStreamCreateWithFlags(&c->lvStream[l], cudaStreamNonBlocking));
+    CKF(cudaStreamCreateWithPriority(&c->lvStream[l], cudaStreamNonBlocking, prGreatest));
     CKF(cudaEventCreateWithFlags(&c->lvReady[l], cudaEventDisableTiming));
     CKF(cudaEventCreateWithFlags(&c->lvDone[l], cudaEventDisableTiming));
   }

@@ -472,11 +472,27 @@ template <typename BlockedFn>
 __device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32_t* gList, int len, float nnratio,
                                               BlockedFn blocked, bool* cont, bool bestOnly = false) {
   int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-  for (int k = 0; k < len; k++) {
-    const uint32_t e = k < RS_LCAP ? sEnt[k * RS_THREADS] : __ldg(gList + k);
-    const int idx = (int)(e & 0xFFFFu);
+  // The cached entries and their "blocked" look-ups are independent of each other: fetch them all first (three waves of
+  // shared-memory loads in flight instead of a chain of 3 * len dependent ones), then run the order-dependent
+  // best / second-best update on registers.
+  uint32_t e[RS_LCAP];
+  bool skip[RS_LCAP];
+#pragma unroll
+  for (int k = 0; k < RS_LCAP; k++) e[k] = k < len ? sEnt[k * RS_THREADS] : 0u;
+#pragma unroll
+  for (int k = 0; k < RS_LCAP; k++) skip[k] = blocked((int)(e[k] & 0xFFFFu)) || k >= len;
+#pragma unroll
+  for (int k = 0; k < RS_LCAP; k++) {
+    if (skip[k]) continue;
+    const int idx = (int)(e[k] & 0xFFFFu), dist = (int)((e[k] >> 16) & 0x1FFu), oct = (int)(e[k] >> 25);
+    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+  }
+  for (int k = RS_LCAP; k < len; k++) {          // longer lists continue from L2 (rare)
+    const uint32_t eg = __ldg(gList + k);
+    const int idx = (int)(eg & 0xFFFFu);
     if (blocked(idx)) continue;
-    const int dist = (int)((e >> 16) & 0x1FFu), oct = (int)(e >> 25);
+    const int dist = (int)((eg >> 16) & 0x1FFu), oct = (int)(eg >> 25);
     if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
     else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
   }
@@ -567,7 +583,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
       bool cont = false;
       const int t = 2 * mp;
       if (len.x > 0) {
-        auto blk = [&](int idx) { return pre[idx] || mkS[idx] < t; };
+        auto blk = [&](int idx) { return (pre[idx] != 0) | (mkS[idx] < t); };     // both loads issued, no short circuit
         newL = mine ? ft_scan_cached(entL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly)
                     : ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly);
       }
@@ -575,7 +591,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
         // own left writes (stamp 2mp) are handled explicitly, older stamps through the table
         const int ownMirror = (a.mode == 0 && blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
         bool contR = false;
-        auto blk = [&](int idx) { const int slot = idx + a.nLeft; return pre[slot] || mkS[slot] < t || idx == ownMirror; };
+        auto blk = [&](int idx) { const int slot = idx + a.nLeft; return (pre[slot] != 0) | (mkS[slot] < t) | (idx == ownMirror); };
         newR = mine ? ft_scan_cached(entR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly)
                     : ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly);
       }
