@@ -297,6 +297,8 @@ __device__ int oct_careful(const View& view, const OctNodes& nd, OctShared& sh, 
         }
       }
     }
+    __syncthreads();   // posA / posB / posC of the processing order are consumed (every thread has read its prefix values and
+                       // the entries at P): posB is reused below
     if (iter == 0) OCT_CTICK(35);
     // surviving old nodes keep their relative order behind the new children
     for (int i = tid; i < n; i += T) {
