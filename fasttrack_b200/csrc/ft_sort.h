@@ -290,34 +290,17 @@ __device__ __forceinline__ void cta_introsort_loop(elem_t* base, int n, int* pos
 }
 
 // out[rank] = in[i] with rank = #(smaller keys) + #(equal keys before i): the stable sort an insertion sort yields.
-// Call with `nthreads` cooperating threads (tid in [0, nthreads), nthreads a multiple of 32); caller synchronises before
-// and after. While there are more threads than elements, 2 / 4 / 8 / 16 / 32 lanes share one element, each counting over
-// its slice of the array, and the partial ranks are summed with shuffles: the dependent-load chain per thread is n / lanes.
+// Call with `nthreads` cooperating threads (tid in [0, nthreads)); caller synchronises before and after.
 __device__ __forceinline__ void stable_rank(const elem_t* in, elem_t* out, int n, int tid, int nthreads) {
-  int lg = 0;
-  while (lg < 5 && ((n << (lg + 1)) <= nthreads)) lg++;
-  const int lanes = 1 << lg;
-  const int sub = tid & (lanes - 1);
-  const int per = nthreads >> lg;                   // elements handled per sweep
-  const int jb = (n * sub) >> lg, je = (n * (sub + 1)) >> lg;     // this lane's slice of the array (n < 2^16)
-  for (int i0 = 0; i0 < n; i0 += per) {             // uniform trip count over the block (shuffles inside)
-    const int i = i0 + (tid >> lg);
-    const bool valid = i < n;
-    const elem_t e = valid ? in[i] : 0;
+  for (int i = tid; i < n; i += nthreads) {
+    const elem_t e = in[i];
     const uint32_t k = (uint32_t)(e >> 32);
     int r = 0;
-    if (valid) {
-      int j = jb;
-      for (; j + 4 <= je; j += 4) {                 // four independent loads in flight
-        const uint32_t k0 = (uint32_t)(in[j] >> 32), k1 = (uint32_t)(in[j + 1] >> 32), k2 = (uint32_t)(in[j + 2] >> 32),
-                       k3 = (uint32_t)(in[j + 3] >> 32);
-        r += ((k0 < k) || (k0 == k && j < i)) + ((k1 < k) || (k1 == k && j + 1 < i)) + ((k2 < k) || (k2 == k && j + 2 < i)) +
-             ((k3 < k) || (k3 == k && j + 3 < i));
-      }
-      for (; j < je; j++) { const uint32_t kj = (uint32_t)(in[j] >> 32); r += (kj < k) || (kj == k && j < i); }
+    for (int j = 0; j < n; j++) {
+      const uint32_t kj = (uint32_t)(in[j] >> 32);
+      r += (kj < k) || (kj == k && j < i);
     }
-    for (int o = lanes >> 1; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
-    if (valid && sub == 0) out[r] = e;
+    out[r] = e;
   }
 }
 #endif
