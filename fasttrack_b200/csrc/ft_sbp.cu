@@ -26,6 +26,7 @@
 #define GRID_CELLS (FT_GRID_COLS * FT_GRID_ROWS)
 
 // ---- frame grid -------------------------------------------------------------------------
+#define GRID_SIDX 4096   // keypoints whose index lists are built in shared memory
 __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                      const __grid_constant__ FtGridBuffers g, int fisheye, float minX,
                                                      float minY, float gridWInv, float gridHInv,
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
   __shared__ int sCnt[GRID_CELLS];
   __shared__ int sStart[GRID_CELLS + 1];
   __shared__ int sWarp[32];
+  __shared__ int sIdx[GRID_SIDX];
   const int tid = threadIdx.x;
   const int nEyes = fisheye ? 2 : 1;
   for (int eye = 0; eye < nEyes; eye++) {
@@ -88,24 +90,33 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
     __syncthreads();
     for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
     __syncthreads();
+    // the index lists are built and ordered in shared memory (one coalesced write at the end) whenever the frame's
+    // keypoints fit; larger frames build them in place in global memory
+    const bool inS = n <= GRID_SIDX;
+    int* idxW = inS ? sIdx : cellIdx;
     for (int i = tid; i < n; i += 1024) {
       const float4 kr = rec[i];   // written above by this thread
       const int px = (int)roundf(__fmul_rn(__fsub_rn(kr.x, minX), gridWInv));
       const int py = (int)roundf(__fmul_rn(__fsub_rn(kr.y, minY), gridHInv));
       if (px < 0 || px >= FT_GRID_COLS || py < 0 || py >= FT_GRID_ROWS) continue;
       const int c = px * FT_GRID_ROWS + py;
-      cellIdx[sStart[c] + atomicAdd(&sCnt[c], 1)] = i;
+      idxW[sStart[c] + atomicAdd(&sCnt[c], 1)] = i;
     }
     __syncthreads();
     // cells list keypoints in ascending index (insertion order of the reference's push_back loop)
     for (int c = tid; c < GRID_CELLS; c += 1024) {
       const int s0 = sStart[c], s1 = sStart[c + 1];
       for (int i = s0 + 1; i < s1; i++) {
-        const int v = cellIdx[i];
+        const int v = idxW[i];
         int j = i - 1;
-        while (j >= s0 && cellIdx[j] > v) { cellIdx[j + 1] = cellIdx[j]; j--; }
-        cellIdx[j + 1] = v;
+        while (j >= s0 && idxW[j] > v) { idxW[j + 1] = idxW[j]; j--; }
+        idxW[j + 1] = v;
       }
+    }
+    if (inS) {
+      __syncthreads();
+      const int total = sStart[GRID_CELLS];
+      for (int i = tid; i < total; i += 1024) cellIdx[i] = sIdx[i];
     }
     for (int c = tid; c <= GRID_CELLS; c += 1024) cellStart[c] = sStart[c];
     __syncthreads();
