@@ -38,6 +38,7 @@
 // candidates, so the passes run deep; or a third careful pass) the kernel falls back to the general sort-based path,
 // which reads the per-cell slabs and computes the same list.
 #include <cstdio>
+#include <cstdlib>
 
 #include "ft_device.cuh"
 #include "ft_sort.h"
@@ -837,6 +838,15 @@ bool ft_octree_plan(FtLevel& L, size_t smemBudget) {
     int d = 0;
     while (d < 6 && (L.nIni << (2 * (d + 1))) <= 8192 && fminf(rootW, rootH) / (float)(1 << (d + 1)) >= 1.5f) d++;
     if (d >= 2 && oct_node_bytes(L) + oct_dense_bytes(L, d) + 48 <= smemBudget) L.octDenseDepth = d;
+  }
+  // With the dense path on, the general path is the rare fallback: give it only as much shared memory as the dense path
+  // needs anyway (its candidates spill to the HBM scratch beyond that), so that an SM hosting an octree CTA keeps about
+  // 100 KB for the FAST / blur CTAs of the frames in flight. FT_OCT_SMEM=full keeps the large reservation.
+  const char* e = getenv("FT_OCT_SMEM");
+  if (L.octDenseDepth > 0 && !(e && e[0] == 'f')) {
+    const size_t dense = oct_dense_bytes(L, L.octDenseDepth), gfix = oct_general_fixed_bytes(L) + 16;
+    const size_t fit = dense > gfix + 24 * 64 ? (dense - gfix) / 24 : 64;
+    if ((size_t)L.octCandSmem > fit) L.octCandSmem = (int)fit;
   }
   return true;
 }
