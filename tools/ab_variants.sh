@@ -1,19 +1,14 @@
 #!/bin/bash
 # A/B run of prebuilt library variants (variants/*.so, git-ignored) on one GPU box: swaps the library in place and prints the
-# bench's key numbers for each. Usage: tools/ab_variants.sh v0 v1 ...
-set -e
+# bench's key numbers for each, interleaved twice. Usage: tools/ab_variants.sh v0 v1 ...
 LIB=fasttrack_b200/_build/libfasttrack_b200.so
 cp $LIB /tmp/lib_orig.so
+for rep in 1 2; do
 for v in "$@"; do
   cp variants/$v.so $LIB
-  python bench.py --steps 400 --warmup 10 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || { echo "$v failed"; tail -3 gpurun_out/ab_$v.err; continue; }
-  python - "$v" <<'PY'
-import json, sys
-d = json.load(open("gpurun_out/ab_%s.json" % sys.argv[1]))
-s = d["stages_ms"]
-print("%-4s value %.0f fps (%.1f us)  latency p50 %.1f us  e2e %.1f us  store %.1f us  gather %.1f resolve %.1f stereo %.1f" % (
-    sys.argv[1], d["value"], d["ms_per_step"] * 1e3, d["latency"]["p50"] * 1e3, d["e2e"]["ms_per_step"] * 1e3,
-    d["e2e"]["map_store"]["ms_per_step"] * 1e3, s["gather"] * 1e3, s["resolve"] * 1e3, s["stereo_match"] * 1e3))
-PY
+  python bench.py --no-configs --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stages_isolated_ms']
+print('%-8s value %.0f  lat p50 %.1f  e2e %.0f  snapshot %.0f  gather %.1f resolve %.1f octree_l0 %.1f' % ('$v', d['value'], d['latency']['p50']*1e3, d['e2e']['value'], d['e2e']['snapshot']['value'], s['gather']*1e3, s['resolve']*1e3, s['octree_l0']*1e3))"
+done
 done
 cp /tmp/lib_orig.so $LIB
