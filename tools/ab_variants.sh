@@ -6,9 +6,18 @@ cp $LIB /tmp/lib_orig.so
 for rep in 1 2; do
 for v in "$@"; do
   cp variants/$v.so $LIB
-  python bench.py --no-configs --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stages_isolated_ms']
-print('%-8s value %.0f  lat p50 %.1f  e2e %.0f  snapshot %.0f  gather %.1f resolve %.1f octree_l0 %.1f' % ('$v', d['value'], d['latency']['p50']*1e3, d['e2e']['value'], d['e2e']['snapshot']['value'], s['gather']*1e3, s['resolve']*1e3, s['octree_l0']*1e3))"
+  python bench.py --no-configs --no-cpu-baseline > /tmp/ab_out.json 2> /tmp/ab_err.txt
+  if [ -s /tmp/ab_out.json ]; then
+    python - "$v" <<'PY'
+import json, sys
+d = json.loads(open("/tmp/ab_out.json").read().strip().splitlines()[-1]); s = d["stages_isolated_ms"]
+print("%-8s value %.0f  lat p50 %.1f  e2e %.0f  snapshot %.0f  gather %.1f resolve %.1f octree_l0 %.1f orient %.1f stereo %.1f" % (
+    sys.argv[1], d["value"], d["latency"]["p50"] * 1e3, d["e2e"]["value"], d["e2e"]["snapshot"]["value"], s["gather"] * 1e3,
+    s["resolve"] * 1e3, s["octree_l0"] * 1e3, s["orient_desc"] * 1e3, s["stereo_match"] * 1e3))
+PY
+  else
+    echo "$v FAILED: $(tail -2 /tmp/ab_err.txt | cut -c1-300)"
+  fi
 done
 done
 cp /tmp/lib_orig.so $LIB
