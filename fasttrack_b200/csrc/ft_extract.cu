@@ -467,6 +467,7 @@ __device__ __forceinline__ float ft_fast_atan2(float y, float x) {
 
 #define OCT_THREADS 512      // k_debug_sort (the octree kernel itself lives in ft_octree.cu)
 #define OD_WARPS 8
+static_assert(OD_WARPS * 32 == 256, "k_orient_desc stages the 256-word rBRIEF pattern with one word per thread");
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(const __grid_constant__ FtParams p,
                                                                const __grid_constant__ FtBuffers b) {
   __shared__ int sLvlOff[FT_MAX_LEVELS + 1], sLvlCnt[FT_MAX_LEVELS];

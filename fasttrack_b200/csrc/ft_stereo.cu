@@ -12,6 +12,7 @@
 #include "ft_camera.cuh"
 
 #define ST_WARPS 8
+static_assert(ST_WARPS * 32 == 256, "the outlier filter of k_stereo_match keeps one histogram bin per thread");
 
 // per-warp body of k_stereo_match: one left keypoint
 struct FtRightKp {   // right keypoint as the row-band scan needs it (staged in shared memory once per CTA)
