@@ -445,7 +445,7 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   CKF(dalloc(c, &c->S.stats, (size_t)8));
   c->B.stereoStats = c->S.stats;
   // grid
-  CKF(dalloc(c, &c->G.cellStart, (size_t)2 * (FT_GRID_COLS * FT_GRID_ROWS + 1)));
+  CKF(dalloc(c, &c->G.cellStart, (size_t)2 * FT_GRID_STRIDE));
   CKF(dalloc(c, &c->G.cellIdx, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &c->G.rec, (size_t)2 * P.maxKp));
   CKF(dalloc(c, &c->G.kpUn, (size_t)P.maxKp));
@@ -481,9 +481,6 @@ extern "C" ft_status ft_context_create(const ft_config* cfg, ft_context** out) {
   Q.poolCap = MM * 96;
   CKF(dalloc(c, &Q.pool, (size_t)Q.poolCap));
   CKF(dalloc(c, &Q.active, (size_t)MM));
-  CKF(dalloc(c, &Q.minKey, (size_t)3 * 2 * P.maxKp));   // three stamp buffers rotated by k_resolve
-  CKF(dalloc(c, &Q.lastKey, (size_t)2 * P.maxKp));
-  CKF(dalloc(c, &Q.rotHist, (size_t)32));
   CKF(cudaMallocHost((void**)&c->hCounts, 64 * sizeof(int)));
   memset(c->hCounts, 0, 64 * sizeof(int));
   // Launch priorities (captured into the graph's kernel nodes): the blur is only read by the orientation + descriptor kernel
@@ -1707,7 +1704,7 @@ extern "C" ft_status ft_debug_grid(ft_context* c, int right, int* counts, int* i
   const int cells = FT_GRID_COLS * FT_GRID_ROWS;
   std::vector<int> start(cells + 1);
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(start.data(), c->G.cellStart + (right ? cells + 1 : 0), sizeof(int) * (cells + 1), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(start.data(), c->G.cellStart + (right ? FT_GRID_STRIDE : 0), sizeof(int) * (cells + 1), cudaMemcpyDeviceToHost));
   for (int i = 0; i < cells; i++) counts[i] = start[i + 1] - start[i];
   *n = start[cells];
   if (*n) CK(cudaMemcpy(indices, c->G.cellIdx + (right ? c->P.maxKp : 0), sizeof(int) * (*n), cudaMemcpyDeviceToHost));
@@ -1741,6 +1738,16 @@ extern "C" ft_status ft_debug_level_counts(ft_context* c, int eye, int* cand, in
   CK(cudaMemcpy(kp, c->B.eye[eye].lvlKpCount, sizeof(int) * c->P.nlevels, cudaMemcpyDeviceToHost));
   return FT_OK;
 }
+
+#ifdef FT_RS_CLOCK
+extern "C" ft_status ft_debug_rs_clock(ft_context* c, long long* out /* [16][64] */) {
+  if (!c || !out) { set_err("bad argument"); return FT_ERR_INVALID; }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, c->B.eye[1].octClock, sizeof(long long) * 16 * 64, cudaMemcpyDeviceToHost));
+  return FT_OK;
+}
+#endif
 
 extern "C" ft_status ft_debug_oct_clock(ft_context* c, long long* out /* [2][FT_MAX_LEVELS][64] */) {
   if (!c || !out) { set_err("bad argument"); return FT_ERR_INVALID; }

@@ -141,8 +141,10 @@ struct FtPose {
   float Rlr[9], tlr[3], Rrl[9], trl[3];   // fisheye rig extrinsics (Tlr = T_c1_c2 and its inverse)
 };
 
+// per-eye stride of the grid CSR's cell starts: 64*48+1 entries padded to a multiple of 16 bytes (bulk copies)
+#define FT_GRID_STRIDE (FT_GRID_COLS * FT_GRID_ROWS + 4)
 struct FtGridBuffers {
-  int* cellStart;          // [2][64*48+1] (left, right)
+  int* cellStart;          // [2][FT_GRID_STRIDE] (left, right), 64*48+1 entries used in each
   int* cellIdx;            // [2][maxKp]
   float4* rec;             // [2][maxKp] per keypoint {x, y, uRight (pinhole; -1 otherwise), octave as float bits}
   float2* kpUn;            // [maxKp] mvKeysUn coordinates of the left eye (Frame::UndistortKeyPoints)
@@ -177,9 +179,6 @@ struct FtSbpBuffers {
   uint8_t* holderObsInit;  // [2*maxKp]
   int* holder;             // [2*maxKp] result
   uint8_t* holderObs;      // [2*maxKp]
-  int* minKey;             // [2*maxKp]
-  int* lastKey;            // [2*maxKp]
-  int* rotHist;            // [32] rotation histogram of the last-frame search
 };
 
 // ---- projection-search kernel arguments ----

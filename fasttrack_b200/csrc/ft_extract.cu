@@ -218,8 +218,10 @@ __device__ __forceinline__ int ft_fast_score(const uint8_t* c, int stride) {
 __constant__ unsigned c_recip[FT_RECIP_N];
 __device__ __forceinline__ int ft_div_small(int i, int n, unsigned m) { return n == 1 ? i : (int)__umulhi((unsigned)i, m); }
 
+#ifndef FAST_THREADS
 #define FAST_THREADS 256
-__global__ void __launch_bounds__(FAST_THREADS, 6) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
+#endif
+__global__ void __launch_bounds__(FAST_THREADS, 1536 / FAST_THREADS) k_fast_cells(const __grid_constant__ FtParams p, const __grid_constant__ FtBuffers b,
                                                     int levelBegin, int levelEnd) {
   extern __shared__ uint8_t smem[];
   __shared__ int sWarp[FAST_THREADS / 32];

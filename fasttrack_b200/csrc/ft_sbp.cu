@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(1024) k_grid_build(const __grid_constant__ FtP
   for (int eye = 0; eye < nEyes; eye++) {
     const FtEye& E = b.eye[eye];
     const int n = E.counts[0];
-    int* cellStart = g.cellStart + eye * (GRID_CELLS + 1);
+    int* cellStart = g.cellStart + eye * FT_GRID_STRIDE;
     int* cellIdx = g.cellIdx + eye * p.maxKp;
     for (int c = tid; c < GRID_CELLS; c += 1024) sCnt[c] = 0;
     __syncthreads();
@@ -174,6 +174,28 @@ __device__ bool ft_frustum_checks(const FtFrustumArgs& a, const float* P, const 
   return true;
 }
 
+// ---- bulk asynchronous copies (TMA engine, 1-D) with an mbarrier that counts the bytes landed --------------------
+__device__ __forceinline__ uint32_t ft_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ft_saddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ft_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ft_saddr(bar)), "r"(bytes) : "memory");
+}
+// size: multiple of 16 bytes; source and destination 16-byte aligned
+__device__ __forceinline__ void ft_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(ft_saddr(dst)), "l"(src), "r"(bytes), "r"(ft_saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(ft_saddr(bar)), "r"(parity) : "memory");
+  }
+}
+
 // ---- frustum + candidate gathering, one warp per map point ---------------------------------------
 // All lanes evaluate the (cheap) frustum test redundantly from broadcast loads, so the scratch values never make
 // a round trip through memory; lane 0 stores them for the caller. In-view map points then walk their grid window
@@ -200,37 +222,49 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
   // kernel's critical resource): active map points of this CTA, candidates found, searched non-blocking map points
   __shared__ int sActive[GA_ACTIVE_CAP];
   __shared__ int sNActive, sNCand, sNNonBlocking, sActiveBase;
+  __shared__ __align__(8) unsigned long long sStageBar;
   FT_PDL_TRIGGER();     // the claim-resolution cluster may be scheduled; it waits for this grid before it reads
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nEyes = a.fisheye ? 2 : 1;
-  if (tid == 0) { sNActive = 0; sNCand = 0; sNNonBlocking = 0; }   // visible after the staging barrier / the one below
-  if (!stage) __syncthreads();
+  if (tid == 0) { sNActive = 0; sNCand = 0; sNNonBlocking = 0; }   // visible after the barrier below
   // The frame-side search structure (grid CSR + 16-byte keypoint records + uRight) is ~40 KB: every CTA stages it
-  // in shared memory once, so the window walks below never leave the SM. (stage == 0: structure too large for
-  // shared memory, e.g. 10k features; the same code then reads it from L2.)
+  // in shared memory once, so the window walks below never leave the SM. One thread issues four to seven bulk copies
+  // (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier: the TMA engine moves the arrays while
+  // the warps already run the frustum tests of their first map points); a warp waits for the barrier in front of
+  // its first window walk. Whole arrays are copied (capacity, not the frame's keypoint count), so nothing has to be read
+  // before the copies can be issued. (stage == 0: structure too large for shared memory, e.g. 10k features; the same
+  // code then reads it from L2.)
   const float4* recP[2] = {g.rec, g.rec + p.maxKp};
-  const int* cellStartP[2] = {g.cellStart, g.cellStart + (GRID_CELLS + 1)};
+  const int* cellStartP[2] = {g.cellStart, g.cellStart + FT_GRID_STRIDE};
   const int* cellIdxP[2] = {g.cellIdx, g.cellIdx + p.maxKp};
   const float* uRightP = st.uRight;
+  bool staged = !stage;
   if (stage) {
     uint8_t* q = gaSmem;
+    const uint32_t recBytes = (uint32_t)sizeof(float4) * p.maxKp, csBytes = (uint32_t)sizeof(int) * FT_GRID_STRIDE,
+                   ciBytes = (uint32_t)sizeof(int) * p.maxKp, urBytes = (uint32_t)sizeof(float) * p.maxKp;
+    if (tid == 0) {
+      ft_mbar_init(&sStageBar, 1);
+      ft_mbar_expect_tx(&sStageBar, (uint32_t)nEyes * (recBytes + csBytes + ciBytes) + (a.fisheye ? 0u : urBytes));
+    }
     for (int e = 0; e < nEyes; e++) {
-      const int n = b.eye[e].counts[0];
-      float4* r = reinterpret_cast<float4*>(q); q += sizeof(float4) * p.maxKp;
-      int* cs = reinterpret_cast<int*>(q); q += sizeof(int) * (GRID_CELLS + 4);
-      int* ci = reinterpret_cast<int*>(q); q += sizeof(int) * p.maxKp;
-      for (int i = tid; i < n; i += GA_WARPS * 32) { r[i] = recP[e][i]; ci[i] = cellIdxP[e][i]; }
-      for (int i = tid; i <= GRID_CELLS; i += GA_WARPS * 32) cs[i] = cellStartP[e][i];
+      float4* r = reinterpret_cast<float4*>(q); q += recBytes;
+      int* cs = reinterpret_cast<int*>(q); q += csBytes;
+      int* ci = reinterpret_cast<int*>(q); q += ciBytes;
+      if (tid == 0) {
+        ft_bulk_g2s(r, recP[e], recBytes, &sStageBar);
+        ft_bulk_g2s(cs, cellStartP[e], csBytes, &sStageBar);
+        ft_bulk_g2s(ci, cellIdxP[e], ciBytes, &sStageBar);
+      }
       recP[e] = r; cellStartP[e] = cs; cellIdxP[e] = ci;
     }
     if (!a.fisheye) {
       float* u = reinterpret_cast<float*>(q);
-      const int n = b.eye[0].counts[0];
-      for (int i = tid; i < n; i += GA_WARPS * 32) u[i] = st.uRight[i];
+      if (tid == 0) ft_bulk_g2s(u, st.uRight, urBytes, &sStageBar);
       uRightP = u;
     }
-    __syncthreads();
   }
+  __syncthreads();      // the counters above and the initialised mbarrier are visible to every warp
   // cursors [0] pool, [3] non-blocking count, [4] active count are accumulated here; they are zero on entry
   // (cleared at allocation and by the resolve kernel of the previous search)
   for (int mp = blockIdx.x * GA_WARPS + warp; mp < M; mp += gridDim.x * GA_WARPS) {
@@ -327,6 +361,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
           if (a.mode == 1 && br == 0) break;
           continue;
         }
+        if (!staged) { ft_mbar_wait(&sStageBar, 0); staged = true; }   // the bulk copies of the search structure have landed
         const int* cellStart = cellStartP[br];
         const int* cellIdx = cellIdxP[br];
         const float4* rec = recP[br];
@@ -430,6 +465,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) k_gather(const __grid_constant_
       }
     }
   }
+  if (!staged) ft_mbar_wait(&sStageBar, 0);   // no CTA retires while bulk copies into its shared memory are in flight
   __syncthreads();
   const int nAct = min(sNActive, GA_ACTIVE_CAP);
   if (tid == 0) {
@@ -466,45 +502,56 @@ __device__ __forceinline__ int ft_scan_list(const uint32_t* list, int len, float
 }
 
 // One thread-block cluster (8 or 16 CTAs, co-scheduled on one GPC) so that the best/second-best scans of all
-// candidate lists issue from several SMs at once: the rounds are instruction-bound, not bandwidth-bound. The
-// pre-blocked flags are replicated into every CTA's shared memory; the per-slot minimum stamps live in global
-// memory (atomicMin at L2, read back with ld.global.cg) in two buffers used alternately, so a round needs only
-// two cluster barriers: scatter | evaluate (+ reset of the other buffer). Only map points with a non-empty
-// candidate list are visited (compact list written by k_gather).
+// candidate lists issue from several SMs at once: the rounds are latency-bound, not bandwidth-bound. The
+// pre-blocked flags are replicated into every CTA's shared memory. The per-slot minimum stamps never leave the
+// cluster: slot i is OWNED by CTA i / per, which keeps three rotating stamp buffers for its slots in its own shared
+// memory; decisions are scattered with red.min through distributed shared memory into the owner's buffer, and after
+// the round's single cluster barrier every CTA copies the whole table (a few KB) from the owners into its local
+// mkS[] for the next round's scans. Against the round-1 scheme (atomicMin at L2 + read back with ld.global.cg) this
+// takes two L2 round trips and the wait for the atomics' acknowledgements out of every round. The "something changed"
+// flags, the final highest-stamp table and the rotation histogram live in shared memory the same way (flags and
+// histogram in CTA 0). Only map points with a non-empty candidate list are visited (compact list written by k_gather).
 #include <cooperative_groups.h>
+#include <type_traits>
+#include <algorithm>
 namespace cg = cooperative_groups;
 
 #define RS_THREADS 512
 #define RS_LCAP 12   // candidate entries per thread cached in shared memory (longer lists continue from L2)
 
-// best / second-best scan over a list whose first RS_LCAP entries sit in shared memory (column-major, one column
-// per thread) and the rest in global memory
+// best / second-best scan over a list whose first RS_LCAP entries sit in shared memory as sort keys (column-major, one
+// column per thread) and the rest in global memory. Key of the entry at list position k: dist << 23 | k << 19 | octave << 15
+// (0xFFFFFFFF beyond the end of the list): the reference's in-order loop with its two strict comparisons keeps exactly
+// the two smallest (dist, position) pairs -- the old best becomes the second best, ties keep the earlier entry -- so the
+// scan is a branch-free (min, second-min) reduction over keys whose blocked entries are replaced by 0xFFFFFFFF.
 template <typename BlockedFn>
-__device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32_t* gList, int len, float nnratio,
+__device__ __forceinline__ int ft_scan_cached(const uint32_t* sKey, const uint16_t* sIdx, const uint32_t* gList, int len, float nnratio,
                                               BlockedFn blocked, bool* cont, bool bestOnly = false) {
-  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-  // The cached entries and their "blocked" look-ups are independent of each other: fetch them all first (three waves of
-  // shared-memory loads in flight instead of a chain of 3 * len dependent ones), then run the order-dependent
-  // best / second-best update on registers.
-  uint32_t e[RS_LCAP];
-  bool skip[RS_LCAP];
+  // The cached entries and their "blocked" look-ups are independent of each other: fetch them all first (waves of
+  // shared-memory loads in flight instead of a chain of dependent ones), then reduce on registers.
+  uint32_t key[RS_LCAP];
+  int idx[RS_LCAP];
+  bool blk[RS_LCAP];
 #pragma unroll
-  for (int k = 0; k < RS_LCAP; k++) e[k] = k < len ? sEnt[k * RS_THREADS] : 0u;
+  for (int k = 0; k < RS_LCAP; k++) { key[k] = sKey[k * RS_THREADS]; idx[k] = sIdx[k * RS_THREADS]; }
 #pragma unroll
-  for (int k = 0; k < RS_LCAP; k++) skip[k] = blocked((int)(e[k] & 0xFFFFu)) || k >= len;
+  for (int k = 0; k < RS_LCAP; k++) blk[k] = blocked(idx[k]);
+  uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
 #pragma unroll
   for (int k = 0; k < RS_LCAP; k++) {
-    if (skip[k]) continue;
-    const int idx = (int)(e[k] & 0xFFFFu), dist = (int)((e[k] >> 16) & 0x1FFu), oct = (int)(e[k] >> 25);
-    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
-    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+    const uint32_t x = blk[k] ? 0xFFFFFFFFu : key[k];
+    m2 = min(m2, max(m1, x));
+    m1 = min(m1, x);
   }
+  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+  if ((m1 >> 23) < 256u) { bestDist = (int)(m1 >> 23); bestLevel = (int)((m1 >> 15) & 15u); bestIdx = sIdx[((m1 >> 19) & 15u) * RS_THREADS]; }
+  if ((m2 >> 23) < 256u) { bestDist2 = (int)(m2 >> 23); bestLevel2 = (int)((m2 >> 15) & 15u); }
   for (int k = RS_LCAP; k < len; k++) {          // longer lists continue from L2 (rare)
     const uint32_t eg = __ldg(gList + k);
-    const int idx = (int)(eg & 0xFFFFu);
-    if (blocked(idx)) continue;
+    const int id = (int)(eg & 0xFFFFu);
+    if (blocked(id)) continue;
     const int dist = (int)((eg >> 16) & 0x1FFu), oct = (int)(eg >> 25);
-    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = id; }
     else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
   }
   *cont = false;
@@ -515,45 +562,87 @@ __device__ __forceinline__ int ft_scan_cached(const uint32_t* sEnt, const uint32
   return -1;
 }
 
+#ifdef FT_RS_CLOCK
+#define RS_TICK(slot) do { if (threadIdx.x == 0 && b.eye[1].octClock) b.eye[1].octClock[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#else
+#define RS_TICK(slot) do { } while (0)
+#endif
+__device__ __forceinline__ int rs_per(int nSlots, int nCta) { return max(8, (((nSlots + nCta - 1) / nCta) + 7) & ~7); }
+// distributed shared memory through the shared::cluster window (no generic addressing, reductions without a return value)
+__device__ __forceinline__ uint32_t rs_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t rs_mapa(uint32_t saddr, int rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void rs_red_min(uint32_t a, int v) { asm volatile("red.relaxed.cluster.shared::cluster.min.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void rs_red_max(uint32_t a, int v) { asm volatile("red.relaxed.cluster.shared::cluster.max.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void rs_red_add(uint32_t a, int v) { asm volatile("red.relaxed.cluster.shared::cluster.add.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void rs_st(uint32_t a, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int rs_ld(uint32_t a) { int v; asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+
 __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant__ FtBuffers b, const __grid_constant__ FtSbpBuffers s,
                                                            const __grid_constant__ FtStereoBuffers st,
                                                            const __grid_constant__ FtResolveArgs a0) {
   extern __shared__ int sMem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
-  const int nThreads = gridDim.x * RS_THREADS;
+  const int nCta = gridDim.x;
+  const int nThreads = nCta * RS_THREADS;
   const int gtid = blockIdx.x * RS_THREADS + tid;
   // map points are dealt round-robin over the CTAs of the cluster so that every SM gets an equal share of the
   // candidate-list scans (the active list is usually shorter than the cluster's thread count)
-  const int vid = tid * gridDim.x + blockIdx.x;
-  FT_PDL_WAIT();        // launched as a programmatic dependent of k_gather
+  const int vid = tid * nCta + blockIdx.x;
+  RS_TICK(0);
+  // Everything up to FT_PDL_WAIT reads only what was complete before k_gather started (keypoint counts, the caller's
+  // holders) and writes only shared memory: it overlaps the tail of k_gather.
   FtResolveArgs a = a0;
   a.nLeft = b.eye[0].counts[0];
   a.nSlots = a.fisheye ? a.nLeft + b.eye[1].counts[0] : a.nLeft;
   const int nS = a.nSlots;
+  const bool bestOnly = a.mode == 1;
+  // shared memory: mkS[cap] int (this round's stamps, whole table; slots that were taken on entry hold INT_MIN),
+  // own[3][perCap] (the stamp buffers of the slots this CTA owns), ownInit[perCap] (their value when nobody claims them),
+  // last[perCap] (highest stamp per owned slot), flag[4] + hist[32] (used in CTA 0 only), keyL / keyR [RS_LCAP][RS_THREADS] u32,
+  // idxL / idxR [RS_LCAP][RS_THREADS] u16 (the right eye's only for fisheye rigs). a0.nSlots = capacity bound (2*maxKp).
+  const int perCap = rs_per(a0.nSlots, nCta);
+  const int per = rs_per(nS, nCta);              // slots per owner for this frame
+  const uint32_t perMagic = 0xFFFFFFFFu / (uint32_t)per + 1u;   // slot / per == __umulhi(slot, perMagic) for slot * per < 2^32
+  int* mkS = sMem;
+  int* own = mkS + a0.nSlots;
+  int* ownInit = own + 3 * perCap;
+  int* last = ownInit + perCap;
+  int* flag = last + perCap;
+  int* hist = flag + 4;
+  uint32_t* keyL = reinterpret_cast<uint32_t*>(hist + 32);
+  uint32_t* keyR = keyL + RS_LCAP * RS_THREADS;
+  uint16_t* idxL = reinterpret_cast<uint16_t*>(keyL + (a0.fisheye ? 2 : 1) * RS_LCAP * RS_THREADS);
+  uint16_t* idxR = idxL + RS_LCAP * RS_THREADS;
+  const uint32_t flag0 = rs_mapa(rs_saddr(flag), 0), hist0 = rs_mapa(rs_saddr(hist), 0);
+  // the first slot whose final holder this thread writes (the owner CTA writes its slots): caller's holder fetched early
+  const int mySlot = (tid < per && blockIdx.x * per + tid < nS) ? blockIdx.x * per + tid : -1;
+  int hInit = -1; uint8_t hObsInit = 0;
+  if (mySlot >= 0) { hInit = s.holderInit[mySlot]; hObsInit = s.holderObsInit[mySlot]; }
+  // round 0 sees no stamps except the slots that hold a map point with observations on entry: blocked for everybody
+  for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = (s.holderInit[i] != -1 && s.holderObsInit[i]) ? (int)0x80000000 : 0x7FFFFFFF;
+  for (int i = tid; i < per; i += RS_THREADS) {
+    const int slot = blockIdx.x * per + i;
+    const int v = (slot < nS && s.holderInit[slot] != -1 && s.holderObsInit[slot]) ? (int)0x80000000 : 0x7FFFFFFF;
+    ownInit[i] = v; own[perCap + i] = v; last[i] = -1;     // buffer 1: round 0 scatters into it
+  }
+  if (tid < 4) flag[tid] = 0;
+  if (tid >= 32 && tid < 64) hist[tid - 32] = 0;
+  FT_PDL_WAIT();        // launched as a programmatic dependent of k_gather
   const int nA = s.cursor[4];
+  RS_TICK(1);
   // k_resolve_seq resolves fisheye local-map searches with non-blocking map points (uniform over the cluster); the
   // last-frame search has no mirrored writes, so the stamp rule is exact for it in every case
   const bool seqMode = a.fisheye && a.mode == 0 && s.cursor[3] > 0;
-  const bool bestOnly = a.mode == 1;
-  const int stride = a0.nSlots;               // a0.nSlots = capacity bound (2*maxKp): distance between stamp buffers
-  // shared memory: mkS[cap] int (this round's stamps), pre[cap] u8, entL / entR [RS_LCAP][RS_THREADS] u32
-  int* mkS = sMem;
-  uint8_t* pre = reinterpret_cast<uint8_t*>(sMem + a0.nSlots);
-  uint32_t* entL = reinterpret_cast<uint32_t*>(sMem + a0.nSlots + (a0.nSlots + 3) / 4);
-  uint32_t* entR = entL + RS_LCAP * RS_THREADS;
-  // working holders start from the caller's (F.mvpMapPoints on entry)
-  for (int i = gtid; i < nS; i += nThreads) { s.holder[i] = s.holderInit[i]; s.holderObs[i] = s.holderObsInit[i]; }
-  if (seqMode) return;
-  for (int i = tid; i < nS; i += RS_THREADS) pre[i] = (s.holderInit[i] != -1 && s.holderObsInit[i]) ? 1 : 0;
-  for (int i = gtid; i < nS; i += nThreads) {
-    s.minKey[i] = 0x7FFFFFFF; s.minKey[stride + i] = 0x7FFFFFFF; s.minKey[2 * stride + i] = 0x7FFFFFFF;
-    s.lastKey[i] = -1;
+  if (seqMode) {
+    // working holders start from the caller's (F.mvpMapPoints on entry); k_resolve_seq continues from them
+    for (int i = gtid; i < nS; i += nThreads) { s.holder[i] = s.holderInit[i]; s.holderObs[i] = s.holderObsInit[i]; }
+    return;
   }
-  if (gtid < 3) s.cursor[5 + gtid] = 0;
   if (gtid == 3) s.cursor[1] = 0;
-  if (gtid >= 32 && gtid < 64) s.rotHist[gtid - 32] = 0;
-  // this thread's first map point: list heads cached in shared memory, decision kept in registers
+  // this thread's first map point: list heads cached in shared memory as sort keys, decision kept in registers
   int myMp = -1, myFlags = 0;
   int2 myOff = make_int2(0, 0), myLen = make_int2(0, 0);
   int selL = -1, selR = -1;
@@ -562,51 +651,65 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     myFlags = __ldg(&s.flags[myMp]);
     myOff = __ldg(reinterpret_cast<const int2*>(s.listOff) + myMp);
     myLen = __ldg(reinterpret_cast<const int2*>(s.listLen) + myMp);
+    uint32_t eL[RS_LCAP], eR[RS_LCAP];
 #pragma unroll
     for (int k = 0; k < RS_LCAP; k++) {
-      if (k < myLen.x) entL[k * RS_THREADS + tid] = __ldg(s.pool + myOff.x + k);
-      if (k < myLen.y) entR[k * RS_THREADS + tid] = __ldg(s.pool + myOff.y + k);
+      eL[k] = k < myLen.x ? __ldg(s.pool + myOff.x + k) : 0xFFFFFFFFu;
+      eR[k] = k < myLen.y ? __ldg(s.pool + myOff.y + k) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int k = 0; k < RS_LCAP; k++) {
+      keyL[k * RS_THREADS + tid] = k < myLen.x ? (((eL[k] >> 16) & 0x1FFu) << 23) | ((uint32_t)k << 19) | ((eL[k] >> 25) << 15) : 0xFFFFFFFFu;
+      idxL[k * RS_THREADS + tid] = k < myLen.x ? (uint16_t)(eL[k] & 0xFFFFu) : (uint16_t)0;
+      if (a.fisheye) {
+        keyR[k * RS_THREADS + tid] = k < myLen.y ? (((eR[k] >> 16) & 0x1FFu) << 23) | ((uint32_t)k << 19) | ((eR[k] >> 25) << 15) : 0xFFFFFFFFu;
+        idxR[k * RS_THREADS + tid] = k < myLen.y ? (uint16_t)(eR[k] & 0xFFFFu) : (uint16_t)0;
+      }
     }
   }
-  cluster.sync();
-  // Round r reads the stamps of buffer r%3 (all empty in round 0), scatters the decisions it makes into buffer
-  // (r+1)%3 and clears buffer (r+2)%3: one cluster barrier per round.
+  RS_TICK(2);
+  cluster.sync();       // every CTA's tables are initialised before anybody scatters into them
+  RS_TICK(3);
+  // Round r scans against mkS (the stamps scattered in round r - 1), scatters the decisions it makes into the owners'
+  // buffer (r+1)%3 and resets its own buffer (r+2)%3: one cluster barrier per round.
+  auto stampMin = [&](uint32_t buf, int slot, int key) {
+    const int o = (int)__umulhi((uint32_t)slot, perMagic);
+    rs_red_min(rs_mapa(buf, o) + 4u * (uint32_t)(slot - o * per), key);
+  };
   int rounds = 0;
-  for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = 0x7FFFFFFF;   // round 0: buffer 0 is empty, no need to read it back
   for (;;) {
-    int* mkNext = s.minKey + ((rounds + 1) % 3) * stride;
-    int* mkClear = s.minKey + ((rounds + 2) % 3) * stride;
-    __syncthreads();
-    for (int i = gtid; i < nS; i += nThreads) mkClear[i] = 0x7FFFFFFF;
-    // The "changed" flag of round r lives in cursor[5 + r % 3]. Clear the flag of round r + 1 here: it was last read at the
-    // end of round r - 2, and the cluster barrier of round r - 1 lies in between. (Clearing the flag of round r + 2 = r - 1
-    // would race with CTAs that have not read it yet at the end of round r - 1: a CTA reading 0 leaves the loop while the
-    // others continue, and the cluster deadlocks in its next barrier.)
-    if (gtid == 0) s.cursor[5 + ((rounds + 1) % 3)] = 0;
+    int* ownNext = own + ((rounds + 1) % 3) * perCap;
+    int* ownClear = own + ((rounds + 2) % 3) * perCap;
+    const uint32_t ownNextS = rs_saddr(ownNext);
+    __syncthreads();    // mkS is complete (copied at the end of the previous round)
+    for (int i = tid; i < per; i += RS_THREADS) ownClear[i] = ownInit[i];
+    // The "changed" flag of round r lives in CTA 0's flag[r % 3]. Clear the flag of round r + 1 here: it was last read at
+    // the end of round r - 2, and the cluster barrier of round r - 1 lies in between. (Clearing the flag of round r + 2 =
+    // r - 1 would race with CTAs that have not read it yet at the end of round r - 1: a CTA reading 0 leaves the loop
+    // while the others continue, and the cluster deadlocks in its next barrier.)
+    if (gtid == 0) flag[(rounds + 1) % 3] = 0;
+    if (rounds < 8) RS_TICK(4 + 4 * rounds);
     int changed = 0;
-    for (int k = vid; k < nA; k += nThreads) {
-      const bool mine = (k == vid);
-      const int mp = mine ? myMp : __ldg(&s.active[k]);
-      const int2 off = mine ? myOff : __ldg(reinterpret_cast<const int2*>(s.listOff) + mp);
-      const int2 len = mine ? myLen : __ldg(reinterpret_cast<const int2*>(s.listLen) + mp);
-      const bool blocking = ((mine ? myFlags : __ldg(&s.flags[mp])) & 2) != 0;
+    // one map point: scans, comparison with the previous decision, stamps for the next round
+    auto decide = [&](int mp, int2 off, int2 len, bool blocking, auto mineTag) {
+      constexpr bool mine = decltype(mineTag)::value;
       int newL = -1, newR = -1;
       bool cont = false;
       const int t = 2 * mp;
       if (len.x > 0) {
-        auto blk = [&](int idx) { return (pre[idx] != 0) | (mkS[idx] < t); };     // both loads issued, no short circuit
-        newL = mine ? ft_scan_cached(entL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly)
-                    : ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly);
+        auto blk = [&](int idx) { return mkS[idx] < t; };
+        if constexpr (mine) newL = ft_scan_cached(keyL + tid, idxL + tid, s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly);
+        else newL = ft_scan_list(s.pool + off.x, len.x, a.nnratio, blk, &cont, bestOnly);
       }
       if (len.y > 0 && !cont) {
         // own left writes (stamp 2mp) are handled explicitly, older stamps through the table
         const int ownMirror = (a.mode == 0 && blocking && newL >= 0 && st.l2r[newL] != -1) ? st.l2r[newL] : -1;
         bool contR = false;
-        auto blk = [&](int idx) { const int slot = idx + a.nLeft; return (pre[slot] != 0) | (mkS[slot] < t) | (idx == ownMirror); };
-        newR = mine ? ft_scan_cached(entR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly)
-                    : ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly);
+        auto blk = [&](int idx) { return (mkS[idx + a.nLeft] < t) | (idx == ownMirror); };
+        if constexpr (mine) newR = ft_scan_cached(keyR + tid, idxR + tid, s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly);
+        else newR = ft_scan_list(s.pool + off.y, len.y, a.nnratio, blk, &contR, bestOnly);
       }
-      if (mine) {
+      if constexpr (mine) {
         if (newL != selL || newR != selR) { changed = 1; selL = newL; selR = newR; }
       } else {
         const int2 old = make_int2(__ldcg(&s.sel[2 * mp]), __ldcg(&s.sel[2 * mp + 1]));
@@ -615,21 +718,36 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
       if (blocking) {   // stamps the next round reads (writes of map points without observations never block)
         const bool mirror = a.fisheye && a.mode == 0;   // mirrored assignments exist only in the local-map search
         if (newL >= 0) {
-          atomicMin(&mkNext[newL], 2 * mp);
-          if (mirror && st.l2r[newL] != -1) atomicMin(&mkNext[st.l2r[newL] + a.nLeft], 2 * mp);
+          stampMin(ownNextS, newL, 2 * mp);
+          if (mirror && st.l2r[newL] != -1) stampMin(ownNextS, st.l2r[newL] + a.nLeft, 2 * mp);
         }
         if (newR >= 0) {
-          atomicMin(&mkNext[newR + a.nLeft], 2 * mp + 1);
-          if (mirror && st.r2l[newR] != -1) atomicMin(&mkNext[st.r2l[newR]], 2 * mp + 1);
+          stampMin(ownNextS, newR + a.nLeft, 2 * mp + 1);
+          if (mirror && st.r2l[newR] != -1) stampMin(ownNextS, st.r2l[newR], 2 * mp + 1);
         }
       }
+    };
+    if (vid < nA) decide(myMp, myOff, myLen, (myFlags & 2) != 0, std::true_type());
+    for (int k = vid + nThreads; k < nA; k += nThreads) {      // more active map points than threads in the cluster (rare)
+      const int mp = __ldg(&s.active[k]);
+      decide(mp, __ldg(reinterpret_cast<const int2*>(s.listOff) + mp), __ldg(reinterpret_cast<const int2*>(s.listLen) + mp),
+             (__ldg(&s.flags[mp]) & 2) != 0, std::false_type());
     }
-    if (changed) s.cursor[5 + (rounds % 3)] = 1;
+    if (__any_sync(0xFFFFFFFFu, changed) && (tid & 31) == 0) rs_st(flag0 + 4u * (uint32_t)(rounds % 3), 1);
+    if (rounds < 8) RS_TICK(5 + 4 * rounds);
     cluster.sync();
-    // the "anything changed" flag and the stamps the next round reads are fetched together (one L2 round trip, not two);
-    // every thread of the CTA is past its scans, so the shared copy may be overwritten
-    const int ch = __ldcg(&s.cursor[5 + (rounds % 3)]);
-    for (int i = tid; i < nS; i += RS_THREADS) mkS[i] = __ldcg(&mkNext[i]);
+    if (rounds < 8) RS_TICK(6 + 4 * rounds);
+    // the "anything changed" flag and the stamps the next round reads are fetched together (one trip through distributed
+    // shared memory); every thread of the CTA is past its scans, so the local copy may be overwritten. Every CTA starts
+    // with the slots it owns and walks the owners in its own rotation, so the 16 readers do not queue up at one owner.
+    const int ch = rs_ld(flag0 + 4u * (uint32_t)(rounds % 3));
+    for (int w = tid >> 5; w < nCta; w += RS_THREADS / 32) {     // one warp per owner: coalesced rows, no address arithmetic
+      int o = w + blockIdx.x; if (o >= nCta) o -= nCta;
+      const uint32_t src = rs_mapa(ownNextS, o);
+      const int base = o * per;
+      for (int j = tid & 31; j < per && base + j < nS; j += 32) mkS[base + j] = rs_ld(src + 4u * (uint32_t)j);
+    }
+    if (rounds < 8) RS_TICK(7 + 4 * rounds);
     rounds++;
     if (!ch) break;
     if (rounds > a.M + 2) { if (gtid == 0) atomicOr(b.status, FT_ST_RESOLVE_NOCONV); break; }
@@ -646,6 +764,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if (bin == 30) bin = 0;
     return bin;
   };
+  const uint32_t lastS = rs_saddr(last);
+  auto stampMax = [&](int slot, int key) {
+    const int o = (int)__umulhi((uint32_t)slot, perMagic);
+    rs_red_max(rs_mapa(lastS, o) + 4u * (uint32_t)(slot - o * per), key);
+  };
   int nm = 0;
   for (int k = vid; k < nA; k += nThreads) {
     const bool mine = (k == vid);
@@ -653,35 +776,41 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     const int sl = mine ? selL : __ldcg(&s.sel[2 * mp]), sr = mine ? selR : __ldcg(&s.sel[2 * mp + 1]);
     if (mine) *reinterpret_cast<int2*>(s.sel + 2 * mp) = make_int2(sl, sr);
     if (sl >= 0) {
-      atomicMax(&s.lastKey[sl], 2 * mp); nm++;
-      if (mirror && st.l2r[sl] != -1) { atomicMax(&s.lastKey[st.l2r[sl] + a.nLeft], 2 * mp); nm++; }
-      if (rotCheck) atomicAdd(&s.rotHist[rotBin(mp, sl, false)], 1);
+      stampMax(sl, 2 * mp); nm++;
+      if (mirror && st.l2r[sl] != -1) { stampMax(st.l2r[sl] + a.nLeft, 2 * mp); nm++; }
+      if (rotCheck) rs_red_add(hist0 + 4u * (uint32_t)rotBin(mp, sl, false), 1);
     }
     if (sr >= 0) {
-      atomicMax(&s.lastKey[sr + a.nLeft], 2 * mp + 1); nm++;
-      if (mirror && st.r2l[sr] != -1) { atomicMax(&s.lastKey[st.r2l[sr]], 2 * mp + 1); nm++; }
-      if (rotCheck) atomicAdd(&s.rotHist[rotBin(mp, sr, true)], 1);
+      stampMax(sr + a.nLeft, 2 * mp + 1); nm++;
+      if (mirror && st.r2l[sr] != -1) { stampMax(st.r2l[sr], 2 * mp + 1); nm++; }
+      if (rotCheck) rs_red_add(hist0 + 4u * (uint32_t)rotBin(mp, sr, true), 1);
     }
   }
   if (nm) atomicAdd(&s.cursor[1], nm);
+  RS_TICK(40);
   cluster.sync();
-  for (int i = gtid; i < nS; i += nThreads) {
-    const int k = __ldcg(&s.lastKey[i]);
-    if (k >= 0) { s.holder[i] = k >> 1; s.holderObs[i] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
+  RS_TICK(41);
+  for (int i = tid; i < per; i += RS_THREADS) {    // the owner writes each slot's holder exactly once
+    const int slot = blockIdx.x * per + i;
+    if (slot >= nS) break;
+    const int k = last[i];
+    if (k >= 0) { s.holder[slot] = k >> 1; s.holderObs[slot] = (uint8_t)((s.flags[k >> 1] >> 1) & 1); }
+    else if (i == tid) { s.holder[slot] = hInit; s.holderObs[slot] = hObsInit; }
+    else { s.holder[slot] = s.holderInit[slot]; s.holderObs[slot] = s.holderObsInit[slot]; }
   }
   if (rotCheck) {
     // ComputeThreeMaxima (ORBmatcher.cc:2210-2254) on the bin counts, then every match outside the three strongest
     // bins is withdrawn (:2057-2079)
-    cluster.sync();
     int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
     for (int i = 0; i < 30; i++) {
-      const int c = __ldcg(&s.rotHist[i]);
+      const int c = rs_ld(hist0 + 4u * (uint32_t)i);
       if (c > max1) { max3 = max2; max2 = max1; max1 = c; ind3 = ind2; ind2 = ind1; ind1 = i; }
       else if (c > max2) { max3 = max2; max2 = c; ind3 = ind2; ind2 = i; }
       else if (c > max3) { max3 = c; ind3 = i; }
     }
     if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+    cluster.sync();     // holders are written and CTA 0's histogram has been read by everybody
     int removed = 0;
     for (int k = vid; k < nA; k += nThreads) {
       const int mp = __ldg(&s.active[k]);
@@ -698,6 +827,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_resolve(const __grid_constant
     if (removed) atomicSub(&s.cursor[1], removed);
     cluster.sync();
   }
+  RS_TICK(42);
   if (gtid == 0) { s.cursor[2] = rounds; s.cursor[7] = s.cursor[9]; s.cursor[9] = 0; s.cursor[0] = 0; s.cursor[3] = 0; s.cursor[4] = 0; s.cursor[8] = *b.status; }
 }
 
@@ -745,7 +875,11 @@ static size_t ft_gather_smem(const FtParams& p, int fisheye) {
   const size_t perEye = sizeof(float4) * p.maxKp + sizeof(int) * (GRID_CELLS + 4) + sizeof(int) * p.maxKp;
   return (fisheye ? 2 : 1) * perEye + (fisheye ? 0 : sizeof(float) * p.maxKp) + 16;
 }
-static size_t ft_resolve_smem(int slotCap) { return (size_t)slotCap * 4 + (size_t)((slotCap + 3) / 4) * 4 + 2 * RS_LCAP * RS_THREADS * 4 + 16; }
+static int ft_resolve_per(int slots, int nCta) { return std::max(8, (((slots + nCta - 1) / nCta) + 7) & ~7); }   // = rs_per on the device
+static size_t ft_resolve_smem(int slotCap, int nCta, int fisheye) {
+  return (size_t)slotCap * 4 + (size_t)5 * ft_resolve_per(slotCap, nCta) * 4 + (4 + 32) * 4 +
+         (size_t)(fisheye ? 2 : 1) * RS_LCAP * RS_THREADS * (4 + 2) + 16;
+}
 cudaError_t ft_launch_sbp_setup(const FtParams& p) {
   // per function and per device: the opt-in maximum once, never lowered by a later, smaller context
   cudaError_t e = ft_set_max_dynamic_smem((const void*)k_resolve);
@@ -756,7 +890,7 @@ cudaError_t ft_launch_sbp_setup(const FtParams& p) {
   g_resolveCluster = 8;
   if (cudaFuncSetAttribute(k_resolve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(16); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(2 * p.maxKp);
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(2 * p.maxKp, 16, 1);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -811,7 +945,7 @@ void ft_launch_gather(const FtParams& p, const FtBuffers& b, const FtGridBuffers
 void ft_launch_resolve(const FtBuffers& b, const FtSbpBuffers& s, const FtStereoBuffers& stb, const FtResolveArgs& ra,
                        cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(ra.nSlots); cfg.stream = st;
+  cfg.gridDim = dim3(g_resolveCluster); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = ft_resolve_smem(ra.nSlots, g_resolveCluster, ra.fisheye); cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = g_resolveCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -871,7 +1005,7 @@ cudaError_t ft_search_graph_run(FtSearchGraph* G, const FtParams& p, const FtBuf
     void* kr[4] = {(void*)&b, (void*)&s, (void*)&stb, (void*)&ra};
     cudaKernelNodeParams kq = {};
     kq.func = (void*)k_resolve; kq.gridDim = dim3(g_resolveCluster); kq.blockDim = dim3(RS_THREADS);
-    kq.sharedMemBytes = (unsigned)ft_resolve_smem(ra.nSlots); kq.kernelParams = kr;
+    kq.sharedMemBytes = (unsigned)ft_resolve_smem(ra.nSlots, g_resolveCluster, ra.fisheye); kq.kernelParams = kr;
     e = cudaGraphExecKernelNodeSetParams(G->exec, G->resolve, &kq);
     if (e != cudaSuccess) return e;
     if (G->seq) {
