@@ -16,11 +16,13 @@ for line in txt.splitlines():
     if m and cur:
         kern[cur].append(m.group(1).strip())
 FEATURE = ("ATOMS", "ATOMG", "RED.", "REDUX", "SHFL", "VOTE", "MATCH", "BAR.", "UCGABAR", "ACQBULK", "PREEXIT", "LDS", "STS", "LDG", "STG",
-           "VIMNMX", "VABSDIFF", "POPC", "LDSM", "UTMALDG", "UTMASTG", "SYNCS", "CCTL", "ERRBAR", "MEMBAR", "DEPBAR", "NANOSLEEP")
+           "VIMNMX", "VABSDIFF", "POPC", "LDSM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "CCTL", "ERRBAR", "MEMBAR", "DEPBAR", "NANOSLEEP")
 with open(out, "w") as f:
     f.write("# SASS of the built kernels (cuobjdump -sass, sm_100a)\n\n")
-    f.write("No dense contraction exists on this path, so there is no UTCMMA / tcgen05 instruction; tile movement is LDG.32/64/128 -> STS\n"
-            "(the tiles are 1-4 KB per CTA with reflected borders, see DESIGN.md section 4). Programmatic dependent launch shows up as\n"
+    f.write("No dense contraction exists on this path, so there is no UTCMMA / tcgen05 instruction; image-tile movement is LDG.32/64/128 -> STS\n"
+            "(the tiles are 1-4 KB per CTA with reflected borders, see DESIGN.md section 4); the 40 KB search structure of k_gather is moved by\n"
+            "the TMA engine as 1-D bulk copies (UBLKCP = cp.async.bulk global -> shared, completion on an mbarrier: SYNCS.*), and k_resolve\n"
+            "keeps its stamp tables in distributed shared memory (red / ld / st .shared::cluster, no L2 round trip). Programmatic dependent launch shows up as\n"
             "ACQBULK (griddepcontrol.wait) / PREEXIT-class instructions, the claim-resolution cluster barrier as UCGABAR_ARV / UCGABAR_WAIT.\n\n")
     f.write("| kernel | SASS instructions | " + " | ".join(FEATURE) + " |\n|---|---|" + "---|" * len(FEATURE) + "\n")
     for k, ins in kern.items():
