@@ -1028,14 +1028,20 @@ def main():
     native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), 20, TH, 0, 0, C.byref(nmatch[1])))      # warm-up
     n_serial_s = native(lambda: drv.ftd_run_serial(ctxs[0].h, C.byref(seq), args.steps, TH, C.byref(nmatch[0])))
     n_pipe_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 0, 0, C.byref(nmatch[1])))
-    n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[2])))
+    # store loop with the synchronous ft_search_store (round 1 / early round 2 headline), then the same loop with the search
+    # split into ft_search_store_submit / ft_search_collect and the next frame's ft_frame_submit issued between the halves
+    nm_sync = C.c_longlong()
+    n_store_sync_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nm_sync)))
+    n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[2])))
+    if nm_sync.value != nmatch[2].value:
+        raise SystemExit("bench.py: the split-search loop disagrees with the synchronous one on the matches found")
     # the same store loop with PAGEABLE input images (what a caller holding a plain cv::Mat hands over): upload_images stages
     # them through the context's pinned buffer (ft_context.cu), one extra host copy of both images per frame
     pg = dict(imgL=arr([f[0].ctypes.data for f in frames]), imgR=arr([f[1].ctypes.data for f in frames]))
     seq_pg = Seq(N_FRAMES, E["width"], E["height"], M_POINTS, C.cast(pg["imgL"], C.POINTER(C.c_void_p)), C.cast(pg["imgR"], C.POINTER(C.c_void_p)),
                  *[C.cast(keep[k_], C.POINTER(C.c_void_p)) for k_ in ("pos", "normal", "minmax", "desc", "flags", "rows")])
     nmatch.append(C.c_longlong())
-    n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[3])))
+    n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[3])))
     if nmatch[3].value != nmatch[2].value:
         raise SystemExit("bench.py: pageable-input loop disagrees on the matches found")
     # ... and with the same pageable buffers registered once (ft_host_register): what INTEGRATION.md recommends for a caller
@@ -1044,7 +1050,7 @@ def main():
         for im in f_:
             ctx._ck(L_.ft_host_register(im.ctypes.data, im.nbytes))
     nmatch.append(C.c_longlong())
-    n_store_reg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 1, STORE_UPSERTS, C.byref(nmatch[4])))
+    n_store_reg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[4])))
     for f_ in frames:
         for im in f_:
             L_.ft_host_unregister(im.ctypes.data)
@@ -1146,11 +1152,17 @@ def main():
                     "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
                     "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": n_store_s * 1e3 / args.steps, "frames_in_flight": DE,
-                    "path": "ft_frame_submit / ft_frame_collect + ft_map_store_update(%d rows) + ft_search_store (SURVEY 8f row 3)" % STORE_UPSERTS,
-                    "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp): ft_frame_submit(t+1..) "
-                              "overlaps marshal + search(t); host wall clock, max over ranks; pinned host images",
+                    "path": "ft_frame_collect + ft_map_store_update(%d rows) + ft_search_store_submit + ft_frame_submit(next frame) + "
+                            "ft_search_collect (SURVEY 8f row 3)" % STORE_UPSERTS,
+                    "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp): the search of frame t is "
+                              "enqueued first and the next camera frame is handed over while it runs; host wall clock, max over "
+                              "ranks; pinned host images",
                     "upserts_per_step": STORE_UPSERTS,
                     "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s), "ms_per_step": n_store_s * 1e3 / args.steps},
+                    "sync_search": {"value": replicas.aggregate_throughput(world, args.steps, n_store_sync_s),
+                                    "ms_per_step": n_store_sync_s * 1e3 / args.steps,
+                                    "note": "the same loop with ft_frame_submit(next frame) in front of the synchronous "
+                                            "ft_search_store (the headline loop until the search was split)"},
                     "pageable_images": {"value": replicas.aggregate_throughput(world, args.steps, n_store_pg_s),
                                         "ms_per_step": n_store_pg_s * 1e3 / args.steps,
                                         "note": "same loop, input images in pageable host memory (a plain cv::Mat): staged through the "

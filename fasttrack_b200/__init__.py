@@ -23,7 +23,7 @@ EXPORTS = [
     "ft_frame_download", "ft_set_pose", "ft_search_local_points", "ft_synchronize", "ft_debug_level_dims",
     "ft_debug_level_image", "ft_debug_level_candidates", "ft_debug_track", "ft_debug_grid", "ft_debug_stats",
     "ft_context_stream", "ft_set_use_graph", "ft_launch_counts", "ft_upload_map_points", "ft_upload_holders",
-    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_sensor", "ft_extract_mono", "ft_depth_from_rgbd", "ft_debug_sincosf", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store",
+    "ft_search_resident", "ft_search_download", "ft_set_stage_timing", "ft_get_stage_times", "ft_debug_level_counts", "ft_debug_sort", "ft_max_keypoints", "ft_frame_construct", "ft_frame_enqueue_device", "ft_map_point_staging", "ft_search_staged", "ft_search_last_frame", "ft_set_rectification", "ft_bind_map_points_device", "ft_frame_submit", "ft_frame_collect", "ft_set_sensor", "ft_extract_mono", "ft_depth_from_rgbd", "ft_debug_sincosf", "ft_set_input_resize", "ft_set_distortion", "ft_image_bounds", "ft_frame_keypoints_undistorted", "ft_map_store_create", "ft_map_store_attach", "ft_map_store_update", "ft_search_store", "ft_search_store_submit", "ft_search_collect",
     "ft_vocabulary_load_text", "ft_vocabulary_create", "ft_vocabulary_destroy", "ft_vocabulary_info", "ft_vocabulary_transform",
     "ft_compute_bow", "ft_bow_download", "ft_search_by_bow",
 ]
@@ -123,6 +123,8 @@ def load_library():
     L.ft_map_store_attach.argtypes = [vp, vp]
     L.ft_map_store_update.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     L.ft_search_store.argtypes = [vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]
+    L.ft_search_store_submit.argtypes = [vp, C.c_int, vp, vp, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int]
+    L.ft_search_collect.argtypes = [vp, vp, vp, vp, vp]
     L.ft_frame_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ft_vocabulary_load_text.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
     L.ft_vocabulary_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]
@@ -400,6 +402,23 @@ class Context:
         nm = C.c_int()
         self._ck(self.L.ft_search_store(self.h, M, _ptr(slots), _ptr(flags), th, int(b_far), th_far, nnratio,
                                         _ptr(holder), _ptr(holder_obs), _ptr(best), C.byref(nm)))
+        return nm.value, holder, holder_obs, best[:M]
+
+    def search_store_submit(self, slots, flags, th, holder, holder_obs, b_far=False, th_far=50.0, nnratio=0.8, want_best=True):
+        """first half of search_store: everything is enqueued, nothing is waited for (ft_search_store_submit)"""
+        slots = np.ascontiguousarray(slots, np.int32); flags = np.ascontiguousarray(flags, np.int32)
+        holder = np.ascontiguousarray(holder, np.int32).copy()
+        holder_obs = np.ascontiguousarray(holder_obs, np.uint8).copy()
+        self._ck(self.L.ft_search_store_submit(self.h, len(slots), _ptr(slots), _ptr(flags), th, int(b_far), th_far, nnratio,
+                                               _ptr(holder), _ptr(holder_obs), int(want_best)))
+        self._pending_search = (len(slots), holder, holder_obs)
+
+    def search_collect(self):
+        """second half: waits for the submitted search; returns what search_store returns (ft_search_collect)"""
+        M, holder, holder_obs = self._pending_search
+        best = np.full((max(M, 1), 2), -1, np.int32)
+        nm = C.c_int()
+        self._ck(self.L.ft_search_collect(self.h, _ptr(holder), _ptr(holder_obs), _ptr(best), C.byref(nm)))
         return nm.value, holder, holder_obs, best[:M]
 
     def set_pose(self, Rcw, tcw, Rwc=None, Ow=None):

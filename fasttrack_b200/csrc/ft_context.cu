@@ -106,6 +106,11 @@ struct ft_context {
   bool storeSearchedValid = false, updStagedValid = false, storeUpdatedValid = false;
   uint8_t *hUpd = nullptr, *dUpd = nullptr;
   int updCap = 0;
+  // asynchronous halves of ft_search_store: mpStaged = the H2D that reads hMp has finished (the staging buffer may be
+  // rewritten), searchDone = the D2H of the result slab has landed in hOut
+  cudaEvent_t mpStaged = nullptr, searchDone = nullptr;
+  bool mpStagedValid = false, searchPending = false, searchWantBest = false, searchEmpty = false;
+  int searchN = 0;
   // bag of words (ft_bow.cu): BowVector / FeatureVector of the current frame, SearchByBoW scratch; allocated on first use
   FtBowFrame W = {};
   FtBowSearch WQ = {};
@@ -540,6 +545,8 @@ extern "C" ft_status ft_context_destroy(ft_context* c) {
   if (c->storeSearched) cudaEventDestroy(c->storeSearched);
   if (c->storeUpdated) cudaEventDestroy(c->storeUpdated);
   if (c->updStaged) cudaEventDestroy(c->updStaged);
+  if (c->mpStaged) cudaEventDestroy(c->mpStaged);
+  if (c->searchDone) cudaEventDestroy(c->searchDone);
   for (void* p : c->allocs) cudaFree(p);
   for (int e = 0; e < 2; e++) if (c->hIn[e]) cudaFreeHost(c->hIn[e]);
   if (c->hCounts) cudaFreeHost(c->hCounts);
@@ -1169,6 +1176,7 @@ extern "C" ft_status ft_upload_map_points(ft_context* c, int M, const float* pos
     if (desc != d) memcpy(d, desc, (size_t)32 * M);
     if (flags != f) memcpy(f, flags, sizeof(int) * M);
     CK(cudaMemcpyAsync(c->dMp + c->mpHolderBytes, c->hMp + c->mpHolderBytes, (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
+    c->mpStagedValid = false;   // a copy out of the staging buffer that no event covers: the next user synchronises the stream
   }
   mp_bind_device(c, M);
   return FT_OK;
@@ -1213,6 +1221,7 @@ static ft_status search_run(ft_context* c, float th, int bFar, float thFar, floa
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
   if (!c->extracted) { set_err("ft_search_resident: no extracted frame"); return FT_ERR_STATE; }
   if (!c->stereoDone) { set_err("ft_search_resident: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
+  if (c->searchPending) { set_err("a search submitted with ft_search_store_submit has not been collected (ft_search_collect)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
   FtSbpBuffers& Q = c->Q;
   cudaStream_t s = c->stream;
@@ -1279,6 +1288,7 @@ extern "C" ft_status ft_search_staged(ft_context* c, int M, float th, int bFar, 
                                       int* nmatches) {
   if (!c || M < 0 || M > c->cfg.max_map_points) { set_err("ft_search_staged: bad argument"); return FT_ERR_INVALID; }
   if (!c->extracted || !c->stereoDone) { set_err("ft_search_staged: no stereo-matched frame"); return FT_ERR_STATE; }
+  if (c->searchPending) { set_err("a search submitted with ft_search_store_submit has not been collected (ft_search_collect)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
   if (nmatches) *nmatches = 0;
   CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)68 * M, cudaMemcpyHostToDevice, c->stream));
@@ -1308,6 +1318,7 @@ extern "C" ft_status ft_search_local_points(ft_context* c, int M, const float* p
   }
   if (!c->extracted) { set_err("ft_search_local_points: no extracted frame"); return FT_ERR_STATE; }
   if (!c->stereoDone) { set_err("ft_search_local_points: stereo matching has not run (mvuRight / match tables are read)"); return FT_ERR_STATE; }
+  if (c->searchPending) { set_err("a search submitted with ft_search_store_submit has not been collected (ft_search_collect)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
   ft_status st = fetch_counts(c);   // synchronises: the staging buffers are free afterwards
   if (st != FT_OK) return st;
@@ -1416,29 +1427,41 @@ extern "C" ft_status ft_map_store_update(ft_context* c, int n, const int* slots,
 
 // Tracking::SearchLocalPoints against the store: the local map is a list of rows (mvpLocalMapPoints order) plus the
 // per-call flags; 8 bytes per map point cross PCIe instead of 68.
-extern "C" ft_status ft_search_store(ft_context* c, int M, const int* slots, const int* flags, float th, int bFar,
-                                     float thFar, float nnratio, int* holder, uint8_t* holderObs, int* best_idx,
-                                     int* nmatches) {
+// ft_search_store_submit enqueues everything (H2D of holders + rows + flags, gather -> resolve, D2H of the result slab) and
+// returns; ft_search_collect waits for the slab and scatters it into the caller's arrays. Between the two the tracking
+// thread is free, e.g. to submit the next camera frame on another context (ft_sequence_driver.cpp does that).
+extern "C" ft_status ft_search_store_submit(ft_context* c, int M, const int* slots, const int* flags, float th, int bFar,
+                                            float thFar, float nnratio, const int* holder, const uint8_t* holderObs,
+                                            int want_best_idx) {
   if (!c || !holder || !holderObs || M < 0 || (M > 0 && (!slots || !flags))) { set_err("ft_search_store: null argument"); return FT_ERR_INVALID; }
   ft_map_store* st = c->store;
   if (!st) { set_err("ft_search_store: no map store (ft_map_store_create / ft_map_store_attach first)"); return FT_ERR_STATE; }
   if (M > c->cfg.max_map_points) { set_err("more map points than ft_config.max_map_points (the reference raises SIGSEGV beyond 25000)"); return FT_ERR_CAPACITY; }
   if (!c->extracted || !c->stereoDone) { set_err("ft_search_store: no stereo-matched frame"); return FT_ERR_STATE; }
+  if (c->searchPending) { set_err("ft_search_store_submit: the previous submitted search has not been collected"); return FT_ERR_STATE; }
   for (int i = 0; i < M; i++)
     if (slots[i] < 0 || slots[i] >= st->cap) { set_err("ft_search_store: slot outside the store's capacity"); return FT_ERR_CAPACITY; }
   CK(cudaSetDevice(c->cfg.device_id));
-  ft_status rs = fetch_counts(c);   // synchronises: the staging buffers are free afterwards
+  ft_status rs = fetch_counts(c);
   if (rs != FT_OK) return rs;
   const int N = c->fisheye ? c->hCounts[0] + c->hCounts[2] : c->hCounts[0];
-  if (nmatches) *nmatches = 0;
-  if (M == 0 || N == 0) { c->lastM = 0; return FT_OK; }
+  c->searchN = N; c->searchWantBest = want_best_idx != 0;
+  c->searchEmpty = false;
+  if (M == 0 || N == 0) { c->lastM = 0; c->searchEmpty = true; return FT_OK; }   // nothing enqueued: the caller's holders are the result
   cudaStream_t s = c->stream;
-  CK(cudaStreamSynchronize(s));
+  // the staging buffer is free once the last H2D that read it has finished: wait for exactly that (an upsert or a frame
+  // enqueued on this stream since then is not waited for); copies enqueued by the other search calls are followed by a
+  // stream synchronisation inside those calls, so the event of the last split search is the only one that can be open
+  if (c->mpStagedValid) CK(cudaEventSynchronize(c->mpStaged));
+  else CK(cudaStreamSynchronize(s));
   memcpy(c->hMp, holder, sizeof(int) * N);
   memcpy(c->hMp + (size_t)2 * c->P.maxKp * 4, holderObs, (size_t)N);
   uint8_t* hs = c->hMp + c->mpHolderBytes;
   memcpy(hs, slots, (size_t)4 * M); memcpy(hs + (size_t)4 * M, flags, (size_t)4 * M);
   CK(cudaMemcpyAsync(c->dMp, c->hMp, c->mpHolderBytes + (size_t)8 * M, cudaMemcpyHostToDevice, s));
+  if (!c->mpStaged) CK(cudaEventCreateWithFlags(&c->mpStaged, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->mpStaged, s));
+  c->mpStagedValid = true;
   FtSbpBuffers& Q = c->Q;
   Q.pos = st->pos; Q.normal = st->normal; Q.minmax = st->minmax; Q.desc = st->desc;
   Q.slot = reinterpret_cast<const int*>(c->dMp + c->mpHolderBytes);
@@ -1455,7 +1478,45 @@ extern "C" ft_status ft_search_store(ft_context* c, int M, const int* slots, con
     CK(cudaEventRecord(c->storeSearched, s));
     c->storeSearchedValid = true;
   }
-  return search_fetch(c, N, holder, holderObs, best_idx, nmatches);
+  // one D2H of the search result slab (cursors + status, holders, per-point selections)
+  const size_t bytes = c->offOutSel + (c->searchWantBest ? (size_t)8 * c->lastM : 0);
+  CK(cudaMemcpyAsync(c->hOut, c->dOut, bytes, cudaMemcpyDeviceToHost, s));
+  if (!c->searchDone) CK(cudaEventCreateWithFlags(&c->searchDone, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->searchDone, s));
+  c->searchPending = true;
+  return FT_OK;
+}
+
+extern "C" ft_status ft_search_collect(ft_context* c, int* holder, uint8_t* holderObs, int* best_idx, int* nmatches) {
+  if (!c) { set_err("ft_search_collect: null context"); return FT_ERR_INVALID; }
+  if (nmatches) *nmatches = 0;
+  if (!c->searchPending) {
+    // the submit found nothing to search (no map points or no keypoints): the holders handed to it are the result, the
+    // output arrays are left as they are
+    if (c->searchEmpty) { c->searchEmpty = false; return FT_OK; }
+    set_err("ft_search_collect: no submitted search"); return FT_ERR_STATE;
+  }
+  CK(cudaSetDevice(c->cfg.device_id));
+  CK(cudaEventSynchronize(c->searchDone));
+  c->searchPending = false;
+  const int N = c->searchN;
+  const int* hdr = reinterpret_cast<const int*>(c->hOut);
+  memcpy(c->hCounts + 8, hdr, 8 * sizeof(int));
+  if (holder && N) memcpy(holder, c->hOut + c->offOutHolder, sizeof(int) * N);
+  if (holderObs && N) memcpy(holderObs, c->hOut + c->offOutObs, (size_t)N);
+  if (best_idx && c->searchWantBest && c->lastM) memcpy(best_idx, c->hOut + c->offOutSel, sizeof(int) * 2 * c->lastM);
+  if (nmatches) *nmatches = hdr[1];
+  return check_device_status(c, hdr[8]);
+}
+
+extern "C" ft_status ft_search_store(ft_context* c, int M, const int* slots, const int* flags, float th, int bFar,
+                                     float thFar, float nnratio, int* holder, uint8_t* holderObs, int* best_idx,
+                                     int* nmatches) {
+  if (nmatches) *nmatches = 0;
+  ft_status rs = ft_search_store_submit(c, M, slots, flags, th, bFar, thFar, nnratio, holder, holderObs, best_idx != nullptr);
+  if (rs != FT_OK) return rs;
+  if (!c->searchPending) { c->searchEmpty = false; return FT_OK; }   // M == 0 or no keypoints
+  return ft_search_collect(c, holder, holderObs, best_idx, nmatches);
 }
 
 // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (reference src/ORBmatcher.cc:1775-2085), the
@@ -1469,6 +1530,7 @@ extern "C" ft_status ft_search_last_frame(ft_context* c, int n, const float* pos
     set_err("ft_search_last_frame: null argument"); return FT_ERR_INVALID;
   }
   if (!c->extracted || !c->stereoDone) { set_err("ft_search_last_frame: no stereo-matched frame"); return FT_ERR_STATE; }
+  if (c->searchPending) { set_err("a search submitted with ft_search_store_submit has not been collected (ft_search_collect)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
   ft_status st = fetch_counts(c);
   if (st != FT_OK) return st;

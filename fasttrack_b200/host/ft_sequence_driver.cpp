@@ -76,7 +76,9 @@ double ftd_run_serial(ft_context* c, const ftd_sequence* s, int steps, float th,
 // D frames in flight over D contexts of one sequence: frame i+D-1 is submitted (upload + extraction + stereo + result
 // download enqueued) before frame i is collected, marshalled and searched. use_store != 0: the local map is named as
 // rows of the persistent store (created by the caller on ctxs[0], attached to the others), `upserts` rows are
-// re-uploaded per frame.
+// re-uploaded per frame. use_store == 2: the search is issued as ft_search_store_submit / ft_search_collect and frame
+// i+D-1 is handed to ft_frame_submit BETWEEN the two halves: the search of frame i is first in the GPU's queues and the
+// host's work for the next camera frame (two image uploads, one graph launch) overlaps the search instead of preceding it.
 double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int steps, float th, int use_store, int upserts,
                          long long* matches) {
   if (D < 1) return -1.0;
@@ -88,9 +90,10 @@ double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int st
     const int k = j % s->n_frames;
     FTD(ft_frame_submit(ctxs[j % D], s->imgL[k], s->width, s->imgR[k], s->width));
   }
+  const bool split = use_store == 2 && D >= 2;   // with one context the next frame would overwrite the one being searched
   for (int i = 0; i < steps; i++) {
     const int j = i + D - 1;
-    if (j < steps) {
+    if (j < steps && !split) {
       const int kj = j % s->n_frames;
       FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
     }
@@ -106,7 +109,16 @@ double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int st
       std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
       std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
       int nm = 0;
-      FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      if (!split) {
+        FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      } else {
+        FTD(ft_search_store_submit(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), 1));
+        if (j < steps) {
+          const int kj = j % s->n_frames;
+          FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
+        }
+        FTD(ft_search_collect(c, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      }
       *matches += nm;
     }
   }

@@ -231,6 +231,15 @@ ft_status ft_search_staged(ft_context* ctx, int M, float th, int b_far_points, f
  * and searches are ordered across the contexts' streams inside the library. The store is freed with its last context.
  * ft_map_store_update: upsert n rows (slots[i] in [0, capacity)); arrays as in ft_search_local_points.
  * ft_search_store: as ft_search_local_points with (slots[M], flags[M]) in place of the five arrays.
+ * ft_search_store_submit / ft_search_collect: the two halves of ft_search_store. The reference's launch is synchronous
+ * (SearchLocalPointsKernel::launch copies in, runs the kernel and copies out before it returns,
+ * src/Kernels/SearchLocalPointsKernel.cu:346-478); here the submit enqueues the H2D of holders + rows + flags, the two
+ * kernels and the D2H of the result and returns, and the collect waits for the result and fills holder / holder_obs /
+ * best_idx (best_idx only when want_best_idx was set) and nmatches. Between the two the tracking thread is free -- e.g.
+ * to hand the next camera frame to ft_frame_submit on another context. holder / holder_obs of the submit are read before
+ * it returns. One search per context may be outstanding: every other search call on the context returns FT_ERR_STATE
+ * until it has been collected. With M == 0 or a frame without keypoints nothing is enqueued and the collect returns
+ * FT_OK with nmatches = 0 and the output arrays untouched (the holders handed to the submit are the result).
  * Errors: FT_ERR_STATE without a store / frame, FT_ERR_CAPACITY for a row outside the store or M > max_map_points. */
 ft_status ft_map_store_create(ft_context* ctx, int capacity);
 ft_status ft_map_store_attach(ft_context* ctx, ft_context* owner);
@@ -239,6 +248,10 @@ ft_status ft_map_store_update(ft_context* ctx, int n, const int* slots, const fl
 ft_status ft_search_store(ft_context* ctx, int M, const int* slots, const int* flags, float th, int bFarPoints,
                           float thFarPoints, float nnratio, int* holder, uint8_t* holder_obs, int* best_idx,
                           int* nmatches);
+ft_status ft_search_store_submit(ft_context* ctx, int M, const int* slots, const int* flags, float th, int bFarPoints,
+                                 float thFarPoints, float nnratio, const int* holder, const uint8_t* holder_obs,
+                                 int want_best_idx);
+ft_status ft_search_collect(ft_context* ctx, int* holder, uint8_t* holder_obs, int* best_idx, int* nmatches);
 
 /* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) -- the frame-to-last-frame search of
  * Tracking::TrackWithMotionModel (reference src/ORBmatcher.cc:1775-2085, src/Tracking.cc:2911-2990), incl. the

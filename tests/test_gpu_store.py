@@ -120,3 +120,58 @@ def test_store_errors(frame):
     nm, h2, ho2, _ = c.search_store(np.zeros(0, np.int32), np.zeros(0, np.int32), 3.0, h, ho)
     assert nm == 0 and np.array_equal(h2, h)
     c.close()
+
+
+def test_split_search_equals_synchronous_search(frame):
+    """ft_search_store_submit / ft_search_collect (the asynchronous halves of ft_search_store) return exactly what the
+    synchronous call returns, also with the next frame submitted on another context of the sequence between the two halves
+    and with upserts enqueued in front of the search (the order of the end-to-end loop in ft_sequence_driver.cpp)."""
+    M, CAP = 8000, 12000
+    mp = synth.mappoints(frame["kL"], frame["dL"], frame["scale"], M, seed=401)
+    rng = np.random.default_rng(9)
+    slots = rng.permutation(CAP)[:M].astype(np.int32)
+    a, b = _ctx(), _ctx()
+    try:
+        for c in (a, b):
+            c.set_pose(np.eye(3), np.zeros(3))
+        a.frame_construct(frame["L"], frame["R"])
+        a.map_store_create(CAP)
+        b.map_store_attach(a)
+        a.map_store_update(slots, mp["pos"], mp["normal"], mp["minmax"], mp["desc"])
+        n = a.counts()["n_left"]
+        h, ho = np.full(n, -1, np.int32), np.zeros(n, np.uint8)
+        ref = a.search_store(slots, mp["flags"], 3.0, h, ho)
+        assert ref[0] > 100
+        sc = synth.StereoScene(seed=21)
+        for it in range(4):
+            # upserts that do not change the data, in front of the search on the same stream
+            ch = rng.choice(M, 400, replace=False)
+            a.map_store_update(slots[ch], mp["pos"][ch], mp["normal"][ch], mp["minmax"][ch], mp["desc"][ch])
+            a.search_store_submit(slots, mp["flags"], 3.0, h, ho)
+            # a second search on the same context cannot be issued before the first one has been collected
+            with pytest.raises(RuntimeError, match="not been collected"):
+                a.search_store_submit(slots, mp["flags"], 3.0, h, ho)
+            with pytest.raises(RuntimeError, match="not been collected"):
+                a.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, h, ho)
+            L2, R2 = sc.pair(pan=(3 * it, it), noise_seed=it)
+            b.frame_submit(L2, R2)                       # the next camera frame, on the other context
+            got = a.search_collect()
+            assert _same(ref, got), it
+            b.frame_collect()
+        with pytest.raises(RuntimeError, match="no submitted search"):
+            a.search_collect()
+        # without the per-point selections
+        a.search_store_submit(slots, mp["flags"], 3.0, h, ho, want_best=False)
+        got = a.search_collect()
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        # empty local map: nothing is enqueued, the collect reports no matches
+        a.search_store_submit(np.zeros(0, np.int32), np.zeros(0, np.int32), 3.0, h, ho)
+        nm, h2, _, _ = a.search_collect()
+        assert nm == 0 and np.array_equal(h2, h)
+        # the synchronous call still works afterwards and a snapshot search after a split one sees a free staging buffer
+        assert _same(ref, a.search_store(slots, mp["flags"], 3.0, h, ho))
+        assert _same(ref, a.search_local_points(mp["pos"], mp["normal"], mp["minmax"], mp["desc"], mp["flags"], 3.0, h, ho))
+        a.search_store_submit(slots, mp["flags"], 3.0, h, ho)
+        assert _same(ref, a.search_collect())
+    finally:
+        b.close(); a.close()
