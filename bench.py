@@ -1032,16 +1032,20 @@ def main():
     # split into ft_search_store_submit / ft_search_collect and the next frame's ft_frame_submit issued between the halves
     nm_sync = C.c_longlong()
     n_store_sync_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nm_sync)))
-    n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[2])))
-    if nm_sync.value != nmatch[2].value:
-        raise SystemExit("bench.py: the split-search loop disagrees with the synchronous one on the matches found")
+    nm_split = C.c_longlong()
+    n_store_split_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 2, STORE_UPSERTS, C.byref(nm_split)))
+    # ... and with frame t+1's host vectors collected and its upserts enqueued in the shadow of the search of frame t as well
+    # (needs three frames in flight; falls back to the split loop otherwise)
+    n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 3, STORE_UPSERTS, C.byref(nmatch[2])))
+    if not (nm_sync.value == nm_split.value == nmatch[2].value):
+        raise SystemExit("bench.py: the split-search loops disagree with the synchronous one on the matches found")
     # the same store loop with PAGEABLE input images (what a caller holding a plain cv::Mat hands over): upload_images stages
     # them through the context's pinned buffer (ft_context.cu), one extra host copy of both images per frame
     pg = dict(imgL=arr([f[0].ctypes.data for f in frames]), imgR=arr([f[1].ctypes.data for f in frames]))
     seq_pg = Seq(N_FRAMES, E["width"], E["height"], M_POINTS, C.cast(pg["imgL"], C.POINTER(C.c_void_p)), C.cast(pg["imgR"], C.POINTER(C.c_void_p)),
                  *[C.cast(keep[k_], C.POINTER(C.c_void_p)) for k_ in ("pos", "normal", "minmax", "desc", "flags", "rows")])
     nmatch.append(C.c_longlong())
-    n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[3])))
+    n_store_pg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 3, STORE_UPSERTS, C.byref(nmatch[3])))
     if nmatch[3].value != nmatch[2].value:
         raise SystemExit("bench.py: pageable-input loop disagrees on the matches found")
     # ... and with the same pageable buffers registered once (ft_host_register): what INTEGRATION.md recommends for a caller
@@ -1050,7 +1054,7 @@ def main():
         for im in f_:
             ctx._ck(L_.ft_host_register(im.ctypes.data, im.nbytes))
     nmatch.append(C.c_longlong())
-    n_store_reg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 2, STORE_UPSERTS, C.byref(nmatch[4])))
+    n_store_reg_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq_pg), args.steps, TH, 3, STORE_UPSERTS, C.byref(nmatch[4])))
     for f_ in frames:
         for im in f_:
             L_.ft_host_unregister(im.ctypes.data)
@@ -1152,13 +1156,17 @@ def main():
                     "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
                     "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": n_store_s * 1e3 / args.steps, "frames_in_flight": DE,
-                    "path": "ft_frame_collect + ft_map_store_update(%d rows) + ft_search_store_submit + ft_frame_submit(next frame) + "
-                            "ft_search_collect (SURVEY 8f row 3)" % STORE_UPSERTS,
-                    "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp): the search of frame t is "
-                              "enqueued first and the next camera frame is handed over while it runs; host wall clock, max over "
-                              "ranks; pinned host images",
+                    "path": "ft_search_store_submit(t) + ft_frame_submit(t+2) + ft_frame_collect(t+1) + ft_map_store_update(%d rows, t+1) + "
+                            "ft_search_collect(t) (SURVEY 8f row 3)" % STORE_UPSERTS,
+                    "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp, use_store = 3): the search of "
+                              "frame t is enqueued first; while it runs the next camera frame is handed over and frame t+1 delivers "
+                              "its host vectors and takes its upserts; host wall clock, max over ranks; pinned host images",
                     "upserts_per_step": STORE_UPSERTS,
                     "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s), "ms_per_step": n_store_s * 1e3 / args.steps},
+                    "split_search": {"value": replicas.aggregate_throughput(world, args.steps, n_store_split_s),
+                                     "ms_per_step": n_store_split_s * 1e3 / args.steps,
+                                     "note": "use_store = 2: only ft_frame_submit(next frame) between ft_search_store_submit and "
+                                             "ft_search_collect; frame t+1 is collected after the search of frame t"},
                     "sync_search": {"value": replicas.aggregate_throughput(world, args.steps, n_store_sync_s),
                                     "ms_per_step": n_store_sync_s * 1e3 / args.steps,
                                     "note": "the same loop with ft_frame_submit(next frame) in front of the synchronous "

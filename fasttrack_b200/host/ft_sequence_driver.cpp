@@ -73,16 +73,30 @@ double ftd_run_serial(ft_context* c, const ftd_sequence* s, int steps, float th,
   return now_s() - t0;
 }
 
+// Frame i's host vectors + the rows the mapping side changed for it (store variants)
+static ft_status collect_frame(ft_context* c, const ftd_sequence* s, int k, HostFrame& F, int use_store, int upserts) {
+  ft_status st = ft_frame_collect(c, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(), F.counts, F.ur.data(), F.dp.data(), nullptr,
+                                  nullptr, nullptr);
+  if (st != FT_OK || !use_store) return st;
+  return ft_map_store_update(c, upserts, s->rows[k], s->pos[k], s->normal[k], s->minmax[k], s->desc[k]);
+}
+
 // D frames in flight over D contexts of one sequence: frame i+D-1 is submitted (upload + extraction + stereo + result
 // download enqueued) before frame i is collected, marshalled and searched. use_store != 0: the local map is named as
 // rows of the persistent store (created by the caller on ctxs[0], attached to the others), `upserts` rows are
-// re-uploaded per frame. use_store == 2: the search is issued as ft_search_store_submit / ft_search_collect and frame
-// i+D-1 is handed to ft_frame_submit BETWEEN the two halves: the search of frame i is first in the GPU's queues and the
-// host's work for the next camera frame (two image uploads, one graph launch) overlaps the search instead of preceding it.
+// re-uploaded per frame.
+// use_store == 2: the search is issued as ft_search_store_submit / ft_search_collect and frame i+D-1 is handed to
+// ft_frame_submit BETWEEN the two halves: the search of frame i is first in the GPU's queues and the host's work for the
+// next camera frame (two image uploads, one graph launch) overlaps the search instead of preceding it.
+// use_store == 3 (D >= 3): additionally the host vectors of frame i+1 are collected and its upserts enqueued while the
+// search of frame i runs (they do not depend on the tracking of frame i: the Frame constructor's outputs and the mapping
+// side's changed rows); only the holders of frame i+1 -- F.mvpMapPoints after tracking -- wait for the search of frame i.
+// Two host frames alternate, so frame i's vectors stay valid until its search has been collected.
 double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int steps, float th, int use_store, int upserts,
                          long long* matches) {
   if (D < 1) return -1.0;
-  HostFrame F(ft_max_keypoints(ctxs[0]), s->M);
+  HostFrame F0(ft_max_keypoints(ctxs[0]), s->M), F1(ft_max_keypoints(ctxs[0]), s->M);
+  HostFrame* Fs[2] = {&F0, &F1};
   *matches = 0;
   for (int j = 0; j < D; j++) FTD(ft_synchronize(ctxs[j]));
   const double t0 = now_s();
@@ -90,37 +104,37 @@ double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int st
     const int k = j % s->n_frames;
     FTD(ft_frame_submit(ctxs[j % D], s->imgL[k], s->width, s->imgR[k], s->width));
   }
-  const bool split = use_store == 2 && D >= 2;   // with one context the next frame would overwrite the one being searched
+  const bool split = use_store >= 2 && D >= 2;   // with one context the next frame would overwrite the one being searched
+  const bool early = use_store == 3 && D >= 3;   // frame i+1 must have been submitted in an earlier iteration
+  if (early && steps > 0) FTD(collect_frame(ctxs[0], s, 0, *Fs[0], use_store, upserts));
   for (int i = 0; i < steps; i++) {
-    const int j = i + D - 1;
-    if (j < steps && !split) {
-      const int kj = j % s->n_frames;
-      FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
-    }
+    const int j = i + D - 1;                     // the camera frame handed over in this iteration
+    const int kj = j % s->n_frames;
+    if (j < steps && !split) FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
     ft_context* c = ctxs[i % D];
     const int k = i % s->n_frames;
-    FTD(ft_frame_collect(c, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(), F.counts, F.ur.data(), F.dp.data(), nullptr,
-                         nullptr, nullptr));
+    HostFrame& F = *Fs[early ? (i & 1) : 0];
+    if (!early) FTD(collect_frame(c, s, k, F, use_store, upserts));
     const int nl = F.counts[0];
     if (!use_store) {
       FTD(search_snapshot(c, s, k, nl, th, matches));
-    } else {
-      FTD(ft_map_store_update(c, upserts, s->rows[k], s->pos[k], s->normal[k], s->minmax[k], s->desc[k]));
-      std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
-      std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
-      int nm = 0;
-      if (!split) {
-        FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
-      } else {
-        FTD(ft_search_store_submit(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), 1));
-        if (j < steps) {
-          const int kj = j % s->n_frames;
-          FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
-        }
-        FTD(ft_search_collect(c, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
-      }
-      *matches += nm;
+      continue;
     }
+    std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
+    std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
+    int nm = 0;
+    if (!split) {
+      FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+    } else {
+      FTD(ft_search_store_submit(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), 1));
+      // in the shadow of the search: the next camera frame goes to the context frame i-1 left ...
+      if (j < steps) FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
+      // ... and frame i+1, in flight since the previous iteration, delivers its vectors and takes its upserts
+      if (early && i + 1 < steps)
+        FTD(collect_frame(ctxs[(i + 1) % D], s, (i + 1) % s->n_frames, *Fs[(i + 1) & 1], use_store, upserts));
+      FTD(ft_search_collect(c, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+    }
+    *matches += nm;
   }
   for (int j = 0; j < D; j++) FTD(ft_synchronize(ctxs[j]));
   return now_s() - t0;

@@ -64,5 +64,12 @@ def test_native_sequence_loops_agree(euroc_pair):
     assert drv.ftd_run_pipelined(hctx, D, C.byref(seq), steps, 3.0, 0, 0, C.byref(nm)) > 0 and nm.value == total
     assert drv.ftd_run_pipelined(hctx, D, C.byref(seq), steps, 3.0, 1, 300, C.byref(nm)) > 0 and nm.value == total
     assert drv.ftd_run_pipelined(hctx, 1, C.byref(seq), steps, 3.0, 0, 0, C.byref(nm)) > 0 and nm.value == total
+    # the search as ft_search_store_submit / ft_search_collect with the next frame handed over between the halves (2), and with
+    # frame t+1 collected + upserted in the shadow of the search of frame t as well (3); fewer contexts fall back
+    for mode in (2, 3):
+        for d in (3, 2, 1):
+            assert drv.ftd_run_pipelined(hctx, d, C.byref(seq), steps, 3.0, mode, 300, C.byref(nm)) > 0 and nm.value == total, (mode, d)
+    assert drv.ftd_run_pipelined(hctx, D, C.byref(seq), 1, 3.0, 3, 300, C.byref(nm)) > 0 and nm.value == expect[0]
+    assert drv.ftd_run_pipelined(hctx, D, C.byref(seq), 2, 3.0, 3, 300, C.byref(nm)) > 0 and nm.value == expect[0] + expect[1]
     for c in ctxs:
         c.close()

@@ -11,9 +11,9 @@ import json
 try:
     d = json.loads(open("gpurun_out/quick_bench_n1.json").read().strip().splitlines()[-1])
     e = d["e2e"]
-    print("value %.0f lat p50 %.1f warm %.1f | e2e %.0f (%.1f us) sync_search %.0f snapshot %.0f pageable %.0f registered %.0f serial %.0f" % (
+    print("value %.0f lat p50 %.1f warm %.1f | e2e %.0f (%.1f us) split_search %.0f sync_search %.0f snapshot %.0f pageable %.0f registered %.0f serial %.0f" % (
         d["value"], d["latency"]["p50"] * 1e3, d["latency"].get("warm_p50", 0) * 1e3, e["value"], e["ms_per_step"] * 1e3,
-        e.get("sync_search", {}).get("value", 0), e["snapshot"]["value"], e["pageable_images"]["value"], e["registered_images"]["value"], e["serial_value"]))
+        e.get("split_search", {}).get("value", 0), e.get("sync_search", {}).get("value", 0), e["snapshot"]["value"], e["pageable_images"]["value"], e["registered_images"]["value"], e["serial_value"]))
 except Exception as ex:
     print("no bench line:", ex)
 PY
