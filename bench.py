@@ -699,7 +699,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.3, help="the K-step timed region is repeated until this much device time is measured")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration / next-row / reference-GPU legs")
     ap.add_argument("--profile-steps", type=int, default=40, help="steps of the per-kernel CUDA-event pass")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight in the end-to-end legs (<= pipeline depth)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="frames in flight in the end-to-end legs (<= pipeline depth); the headline loop collects frame t+1 while frame t is searched, so three is one too few: frame t+1 would still be extracting")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight in the throughput leg (contexts/streams)")
     ap.add_argument("--ref-gpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--watchdog", type=float, default=900.0, help="dump every thread's Python stack to stderr and exit if the run takes longer (s)")
@@ -1032,11 +1032,22 @@ def main():
     # split into ft_search_store_submit / ft_search_collect and the next frame's ft_frame_submit issued between the halves
     nm_sync = C.c_longlong()
     n_store_sync_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 1, STORE_UPSERTS, C.byref(nm_sync)))
+    drv.ftd_phase_seconds.argtypes = [C.POINTER(C.c_double)]
+    drv.ftd_phase_seconds.restype = None
+    PHASES = ("frame_submit", "frame_collect", "store_update", "search_submit", "search_collect", "search_sync", "marshal")
+
+    def host_phases():
+        """host wall clock per phase of the last ftd_run_pipelined call, us per frame (the tracking thread's time line)"""
+        buf = (C.c_double * len(PHASES))()
+        drv.ftd_phase_seconds(buf)
+        return {k_: buf[i_] * 1e6 / args.steps for i_, k_ in enumerate(PHASES) if buf[i_] > 0}
+    phases_sync = host_phases()
     nm_split = C.c_longlong()
     n_store_split_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 2, STORE_UPSERTS, C.byref(nm_split)))
     # ... and with frame t+1's host vectors collected and its upserts enqueued in the shadow of the search of frame t as well
     # (needs three frames in flight; falls back to the split loop otherwise)
     n_store_s = native(lambda: drv.ftd_run_pipelined(hctx, DE, C.byref(seq), args.steps, TH, 3, STORE_UPSERTS, C.byref(nmatch[2])))
+    phases_e2e = host_phases()
     if not (nm_sync.value == nm_split.value == nmatch[2].value):
         raise SystemExit("bench.py: the split-search loops disagree with the synchronous one on the matches found")
     # the same store loop with PAGEABLE input images (what a caller holding a plain cv::Mat hands over): upload_images stages
@@ -1162,13 +1173,14 @@ def main():
                               "frame t is enqueued first; while it runs the next camera frame is handed over and frame t+1 delivers "
                               "its host vectors and takes its upserts; host wall clock, max over ranks; pinned host images",
                     "upserts_per_step": STORE_UPSERTS,
+                    "host_phases_us_per_frame": phases_e2e,
                     "map_store": {"value": replicas.aggregate_throughput(world, args.steps, n_store_s), "ms_per_step": n_store_s * 1e3 / args.steps},
                     "split_search": {"value": replicas.aggregate_throughput(world, args.steps, n_store_split_s),
                                      "ms_per_step": n_store_split_s * 1e3 / args.steps,
                                      "note": "use_store = 2: only ft_frame_submit(next frame) between ft_search_store_submit and "
                                              "ft_search_collect; frame t+1 is collected after the search of frame t"},
                     "sync_search": {"value": replicas.aggregate_throughput(world, args.steps, n_store_sync_s),
-                                    "ms_per_step": n_store_sync_s * 1e3 / args.steps,
+                                    "ms_per_step": n_store_sync_s * 1e3 / args.steps, "host_phases_us_per_frame": phases_sync,
                                     "note": "the same loop with ft_frame_submit(next frame) in front of the synchronous "
                                             "ft_search_store (the headline loop until the search was split)"},
                     "pageable_images": {"value": replicas.aggregate_throughput(world, args.steps, n_store_pg_s),

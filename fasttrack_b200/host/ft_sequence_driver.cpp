@@ -57,6 +57,18 @@ static ft_status search_snapshot(ft_context* c, const ftd_sequence* s, int k, in
 
 #define FTD(call) do { ft_status st_ = (call); if (st_ != FT_OK) return -(double)st_; } while (0)
 
+// Host wall clock per phase of the pipelined loop, summed over the last ftd_run_pipelined call (two clock reads per
+// phase, about 50 ns): what the tracking thread spends where. ftd_phase_seconds copies the sums out.
+enum { PH_FRAME_SUBMIT, PH_FRAME_COLLECT, PH_STORE_UPDATE, PH_SEARCH_SUBMIT, PH_SEARCH_COLLECT, PH_SEARCH_SYNC, PH_MARSHAL, PH_COUNT };
+static double g_phase[PH_COUNT];
+struct PhaseTimer {
+  int id; double t0;
+  explicit PhaseTimer(int id_) : id(id_), t0(now_s()) {}
+  ~PhaseTimer() { g_phase[id] += now_s() - t0; }
+};
+#define FTD_PH(id, call) do { PhaseTimer pt_(id); FTD(call); } while (0)
+void ftd_phase_seconds(double* out7) { for (int i = 0; i < PH_COUNT; i++) out7[i] = g_phase[i]; }
+
 // one frame at a time on one context: returns wall seconds for `steps` frames, < 0 on error (ft_last_error has the text)
 double ftd_run_serial(ft_context* c, const ftd_sequence* s, int steps, float th, long long* matches) {
   HostFrame F(ft_max_keypoints(c), s->M);
@@ -75,9 +87,14 @@ double ftd_run_serial(ft_context* c, const ftd_sequence* s, int steps, float th,
 
 // Frame i's host vectors + the rows the mapping side changed for it (store variants)
 static ft_status collect_frame(ft_context* c, const ftd_sequence* s, int k, HostFrame& F, int use_store, int upserts) {
-  ft_status st = ft_frame_collect(c, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(), F.counts, F.ur.data(), F.dp.data(), nullptr,
-                                  nullptr, nullptr);
+  ft_status st;
+  {
+    PhaseTimer pt(PH_FRAME_COLLECT);
+    st = ft_frame_collect(c, F.kL.data(), F.dL.data(), F.kR.data(), F.dR.data(), F.counts, F.ur.data(), F.dp.data(), nullptr,
+                          nullptr, nullptr);
+  }
   if (st != FT_OK || !use_store) return st;
+  PhaseTimer pt(PH_STORE_UPDATE);
   return ft_map_store_update(c, upserts, s->rows[k], s->pos[k], s->normal[k], s->minmax[k], s->desc[k]);
 }
 
@@ -98,11 +115,12 @@ double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int st
   HostFrame F0(ft_max_keypoints(ctxs[0]), s->M), F1(ft_max_keypoints(ctxs[0]), s->M);
   HostFrame* Fs[2] = {&F0, &F1};
   *matches = 0;
+  for (int i = 0; i < PH_COUNT; i++) g_phase[i] = 0.0;
   for (int j = 0; j < D; j++) FTD(ft_synchronize(ctxs[j]));
   const double t0 = now_s();
   for (int j = 0; j < D - 1 && j < steps; j++) {
     const int k = j % s->n_frames;
-    FTD(ft_frame_submit(ctxs[j % D], s->imgL[k], s->width, s->imgR[k], s->width));
+    FTD_PH(PH_FRAME_SUBMIT, ft_frame_submit(ctxs[j % D], s->imgL[k], s->width, s->imgR[k], s->width));
   }
   const bool split = use_store >= 2 && D >= 2;   // with one context the next frame would overwrite the one being searched
   const bool early = use_store == 3 && D >= 3;   // frame i+1 must have been submitted in an earlier iteration
@@ -110,29 +128,32 @@ double ftd_run_pipelined(ft_context** ctxs, int D, const ftd_sequence* s, int st
   for (int i = 0; i < steps; i++) {
     const int j = i + D - 1;                     // the camera frame handed over in this iteration
     const int kj = j % s->n_frames;
-    if (j < steps && !split) FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
+    if (j < steps && !split) FTD_PH(PH_FRAME_SUBMIT, ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
     ft_context* c = ctxs[i % D];
     const int k = i % s->n_frames;
     HostFrame& F = *Fs[early ? (i & 1) : 0];
     if (!early) FTD(collect_frame(c, s, k, F, use_store, upserts));
     const int nl = F.counts[0];
     if (!use_store) {
-      FTD(search_snapshot(c, s, k, nl, th, matches));
+      FTD_PH(PH_SEARCH_SYNC, search_snapshot(c, s, k, nl, th, matches));
       continue;
     }
-    std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
-    std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
+    {
+      PhaseTimer pt(PH_MARSHAL);
+      std::fill(F.holder.begin(), F.holder.begin() + nl, -1);
+      std::fill(F.hobs.begin(), F.hobs.begin() + nl, (uint8_t)0);
+    }
     int nm = 0;
     if (!split) {
-      FTD(ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      FTD_PH(PH_SEARCH_SYNC, ft_search_store(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
     } else {
-      FTD(ft_search_store_submit(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), 1));
+      FTD_PH(PH_SEARCH_SUBMIT, ft_search_store_submit(c, s->M, s->rows[k], s->flags[k], th, 0, 50.f, 0.8f, F.holder.data(), F.hobs.data(), 1));
       // in the shadow of the search: the next camera frame goes to the context frame i-1 left ...
-      if (j < steps) FTD(ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
+      if (j < steps) FTD_PH(PH_FRAME_SUBMIT, ft_frame_submit(ctxs[j % D], s->imgL[kj], s->width, s->imgR[kj], s->width));
       // ... and frame i+1, in flight since the previous iteration, delivers its vectors and takes its upserts
       if (early && i + 1 < steps)
         FTD(collect_frame(ctxs[(i + 1) % D], s, (i + 1) % s->n_frames, *Fs[(i + 1) & 1], use_store, upserts));
-      FTD(ft_search_collect(c, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
+      FTD_PH(PH_SEARCH_COLLECT, ft_search_collect(c, F.holder.data(), F.hobs.data(), F.best.data(), &nm));
     }
     *matches += nm;
   }
