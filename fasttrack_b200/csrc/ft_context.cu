@@ -1274,6 +1274,7 @@ static ft_status search_fetch(ft_context* c, int N, int* holder, uint8_t* holder
 
 extern "C" ft_status ft_search_download(ft_context* c, int* holder, uint8_t* holderObs, int* best_idx, int* nmatches) {
   if (!c) { set_err("null context"); return FT_ERR_INVALID; }
+  if (c->searchPending) { set_err("a search submitted with ft_search_store_submit has not been collected (ft_search_collect)"); return FT_ERR_STATE; }
   CK(cudaSetDevice(c->cfg.device_id));
   ft_status st = fetch_counts(c);
   if (st != FT_OK) return st;
