@@ -37,6 +37,14 @@ WORKLOAD = ("euroc_752x480_stereo_sequence: extract(L,R; 1200 features, 8 levels
 METRIC = "frames/sec (ORB extract L+R + stereo match + projection search)"
 
 
+def shared_config(n_seq):
+    """`config` of the JSON line, identical for both arms (the driver compares the two dicts): the workload, the number of
+    independent sequences, and how the GPU arm keeps its inputs out of L2 (the CPU arm has no such cache to defeat)."""
+    return {"workload": WORKLOAD, "sequences": n_seq,
+            "l2": "GPU arm: throughput leg cycles %d distinct frames (inputs %.0f MB > 126 MB L2), latency leg flushes L2 between steps "
+                  "(256 MiB write); CPU arm: n/a" % (N_FRAMES, N_FRAMES * (2 * E["width"] * E["height"] + 68 * M_POINTS) / 1e6)}
+
+
 _T0 = time.perf_counter()
 
 
@@ -624,7 +632,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)", "sequences": n_seq},
+            "config": shared_config(n_seq),
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "%d frames of the bench workload on each of %d concurrent sequences; L/R extraction on 2 threads "
                                        "per sequence as Frame.cc:127-130, stereo + SearchLocalPoints on 1; host has %d cores"
@@ -1153,13 +1161,12 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_cycled": N_FRAMES,
-                       "l2": "throughput leg: %d distinct frames cycled, inputs %.0f MB > 126 MB L2; latency leg: L2 flushed "
-                             "between steps (256 MiB write)" % (N_FRAMES, N_FRAMES * (2 * E["width"] * E["height"] + 68 * M_POINTS) / 1e6),
-                       "pipeline": "%d frames in flight over one sequence (extract t+1.. || search t); searches stay ordered" % D,
-                       "pipeline_depth": D,
-                       "sequences": world, "parallelism": "independent sequence per GPU, no collective (gloo barrier + MAX only)",
-                       "pinned_cores": pinned_cores},
+            "config": shared_config(world),
+            "config_detail": {"frames_cycled": N_FRAMES,
+                              "pipeline": "%d frames in flight over one sequence (extract t+1.. || search t); searches stay ordered" % D,
+                              "pipeline_depth": D, "e2e_depth": DE,
+                              "parallelism": "independent sequence per GPU, no collective (gloo barrier + MAX only)",
+                              "pinned_cores": pinned_cores},
             # headline end-to-end path = the design's answer to the per-frame CudaMapPoint marshalling of the reference:
             # host images in, every host vector of the Frame out, the local map named as rows of the persistent device-side
             # store (8 B / point + the rows the mapping side changed). The 68 B / point snapshot variant is reported beside it.
