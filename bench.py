@@ -1174,7 +1174,7 @@ def main():
                     "h2d_bytes_per_step": int(2 * E["width"] * E["height"] + 8 * M_POINTS + 72 * STORE_UPSERTS + 2 * cap_dev * 5),
                     "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": n_store_s * 1e3 / args.steps, "frames_in_flight": DE,
-                    "path": "ft_search_store_submit(t) + ft_frame_submit(t+2) + ft_frame_collect(t+1) + ft_map_store_update(%d rows, t+1) + "
+                    "path": "ft_search_store_submit(t) + ft_frame_submit(t+D-1) + ft_frame_collect(t+1) + ft_map_store_update(%d rows, t+1) + "
                             "ft_search_collect(t) (SURVEY 8f row 3)" % STORE_UPSERTS,
                     "driver": "C++ loop over the C ABI (fasttrack_b200/host/ft_sequence_driver.cpp, use_store = 3): the search of "
                               "frame t is enqueued first; while it runs the next camera frame is handed over and frame t+1 delivers "
