@@ -238,7 +238,8 @@ ft_status ft_search_staged(ft_context* ctx, int M, float th, int b_far_points, f
  * best_idx (best_idx only when want_best_idx was set) and nmatches. Between the two the tracking thread is free -- e.g.
  * to hand the next camera frame to ft_frame_submit on another context. holder / holder_obs of the submit are read before
  * it returns. One search per context may be outstanding: every other search call on the context returns FT_ERR_STATE
- * until it has been collected. With M == 0 or a frame without keypoints nothing is enqueued and the collect returns
+ * until it has been collected, and the staging arrays of ft_map_point_staging must not be written in between (the submit's
+ * upload reads the same pinned buffer). With M == 0 or a frame without keypoints nothing is enqueued and the collect returns
  * FT_OK with nmatches = 0 and the output arrays untouched (the holders handed to the submit are the result).
  * Errors: FT_ERR_STATE without a store / frame, FT_ERR_CAPACITY for a row outside the store or M > max_map_points. */
 ft_status ft_map_store_create(ft_context* ctx, int capacity);
