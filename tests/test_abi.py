@@ -150,3 +150,31 @@ def test_host_mirror_and_driver_compile_and_link(lib, tmp_path):
     # without a GPU the demo must fail loudly through the mirror's exception path, not crash or fall back
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert out.returncode != 0
+
+
+def test_sequence_driver_exports_and_rejects_bad_arguments(lib):
+    """The host-side C++ loop bench.py times (fasttrack_b200/host/ft_sequence_driver.cpp) is built next to the library, binds to
+    it, and exports the three entry points; without contexts it fails with a negative return instead of touching anything."""
+    import fasttrack_b200
+    drv = ctypes.CDLL(os.path.join(os.path.dirname(fasttrack_b200.library_path()), "libft_sequence_driver.so"))
+    for name in ("ftd_run_serial", "ftd_run_pipelined", "ftd_phase_seconds"):
+        assert hasattr(drv, name), name
+    drv.ftd_run_pipelined.restype = ctypes.c_double
+    nm = ctypes.c_longlong(7)
+    assert drv.ftd_run_pipelined(None, 0, None, 0, ctypes.c_float(3.0), 0, 0, ctypes.byref(nm)) < 0   # D < 1
+    buf = (ctypes.c_double * 7)()
+    drv.ftd_phase_seconds.restype = None
+    drv.ftd_phase_seconds(buf)
+    assert all(v >= 0 for v in buf)
+
+
+def test_split_search_entry_points_check_their_arguments(lib):
+    """ft_search_store_submit / ft_search_collect (the asynchronous halves of ft_search_store) reject null arguments before any
+    CUDA call, like the rest of the ABI."""
+    lib.ft_search_store_submit.restype = ctypes.c_int
+    lib.ft_search_collect.restype = ctypes.c_int
+    vp = ctypes.c_void_p
+    assert lib.ft_search_store_submit(vp(), 0, vp(), vp(), ctypes.c_float(3.0), 0, ctypes.c_float(50.0), ctypes.c_float(0.8), vp(), vp(), 1) == 1
+    assert b"null argument" in lib.ft_last_error()
+    assert lib.ft_search_collect(vp(), vp(), vp(), vp(), vp()) == 1
+    assert b"null context" in lib.ft_last_error()
